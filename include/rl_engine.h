@@ -1,0 +1,185 @@
+/*
+ * rl_engine.h — C-ABI of the B200-native batched rate-limit engine (librl_engine.so).
+ *
+ * This is the drop-in boundary for ONE path of Kuadrant/limitador:
+ *   RateLimiter::check_rate_limited_and_update  (limitador/src/lib.rs:425-464)
+ *   = is_rate_limited + update_counters over the in-memory CounterStorage
+ *   (limitador/src/storage/in_memory.rs, atomic_expiring_value.rs).
+ *
+ * Each entry point replaces one method of `trait CounterStorage`
+ * (limitador/src/storage/mod.rs:279-292), batched: the caller (the Rust crate's batching
+ * front) performs limit matching on the CPU (lib.rs:507-522) and
+ * ships plain arrays; the engine owns an HBM-resident counter table and runs hand-written
+ * sm_100a kernels.  A batch is applied EXACTLY as if its requests had been submitted one
+ * at a time, in array order, to the reference's InMemoryStorage with the clock reading
+ * now_us[i] at request i.
+ *
+ * Conventions
+ *   - All functions return RL_OK / RL_TRANSIENT / RL_FATAL (storage/mod.rs:312-339:
+ *     StorageErr{msg, transient}); rl_last_error() gives the message.  A full table is an
+ *     error (RL_TRANSIENT), never a silent allow or eviction.
+ *   - No pointer is retained after a call returns.  `mem` says where EVERY array argument
+ *     of that call lives: RL_MEM_HOST (pageable or pinned) or RL_MEM_DEVICE (same device
+ *     as the engine).  RL_MEM_DEVICE calls are enqueued on the engine's stream and return
+ *     immediately; rl_sync() waits and reports deferred errors.
+ *   - Time is µs since the UNIX epoch (atomic_expiring_value.rs:62-66); 1 <= now_us < 2^62.
+ *   - Counter identity = (limit_id, key_lo, key_hi) with key_hi < 2^32: a 96-bit digest of
+ *     the counter's resolved variable values (counter.rs:123-138); ignored for
+ *     unqualified limits (no variables).
+ *   - The engine handle may be used from one thread at a time (the batching front owns it).
+ */
+#ifndef RL_ENGINE_H
+#define RL_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rl_engine rl_engine;
+
+enum { RL_OK = 0, RL_TRANSIENT = 1, RL_FATAL = 2 };
+enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1 };
+#define RL_NONE 0xFFFFFFFFu
+
+typedef struct rl_config {
+    uint32_t struct_size;    /* sizeof(rl_config) */
+    int32_t device;          /* CUDA device ordinal */
+    uint64_t capacity_rows;  /* table rows (distinct counter keys per row group); rounded up to 2^k.
+                                Replaces InMemoryStorage::new(cache_size), in_memory.rs:205-212 */
+    uint32_t cells_per_row;  /* 1, 3 or 7: limits of one namespace sharing one variable set live
+                                in one row (row bytes = 16 * (1 + cells)) */
+    uint32_t max_batch;      /* max requests per call */
+    uint32_t max_counters;   /* max total counters per CSR call (0 = 4 * max_batch) */
+    uint32_t regions;        /* 0 = auto; power of two */
+    uint32_t flags;          /* reserved, 0 */
+    uint32_t _pad;
+} rl_config;
+
+/* A limit as the storage sees it (limit.rs:177-214: identity excludes max_value/name).
+ * limit_id is a dense id interned by the caller; (ns_id, varset_id) tells the engine
+ * which limits share a variable set (varset_id 0 = no variables = unqualified). */
+typedef struct rl_limit_desc {
+    uint32_t limit_id;
+    uint32_t ns_id;
+    uint32_t varset_id;
+    uint32_t qualified; /* !variables.is_empty(), counter.rs:108-110 */
+    uint64_t max_value;
+    uint64_t window_us; /* seconds * 1e6, counter.rs:76-78 */
+} rl_limit_desc;
+
+/* 32-byte request record: limit set implied by ns_id (every limit of the
+ * namespace applies, registration order), one key for all qualified limits. */
+typedef struct rl_record {
+    uint32_t ns_id;
+    uint32_t hits_addend; /* RLS uint32 hits_addend (envoy_rls/server.rs:131-135), used as delta */
+    uint64_t key_lo;
+    uint64_t key_hi;
+    uint64_t now_us;
+} rl_record;
+
+/* One counter of a request in the general (CSR) form: Counter = limit + set_variables. */
+typedef struct rl_counter {
+    uint32_t limit_id;
+    uint32_t _pad;
+    uint64_t key_lo;
+    uint64_t key_hi;
+} rl_counter;
+
+typedef struct rl_stats {
+    uint64_t kernel_launches; /* kernels launched by this engine since creation */
+    uint64_t batches;
+    uint64_t requests;
+    uint64_t capacity_rows;
+    uint32_t regions;
+    uint32_t row_bytes;
+    uint32_t fixed_point_rounds; /* speculative rounds run for multi-row requests (last batch) */
+    uint32_t _pad;
+} rl_stats;
+
+int rl_engine_create(const rl_config *cfg, rl_engine **out);
+void rl_engine_destroy(rl_engine *e);
+/* Message of the last non-OK status on this engine (never NULL). */
+const char *rl_last_error(rl_engine *e);
+/* Use the caller's CUDA stream (a cudaStream_t) for all subsequent work; NULL = the
+ * engine's own stream.  rl_engine_stream returns the stream in use. */
+int rl_engine_set_stream(rl_engine *e, void *cuda_stream);
+void *rl_engine_stream(rl_engine *e);
+/* Wait for all enqueued work; returns and clears any deferred device-side error. */
+int rl_sync(rl_engine *e);
+int rl_get_stats(rl_engine *e, rl_stats *out);
+
+/* CounterStorage::add_counter (storage/mod.rs:281, in_memory.rs:38-44) + Storage::update_limit
+ * (storage/mod.rs:67-83): new ids are registered (unqualified ⇒ counter pre-created as
+ * (0, EPOCH)); for a live id only max_value may change. */
+int rl_limits_set(rl_engine *e, const rl_limit_desc *limits, uint32_t n);
+/* Storage::delete_limit (storage/mod.rs:93-117): delete_counters + forget the limits. */
+int rl_limits_delete(rl_engine *e, const uint32_t *limit_ids, uint32_t n);
+
+/* CounterStorage::check_and_update (storage/mod.rs:283-288, in_memory.rs:72-156), batched.
+ * Record form.  out_limited[i] = 1 iff Authorization::Limited; out_first_limited[i] =
+ * limit id the reference would name (in_memory.rs:91-94,99-101) or RL_NONE;
+ * with load_counters != 0, out_remaining/out_ttl_us[i*out_stride + k] describe the k-th
+ * limit of the namespace (Counter::set_remaining / set_expires_in).  Nullable outputs:
+ * out_first_limited, out_remaining, out_ttl_us. */
+int rl_check_and_update_records(rl_engine *e, uint64_t n, const rl_record *recs, int load_counters,
+                                int mem, uint8_t *out_limited, uint32_t *out_first_limited,
+                                uint64_t *out_remaining, uint64_t *out_ttl_us, uint32_t out_stride);
+/* General form: request i owns ctrs[ctr_off[i] .. ctr_off[i+1]) (at most 16), counters are
+ * processed unqualified-first then in the given order (in_memory.rs:105,121);
+ * out_remaining/out_ttl_us are indexed like ctrs.  An empty counter list is "not limited"
+ * (lib.rs:434-440). */
+int rl_check_and_update_batch(rl_engine *e, uint64_t n, const uint32_t *ctr_off, const rl_counter *ctrs,
+                              const uint64_t *delta, const uint64_t *now_us, int load_counters, int mem,
+                              uint8_t *out_limited, uint32_t *out_first_limited,
+                              uint64_t *out_remaining, uint64_t *out_ttl_us);
+
+/* CounterStorage::is_within_limits (in_memory.rs:20-35) folded over a request's counters
+ * as RateLimiter::is_rate_limited does (lib.rs:362-409): read-only, given order, first
+ * counter over its limit wins. */
+int rl_is_within_limits_batch(rl_engine *e, uint64_t n, const uint32_t *ctr_off, const rl_counter *ctrs,
+                              const uint64_t *delta, const uint64_t *now_us, int mem,
+                              uint8_t *out_limited, uint32_t *out_first_limited);
+int rl_is_within_limits_records(rl_engine *e, uint64_t n, const rl_record *recs, int mem,
+                                uint8_t *out_limited, uint32_t *out_first_limited);
+
+/* CounterStorage::update_counter (in_memory.rs:47-69) for every counter of every request
+ * (RateLimiter::update_counters, lib.rs:411-423): unconditional, may exceed max_value. */
+int rl_update_batch(rl_engine *e, uint64_t n, const uint32_t *ctr_off, const rl_counter *ctrs,
+                    const uint64_t *delta, const uint64_t *now_us, int mem);
+int rl_update_records(rl_engine *e, uint64_t n, const rl_record *recs, int mem);
+
+/* CounterStorage::get_counters (in_memory.rs:158-187): every counter of the namespaces of
+ * the given limits with ttl(now_us) > 0.  Host output arrays of capacity cap; *out_count =
+ * number found (may exceed cap). */
+int rl_get_counters(rl_engine *e, const uint32_t *limit_ids, uint32_t n, uint64_t now_us, uint64_t cap,
+                    uint32_t *out_limit_id, uint64_t *out_key_lo, uint64_t *out_key_hi,
+                    uint64_t *out_remaining, uint64_t *out_ttl_us, uint64_t *out_count);
+/* CounterStorage::delete_counters (in_memory.rs:189-195,241-257). */
+int rl_delete_counters(rl_engine *e, const uint32_t *limit_ids, uint32_t n);
+/* CounterStorage::clear (in_memory.rs:197-201): drops ONLY unqualified counters. */
+int rl_clear(rl_engine *e);
+/* TTL sweep (no reference function; north_star's companion kernel): invalidate every
+ * qualified counter with expiry <= now_us and free rows left empty.  Mirrored in the
+ * oracle as lo_invalidate_expired.  *out_invalidated (nullable) = counters dropped. */
+int rl_sweep(rl_engine *e, uint64_t now_us, uint64_t *out_invalidated);
+/* Parity aid: every present counter (limit_id, key, value, expiry_us), unordered. */
+int rl_dump_table(rl_engine *e, uint64_t cap, uint32_t *out_limit_id, uint64_t *out_key_lo,
+                  uint64_t *out_key_hi, uint64_t *out_value, uint64_t *out_expiry_us,
+                  uint64_t *out_count);
+
+/* Multi-GPU exchange helper: stable bucketing of n device-resident records by
+ * owner = rl_owner_of(ns_id, world).  Writes the permuted records to d_out_recs, the
+ * source index of every permuted record to d_out_src (uint32), and the per-owner counts
+ * to h_counts[world] (host).  All d_* pointers are device memory. */
+int rl_bucket_by_owner(rl_engine *e, uint64_t n, const rl_record *d_recs, uint32_t world,
+                       rl_record *d_out_recs, uint32_t *d_out_src, uint64_t *h_counts);
+/* out[src[i]] = in[i] for i < n (device pointers): return verdict bytes to request order. */
+int rl_unpermute_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *d_src, uint8_t *d_out);
+uint32_t rl_owner_of(uint32_t ns_id, uint32_t world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

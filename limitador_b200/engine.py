@@ -1,0 +1,303 @@
+"""ctypes binding of librl_engine.so (include/rl_engine.h).
+
+The engine is the product: hand-written sm_100a kernels behind a C-ABI.  There is no CPU
+fallback — constructing an Engine without the built library or without a CUDA device
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+RL_OK, RL_TRANSIENT, RL_FATAL = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+NONE = 0xFFFFFFFF
+
+RECORD_DTYPE = np.dtype(
+    [("ns_id", "<u4"), ("hits_addend", "<u4"), ("key_lo", "<u8"), ("key_hi", "<u8"), ("now_us", "<u8")]
+)
+COUNTER_DTYPE = np.dtype([("limit_id", "<u4"), ("_pad", "<u4"), ("key_lo", "<u8"), ("key_hi", "<u8")])
+LIMIT_DESC_DTYPE = np.dtype(
+    [("limit_id", "<u4"), ("ns_id", "<u4"), ("varset_id", "<u4"), ("qualified", "<u4"),
+     ("max_value", "<u8"), ("window_us", "<u8")]
+)
+
+# every symbol include/rl_engine.h declares (tests check the library exports them all)
+ABI_SYMBOLS = [
+    "rl_engine_create", "rl_engine_destroy", "rl_last_error", "rl_engine_set_stream", "rl_engine_stream",
+    "rl_sync", "rl_get_stats", "rl_limits_set", "rl_limits_delete", "rl_check_and_update_records",
+    "rl_check_and_update_batch", "rl_is_within_limits_batch", "rl_is_within_limits_records",
+    "rl_update_batch", "rl_update_records", "rl_get_counters", "rl_delete_counters", "rl_clear",
+    "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
+]
+
+
+class RlConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("capacity_rows", C.c_uint64),
+        ("cells_per_row", C.c_uint32), ("max_batch", C.c_uint32), ("max_counters", C.c_uint32),
+        ("regions", C.c_uint32), ("flags", C.c_uint32), ("_pad", C.c_uint32),
+    ]
+
+
+class RlStats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64), ("batches", C.c_uint64), ("requests", C.c_uint64),
+        ("capacity_rows", C.c_uint64), ("regions", C.c_uint32), ("row_bytes", C.c_uint32),
+        ("fixed_point_rounds", C.c_uint32), ("_pad", C.c_uint32),
+    ]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"[{'TRANSIENT' if status == RL_TRANSIENT else 'FATAL'}] {msg}")
+        self.status = status
+        self.transient = status == RL_TRANSIENT
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Load librl_engine.so and declare the ABI.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -m limitador_b200.build` "
+            "(limitador_b200 has no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.rl_engine_create.argtypes = [C.POINTER(RlConfig), C.POINTER(vp)]
+    L.rl_engine_destroy.argtypes = [vp]
+    L.rl_engine_destroy.restype = None
+    L.rl_last_error.argtypes = [vp]
+    L.rl_last_error.restype = C.c_char_p
+    L.rl_engine_set_stream.argtypes = [vp, vp]
+    L.rl_engine_stream.argtypes = [vp]
+    L.rl_engine_stream.restype = vp
+    L.rl_sync.argtypes = [vp]
+    L.rl_get_stats.argtypes = [vp, C.POINTER(RlStats)]
+    L.rl_limits_set.argtypes = [vp, vp, u32]
+    L.rl_limits_delete.argtypes = [vp, vp, u32]
+    L.rl_check_and_update_records.argtypes = [vp, u64, vp, i32, i32, vp, vp, vp, vp, u32]
+    L.rl_check_and_update_batch.argtypes = [vp, u64, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.rl_is_within_limits_batch.argtypes = [vp, u64, vp, vp, vp, vp, i32, vp, vp]
+    L.rl_is_within_limits_records.argtypes = [vp, u64, vp, i32, vp, vp]
+    L.rl_update_batch.argtypes = [vp, u64, vp, vp, vp, vp, i32]
+    L.rl_update_records.argtypes = [vp, u64, vp, i32]
+    L.rl_get_counters.argtypes = [vp, vp, u32, u64, u64, vp, vp, vp, vp, vp, vp]
+    L.rl_delete_counters.argtypes = [vp, vp, u32]
+    L.rl_clear.argtypes = [vp]
+    L.rl_sweep.argtypes = [vp, u64, vp]
+    L.rl_dump_table.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+    L.rl_bucket_by_owner.argtypes = [vp, u64, vp, u32, vp, vp, vp]
+    L.rl_unpermute_u8.argtypes = [vp, u64, vp, vp, vp]
+    L.rl_owner_of.argtypes = [u32, u32]
+    L.rl_owner_of.restype = u32
+    if path == _build.LIB_PATH:
+        _lib = L
+    return L
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One GPU-resident counter table (one per process / per GPU)."""
+
+    def __init__(self, capacity_rows: int, cells_per_row: int = 1, max_batch: int = 65536,
+                 max_counters: int = 0, regions: int = 0, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        cfg = RlConfig(C.sizeof(RlConfig), device, capacity_rows, cells_per_row, max_batch, max_counters,
+                       regions, 0, 0)
+        st = self._lib.rl_engine_create(C.byref(cfg), C.byref(self._h))
+        if st != RL_OK:
+            msg = "rl_engine_create failed (no CUDA device? limitador_b200 has no CPU fallback)"
+            if self._h:
+                msg = self._lib.rl_last_error(self._h).decode() or msg
+                self._lib.rl_engine_destroy(self._h)
+                self._h = C.c_void_p()
+            raise EngineError(st, msg)
+        self.cells_per_row = cells_per_row
+        self.max_batch = max_batch
+        self.device = device
+
+    # -- lifecycle --
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rl_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != RL_OK:
+            raise EngineError(st, self._lib.rl_last_error(self._h).decode())
+
+    def sync(self):
+        self._check(self._lib.rl_sync(self._h))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.rl_engine_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.rl_engine_stream(self._h) or 0)
+
+    def stats(self) -> dict:
+        s = RlStats()
+        self._check(self._lib.rl_get_stats(self._h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in RlStats._fields_ if not f[0].startswith("_")}
+
+    # -- limits --
+    def limits_set(self, descs):
+        """descs: iterable of (limit_id, ns_id, varset_id, qualified, max_value, window_us) or array."""
+        if not isinstance(descs, np.ndarray):
+            descs = np.array([tuple(d) for d in descs], dtype=LIMIT_DESC_DTYPE)
+        descs = np.ascontiguousarray(descs, dtype=LIMIT_DESC_DTYPE)
+        self._check(self._lib.rl_limits_set(self._h, _p(descs), len(descs)))
+
+    def limits_delete(self, limit_ids):
+        ids = np.ascontiguousarray(limit_ids, dtype=np.uint32)
+        self._check(self._lib.rl_limits_delete(self._h, _p(ids), len(ids)))
+
+    # -- host-memory (numpy) calls: synchronous --
+    def check_and_update_records(self, recs, load_counters=False, stride=None, want_first=True):
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        n = len(recs)
+        stride = stride or self.cells_per_row
+        lim = np.zeros(n, dtype=np.uint8)
+        fl = np.full(n, NONE, dtype=np.uint32) if want_first else None
+        rem = np.zeros(n * stride, dtype=np.uint64) if load_counters else None
+        ttl = np.zeros(n * stride, dtype=np.uint64) if load_counters else None
+        self._check(self._lib.rl_check_and_update_records(
+            self._h, n, _p(recs), int(load_counters), MEM_HOST, _p(lim), _p(fl), _p(rem), _p(ttl), stride))
+        return lim, fl, rem, ttl
+
+    def check_and_update_batch(self, off, ctrs, delta, now_us, load_counters=False):
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        ctrs = np.ascontiguousarray(ctrs, dtype=COUNTER_DTYPE)
+        delta = np.ascontiguousarray(delta, dtype=np.uint64)
+        now_us = np.ascontiguousarray(now_us, dtype=np.uint64)
+        n = len(delta)
+        lim = np.zeros(n, dtype=np.uint8)
+        fl = np.full(n, NONE, dtype=np.uint32)
+        rem = np.zeros(len(ctrs), dtype=np.uint64)
+        ttl = np.zeros(len(ctrs), dtype=np.uint64)
+        self._check(self._lib.rl_check_and_update_batch(
+            self._h, n, _p(off), _p(ctrs), _p(delta), _p(now_us), int(load_counters), MEM_HOST,
+            _p(lim), _p(fl), _p(rem) if load_counters else None, _p(ttl) if load_counters else None))
+        return lim, fl, rem, ttl
+
+    def is_within_limits_batch(self, off, ctrs, delta, now_us):
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        ctrs = np.ascontiguousarray(ctrs, dtype=COUNTER_DTYPE)
+        delta = np.ascontiguousarray(delta, dtype=np.uint64)
+        now_us = np.ascontiguousarray(now_us, dtype=np.uint64)
+        n = len(delta)
+        lim = np.zeros(n, dtype=np.uint8)
+        fl = np.full(n, NONE, dtype=np.uint32)
+        self._check(self._lib.rl_is_within_limits_batch(
+            self._h, n, _p(off), _p(ctrs), _p(delta), _p(now_us), MEM_HOST, _p(lim), _p(fl)))
+        return lim, fl
+
+    def is_within_limits_records(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        n = len(recs)
+        lim = np.zeros(n, dtype=np.uint8)
+        fl = np.full(n, NONE, dtype=np.uint32)
+        self._check(self._lib.rl_is_within_limits_records(self._h, n, _p(recs), MEM_HOST, _p(lim), _p(fl)))
+        return lim, fl
+
+    def update_batch(self, off, ctrs, delta, now_us):
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        ctrs = np.ascontiguousarray(ctrs, dtype=COUNTER_DTYPE)
+        delta = np.ascontiguousarray(delta, dtype=np.uint64)
+        now_us = np.ascontiguousarray(now_us, dtype=np.uint64)
+        self._check(self._lib.rl_update_batch(self._h, len(delta), _p(off), _p(ctrs), _p(delta), _p(now_us), MEM_HOST))
+
+    def update_records(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        self._check(self._lib.rl_update_records(self._h, len(recs), _p(recs), MEM_HOST))
+
+    # -- raw-pointer calls (device or pinned host memory; ints from tensor.data_ptr()) --
+    def check_and_update_records_ptr(self, n, recs_ptr, out_limited_ptr, mem, load_counters=False,
+                                     out_first_ptr=0, out_rem_ptr=0, out_ttl_ptr=0, stride=0):
+        self._check(self._lib.rl_check_and_update_records(
+            self._h, n, C.c_void_p(recs_ptr), int(load_counters), mem, C.c_void_p(out_limited_ptr),
+            C.c_void_p(out_first_ptr or 0), C.c_void_p(out_rem_ptr or 0), C.c_void_p(out_ttl_ptr or 0),
+            stride or self.cells_per_row))
+
+    def bucket_by_owner_ptr(self, n, recs_ptr, world, out_recs_ptr, out_src_ptr):
+        counts = np.zeros(world, dtype=np.uint64)
+        self._check(self._lib.rl_bucket_by_owner(self._h, n, C.c_void_p(recs_ptr), world,
+                                                 C.c_void_p(out_recs_ptr), C.c_void_p(out_src_ptr), _p(counts)))
+        return counts
+
+    def unpermute_u8_ptr(self, n, in_ptr, src_ptr, out_ptr):
+        self._check(self._lib.rl_unpermute_u8(self._h, n, C.c_void_p(in_ptr), C.c_void_p(src_ptr), C.c_void_p(out_ptr)))
+
+    # -- maintenance --
+    def get_counters(self, limit_ids, now_us, cap=1 << 20):
+        ids = np.ascontiguousarray(limit_ids, dtype=np.uint32)
+        lid = np.zeros(cap, dtype=np.uint32)
+        lo = np.zeros(cap, dtype=np.uint64)
+        hi = np.zeros(cap, dtype=np.uint64)
+        rem = np.zeros(cap, dtype=np.uint64)
+        ttl = np.zeros(cap, dtype=np.uint64)
+        cnt = C.c_uint64(0)
+        self._check(self._lib.rl_get_counters(self._h, _p(ids), len(ids), now_us, cap, _p(lid), _p(lo), _p(hi),
+                                              _p(rem), _p(ttl), C.byref(cnt)))
+        c = min(cnt.value, cap)
+        return sorted(zip(lid[:c].tolist(), lo[:c].tolist(), hi[:c].tolist(), rem[:c].tolist(), ttl[:c].tolist()))
+
+    def delete_counters(self, limit_ids):
+        ids = np.ascontiguousarray(limit_ids, dtype=np.uint32)
+        self._check(self._lib.rl_delete_counters(self._h, _p(ids), len(ids)))
+
+    def clear(self):
+        self._check(self._lib.rl_clear(self._h))
+
+    def sweep(self, now_us) -> int:
+        cnt = C.c_uint64(0)
+        self._check(self._lib.rl_sweep(self._h, now_us, C.byref(cnt)))
+        return cnt.value
+
+    def dump_arrays(self, cap=1 << 22):
+        lid = np.zeros(cap, dtype=np.uint32)
+        lo = np.zeros(cap, dtype=np.uint64)
+        hi = np.zeros(cap, dtype=np.uint64)
+        val = np.zeros(cap, dtype=np.uint64)
+        exp = np.zeros(cap, dtype=np.uint64)
+        cnt = C.c_uint64(0)
+        self._check(self._lib.rl_dump_table(self._h, cap, _p(lid), _p(lo), _p(hi), _p(val), _p(exp), C.byref(cnt)))
+        if cnt.value > cap:
+            return self.dump_arrays(cap=int(cnt.value) + 16)
+        c = cnt.value
+        return lid[:c], lo[:c], hi[:c], val[:c], exp[:c]
+
+    def dump(self):
+        """Sorted list of (limit_id, key_lo, key_hi, value, expiry_us) for every present counter."""
+        lid, lo, hi, val, exp = self.dump_arrays()
+        return sorted(zip(lid.tolist(), lo.tolist(), hi.tolist(), val.tolist(), exp.tolist()))
+
+
+def owner_of(ns_id: int, world: int) -> int:
+    return int(load_library().rl_owner_of(ns_id, world))

@@ -1,0 +1,280 @@
+"""GPU parity: the sm_100a kernels, called through the C-ABI, against the CPU oracle on the
+same seeded request streams — verdicts, named limit, remaining/ttl and the full table."""
+import numpy as np
+import pytest
+
+from limitador_b200 import Engine, EngineError
+from limitador_b200 import streams
+from limitador_b200.engine import LIMIT_DESC_DTYPE, NONE, RECORD_DTYPE, COUNTER_DTYPE
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+S = 1_000_000
+
+
+def engine_with_limits(descs, cells, capacity=1 << 14, max_batch=1 << 16, regions=0):
+    e = Engine(capacity_rows=capacity, cells_per_row=cells, max_batch=max_batch, regions=regions)
+    e.limits_set(descs)
+    return e
+
+
+def assert_tables_equal(e, o, descs):
+    assert H.normalise_dump(e.dump(), descs) == H.normalise_dump(o.dump(), descs)
+
+
+def single_row_limits(cells, n_ns=9, seed=0):
+    """Every namespace maps to one row (fast record path): 1..cells limits on one varset, or
+    1..cells unqualified limits."""
+    rng = np.random.default_rng(seed)
+    descs, lid = [], 0
+    for ns in range(n_ns):
+        k = int(rng.integers(1, cells + 1))
+        q = 0 if ns % 4 == 3 else 1
+        for _ in range(k):
+            mx = int(rng.choice([0, 1, 2, 3, 5, 8, 20, 1 << 40]))
+            win = int(rng.choice([1, 2, 10, 60, 3600])) * S
+            descs.append((lid, ns, 1 if q else 0, q, mx, win))
+            lid += 1
+    return np.array(descs, dtype=LIMIT_DESC_DTYPE)
+
+
+@pytest.mark.parametrize("cells", [1, 3, 7])
+@pytest.mark.parametrize("load_counters", [False, True])
+def test_records_fast_path(cells, load_counters):
+    descs = single_row_limits(cells, seed=cells)
+    e = engine_with_limits(descs, cells, regions=16)
+    o = H.oracle_with_limits(descs)
+    for b in range(6):
+        recs = H.random_records(descs, 3000, 10 * cells + b, n_keys=40, monotone=(b % 2 == 0))
+        got = e.check_and_update_records(recs, load_counters, stride=cells)
+        want = o.batch_records(0, recs, load_counters, cells)
+        assert got[0].tolist() == want[0].tolist()
+        assert got[1].tolist() == want[1].tolist()
+        if load_counters:
+            assert got[2].tolist() == want[2].tolist()
+            assert got[3].tolist() == want[3].tolist()
+        assert_tables_equal(e, o, descs)
+    assert e.stats()["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("cells", [1, 3, 7])
+def test_records_with_multi_row_namespaces(cells):
+    descs = H.mixed_limits(n_ns=12, seed=4)
+    e = engine_with_limits(descs, cells, regions=8)
+    o = H.oracle_with_limits(descs)
+    stride = 5
+    for b in range(4):
+        recs = H.random_records(descs, 1500, 77 + b, n_keys=6)
+        got = e.check_and_update_records(recs, True, stride=stride)
+        want = o.batch_records(0, recs, True, stride)
+        for k in range(4):
+            assert got[k].tolist() == want[k].tolist(), f"output {k} differs in batch {b}"
+        assert_tables_equal(e, o, descs)
+
+
+@pytest.mark.parametrize("cells", [1, 3, 7])
+@pytest.mark.parametrize("load_counters", [False, True])
+def test_csr_general_path_with_coupled_requests(cells, load_counters):
+    descs = H.mixed_limits(n_ns=12, seed=cells)
+    e = engine_with_limits(descs, cells, regions=8)
+    o = H.oracle_with_limits(descs)
+    for b in range(5):
+        off, ctrs, delta, now = H.random_csr_stream(descs, 2000, 1000 * cells + b, n_keys=4, monotone=(b != 3))
+        got = e.check_and_update_batch(off, ctrs, delta, now, load_counters)
+        want = o.batch_csr(0, off, ctrs, delta, now, load_counters)
+        assert got[0].tolist() == want[0].tolist()
+        assert got[1].tolist() == want[1].tolist()
+        if load_counters:
+            assert got[2].tolist() == want[2].tolist()
+            assert got[3].tolist() == want[3].tolist()
+        assert_tables_equal(e, o, descs)
+    assert e.stats()["fixed_point_rounds"] >= 1
+
+
+def test_long_dependency_chain():
+    descs = np.array([(0, 0, 1, 1, 1, 3600 * S), (1, 0, 2, 1, 1, 3600 * S)], dtype=LIMIT_DESC_DTYPE)
+    n = 40
+    off = np.arange(0, 2 * n + 1, 2, dtype=np.uint32)
+    ctrs = np.zeros(2 * n, dtype=COUNTER_DTYPE)
+    for i in range(n):
+        ctrs[2 * i] = (0, 0, 1 + i // 2, 0)
+        ctrs[2 * i + 1] = (1, 0, 1 + (i + 1) // 2, 0)
+    delta = np.ones(n, dtype=np.uint64)
+    now = np.full(n, H.T0, dtype=np.uint64)
+    e = engine_with_limits(descs, 1)
+    o = H.oracle_with_limits(descs)
+    got = e.check_and_update_batch(off, ctrs, delta, now)
+    want = o.batch_csr(0, off, ctrs, delta, now)
+    assert got[0].tolist() == want[0].tolist()
+    assert_tables_equal(e, o, descs)
+    assert e.stats()["fixed_point_rounds"] > 2
+
+
+def test_update_and_is_within_limits_batches():
+    descs = H.mixed_limits(n_ns=12, seed=9)
+    e = engine_with_limits(descs, 3, regions=4)
+    o = H.oracle_with_limits(descs)
+    for b in range(4):
+        off, ctrs, delta, now = H.random_csr_stream(descs, 1500, 500 + b, n_keys=4)
+        e.update_batch(off, ctrs, delta, now)
+        o.batch_csr(2, off, ctrs, delta, now)
+        assert_tables_equal(e, o, descs)
+        off, ctrs, delta, now = H.random_csr_stream(descs, 1500, 600 + b, n_keys=4)
+        now = now + np.uint64(int(now[-1] - now[0]))
+        lim, fl = e.is_within_limits_batch(off, ctrs, delta, now)
+        wl, wf, _, _ = o.batch_csr(1, off, ctrs, delta, now)
+        assert lim.tolist() == wl.tolist() and fl.tolist() == wf.tolist()
+        assert_tables_equal(e, o, descs)  # read-only
+    recs = H.random_records(descs, 2000, 5, n_keys=4)
+    e.update_records(recs)
+    o.batch_records(2, recs)
+    assert_tables_equal(e, o, descs)
+    lim, fl = e.is_within_limits_records(recs)
+    wl, wf, _, _ = o.batch_records(1, recs)
+    assert lim.tolist() == wl.tolist() and fl.tolist() == wf.tolist()
+
+
+def test_hot_key_spanning_many_chunks():
+    """One key takes 5000 requests of a batch (20 chunks of the owning CTA) interleaved with
+    other keys; max 1000 so the verdict flips inside the batch; deltas vary (greedy, not a
+    prefix sum)."""
+    descs = np.array([(0, 0, 1, 1, 1000, 60 * S), (1, 0, 1, 1, 100000, 3600 * S)], dtype=LIMIT_DESC_DTYPE)
+    rng = np.random.default_rng(0)
+    n = 12000
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    recs["ns_id"] = 0
+    recs["hits_addend"] = rng.choice([1, 1, 2, 5, 400], size=n)
+    hot = rng.random(n) < 0.45
+    recs["key_lo"] = np.where(hot, 7, rng.integers(8, 3000, size=n))
+    recs["now_us"] = H.T0 + np.arange(n) * 7000  # 84 s: the 60 s window rolls over once
+    e = engine_with_limits(descs, 3, regions=4)
+    o = H.oracle_with_limits(descs)
+    got = e.check_and_update_records(recs, True, stride=3)
+    want = o.batch_records(0, recs, True, 3)
+    for k in range(4):
+        assert got[k].tolist() == want[k].tolist()
+    assert 0 < int(got[0].sum()) < n
+    assert_tables_equal(e, o, descs)
+
+
+def test_maintenance_get_delete_clear_sweep():
+    descs = H.mixed_limits(n_ns=12, seed=2)
+    e = engine_with_limits(descs, 7, regions=4)
+    o = H.oracle_with_limits(descs)
+    off, ctrs, delta, now = H.random_csr_stream(descs, 3000, 42, n_keys=30)
+    e.update_batch(off, ctrs, delta, now)
+    o.batch_csr(2, off, ctrs, delta, now)
+    t = int(now[-1])
+    ids = descs["limit_id"][descs["ns_id"] < 5]
+    assert e.get_counters(ids, t) == o.get_counters(ids, t)
+    assert e.get_counters(ids, t + 30 * S) == o.get_counters(ids, t + 30 * S)
+    # sweep == oracle invalidate event; a later denied check must agree (SURVEY §7 hard part 3c)
+    n_gpu = e.sweep(t + 5 * S)
+    n_cpu = o.invalidate_expired(t + 5 * S)
+    assert n_gpu == n_cpu and n_gpu > 0
+    assert_tables_equal(e, o, descs)
+    off, ctrs, delta, now2 = H.random_csr_stream(descs, 3000, 43, n_keys=30)
+    now2 = now2 + np.uint64(t + 6 * S - H.T0)
+    got = e.check_and_update_batch(off, ctrs, delta, now2, True)
+    want = o.batch_csr(0, off, ctrs, delta, now2, True)
+    for k in range(4):
+        assert got[k].tolist() == want[k].tolist()
+    assert_tables_equal(e, o, descs)
+    # delete by limit, clear
+    kill = descs["limit_id"][::3]
+    e.delete_counters(kill)
+    o.delete_counters(kill)
+    assert_tables_equal(e, o, descs)
+    e.clear()
+    o.clear()
+    assert_tables_equal(e, o, descs)
+    # limits_delete + max_value update
+    e.limits_delete(kill[:2])
+    for k in kill[:2]:
+        o.limit_delete(int(k))
+    d = descs[5].copy()
+    d["max_value"] = 1 << 20
+    e.limits_set(np.array([d], dtype=LIMIT_DESC_DTYPE))
+    o.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    live = np.array([x for x in descs if int(x["limit_id"]) not in set(kill[:2].tolist())], dtype=LIMIT_DESC_DTYPE)
+    off, ctrs, delta, now3 = H.random_csr_stream(live, 2000, 44, n_keys=30)
+    now3 = now3 + np.uint64(int(now2[-1]) - H.T0)
+    got = e.check_and_update_batch(off, ctrs, delta, now3)
+    want = o.batch_csr(0, off, ctrs, delta, now3)
+    assert got[0].tolist() == want[0].tolist() and got[1].tolist() == want[1].tolist()
+    assert_tables_equal(e, o, live)
+
+
+def test_errors_are_loud():
+    descs = np.array([(0, 0, 1, 1, 10, 60 * S)], dtype=LIMIT_DESC_DTYPE)
+    e = engine_with_limits(descs, 1, capacity=64, regions=1)
+    recs = np.zeros(200, dtype=RECORD_DTYPE)
+    recs["hits_addend"] = 1
+    recs["key_lo"] = np.arange(1, 201)
+    recs["now_us"] = H.T0
+    with pytest.raises(EngineError) as ei:
+        e.check_and_update_records(recs)
+    assert ei.value.transient  # table full: RL_TRANSIENT, never a silent allow
+    e2 = engine_with_limits(descs, 1)
+    off = np.array([0, 1], dtype=np.uint32)
+    bad = np.array([(5, 0, 1, 0)], dtype=COUNTER_DTYPE)
+    with pytest.raises(EngineError) as ei:
+        e2.check_and_update_batch(off, bad, [1], [H.T0])
+    assert not ei.value.transient
+    hi = np.array([(0, 0, 1, 1 << 32)], dtype=COUNTER_DTYPE)
+    with pytest.raises(EngineError):
+        e2.check_and_update_batch(off, hi, [1], [H.T0])
+    with pytest.raises(EngineError):
+        e2.check_and_update_records(np.zeros((1 << 16) + 1, dtype=RECORD_DTYPE))
+
+
+@pytest.mark.parametrize("name,kw,nb", [
+    ("C1", dict(batch=65536), 3),
+    ("C2", dict(batch=65536, n_rows=100_000), 4),
+    ("C3", dict(batch=1 << 18, n_keys=1_000_000), 3),
+    ("C5", dict(batch=1 << 17, n_keys=1_000_000, n_ns=500), 2),
+])
+def test_baseline_configs_reduced_size(name, kw, nb):
+    """BASELINE.json's configs at sizes the oracle replays in seconds: full verdict + table parity."""
+    w = streams.WORKLOADS[name](**kw)
+    e = Engine(capacity_rows=w.capacity_rows, cells_per_row=w.cells_per_row, max_batch=w.batch)
+    e.limits_set(w.limits)
+    o = H.oracle_with_limits(w.limits, capacity_hint=1 << 20)
+    for b in range(nb):
+        recs = w.batch_records(b)
+        got = e.check_and_update_records(recs, False, stride=w.cells_per_row)
+        want = o.batch_records(0, recs)
+        assert np.array_equal(got[0], want[0]), f"{name} batch {b}: {int((got[0] != want[0]).sum())} verdicts differ"
+        assert np.array_equal(got[1], want[1])
+    ge, go = e.dump_arrays(), o.dump_arrays()
+    assert len(ge[0]) == len(go[0])
+    def canon(d):
+        order = np.lexsort((d[2], d[1], d[0]))
+        return [x[order] for x in d]
+    for a, b_ in zip(canon(ge), canon(go)):
+        assert np.array_equal(a, b_)
+
+
+def test_full_size_c2_properties():
+    """C2 at BASELINE.json's full size (1M rows, batch 65536): size-independent properties —
+    replaying the same batch twice with load_counters is consistent (remaining never
+    increases inside a window, denied requests change nothing), counters == sum of allowed."""
+    w = streams.WORKLOADS["C2"]()
+    e = Engine(capacity_rows=w.capacity_rows, cells_per_row=w.cells_per_row, max_batch=w.batch)
+    e.limits_set(w.limits)
+    allowed_total = 0
+    for b in range(4):
+        recs = w.batch_records(b)
+        lim, _, _, _ = e.check_and_update_records(recs, False, stride=7)
+        allowed_total += int((lim == 0).sum())
+    lid, lo, hi, val, exp = e.dump_arrays()
+    # every allowed request adds 1 to each of its 4 counters, unless a window rolled over (it
+    # cannot: all stamps lie within 1 ms and the shortest window is 1 s)
+    assert int(val.sum()) == 4 * allowed_total
+    maxes = {int(d["limit_id"]): int(d["max_value"]) for d in w.limits}
+    assert all(int(v) <= maxes[int(l)] for l, v in zip(lid, val))
+    # idempotence of the read-only path: is_within_limits does not change the table
+    recs = w.batch_records(5)
+    e.is_within_limits_records(recs)
+    lid2, lo2, hi2, val2, exp2 = e.dump_arrays()
+    assert int(val2.sum()) == int(val.sum()) and len(lid2) == len(lid)
