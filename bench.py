@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — rate-limit decisions/sec of the B200 engine on BASELINE.json's C2 workload.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle port of the
+                                                            reference's InMemoryStorage path)
+
+A step = one batch (65536 requests per GPU) of `check_rate_limited_and_update`
+(limitador/src/lib.rs:425-464) through the C-ABI.  `value` is measured with the batch
+already resident in HBM; `e2e` goes through the same call with pinned HOST buffers (H2D of
+the records and D2H of the verdicts inside the timed region).  One JSON line on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rate-limit decisions/sec (batched)"
+UNIT = "decisions/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def c2_limits(n_ns):
+    from limitador_b200 import streams
+    return streams.c2_zipf_4limits(batch=1, n_rows=1000, n_ns=n_ns).limits
+
+
+def counters_examined(lim: np.ndarray, first: np.ndarray, L: int):
+    """(N_cnt_read, N_cnt_write) per SURVEY §8(d): an allowed decision examines and writes L
+    counters; a denied one examines up to and including the first limited limit, writes 0."""
+    allowed = lim == 0
+    k = (first[~allowed] % L).astype(np.int64) + 1  # C2: limit_id = ns*4 + k
+    return int(allowed.sum()) * L + int(k.sum()), int(allowed.sum()) * L
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of InMemoryStorage::check_and_update on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from limitador_b200 import streams
+    from oracle import binding as ob
+    cores = os.cpu_count() or 1
+    n_ns, n_rows = 64 * args.gpus, 1_000_000 * args.gpus
+    batch = args.batch * args.gpus
+    limits = c2_limits(n_ns)
+    ldesc = np.zeros(len(limits), dtype=ob.LIMIT_DESC_DTYPE)
+    for f in ("limit_id", "ns_id", "max_value", "window_us", "qualified"):
+        ldesc[f] = limits[f]
+    per_step = max(1, min(16, (4_000_000 // batch) or 1))  # bounded sample: <= ~4M decisions per step
+    total_batches = (args.warmup + args.steps) * per_step
+    recs = streams.c2_device_stream(total_batches, batch, "cpu", n_rows=n_rows, n_ns=n_ns).numpy()
+    recs = recs.view(ob.RECORD_DTYPE).reshape(total_batches, batch)
+    times = []
+    mt = ob.OracleMT(ldesc, cores, 2 * n_rows)
+    for s in range(args.warmup + args.steps):
+        chunk = recs[s * per_step:(s + 1) * per_step].reshape(-1)
+        t, _ = mt.run(chunk)
+        if s >= args.warmup:
+            times.append(t)
+    mt.close()
+    n_dec = args.steps * per_step * batch
+    value = n_dec / sum(times)
+    sample = (f"{per_step} batches of {batch} per step, table kept warm across steps, "
+              f"{cores} threads, namespaces assigned to threads by load")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={batch}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="requests per GPU per step (C2: 65536)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 256)")
+    ap.add_argument("--cpu-sample-batches", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from limitador_b200 import Engine, streams
+    from limitador_b200.engine import MEM_DEVICE, MEM_HOST, RECORD_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    K, W, batch = args.steps, args.warmup, args.batch
+    Ke = args.e2e_steps or min(K, 256)
+    n_ns, n_rows = 64 * world, 1_000_000 * world
+    L = 4
+    limits = c2_limits(n_ns)
+    cap = (1 << 21) if world == 1 else (1 << 22)
+    max_batch = batch if world == 1 else 4 * batch
+    eng = Engine(capacity_rows=cap, cells_per_row=7, max_batch=max_batch, device=local_rank)
+    eng.limits_set(limits)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    total = W + 2 * K + Ke
+    recs = streams.c2_device_stream(total, batch, dev, n_rows=n_rows, n_ns=n_ns,
+                                    first_batch=0, seed=streams.SEED + 1000 * rank)
+    out_lim = torch.zeros((total, batch), dtype=torch.uint8, device=dev)
+    out_first = torch.zeros((total, batch), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    if world > 1:
+        send_buf = torch.empty((batch, 4), dtype=torch.int64, device=dev)
+        src_idx = torch.empty(batch, dtype=torch.int32, device=dev)
+        recv_buf = torch.empty((max_batch, 4), dtype=torch.int64, device=dev)
+        v_recv = torch.empty(max_batch, dtype=torch.uint8, device=dev)
+        v_back = torch.empty(batch, dtype=torch.uint8, device=dev)
+
+    def step_device(s: int):
+        """One step with the batch resident in HBM."""
+        if world == 1:
+            eng.check_and_update_records_ptr(batch, recs[s].data_ptr(), out_lim[s].data_ptr(), MEM_DEVICE,
+                                             out_first_ptr=out_first[s].data_ptr(), stride=7)
+            return
+        # namespace-sharded: bucket by owner, scatter over NVLink (NCCL all-to-all), decide on the
+        # owner, return the verdict bytes (the only collective on the path)
+        counts = eng.bucket_by_owner_ptr(batch, recs[s].data_ptr(), world, send_buf.data_ptr(), src_idx.data_ptr())
+        send_counts = torch.from_numpy(counts.astype(np.int64)).to(dev)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        sc, rc = counts.astype(np.int64).tolist(), recv_counts.cpu().tolist()
+        nrecv = int(sum(rc))
+        if nrecv > max_batch:
+            raise RuntimeError(f"rank {rank}: received {nrecv} > max_batch {max_batch}")
+        dist.all_to_all_single(recv_buf[:nrecv], send_buf, rc, sc)
+        if nrecv:
+            eng.check_and_update_records_ptr(nrecv, recv_buf.data_ptr(), v_recv.data_ptr(), MEM_DEVICE, stride=7)
+        dist.all_to_all_single(v_back, v_recv[:nrecv], sc, rc)
+        eng.unpermute_u8_ptr(batch, v_back.data_ptr(), src_idx.data_ptr(), out_lim[s].data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, first: int, n: int) -> float:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(first, first + n):
+            fn(s)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up -------------------------------------------------------------------------
+    for s in range(W):
+        step_device(s)
+    eng.sync()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- pass A: the headline device-resident throughput ----------------------------------
+    launches0 = eng.stats()["kernel_launches"]
+    ms_a = timed(step_device, W, K)
+    launches = eng.stats()["kernel_launches"] - launches0
+    eng.sync()
+    value = world * batch * K / (ms_a * 1e-3)
+
+    # ---- pass B: same K steps further down the stream, k_main bracketed by CUDA events ------
+    eng.profile_begin()
+    ms_b = timed(step_device, W + K, K)
+    main_ms, main_launches = eng.profile_end()
+    eng.sync()
+
+    # ---- e2e: HOST buffers through the C-ABI (H2D + kernels + D2H per step) ----------------
+    h_recs = torch.empty((Ke, batch, 4), dtype=torch.int64).pin_memory()
+    h_recs.copy_(recs[W + 2 * K:W + 2 * K + Ke])
+    h_lim = torch.empty((Ke, batch), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_host(j: int):
+        if world == 1:
+            eng.check_and_update_records_ptr(batch, h_recs[j].data_ptr(), h_lim[j].data_ptr(), MEM_HOST, stride=7)
+        else:
+            s = W + 2 * K + j
+            recs[s].copy_(h_recs[j], non_blocking=True)
+            step_device(s)
+            h_lim[j].copy_(out_lim[s], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    for j in range(min(3, Ke)):
+        pass  # table and clocks are already warm; the first e2e steps are part of the measurement
+    t0 = time.perf_counter()
+    ms_e = timed(step_host, 0, Ke)
+    wall_e = (time.perf_counter() - t0) * 1e3
+    ms_e = max(ms_e, 0.0)
+    e2e_value = world * batch * Ke / (max(ms_e, 1e-9) * 1e-3)
+
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_main), algorithmic bytes from the verdicts -----
+    peak, peak_src = peaks()
+    roof = None
+    if world == 1 and main_launches:
+        lim_b = out_lim[W + K:W + 2 * K].cpu().numpy().reshape(-1)
+        first_b = out_first[W + K:W + 2 * K].cpu().numpy().reshape(-1).astype(np.int64) & 0xFFFFFFFF
+        n_read, n_write = counters_examined(lim_b, first_b, L)
+        alg = streams.algorithmic_bytes(len(lim_b), n_read, n_write)
+        per_launch = alg / main_launches
+        avg_ms = main_ms / main_launches
+        achieved = per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_main<7,RecordSrc,0>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
+                "allowed_frac": float((lim_b == 0).mean()), "kernel_share_of_step": main_ms / ms_b}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                roof["traffic"] = json.load(open(tp)).get("k_main_dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # ---- CPU baseline (oracle port) on the same stream prefix + live parity check ----------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import binding as ob
+        S = min(args.cpu_sample_batches, W + 2 * K)
+        sample = recs[:S].cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+        ldesc = np.zeros(len(limits), dtype=ob.LIMIT_DESC_DTYPE)
+        for f in ("limit_id", "ns_id", "max_value", "window_us", "qualified"):
+            ldesc[f] = limits[f]
+        cores = os.cpu_count() or 1
+        mt = ob.OracleMT(ldesc, cores, 2 * n_rows)
+        t_cpu, v_cpu = mt.run(sample)
+        mt.close()
+        v_gpu = out_lim[:S].cpu().numpy().reshape(-1)
+        mism = int((v_cpu != v_gpu).sum())
+        cpu = {"value": len(sample) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {S} batches of the same stream ({len(sample)} decisions) from an empty "
+                         f"pre-faulted table, {cores} threads, namespaces assigned to threads by load",
+               "gpu_verdict_mismatches": mism}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_a / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={batch}/GPU, "
+                               f"delta=1, load_counters=false",
+                   "parallelism": "single GPU" if world == 1 else f"namespace-sharded x{world}, NCCL all-to-all",
+                   "l2": "a distinct batch every step (inputs 2 MiB/step, never reused); table 256 MiB > L2",
+                   "table_rows": cap, "row_bytes": 128},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * 32, "d2h_bytes_per_step": batch,
+                "steps": Ke, "ms_per_step": ms_e / Ke, "wall_ms_per_step": wall_e / Ke},
+        "gpu_launches": int(launches),
+        "clocks": sampler.result(),
+    }
+    if roof:
+        line["roofline"] = roof
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -169,6 +169,12 @@ int rl_dump_table(rl_engine *e, uint64_t cap, uint32_t *out_limit_id, uint64_t *
                   uint64_t *out_key_hi, uint64_t *out_value, uint64_t *out_expiry_us,
                   uint64_t *out_count);
 
+/* Measurement aid (bench.py roofline leg): between begin and end the engine brackets every
+ * launch of its dominant kernel (k_main) with CUDA events on the launching stream;
+ * end() synchronises and returns the summed device time and the launch count. */
+int rl_profile_begin(rl_engine *e);
+int rl_profile_end(rl_engine *e, double *out_main_ms, uint64_t *out_main_launches);
+
 /* Multi-GPU exchange helper: stable bucketing of n device-resident records by
  * owner = rl_owner_of(ns_id, world).  Writes the permuted records to d_out_recs, the
  * source index of every permuted record to d_out_src (uint32), and the per-owner counts

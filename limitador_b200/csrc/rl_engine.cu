@@ -106,6 +106,9 @@ struct rl_engine {
 
     rl_stats stats{};
     std::string last_error = "";
+    // rl_profile_begin/end
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
 namespace {
@@ -320,6 +323,12 @@ int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& 
 template <class Src, int MODE>
 int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
     const uint32_t P = 1u << e->log2P;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->profiling) {
+        RL_CUDA(e, cudaEventCreate(&ev0));
+        RL_CUDA(e, cudaEventCreate(&ev1));
+        RL_CUDA(e, cudaEventRecord(ev0, e->stream));
+    }
     switch (e->cells) {
         case 1:
             k_main<1, Src, MODE><<<P, RL_MAIN_THREADS, 0, e->stream>>>(D, B, src);
@@ -332,6 +341,10 @@ int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) 
             break;
     }
     RL_LAUNCH_CHECK(e);
+    if (e->profiling) {
+        RL_CUDA(e, cudaEventRecord(ev1, e->stream));
+        e->prof_events.emplace_back(ev0, ev1);
+    }
     return RL_OK;
 }
 
@@ -562,6 +575,31 @@ int rl_sync(rl_engine* e) {
     if (!e) return RL_FATAL;
     RL_CUDA(e, cudaSetDevice(e->device));
     return check_device_error(e);
+}
+
+int rl_profile_begin(rl_engine* e) {
+    if (!e) return RL_FATAL;
+    e->profiling = true;
+    return RL_OK;
+}
+
+int rl_profile_end(rl_engine* e, double* out_main_ms, uint64_t* out_main_launches) {
+    if (!e) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    e->profiling = false;
+    RL_CUDA(e, cudaStreamSynchronize(e->stream));
+    double ms = 0;
+    for (auto& pr : e->prof_events) {
+        float t = 0;
+        RL_CUDA(e, cudaEventElapsedTime(&t, pr.first, pr.second));
+        ms += t;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (out_main_ms) *out_main_ms = ms;
+    if (out_main_launches) *out_main_launches = e->prof_events.size();
+    e->prof_events.clear();
+    return RL_OK;
 }
 
 int rl_get_stats(rl_engine* e, rl_stats* out) {

@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "rl_check_and_update_batch", "rl_is_within_limits_batch", "rl_is_within_limits_records",
     "rl_update_batch", "rl_update_records", "rl_get_counters", "rl_delete_counters", "rl_clear",
     "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
+    "rl_profile_begin", "rl_profile_end",
 ]
 
 
@@ -99,6 +100,8 @@ def load_library(path: str | None = None):
     L.rl_dump_table.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
     L.rl_bucket_by_owner.argtypes = [vp, u64, vp, u32, vp, vp, vp]
     L.rl_unpermute_u8.argtypes = [vp, u64, vp, vp, vp]
+    L.rl_profile_begin.argtypes = [vp]
+    L.rl_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.rl_owner_of.argtypes = [u32, u32]
     L.rl_owner_of.restype = u32
     if path == _build.LIB_PATH:
@@ -165,6 +168,15 @@ class Engine:
         s = RlStats()
         self._check(self._lib.rl_get_stats(self._h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in RlStats._fields_ if not f[0].startswith("_")}
+
+    def profile_begin(self):
+        self._check(self._lib.rl_profile_begin(self._h))
+
+    def profile_end(self):
+        """(summed k_main device ms, k_main launches) since profile_begin."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        self._check(self._lib.rl_profile_end(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # -- limits --
     def limits_set(self, descs):

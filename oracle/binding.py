@@ -70,6 +70,11 @@ def lib():
         L.lo_dump.argtypes = [vp, u64, vp, vp, vp, vp, vp]
         L.lo_size.restype = u64
         L.lo_size.argtypes = [vp]
+        L.lo_mt_create.restype = vp
+        L.lo_mt_create.argtypes = [vp, u32, u32, u64]
+        L.lo_mt_run.restype = C.c_double
+        L.lo_mt_run.argtypes = [vp, u64, vp, vp]
+        L.lo_mt_destroy.argtypes = [vp]
         L.lo_bench_records_mt.restype = C.c_double
         L.lo_bench_records_mt.argtypes = [vp, u32, u64, vp, u32, u64, vp]
         _lib = L
@@ -238,3 +243,30 @@ def bench_records_mt(limit_descs, recs, threads, capacity_hint):
     t = lib().lo_bench_records_mt(_p(limit_descs), len(limit_descs), len(recs), _p(recs), threads,
                                   capacity_hint, _p(out))
     return float(t), out
+
+
+class OracleMT:
+    """T persistent oracles sharded by namespace: the multi-core CPU baseline."""
+
+    def __init__(self, limit_descs, threads, capacity_hint):
+        limit_descs = np.ascontiguousarray(limit_descs, dtype=LIMIT_DESC_DTYPE)
+        self.threads = threads
+        self._h = lib().lo_mt_create(_p(limit_descs), len(limit_descs), threads, capacity_hint)
+
+    def run(self, recs):
+        """Process recs in stream order per namespace; returns (seconds, verdicts)."""
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        out = np.zeros(len(recs), dtype=np.uint8)
+        t = lib().lo_mt_run(self._h, len(recs), _p(recs), _p(out))
+        return float(t), out
+
+    def close(self):
+        if self._h:
+            lib().lo_mt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -204,6 +204,11 @@ int lo_limit_set(lo_oracle *o, uint32_t limit_id, uint32_t ns_id, uint64_t max_v
         if (l->ns_id != ns_id || l->window_us != window_us || l->qualified != (qualified != 0))
             return -1;
         l->max_value = max_value;
+        if (!l->qualified && !l->simple_present) { /* add_counter again: entry().or_default() */
+            l->simple_present = 1;
+            l->simple.value = 0;
+            l->simple.expiry = 0;
+        }
         return 0;
     }
     l->defined = 1;
@@ -554,6 +559,17 @@ uint64_t lo_size(lo_oracle *o) {
 }
 
 /* ---- multi-threaded CPU baseline --------------------------------------------------- */
+/* T persistent oracles; every namespace is owned by one of them (all counters
+ * of a request belong to its namespace), chosen once by longest-processing-time-first on
+ * the first run's per-namespace request counts so the threads are balanced under Zipf. */
+struct lo_mt {
+    uint32_t threads;
+    lo_oracle **o;
+    uint32_t *ns_owner; /* [ns_cap] */
+    uint32_t ns_cap;
+    int assigned;
+};
+
 typedef struct {
     lo_oracle *o;
     const lo_record *recs;
@@ -585,31 +601,84 @@ static void *mt_worker(void *p) {
     return NULL;
 }
 
-double lo_bench_records_mt(const lo_limit_desc *limits, uint32_t n_limits, uint64_t n,
-                           const lo_record *recs, uint32_t threads, uint64_t capacity_hint,
-                           uint8_t *out_limited) {
+lo_mt *lo_mt_create(const lo_limit_desc *limits, uint32_t n_limits, uint32_t threads, uint64_t capacity_hint) {
     if (threads == 0) threads = 1;
-    mt_arg *args = (mt_arg *)calloc(threads, sizeof(mt_arg));
-    pthread_t *tids = (pthread_t *)calloc(threads, sizeof(pthread_t));
-    uint64_t *cnt = (uint64_t *)calloc(threads, sizeof(uint64_t));
-    uint32_t **idx = (uint32_t **)calloc(threads, sizeof(uint32_t *));
-    for (uint64_t i = 0; i < n; i++) cnt[recs[i].ns_id % threads]++;
+    lo_mt *m = (lo_mt *)calloc(1, sizeof(*m));
+    m->threads = threads;
+    m->o = (lo_oracle **)calloc(threads, sizeof(lo_oracle *));
+    uint32_t ns_cap = 1;
+    for (uint32_t k = 0; k < n_limits; k++)
+        if (limits[k].ns_id + 1 > ns_cap) ns_cap = limits[k].ns_id + 1;
+    m->ns_cap = ns_cap;
+    m->ns_owner = (uint32_t *)calloc(ns_cap, sizeof(uint32_t));
     for (uint32_t t = 0; t < threads; t++) {
+        lo_oracle *o = lo_create(capacity_hint / threads + 1024);
+        /* fault the table in now: the timed runs measure the data path, not page faults */
+        memset(o->slots, 0xff, o->nslots * sizeof(lo_slot));
+        memset(o->slots, 0, o->nslots * sizeof(lo_slot));
+        for (uint32_t k = 0; k < n_limits; k++)
+            lo_limit_set(o, limits[k].limit_id, limits[k].ns_id, limits[k].max_value, limits[k].window_us,
+                         (int)limits[k].qualified);
+        m->o[t] = o;
+    }
+    return m;
+}
+
+void lo_mt_destroy(lo_mt *m) {
+    if (!m) return;
+    for (uint32_t t = 0; t < m->threads; t++) lo_destroy(m->o[t]);
+    free(m->o);
+    free(m->ns_owner);
+    free(m);
+}
+
+double lo_mt_run(lo_mt *m, uint64_t n, const lo_record *recs, uint8_t *out_limited) {
+    const uint32_t T = m->threads;
+    if (!m->assigned) {
+        uint64_t *load = (uint64_t *)calloc(m->ns_cap, sizeof(uint64_t));
+        uint64_t *tl = (uint64_t *)calloc(T, sizeof(uint64_t));
+        uint8_t *done = (uint8_t *)calloc(m->ns_cap, 1);
+        for (uint64_t i = 0; i < n; i++)
+            if (recs[i].ns_id < m->ns_cap) load[recs[i].ns_id]++;
+        for (uint32_t round = 0; round < m->ns_cap; round++) {
+            uint32_t best = 0;
+            int found = 0;
+            for (uint32_t ns = 0; ns < m->ns_cap; ns++)
+                if (!done[ns] && (!found || load[ns] > load[best])) {
+                    best = ns;
+                    found = 1;
+                }
+            uint32_t tmin = 0;
+            for (uint32_t t = 1; t < T; t++)
+                if (tl[t] < tl[tmin]) tmin = t;
+            m->ns_owner[best] = tmin;
+            tl[tmin] += load[best] + 1;
+            done[best] = 1;
+        }
+        free(load);
+        free(tl);
+        free(done);
+        m->assigned = 1;
+    }
+    mt_arg *args = (mt_arg *)calloc(T, sizeof(mt_arg));
+    pthread_t *tids = (pthread_t *)calloc(T, sizeof(pthread_t));
+    uint64_t *cnt = (uint64_t *)calloc(T, sizeof(uint64_t));
+    uint32_t **idx = (uint32_t **)calloc(T, sizeof(uint32_t *));
+#define OWNER(i) (recs[i].ns_id < m->ns_cap ? m->ns_owner[recs[i].ns_id] : 0)
+    for (uint64_t i = 0; i < n; i++) cnt[OWNER(i)]++;
+    for (uint32_t t = 0; t < T; t++) {
         idx[t] = (uint32_t *)malloc((cnt[t] + 1) * sizeof(uint32_t));
         cnt[t] = 0;
     }
     for (uint64_t i = 0; i < n; i++) {
-        uint32_t t = recs[i].ns_id % threads;
+        uint32_t t = OWNER(i);
         idx[t][cnt[t]++] = (uint32_t)i;
     }
+#undef OWNER
     pthread_barrier_t start;
-    pthread_barrier_init(&start, NULL, threads + 1);
-    for (uint32_t t = 0; t < threads; t++) {
-        lo_oracle *o = lo_create(capacity_hint / threads + 1024);
-        for (uint32_t k = 0; k < n_limits; k++)
-            lo_limit_set(o, limits[k].limit_id, limits[k].ns_id, limits[k].max_value,
-                         limits[k].window_us, (int)limits[k].qualified);
-        args[t].o = o;
+    pthread_barrier_init(&start, NULL, T + 1);
+    for (uint32_t t = 0; t < T; t++) {
+        args[t].o = m->o[t];
         args[t].recs = recs;
         args[t].idx = idx[t];
         args[t].n = cnt[t];
@@ -618,18 +687,24 @@ double lo_bench_records_mt(const lo_limit_desc *limits, uint32_t n_limits, uint6
         pthread_create(&tids[t], NULL, mt_worker, &args[t]);
     }
     struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
     pthread_barrier_wait(&start);
-    for (uint32_t t = 0; t < threads; t++) pthread_join(tids[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (uint32_t t = 0; t < T; t++) pthread_join(tids[t], NULL);
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    for (uint32_t t = 0; t < threads; t++) {
-        lo_destroy(args[t].o);
-        free(idx[t]);
-    }
+    for (uint32_t t = 0; t < T; t++) free(idx[t]);
     pthread_barrier_destroy(&start);
     free(idx);
     free(cnt);
     free(tids);
     free(args);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+double lo_bench_records_mt(const lo_limit_desc *limits, uint32_t n_limits, uint64_t n,
+                           const lo_record *recs, uint32_t threads, uint64_t capacity_hint,
+                           uint8_t *out_limited) {
+    lo_mt *m = lo_mt_create(limits, n_limits, threads, capacity_hint);
+    double t = lo_mt_run(m, n, recs, out_limited);
+    lo_mt_destroy(m);
+    return t;
 }

@@ -127,6 +127,11 @@ typedef struct {
     uint64_t max_value, window_us;
     uint32_t qualified, _pad;
 } lo_limit_desc;
+/* Persistent form: the T oracles stay warm across runs (as the GPU table does). */
+typedef struct lo_mt lo_mt;
+lo_mt *lo_mt_create(const lo_limit_desc *limits, uint32_t n_limits, uint32_t threads, uint64_t capacity_hint);
+double lo_mt_run(lo_mt *m, uint64_t n, const lo_record *recs, uint8_t *out_limited);
+void lo_mt_destroy(lo_mt *m);
 double lo_bench_records_mt(const lo_limit_desc *limits, uint32_t n_limits, uint64_t n,
                            const lo_record *recs, uint32_t threads, uint64_t capacity_hint,
                            uint8_t *out_limited);

@@ -188,6 +188,11 @@ def test_maintenance_get_delete_clear_sweep():
     e.clear()
     o.clear()
     assert_tables_equal(e, o, descs)
+    # Storage::clear also forgets the limits (storage/mod.rs:137-140); the front re-adds them,
+    # which re-creates the unqualified counters (add_counter, in_memory.rs:38-44)
+    e.limits_set(descs)
+    for d in descs:
+        o.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
     # limits_delete + max_value update
     e.limits_delete(kill[:2])
     for k in kill[:2]:
