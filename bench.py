@@ -189,8 +189,12 @@ def main():
     max_batch = batch if world == 1 else 4 * batch
     eng = Engine(capacity_rows=cap, cells_per_row=7, max_batch=max_batch, device=local_rank)
     eng.limits_set(limits)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the engine launches on it and the CUDA events that time
+    # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
+    assert eng.stream == stream.cuda_stream
 
     total = W + 2 * K + Ke
     recs = streams.c2_device_stream(total, batch, dev, n_rows=n_rows, n_ns=n_ns,

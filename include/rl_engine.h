@@ -42,6 +42,9 @@ typedef struct rl_engine rl_engine;
 enum { RL_OK = 0, RL_TRANSIENT = 1, RL_FATAL = 2 };
 enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1 };
 #define RL_NONE 0xFFFFFFFFu
+/* test aid: narrow the in-kernel grouping tag so that distinct keys collide and the
+ * collision path (salted re-insertion) is exercised */
+#define RL_FLAG_DEBUG_WEAK_TAGS 1u
 
 typedef struct rl_config {
     uint32_t struct_size;    /* sizeof(rl_config) */
@@ -53,7 +56,7 @@ typedef struct rl_config {
     uint32_t max_batch;      /* max requests per call */
     uint32_t max_counters;   /* max total counters per CSR call (0 = 4 * max_batch) */
     uint32_t regions;        /* 0 = auto; power of two */
-    uint32_t flags;          /* reserved, 0 */
+    uint32_t flags;          /* RL_FLAG_* */
     uint32_t _pad;
 } rl_config;
 

@@ -225,6 +225,58 @@ RL_HD void rl_walk_update(RlRow<CELLS>& row, uint32_t& dirty, const RlCellDesc* 
 }
 
 // ---------------------------------------------------------------------------------------
+// Run-length replay.  A key's requests are replayed in stream order, but
+// not one at a time: starting at position `pos` of the key's request list with row state S,
+//   * hypothesis A — "request i is denied under S and changes nothing": the longest prefix
+//     of such requests is final as-is (a denied check leaves the state untouched,
+//     in_memory.rs:141-143), whatever their deltas and timestamps;
+//   * hypothesis B — "every request from pos up to and including i is allowed and none needs
+//     a window reset or an insert": then request i sees S with the deltas of pos..i-1 added,
+//     so the longest prefix for which that holds is final too (values only accumulate,
+//     atomic_expiring_value.rs:41);
+//   * otherwise request pos is applied alone with the sequential rule.
+// Every step is exact, so the replay equals one-at-a-time execution; saturated hot keys
+// (all denied) and hot keys far from their limit (all allowed) finish in one step.
+template <int CELLS>
+RL_HD bool rl_eval_deny_noeffect(const RlRow<CELLS>& S, const RlCellDesc* desc, uint32_t cells, uint64_t posorig,
+                                 uint64_t delta, uint64_t now, bool load_counters) {
+    RlRow<CELLS> tmp = S;
+    uint32_t dirty = 0;
+    const uint32_t fl =
+        rl_walk_check_single<CELLS>(tmp, dirty, desc, cells, posorig, delta, now, load_counters, nullptr, nullptr);
+    return fl != RL_NONE_U32 && dirty == 0;
+}
+
+// dsum = sum of the deltas of the run INCLUDING this request (wraps like the reference's u64 add).
+template <int CELLS>
+RL_HD bool rl_eval_allow_run(const RlRow<CELLS>& S, const RlCellDesc* desc, uint32_t cells, uint64_t dsum,
+                             uint64_t now) {
+    const uint32_t n = rl_cells_n(cells);
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t c = rl_cells_at(cells, k);
+        if (S.expiry[c] <= now) return false;  // absent or expired: needs insert / reset
+        if (S.value[c] + dsum > desc[c].max_value) return false;
+    }
+    return true;
+}
+
+// update_counters analogue of hypothesis B: no limit test, only "no reset / insert needed".
+template <int CELLS>
+RL_HD bool rl_eval_update_run(const RlRow<CELLS>& S, uint32_t cells, uint64_t now) {
+    const uint32_t n = rl_cells_n(cells);
+    for (uint32_t k = 0; k < n; k++)
+        if (S.expiry[rl_cells_at(cells, k)] <= now) return false;
+    return true;
+}
+
+// State seen by a member of an allowed run: S plus the run's earlier deltas on the touched cells.
+template <int CELLS>
+RL_HD void rl_advance_run(RlRow<CELLS>& S, uint32_t cells, uint64_t dprev) {
+    const uint32_t n = rl_cells_n(cells);
+    for (uint32_t k = 0; k < n; k++) S.value[rl_cells_at(cells, k)] += dprev;
+}
+
+// ---------------------------------------------------------------------------------------
 // Resolve one request's counters into accesses (one per distinct row), in the reference's
 // processing order: unqualified counters first, then qualified, each in the given order
 // (in_memory.rs:105,121).  Writes at most m accesses to acc[0..m) (unused ones get

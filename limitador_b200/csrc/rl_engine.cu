@@ -107,6 +107,7 @@ struct rl_engine {
     rl_stats stats{};
     std::string last_error = "";
     // rl_profile_begin/end
+    unsigned long long tag_mask = ~0ull;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
@@ -160,6 +161,7 @@ RlDev make_dev(rl_engine* e) {
     D.ns_limit_ids = e->d_ns_limit_ids.p;
     D.err = e->d_misc.p + MISC_ERR;
     D.flags = e->d_misc.p + MISC_FLAGS;
+    D.tag_mask = e->tag_mask;
     return D;
 }
 
@@ -320,26 +322,34 @@ int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& 
     return RL_OK;
 }
 
+template <int CELLS, class Src, int MODE>
+int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+    using Smem = RlMainSmem<CELLS, RL_MAIN_THREADS>;
+    auto kern = k_main<CELLS, Src, MODE, RL_MAIN_THREADS>;
+    static bool attr_set = false;  // one per instantiation
+    if (!attr_set) {
+        RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr_set = true;
+    }
+    kern<<<1u << e->log2P, RL_MAIN_THREADS, sizeof(Smem), e->stream>>>(D, B, src);
+    return RL_OK;
+}
+
 template <class Src, int MODE>
 int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
-    const uint32_t P = 1u << e->log2P;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->profiling) {
         RL_CUDA(e, cudaEventCreate(&ev0));
         RL_CUDA(e, cudaEventCreate(&ev1));
         RL_CUDA(e, cudaEventRecord(ev0, e->stream));
     }
+    int r;
     switch (e->cells) {
-        case 1:
-            k_main<1, Src, MODE><<<P, RL_MAIN_THREADS, 0, e->stream>>>(D, B, src);
-            break;
-        case 3:
-            k_main<3, Src, MODE><<<P, RL_MAIN_THREADS, 0, e->stream>>>(D, B, src);
-            break;
-        default:
-            k_main<7, Src, MODE><<<P, RL_MAIN_THREADS, 0, e->stream>>>(D, B, src);
-            break;
+        case 1: r = launch_main_cells<1, Src, MODE>(e, D, B, src); break;
+        case 3: r = launch_main_cells<3, Src, MODE>(e, D, B, src); break;
+        default: r = launch_main_cells<7, Src, MODE>(e, D, B, src); break;
     }
+    if (r) return r;
     RL_LAUNCH_CHECK(e);
     if (e->profiling) {
         RL_CUDA(e, cudaEventRecord(ev1, e->stream));
@@ -496,6 +506,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     e->max_counters = cfg->max_counters ? cfg->max_counters : 4 * e->max_batch;
     e->max_counters = std::max(e->max_counters, e->max_batch);
     e->groups.resize(1);
+    if (cfg->flags & 1u) e->tag_mask = 0xFull << 24;  // RL_FLAG_DEBUG_WEAK_TAGS: 8 distinct tags per salt level
 
     const size_t bytes = (size_t)e->capacity * e->row_bytes;
     RL_CUDA(e, cudaMalloc((void**)&e->d_rows, bytes));

@@ -19,7 +19,7 @@
 #include "../../include/rl_engine.h"
 #include "rl_core.h"
 
-#define RL_MAIN_THREADS 256
+#define RL_MAIN_THREADS 256  // accesses per chunk of k_main (one per thread)
 #define RL_PART_THREADS 256
 #define RL_PART_WARPS (RL_PART_THREADS / 32)
 #define RL_IDENT_POSORIG 0x0654321006543210ull
@@ -36,6 +36,7 @@ struct RlDev {
     const uint32_t* ns_limit_ids;
     uint32_t* err;    // sticky max of RL_DEV_*
     uint32_t* flags;  // bit0: batch has multi-row requests
+    unsigned long long tag_mask;  // ~0; tests narrow it to force in-CTA tag collisions
 };
 
 struct RlBatch {
@@ -406,51 +407,113 @@ __global__ void __launch_bounds__(256) k_colscan(RlDev D, RlBatch B) {
 
 // ---------------------------------------------------------------------------------------
 // The main kernel.  MODE 0 = check_and_update, MODE 2 = update_counters.
-template <int CELLS, class Src, int MODE>
-__global__ void __launch_bounds__(RL_MAIN_THREADS) k_main(RlDev D, RlBatch B, Src src) {
-    constexpr int CH = RL_MAIN_THREADS;
-    constexpr int GT = 2 * CH;
-    constexpr uint32_t RB = RlGeom<CELLS>::ROW_BYTES;
-    __shared__ unsigned long long g_tag[GT];
-    __shared__ uint32_t g_cnt[GT];
-    __shared__ uint32_t g_start[GT];
-    __shared__ uint16_t members[CH];
-    __shared__ uint32_t s_acc[CH];
-    __shared__ uint32_t s_warp[CH / 32];
+//
+// One CTA per table region; the region's accesses (already in stream order) are taken in
+// chunks of CH (one access per thread).  Per chunk:
+//   1. every thread loads its access, and the CTA groups the accesses by row key with a
+//      shared-memory hash table (64-bit tag claimed by CAS, full key verified against the
+//      claimer's; a mismatch re-inserts under a salted tag);
+//   2. every access gets its stable ordinal inside its key group (warps take turns, so the
+//      ordinal order is the stream order) and the inclusive prefix sum of the group's
+//      deltas (one block scan over the group-sorted deltas);
+//   3. the group leader probes / claims the row (one probe per key) and stages the row
+//      state in shared memory;
+//   4. the group is replayed by ALL its threads in lock-step "run-length" rounds
+//      (rl_core.h: hypotheses A and B) — two barriers per round, one round for a saturated
+//      or an unconstrained hot key;
+//   5. the leader writes the dirty cells back.
+// Counter values never need atomics: a region belongs to one CTA, a key to one group.
+template <int CELLS, int CH>
+struct RlMainSmem {
+    static constexpr int GT = 2 * CH;
+    unsigned long long g_tag[GT];
+    unsigned long long key_lo[CH];
+    unsigned long long key_hi[CH];
+    unsigned long long s_val[CH * CELLS];  // row state of the group led by thread `gid`
+    unsigned long long s_exp[CH * CELLS];
+    unsigned long long dsum[CH];           // group-sorted deltas -> inclusive scan
+    unsigned long long g_pbase[CH];        // prefix sum of the deltas of the finalised members
+    uint32_t g_cnt[GT];
+    uint32_t g_start[GT];
+    uint32_t g_rep[GT];
+    uint32_t g_min[2][2][CH];              // [round parity][A|B][gid]
+    uint32_t g_dirty[CH];
+    uint32_t g_rowok[CH];
+    unsigned long long warp_tot[CH / 32];
+};
+
+template <int CELLS, class Src, int MODE, int CH>
+__global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
+    using Smem = RlMainSmem<CELLS, CH>;
+    constexpr int GT = Smem::GT;
+    extern __shared__ __align__(16) unsigned char rl_smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(rl_smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t P = 1u << D.log2P;
+    const bool lc = B.load_counters != 0;
+    const bool write_out = (B.phase == RL_PHASE_COMMIT);
+    const bool snapshot = (B.phase == RL_PHASE_SNAPSHOT);
 
     for (uint32_t region = blockIdx.x; region < P; region += gridDim.x) {
         const uint32_t lo = B.part_base[region], hi = B.part_base[region + 1];
         for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
             for (uint32_t i = tid; i < GT; i += CH) {
-                g_tag[i] = 0ull;
-                g_cnt[i] = 0;
+                sm.g_tag[i] = 0ull;
+                sm.g_cnt[i] = 0;
             }
+            sm.dsum[tid] = 0ull;
             __syncthreads();
 
+            // ---- 1. load my access, group by key --------------------------------------------
             const uint32_t p = c0 + tid;
             const bool valid = p < hi;
-            uint32_t a = 0, slot = 0;
-            uint64_t key_lo = 0, hdr_hi = 0, h = 0;
+            RlAccess acc;
+            acc.key_lo = 0;
+            acc.hdr_hi = 0;
+            acc.req = 0;
+            acc.cells = 0;
+            acc.posorig = 0;
+            uint64_t delta = 0, now = 0, h = 0;
             if (valid) {
-                a = B.part_idx[p];
-                src.ident(D, a, key_lo, hdr_hi);
-                h = rl_row_hash(key_lo, hdr_hi);
-                const unsigned long long tag = h | 1ull;
-                uint32_t s = (uint32_t)(h >> 24) & (GT - 1);
-                for (;;) {
-                    const unsigned long long old = atomicCAS(&g_tag[s], 0ull, tag);
-                    if (old == 0ull || old == tag) break;
-                    s = (s + 1) & (GT - 1);
-                }
-                slot = s;
+                src.full(D, B.part_idx[p], acc, delta, now);
+                h = rl_row_hash(acc.key_lo, acc.hdr_hi);
             }
-            s_acc[tid] = a;
-            __syncthreads();
+            sm.key_lo[tid] = acc.key_lo;
+            sm.key_hi[tid] = acc.hdr_hi;
+            uint32_t slot = 0;
+            {
+                bool pending = valid;
+                uint32_t salt = 0;
+                for (;;) {
+                    if (pending) {
+                        // 56 hash bits + the salt level in the top byte: keys that collided on one
+                        // level meet fresh tags on the next, so every level places >= 1 key
+                        unsigned long long tag = (salt ? rl_mix64(h + salt) : h) & D.tag_mask;
+                        tag = (tag & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)(salt & 0xFFu) << 56) | 1ull;
+                        uint32_t s = (uint32_t)(tag >> 24) & (GT - 1);
+                        for (;;) {
+                            const unsigned long long old = atomicCAS(&sm.g_tag[s], 0ull, tag);
+                            if (old == 0ull) {
+                                sm.g_rep[s] = tid;  // I claimed the slot: my key defines the group
+                                break;
+                            }
+                            if (old == tag) break;
+                            s = (s + 1) & (GT - 1);
+                        }
+                        slot = s;
+                    }
+                    __syncthreads();
+                    if (pending) {
+                        const uint32_t rep = sm.g_rep[slot];
+                        pending = (sm.key_lo[rep] != acc.key_lo) || (sm.key_hi[rep] != acc.hdr_hi);
+                        salt++;
+                    }
+                    if (!__syncthreads_or(pending)) break;  // a tag collision between different keys: re-insert salted
+                }
+            }
 
-            // stable ordinal of every access inside its key group: warps take turns
+            // ---- 2. stable ordinal inside the key group: warps take turns ---------------------
             uint32_t ord = 0;
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             for (uint32_t w = 0; w < CH / 32; w++) {
@@ -459,133 +522,214 @@ __global__ void __launch_bounds__(RL_MAIN_THREADS) k_main(RlDev D, RlBatch B, Sr
                     const int leader = __ffs(m) - 1;
                     uint32_t basecnt = 0;
                     if ((int)lane == leader) {
-                        basecnt = g_cnt[slot];
-                        g_cnt[slot] = basecnt + __popc(m);
+                        basecnt = sm.g_cnt[slot];
+                        sm.g_cnt[slot] = basecnt + __popc(m);
                     }
                     basecnt = __shfl_sync(m, basecnt, leader);
                     ord = basecnt + __popc(m & ((1u << lane) - 1));
                 }
                 __syncthreads();
             }
-
-            // exclusive scan of g_cnt[0..GT) -> g_start
+            // exclusive scan of the group sizes -> where each group starts in group-sorted order
             {
-                const uint32_t v0 = g_cnt[2 * tid], v1 = g_cnt[2 * tid + 1];
+                uint32_t run = 0;
+                // GT = 2*CH entries, two per thread
+                const uint32_t v0 = sm.g_cnt[2 * tid], v1 = sm.g_cnt[2 * tid + 1];
                 uint32_t x = v0 + v1;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
                     if ((int)lane >= o) x += y;
                 }
-                if (lane == 31) s_warp[warp] = x;
+                if (lane == 31) sm.warp_tot[warp] = x;
                 __syncthreads();
-                uint32_t woff = 0;
-                for (uint32_t w = 0; w < warp; w++) woff += s_warp[w];
-                const uint32_t excl = woff + x - (v0 + v1);
-                g_start[2 * tid] = excl;
-                g_start[2 * tid + 1] = excl + v0;
+                for (uint32_t w = 0; w < warp; w++) run += (uint32_t)sm.warp_tot[w];
+                const uint32_t excl = run + x - (v0 + v1);
+                sm.g_start[2 * tid] = excl;
+                sm.g_start[2 * tid + 1] = excl + v0;
+                __syncthreads();
+            }
+            const uint32_t cnt = valid ? sm.g_cnt[slot] : 0;
+            const uint32_t gstart = valid ? sm.g_start[slot] : 0;
+            const uint32_t q = gstart + ord;  // my position in group-sorted order
+            if (valid) sm.dsum[q] = delta;
+            __syncthreads();
+            // inclusive scan of the group-sorted deltas; P_i = X[q] - X[gstart-1]
+            {
+                unsigned long long x = sm.dsum[tid];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+                    if ((int)lane >= o) x += y;
+                }
+                if (lane == 31) sm.warp_tot[warp] = x;
+                __syncthreads();
+                unsigned long long run = 0;
+                for (uint32_t w = 0; w < warp; w++) run += sm.warp_tot[w];
+                sm.dsum[tid] = run + x;
+                __syncthreads();
+            }
+            const unsigned long long p_incl = valid ? sm.dsum[q] - (gstart ? sm.dsum[gstart - 1] : 0ull) : 0ull;
+            const unsigned long long p_prev = p_incl - delta;
+
+            // ---- 3. leaders probe the row and stage its state ---------------------------------
+            const uint32_t gid = gstart;  // unique per group, < CH
+            const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
+            const RlCellDesc* desc = D.desc + (size_t)group * 8;
+            uint8_t* row = nullptr;
+            const bool is_leader = valid && ord == 0;
+            const uint32_t ucells = acc.cells;  // meaningful on the leader; shared below
+            if (is_leader) {
+                row = rl_probe<CELLS>(D, h, acc.key_lo, acc.hdr_hi, true);
+                RlRow<CELLS> st;
+                rl_row_load<CELLS>(row, CELLS, st);
+#pragma unroll
+                for (int c = 0; c < CELLS; c++) {
+                    sm.s_val[gid * CELLS + c] = st.value[c];
+                    sm.s_exp[gid * CELLS + c] = st.expiry[c];
+                }
+                sm.g_min[0][0][gid] = sm.g_min[0][1][gid] = 0xFFFFFFFFu;
+                sm.g_min[1][0][gid] = sm.g_min[1][1][gid] = 0xFFFFFFFFu;
+                sm.g_pbase[gid] = 0ull;
+                sm.g_dirty[gid] = 0;
+                sm.g_rowok[gid] = (row != nullptr);
+                sm.g_rep[slot] = ucells;  // g_rep is free now: publish the leader's cell list
+                if (snapshot && row != nullptr) {
+                    B.log_row[p] = row;
+#pragma unroll
+                    for (int c = 0; c < CELLS; c++)
+                        B.log_state[(size_t)p * CELLS + c] = make_ulonglong2(st.value[c], st.expiry[c]);
+                }
             }
             __syncthreads();
-            if (valid) members[g_start[slot] + ord] = (uint16_t)tid;
-            __syncthreads();
 
-            if (valid && ord == 0) {
-                // ---- walker: replay this key's requests in stream order --------------------
-                const uint32_t cnt = g_cnt[slot];
-                const uint32_t mbase = g_start[slot];
-                uint32_t remaining_members = cnt;
-                uint32_t first_j = 0;
-                uint64_t rep_lo = key_lo, rep_hi = hdr_hi, rep_h = h;
-                while (remaining_members) {
-                    const uint32_t group = (uint32_t)(rep_hi >> 32);
-                    const RlCellDesc* desc = D.desc + (size_t)group * 8;
-                    uint8_t* row = rl_probe<CELLS>(D, rep_h, rep_lo, rep_hi, true);
-                    RlRow<CELLS> st;
-                    rl_row_load<CELLS>(row, CELLS, st);
-                    uint32_t dirty = 0;
-                    uint32_t next_first = cnt;
-                    const bool snapshot = (B.phase == RL_PHASE_SNAPSHOT);
-                    if (snapshot && row != nullptr) {
-                        const uint32_t lp = c0 + (members[mbase + first_j] & 0x7FFFu);
-                        B.log_row[lp] = row;
+            // ---- 4. lock-step run-length replay -------------------------------------------------
+            bool done = !valid || snapshot || !sm.g_rowok[gid];
+            const uint32_t lead_cells = valid ? sm.g_rep[slot] : 0;
+            const bool multi = rl_cells_multi(acc.cells);
+            uint32_t pos = 0;
+            for (uint32_t round = 0;; round++) {
+                const uint32_t par = round & 1;
+                RlRow<CELLS> st;
+                if (!done) {
 #pragma unroll
-                        for (int c = 0; c < CELLS; c++)
-                            B.log_state[(size_t)lp * CELLS + c] = make_ulonglong2(st.value[c], st.expiry[c]);
+                    for (int c = 0; c < CELLS; c++) {
+                        st.value[c] = sm.s_val[gid * CELLS + c];
+                        st.expiry[c] = sm.s_exp[gid * CELLS + c];
                     }
-                    for (uint32_t j = first_j; j < cnt; j++) {
-                        const uint16_t mm = members[mbase + j];
-                        if (mm & 0x8000u) continue;  // already replayed (tag collision pass)
-                        const uint32_t am = s_acc[mm];
-                        RlAccess acc;
-                        uint64_t delta, now;
-                        src.full(D, am, acc, delta, now);
-                        if (acc.key_lo != rep_lo || acc.hdr_hi != rep_hi) {
-                            if (next_first == cnt) next_first = j;  // different key, same 63-bit tag
-                            continue;
-                        }
-                        members[mbase + j] = mm | 0x8000u;
-                        remaining_members--;
-                        if (row == nullptr || snapshot) continue;  // (table full: error already flagged)
-                        const uint32_t req = acc.req;
-                        if (MODE == 2) {
-                            rl_walk_update<CELLS>(st, dirty, desc, acc.cells, delta, now);
-                            continue;
-                        }
-                        const bool lc = B.load_counters != 0;
-                        const bool write_out = (B.phase == RL_PHASE_COMMIT);
-                        uint64_t* rem = nullptr;
-                        uint64_t* ttl = nullptr;
-                        if (lc && write_out) {
-                            const size_t ob = B.out_off ? (size_t)B.out_off[req] : (size_t)req * B.out_stride;
-                            if (B.out_remaining) rem = B.out_remaining + ob;
-                            if (B.out_ttl) ttl = B.out_ttl + ob;
-                        }
-                        if (!rl_cells_multi(acc.cells)) {
-                            const uint32_t fl = rl_walk_check_single<CELLS>(st, dirty, desc, acc.cells, acc.posorig,
-                                                                            delta, now, lc, rem, ttl);
-                            if (write_out) {
-                                B.out_limited[req] = (fl != RL_NONE_U32);
-                                if (B.out_first_limited) {
-                                    uint32_t lid = RL_NONE_U32;
-                                    if (fl != RL_NONE_U32) {
-                                        const uint32_t n = rl_cells_n(acc.cells);
-                                        for (uint32_t k = 0; k < n; k++)
-                                            if (rl_pos_at(acc.posorig, k) == fl)
-                                                lid = desc[rl_cells_at(acc.cells, k)].limit_id;
-                                    }
-                                    B.out_first_limited[req] = lid;
-                                }
-                            }
+                    bool aok = false, bok = false;
+                    if (!multi) {
+                        if (MODE == 0) {
+                            aok = rl_eval_deny_noeffect<CELLS>(st, desc, acc.cells, acc.posorig, delta, now, lc);
+                            bok = (acc.cells == lead_cells) &&
+                                  rl_eval_allow_run<CELLS>(st, desc, acc.cells, p_incl - sm.g_pbase[gid], now);
                         } else {
-                            const uint32_t fl_in = B.fl_prev[req];
-                            const uint32_t local = rl_walk_check_multi<CELLS>(st, dirty, desc, acc.cells, acc.posorig,
-                                                                             delta, now, lc, fl_in, rem, ttl);
-                            if (!write_out) {
-                                if (local != RL_NONE_U32) atomicMin(&B.fl_next[req], local);
+                            bok = (acc.cells == lead_cells) && rl_eval_update_run<CELLS>(st, acc.cells, now);
+                        }
+                    }
+                    if (!aok) atomicMin(&sm.g_min[par][0][gid], ord);
+                    if (!bok) atomicMin(&sm.g_min[par][1][gid], ord);
+                }
+                __syncthreads();
+                if (!done) {
+                    const uint32_t mA = min(sm.g_min[par][0][gid], cnt);
+                    const uint32_t mB = min(sm.g_min[par][1][gid], cnt);
+                    const unsigned long long pbase = sm.g_pbase[gid];
+                    uint32_t newpos;
+                    bool mine = false;     // am I finalised this round?
+                    bool store = false;    // do I publish the new row state?
+                    uint32_t dirty = 0;
+                    uint32_t fl = RL_NONE_U32;
+                    uint64_t* rem = nullptr;
+                    uint64_t* ttl = nullptr;
+                    if (MODE == 0 && lc && write_out) {
+                        const size_t ob = B.out_off ? (size_t)B.out_off[acc.req] : (size_t)acc.req * B.out_stride;
+                        if (B.out_remaining) rem = B.out_remaining + ob;
+                        if (B.out_ttl) ttl = B.out_ttl + ob;
+                    }
+                    if (mA > pos) {  // run of denied requests: state untouched
+                        newpos = mA;
+                        if (ord < mA) {
+                            mine = true;
+                            fl = rl_walk_check_single<CELLS>(st, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                        }
+                    } else if (mB > pos) {  // run of allowed requests: values accumulate
+                        newpos = mB;
+                        if (ord < mB) {
+                            mine = true;
+                            rl_advance_run<CELLS>(st, acc.cells, p_prev - pbase);
+                            if (MODE == 0)
+                                fl = rl_walk_check_single<CELLS>(st, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                            else
+                                rl_walk_update<CELLS>(st, dirty, desc, acc.cells, delta, now);
+                            store = (ord == mB - 1);
+                            if (store) dirty = 0;
+                            if (store) {
+                                const uint32_t n = rl_cells_n(acc.cells);
+                                for (uint32_t k = 0; k < n; k++) dirty |= 1u << rl_cells_at(acc.cells, k);
+                            }
+                        }
+                    } else {  // the request at `pos` is applied alone, sequential rule
+                        newpos = pos + 1;
+                        if (ord == pos) {
+                            mine = true;
+                            store = true;
+                            if (MODE == 2) {
+                                rl_walk_update<CELLS>(st, dirty, desc, acc.cells, delta, now);
+                            } else if (!multi) {
+                                fl = rl_walk_check_single<CELLS>(st, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
                             } else {
-                                B.out_limited[req] = (fl_in != RL_NONE_U32);
-                                if (B.out_first_limited) {
-                                    if (fl_in == RL_NONE_U32) {
-                                        B.out_first_limited[req] = RL_NONE_U32;
-                                    } else {
-                                        const uint32_t n = rl_cells_n(acc.cells);
-                                        for (uint32_t k = 0; k < n; k++)
-                                            if (rl_pos_at(acc.posorig, k) == fl_in)
-                                                B.out_first_limited[req] = desc[rl_cells_at(acc.cells, k)].limit_id;
-                                    }
-                                }
+                                const uint32_t fl_in = B.fl_prev[acc.req];
+                                const uint32_t local = rl_walk_check_multi<CELLS>(st, dirty, desc, acc.cells, acc.posorig,
+                                                                                 delta, now, lc, fl_in, rem, ttl);
+                                if (!write_out && local != RL_NONE_U32) atomicMin(&B.fl_next[acc.req], local);
+                                fl = fl_in;
                             }
                         }
                     }
-                    if (row != nullptr && !snapshot) rl_row_store<CELLS>(row, dirty, st);
-                    if (remaining_members) {
-                        // a different key shared the tag: replay it next
-                        first_j = next_first;
-                        const uint32_t am = s_acc[members[mbase + first_j] & 0x7FFFu];
-                        src.ident(D, am, rep_lo, rep_hi);
-                        rep_h = rl_row_hash(rep_lo, rep_hi);
+                    if (mine) {
+                        done = true;
+                        if (MODE == 0 && write_out) {
+                            B.out_limited[acc.req] = (fl != RL_NONE_U32);
+                            if (B.out_first_limited) {
+                                if (fl == RL_NONE_U32) {
+                                    B.out_first_limited[acc.req] = RL_NONE_U32;
+                                } else {
+                                    // the access holding position fl names the limit
+                                    const uint32_t n = rl_cells_n(acc.cells);
+                                    for (uint32_t k = 0; k < n; k++)
+                                        if (rl_pos_at(acc.posorig, k) == fl)
+                                            B.out_first_limited[acc.req] = desc[rl_cells_at(acc.cells, k)].limit_id;
+                                }
+                            }
+                        }
+                        if (store && dirty) {
+#pragma unroll
+                            for (int c = 0; c < CELLS; c++)
+                                if (dirty & (1u << c)) {
+                                    sm.s_val[gid * CELLS + c] = st.value[c];
+                                    sm.s_exp[gid * CELLS + c] = st.expiry[c];
+                                }
+                            atomicOr(&sm.g_dirty[gid], dirty);
+                        }
+                        if (ord == newpos - 1) {  // last finalised member re-arms the group
+                            sm.g_pbase[gid] = p_incl;
+                            sm.g_min[par ^ 1][0][gid] = 0xFFFFFFFFu;
+                            sm.g_min[par ^ 1][1][gid] = 0xFFFFFFFFu;
+                        }
                     }
+                    pos = newpos;
                 }
+                if (!__syncthreads_or(!done)) break;
+            }
+
+            // ---- 5. write the dirty cells back ---------------------------------------------------
+            if (is_leader && row != nullptr && !snapshot) {
+                const uint32_t dirty = sm.g_dirty[gid];
+#pragma unroll
+                for (int c = 0; c < CELLS; c++)
+                    if (dirty & (1u << c))
+                        rl_st_cg(row + 16 + 16 * c, sm.s_val[gid * CELLS + c], sm.s_exp[gid * CELLS + c]);
             }
             __syncthreads();
         }

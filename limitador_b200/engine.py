@@ -121,11 +121,11 @@ class Engine:
     """One GPU-resident counter table (one per process / per GPU)."""
 
     def __init__(self, capacity_rows: int, cells_per_row: int = 1, max_batch: int = 65536,
-                 max_counters: int = 0, regions: int = 0, device: int = 0):
+                 max_counters: int = 0, regions: int = 0, device: int = 0, flags: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = RlConfig(C.sizeof(RlConfig), device, capacity_rows, cells_per_row, max_batch, max_counters,
-                       regions, 0, 0)
+                       regions, flags, 0)
         st = self._lib.rl_engine_create(C.byref(cfg), C.byref(self._h))
         if st != RL_OK:
             msg = "rl_engine_create failed (no CUDA device? limitador_b200 has no CPU fallback)"

@@ -76,46 +76,108 @@ int emu_batch_csr(emu* e, int mode, uint32_t n, const uint32_t* off, const emu_c
             auto it = e->table.find(kv.first);
             if (it != e->table.end()) st = it->second;
             else memset(&st, 0, sizeof st);
-            uint32_t dirty = 0;
             const uint32_t group = (uint32_t)(kv.first.second >> 32);
             const RlCellDesc* desc = e->desc.data() + (size_t)group * 8;
-            for (uint32_t a : kv.second) {
-                const RlAccess& A = acc[a];
+            // run-length replay, exactly as k_main's lock-step rounds do it (rl_core.h hypotheses)
+            const std::vector<uint32_t>& mem = kv.second;
+            const uint32_t n = (uint32_t)mem.size();
+            std::vector<uint64_t> P(n);
+            uint64_t run = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                run += delta[acc[mem[i]].req];
+                P[i] = run;
+            }
+            const uint32_t lead_cells = acc[mem[0]].cells;
+            uint32_t pos = 0;
+            uint64_t pbase = 0;
+            auto outputs = [&](const RlAccess& A, uint32_t fl) {
                 const uint32_t req = A.req;
-                if (mode == 2) {
-                    rl_walk_update<RL_MAX_CELLS>(st, dirty, desc, A.cells, delta[req], now[req]);
-                    continue;
+                out_limited[req] = fl != RL_NONE_U32;
+                if (!out_first) return;
+                if (fl == RL_NONE_U32) {
+                    out_first[req] = RL_NONE_U32;
+                    return;
                 }
-                uint64_t* rem = (lc && commit && out_rem) ? out_rem + off[req] : nullptr;
-                uint64_t* ttl = (lc && commit && out_ttl) ? out_ttl + off[req] : nullptr;
-                if (!rl_cells_multi(A.cells)) {
-                    const uint32_t fl = rl_walk_check_single<RL_MAX_CELLS>(st, dirty, desc, A.cells, A.posorig,
-                                                                           delta[req], now[req], lc != 0, rem, ttl);
-                    if (commit) {
-                        out_limited[req] = fl != RL_NONE_U32;
-                        uint32_t lid = RL_NONE_U32;
-                        if (fl != RL_NONE_U32)
-                            for (uint32_t k = 0; k < rl_cells_n(A.cells); k++)
-                                if (rl_pos_at(A.posorig, k) == fl) lid = desc[rl_cells_at(A.cells, k)].limit_id;
-                        if (out_first) out_first[req] = lid;
+                for (uint32_t k = 0; k < rl_cells_n(A.cells); k++)
+                    if (rl_pos_at(A.posorig, k) == fl) out_first[req] = desc[rl_cells_at(A.cells, k)].limit_id;
+            };
+            while (pos < n) {
+                uint32_t mA = n, mB = n;
+                for (uint32_t i = pos; i < n && (mA == n || mB == n); i++) {
+                    const RlAccess& A = acc[mem[i]];
+                    const bool multi = rl_cells_multi(A.cells);
+                    bool aok = false, bok = false;
+                    if (!multi) {
+                        if (mode == 0) {
+                            aok = rl_eval_deny_noeffect<RL_MAX_CELLS>(st, desc, A.cells, A.posorig, delta[A.req], now[A.req], lc != 0);
+                            bok = A.cells == lead_cells &&
+                                  rl_eval_allow_run<RL_MAX_CELLS>(st, desc, A.cells, P[i] - pbase, now[A.req]);
+                        } else {
+                            bok = A.cells == lead_cells && rl_eval_update_run<RL_MAX_CELLS>(st, A.cells, now[A.req]);
+                        }
+                    }
+                    if (!aok && mA == n) mA = i;
+                    if (!bok && mB == n) mB = i;
+                }
+                uint32_t newpos;
+                if (mA > pos) {
+                    newpos = mA;
+                    for (uint32_t i = pos; i < mA; i++) {
+                        const RlAccess& A = acc[mem[i]];
+                        RlRow<RL_MAX_CELLS> loc = st;
+                        uint32_t dd = 0;
+                        uint64_t* rem = (lc && commit && out_rem) ? out_rem + off[A.req] : nullptr;
+                        uint64_t* ttl = (lc && commit && out_ttl) ? out_ttl + off[A.req] : nullptr;
+                        const uint32_t fl = rl_walk_check_single<RL_MAX_CELLS>(loc, dd, desc, A.cells, A.posorig, delta[A.req],
+                                                                               now[A.req], lc != 0, rem, ttl);
+                        if (commit) outputs(A, fl);
+                    }
+                } else if (mB > pos) {
+                    newpos = mB;
+                    for (uint32_t i = pos; i < mB; i++) {
+                        const RlAccess& A = acc[mem[i]];
+                        RlRow<RL_MAX_CELLS> loc = st;
+                        uint32_t dd = 0;
+                        rl_advance_run<RL_MAX_CELLS>(loc, A.cells, (P[i] - delta[A.req]) - pbase);
+                        if (mode == 0) {
+                            uint64_t* rem = (lc && commit && out_rem) ? out_rem + off[A.req] : nullptr;
+                            uint64_t* ttl = (lc && commit && out_ttl) ? out_ttl + off[A.req] : nullptr;
+                            const uint32_t fl = rl_walk_check_single<RL_MAX_CELLS>(loc, dd, desc, A.cells, A.posorig,
+                                                                                   delta[A.req], now[A.req], lc != 0, rem, ttl);
+                            if (commit) outputs(A, fl);
+                        } else {
+                            rl_walk_update<RL_MAX_CELLS>(loc, dd, desc, A.cells, delta[A.req], now[A.req]);
+                        }
+                        if (i == mB - 1) st = loc;
                     }
                 } else {
-                    const uint32_t fl_in = fl_prev[req];
-                    const uint32_t local = rl_walk_check_multi<RL_MAX_CELLS>(st, dirty, desc, A.cells, A.posorig,
-                                                                            delta[req], now[req], lc != 0, fl_in, rem, ttl);
-                    if (!commit) {
-                        if (local < fl_next[req]) fl_next[req] = local;
+                    newpos = pos + 1;
+                    const RlAccess& A = acc[mem[pos]];
+                    const uint32_t req = A.req;
+                    uint32_t dd = 0;
+                    if (mode == 2) {
+                        rl_walk_update<RL_MAX_CELLS>(st, dd, desc, A.cells, delta[req], now[req]);
                     } else {
-                        out_limited[req] = fl_in != RL_NONE_U32;
-                        if (out_first) {
-                            if (fl_in == RL_NONE_U32) out_first[req] = RL_NONE_U32;
-                            else
-                                for (uint32_t k = 0; k < rl_cells_n(A.cells); k++)
-                                    if (rl_pos_at(A.posorig, k) == fl_in)
-                                        out_first[req] = desc[rl_cells_at(A.cells, k)].limit_id;
+                        uint64_t* rem = (lc && commit && out_rem) ? out_rem + off[req] : nullptr;
+                        uint64_t* ttl = (lc && commit && out_ttl) ? out_ttl + off[req] : nullptr;
+                        if (!rl_cells_multi(A.cells)) {
+                            const uint32_t fl = rl_walk_check_single<RL_MAX_CELLS>(st, dd, desc, A.cells, A.posorig, delta[req],
+                                                                                   now[req], lc != 0, rem, ttl);
+                            if (commit) outputs(A, fl);
+                        } else {
+                            const uint32_t fl_in = fl_prev[req];
+                            const uint32_t local = rl_walk_check_multi<RL_MAX_CELLS>(st, dd, desc, A.cells, A.posorig, delta[req],
+                                                                                    now[req], lc != 0, fl_in, rem, ttl);
+                            if (!commit) {
+                                if (local < fl_next[req]) fl_next[req] = local;
+                            } else {
+                                outputs(A, fl_in);
+                            }
                         }
                     }
                 }
+                pbase = P[newpos - 1];
+                pos = newpos;
             }
             if (commit) e->table[kv.first] = st;  // physical row exists once probed (cells may be absent)
         }

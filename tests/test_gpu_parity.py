@@ -91,6 +91,23 @@ def test_csr_general_path_with_coupled_requests(cells, load_counters):
     assert e.stats()["fixed_point_rounds"] >= 1
 
 
+@pytest.mark.parametrize("cells", [1, 7])
+def test_grouping_tag_collisions(cells):
+    """RL_FLAG_DEBUG_WEAK_TAGS: only 16 distinct grouping tags per salt level, so distinct keys
+    collide inside a chunk and take the salted re-insertion path; results must not change."""
+    descs = H.mixed_limits(n_ns=12, seed=3)
+    e = Engine(capacity_rows=1 << 14, cells_per_row=cells, max_batch=1 << 16, regions=2, flags=1)
+    e.limits_set(descs)
+    o = H.oracle_with_limits(descs)
+    for b in range(3):
+        off, ctrs, delta, now = H.random_csr_stream(descs, 2500, 31 + b, n_keys=60)
+        got = e.check_and_update_batch(off, ctrs, delta, now, True)
+        want = o.batch_csr(0, off, ctrs, delta, now, True)
+        for k in range(4):
+            assert got[k].tolist() == want[k].tolist()
+        assert_tables_equal(e, o, descs)
+
+
 def test_long_dependency_chain():
     descs = np.array([(0, 0, 1, 1, 1, 3600 * S), (1, 0, 2, 1, 1, 3600 * S)], dtype=LIMIT_DESC_DTYPE)
     n = 40
