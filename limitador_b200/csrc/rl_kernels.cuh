@@ -410,42 +410,80 @@ __global__ void __launch_bounds__(256) k_colscan(RlDev D, RlBatch B) {
 //
 // One CTA per table region; the region's accesses (already in stream order) are taken in
 // chunks of CH (one access per thread).  Per chunk:
-//   1. every thread loads its access, and the CTA groups the accesses by row key with a
-//      shared-memory hash table (64-bit tag claimed by CAS, full key verified against the
-//      claimer's; a mismatch re-inserts under a salted tag);
-//   2. every access gets its stable ordinal inside its key group (warps take turns, so the
-//      ordinal order is the stream order) and the inclusive prefix sum of the group's
-//      deltas (one block scan over the group-sorted deltas);
-//   3. the group leader probes / claims the row (one probe per key) and stages the row
-//      state in shared memory;
-//   4. the group is replayed by ALL its threads in lock-step "run-length" rounds
-//      (rl_core.h: hypotheses A and B) — two barriers per round, one round for a saturated
-//      or an unconstrained hot key;
-//   5. the leader writes the dirty cells back.
+//   1. every thread loads its access (the next chunk's is prefetched), and the CTA groups
+//      the accesses by row key with a shared-memory hash table: 56-bit tag claimed by CAS,
+//      full key verified against the claimer's, a mismatch re-inserts under a salted tag.
+//      The claimer ("rep") of a key immediately probes / claims the table row — one probe
+//      per key, its HBM latency overlapping the grouping barriers;
+//   2. every access gets its stable ordinal inside its key group from one packed
+//      shared-memory counter per key (8 bits per warp, added warp-aggregated): ordinal order
+//      == thread order == stream order;
+//   3. the rep stages the row state in shared memory;
+//   4. the group is replayed by ALL its threads in lock-step run-length rounds (rl_core.h,
+//      hypotheses A and B; B in closed form for runs of equal deltas) — two barriers per
+//      round, one round for a saturated or an unconstrained hot key;
+//   5. the rep writes the dirty cells back.
 // Counter values never need atomics: a region belongs to one CTA, a key to one group.
 template <int CELLS, int CH>
 struct RlMainSmem {
     static constexpr int GT = 2 * CH;
+    static constexpr int NW = CH / 32;
+    static constexpr int PW = (NW + 7) / 8;
     unsigned long long g_tag[GT];
+    unsigned long long g_packed[GT * PW];  // per key: member count of every warp, 8 bits each
     unsigned long long key_lo[CH];
     unsigned long long key_hi[CH];
-    unsigned long long s_val[CH * CELLS];  // row state of the group led by thread `gid`
+    unsigned long long d_arr[CH];
+    unsigned long long s_val[CH * CELLS];  // row state of the group whose rep is thread `gid`
     unsigned long long s_exp[CH * CELLS];
-    unsigned long long dsum[CH];           // group-sorted deltas -> inclusive scan
-    unsigned long long g_pbase[CH];        // prefix sum of the deltas of the finalised members
-    uint32_t g_cnt[GT];
-    uint32_t g_start[GT];
+    uint32_t cells_arr[CH];
     uint32_t g_rep[GT];
-    uint32_t g_min[2][2][CH];              // [round parity][A|B][gid]
+    uint32_t g_min[2][2][CH];  // [round parity][A|B][gid]
+    uint32_t g_flags[CH];      // by gid: bit0 = members differ in delta or cell list
     uint32_t g_dirty[CH];
-    uint32_t g_rowok[CH];
-    unsigned long long warp_tot[CH / 32];
 };
+
+// Per-thread view of the limits its access touches, in the access's own cell order.
+struct RlMyLimits {
+    uint64_t mx[RL_MAX_CELLS];
+    uint32_t qmask;  // bit k: k-th touched cell belongs to a qualified limit
+};
+
+// Hypotheses A and B for one access against the staged row state (shared memory).
+//   a_ok : denied under S and nothing is created / reset / incremented; fl = position of the
+//          first limited counter (in_memory.rs:110-112,130-132,141-143)
+//   b_ok : every touched cell is live at `now` and stays within its limit after adding
+//          `dsum` (this request's delta plus those of the run before it)
+template <int CELLS>
+__device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const unsigned long long* se,
+                                           const RlMyLimits& L, uint32_t cells, uint64_t posorig, uint64_t delta,
+                                           uint64_t dsum, uint64_t now, bool lc, bool check_limit, bool& a_ok,
+                                           bool& b_ok, uint32_t& fl) {
+    const uint32_t n = rl_cells_n(cells);
+    bool absent_reached = false, live_all = true, within_all = true;
+    fl = RL_NONE_U32;
+#pragma unroll
+    for (int k = 0; k < CELLS; k++) {
+        if ((uint32_t)k < n) {
+            const uint32_t c = rl_cells_at(cells, k);
+            const uint64_t v = sv[c], e = se[c];
+            const bool reached = lc || fl == RL_NONE_U32;  // !lc: the walk returns at the first limited counter
+            if (reached && ((L.qmask >> k) & 1u) && e == 0) absent_reached = true;
+            const uint64_t vv = (e <= now) ? 0 : v;
+            if (reached && fl == RL_NONE_U32 && vv + delta > L.mx[k]) fl = rl_pos_at(posorig, k);
+            if (e <= now) live_all = false;
+            if (v + dsum > L.mx[k]) within_all = false;
+        }
+    }
+    a_ok = (fl != RL_NONE_U32) && !absent_reached;
+    b_ok = live_all && (within_all || !check_limit);
+}
 
 template <int CELLS, class Src, int MODE, int CH>
 __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
+    constexpr int PW = Smem::PW;
     extern __shared__ __align__(16) unsigned char rl_smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(rl_smem_raw);
 
@@ -457,31 +495,54 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
 
     for (uint32_t region = blockIdx.x; region < P; region += gridDim.x) {
         const uint32_t lo = B.part_base[region], hi = B.part_base[region + 1];
-        for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
-            for (uint32_t i = tid; i < GT; i += CH) {
-                sm.g_tag[i] = 0ull;
-                sm.g_cnt[i] = 0;
-            }
-            sm.dsum[tid] = 0ull;
-            __syncthreads();
+        if (lo >= hi) continue;
+        // prefetch of the first chunk
+        RlAccess nacc;
+        uint64_t ndelta = 0, nnow = 0;
+        nacc.key_lo = 0; nacc.hdr_hi = 0; nacc.req = 0; nacc.cells = 0; nacc.posorig = 0;
+        if (lo + tid < hi) src.full(D, B.part_idx[lo + tid], nacc, ndelta, nnow);
 
-            // ---- 1. load my access, group by key --------------------------------------------
+        for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
+            for (uint32_t i = tid; i < GT; i += CH) sm.g_tag[i] = 0ull;
+            for (uint32_t i = tid; i < GT * PW; i += CH) sm.g_packed[i] = 0ull;
+
+            // ---- 1. my access (prefetched); issue the next chunk's loads -----------------------
             const uint32_t p = c0 + tid;
             const bool valid = p < hi;
-            RlAccess acc;
-            acc.key_lo = 0;
-            acc.hdr_hi = 0;
-            acc.req = 0;
-            acc.cells = 0;
-            acc.posorig = 0;
-            uint64_t delta = 0, now = 0, h = 0;
-            if (valid) {
-                src.full(D, B.part_idx[p], acc, delta, now);
-                h = rl_row_hash(acc.key_lo, acc.hdr_hi);
+            const RlAccess acc = nacc;
+            const uint64_t delta = ndelta, now = nnow;
+            if (p + CH < hi) src.full(D, B.part_idx[p + CH], nacc, ndelta, nnow);
+            const uint64_t h = rl_row_hash(acc.key_lo, acc.hdr_hi);
+            const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
+            const RlCellDesc* desc = D.desc + (size_t)group * 8;
+            const uint32_t ncell = rl_cells_n(acc.cells);
+            const bool multi = (MODE == 0) && rl_cells_multi(acc.cells);  // coupled to other rows (check only)
+            RlMyLimits L;
+            L.qmask = 0;
+#pragma unroll
+            for (int k = 0; k < CELLS; k++) {
+                L.mx[k] = 0;
+                if (valid && (uint32_t)k < ncell) {
+                    const RlCellDesc d = desc[rl_cells_at(acc.cells, k)];
+                    L.mx[k] = d.max_value;
+                    L.qmask |= (d.qualified ? 1u : 0u) << k;
+                }
             }
             sm.key_lo[tid] = acc.key_lo;
             sm.key_hi[tid] = acc.hdr_hi;
-            uint32_t slot = 0;
+            sm.d_arr[tid] = delta;
+            sm.cells_arr[tid] = acc.cells;
+            sm.g_flags[tid] = 0;
+            sm.g_dirty[tid] = 0;
+            sm.g_min[0][0][tid] = sm.g_min[0][1][tid] = 0xFFFFFFFFu;
+            sm.g_min[1][0][tid] = sm.g_min[1][1][tid] = 0xFFFFFFFFu;
+            __syncthreads();
+
+            // ---- group by key; the claimer of a key probes its row right away ------------------
+            uint32_t slot = 0, gid = tid;
+            uint8_t* row = nullptr;
+            bool is_rep = false;
+            RlRow<CELLS> st;
             {
                 bool pending = valid;
                 uint32_t salt = 0;
@@ -496,104 +557,45 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                             const unsigned long long old = atomicCAS(&sm.g_tag[s], 0ull, tag);
                             if (old == 0ull) {
                                 sm.g_rep[s] = tid;  // I claimed the slot: my key defines the group
+                                is_rep = true;
                                 break;
                             }
                             if (old == tag) break;
                             s = (s + 1) & (GT - 1);
                         }
                         slot = s;
+                        if (is_rep && row == nullptr) {
+                            row = rl_probe<CELLS>(D, h, acc.key_lo, acc.hdr_hi, true);
+                            rl_row_load<CELLS>(row, CELLS, st);
+                        }
                     }
                     __syncthreads();
                     if (pending) {
-                        const uint32_t rep = sm.g_rep[slot];
-                        pending = (sm.key_lo[rep] != acc.key_lo) || (sm.key_hi[rep] != acc.hdr_hi);
+                        gid = sm.g_rep[slot];
+                        pending = (sm.key_lo[gid] != acc.key_lo) || (sm.key_hi[gid] != acc.hdr_hi);
                         salt++;
                     }
-                    if (!__syncthreads_or(pending)) break;  // a tag collision between different keys: re-insert salted
+                    if (!__syncthreads_or(pending)) break;  // tag collision between different keys: re-insert salted
                 }
             }
 
-            // ---- 2. stable ordinal inside the key group: warps take turns ---------------------
-            uint32_t ord = 0;
+            // ---- 2. stable ordinal: one packed add per (warp, key), one barrier ------------------
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            for (uint32_t w = 0; w < CH / 32; w++) {
-                if (warp == w && valid) {
-                    const unsigned m = __match_any_sync(vmask, slot);
-                    const int leader = __ffs(m) - 1;
-                    uint32_t basecnt = 0;
-                    if ((int)lane == leader) {
-                        basecnt = sm.g_cnt[slot];
-                        sm.g_cnt[slot] = basecnt + __popc(m);
-                    }
-                    basecnt = __shfl_sync(m, basecnt, leader);
-                    ord = basecnt + __popc(m & ((1u << lane) - 1));
-                }
-                __syncthreads();
+            unsigned peers = 0;
+            if (valid) {
+                peers = __match_any_sync(vmask, slot);
+                if (lane == (uint32_t)(__ffs(peers) - 1))
+                    atomicAdd(&sm.g_packed[slot * PW + (warp >> 3)], (unsigned long long)__popc(peers) << (8 * (warp & 7)));
+                if (sm.d_arr[gid] != delta || sm.cells_arr[gid] != acc.cells) atomicOr(&sm.g_flags[gid], 1u);
             }
-            // exclusive scan of the group sizes -> where each group starts in group-sorted order
-            {
-                uint32_t run = 0;
-                // GT = 2*CH entries, two per thread
-                const uint32_t v0 = sm.g_cnt[2 * tid], v1 = sm.g_cnt[2 * tid + 1];
-                uint32_t x = v0 + v1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                    if ((int)lane >= o) x += y;
-                }
-                if (lane == 31) sm.warp_tot[warp] = x;
-                __syncthreads();
-                for (uint32_t w = 0; w < warp; w++) run += (uint32_t)sm.warp_tot[w];
-                const uint32_t excl = run + x - (v0 + v1);
-                sm.g_start[2 * tid] = excl;
-                sm.g_start[2 * tid + 1] = excl + v0;
-                __syncthreads();
-            }
-            const uint32_t cnt = valid ? sm.g_cnt[slot] : 0;
-            const uint32_t gstart = valid ? sm.g_start[slot] : 0;
-            const uint32_t q = gstart + ord;  // my position in group-sorted order
-            if (valid) sm.dsum[q] = delta;
-            __syncthreads();
-            // inclusive scan of the group-sorted deltas; P_i = X[q] - X[gstart-1]
-            {
-                unsigned long long x = sm.dsum[tid];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
-                    if ((int)lane >= o) x += y;
-                }
-                if (lane == 31) sm.warp_tot[warp] = x;
-                __syncthreads();
-                unsigned long long run = 0;
-                for (uint32_t w = 0; w < warp; w++) run += sm.warp_tot[w];
-                sm.dsum[tid] = run + x;
-                __syncthreads();
-            }
-            const unsigned long long p_incl = valid ? sm.dsum[q] - (gstart ? sm.dsum[gstart - 1] : 0ull) : 0ull;
-            const unsigned long long p_prev = p_incl - delta;
-
-            // ---- 3. leaders probe the row and stage its state ---------------------------------
-            const uint32_t gid = gstart;  // unique per group, < CH
-            const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
-            const RlCellDesc* desc = D.desc + (size_t)group * 8;
-            uint8_t* row = nullptr;
-            const bool is_leader = valid && ord == 0;
-            const uint32_t ucells = acc.cells;  // meaningful on the leader; shared below
-            if (is_leader) {
-                row = rl_probe<CELLS>(D, h, acc.key_lo, acc.hdr_hi, true);
-                RlRow<CELLS> st;
-                rl_row_load<CELLS>(row, CELLS, st);
+            // ---- 3. the rep stages the row state --------------------------------------------------
+            if (is_rep) {
 #pragma unroll
                 for (int c = 0; c < CELLS; c++) {
-                    sm.s_val[gid * CELLS + c] = st.value[c];
-                    sm.s_exp[gid * CELLS + c] = st.expiry[c];
+                    sm.s_val[tid * CELLS + c] = st.value[c];
+                    sm.s_exp[tid * CELLS + c] = st.expiry[c];
                 }
-                sm.g_min[0][0][gid] = sm.g_min[0][1][gid] = 0xFFFFFFFFu;
-                sm.g_min[1][0][gid] = sm.g_min[1][1][gid] = 0xFFFFFFFFu;
-                sm.g_pbase[gid] = 0ull;
-                sm.g_dirty[gid] = 0;
-                sm.g_rowok[gid] = (row != nullptr);
-                sm.g_rep[slot] = ucells;  // g_rep is free now: publish the leader's cell list
+                if (row == nullptr) atomicOr(&sm.g_flags[tid], 2u);  // table full: error already flagged
                 if (snapshot && row != nullptr) {
                     B.log_row[p] = row;
 #pragma unroll
@@ -602,29 +604,44 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                 }
             }
             __syncthreads();
+            uint32_t ord = 0, cnt = 0;
+            if (valid) {
+#pragma unroll
+                for (int w = 0; w < Smem::NW; w++) {
+                    const uint32_t f = (uint32_t)(sm.g_packed[slot * PW + (w >> 3)] >> (8 * (w & 7))) & 0xFFu;
+                    cnt += f;
+                    if ((uint32_t)w < warp) ord += f;
+                }
+                ord += __popc(peers & ((1u << lane) - 1));
+            }
+            const uint32_t gflags = valid ? sm.g_flags[gid] : 0;
+            const bool uniform = !(gflags & 1u);
 
-            // ---- 4. lock-step run-length replay -------------------------------------------------
-            bool done = !valid || snapshot || !sm.g_rowok[gid];
-            const uint32_t lead_cells = valid ? sm.g_rep[slot] : 0;
-            const bool multi = rl_cells_multi(acc.cells);
+            // ---- 4. lock-step run-length replay -----------------------------------------------------
+            bool done = !valid || snapshot || (gflags & 2u);
             uint32_t pos = 0;
+            const unsigned long long* sv = &sm.s_val[gid * CELLS];
+            const unsigned long long* se = &sm.s_exp[gid * CELLS];
             for (uint32_t round = 0;; round++) {
                 const uint32_t par = round & 1;
-                RlRow<CELLS> st;
+                uint32_t fl = RL_NONE_U32;
+                RlRow<CELLS> loc;
                 if (!done) {
-#pragma unroll
-                    for (int c = 0; c < CELLS; c++) {
-                        st.value[c] = sm.s_val[gid * CELLS + c];
-                        st.expiry[c] = sm.s_exp[gid * CELLS + c];
-                    }
                     bool aok = false, bok = false;
                     if (!multi) {
-                        if (MODE == 0) {
-                            aok = rl_eval_deny_noeffect<CELLS>(st, desc, acc.cells, acc.posorig, delta, now, lc);
-                            bok = (acc.cells == lead_cells) &&
-                                  rl_eval_allow_run<CELLS>(st, desc, acc.cells, p_incl - sm.g_pbase[gid], now);
-                        } else {
-                            bok = (acc.cells == lead_cells) && rl_eval_update_run<CELLS>(st, acc.cells, now);
+                        const uint64_t dsum = (uint64_t)(ord - pos + 1) * delta;
+                        // update_counters never tests the limit: a run only needs live cells
+                        rl_eval_ab<CELLS>(sv, se, L, acc.cells, acc.posorig, delta, dsum, now, lc, MODE == 0, aok, bok, fl);
+                        if (MODE == 2) aok = false;
+                        bok = bok && uniform;
+                    }
+                    if (lc) {
+                        // remaining/ttl need the state this request sees: copy it before the barrier,
+                        // the run's last member republishes S right after it
+#pragma unroll
+                        for (int c = 0; c < CELLS; c++) {
+                            loc.value[c] = sv[c];
+                            loc.expiry[c] = se[c];
                         }
                     }
                     if (!aok) atomicMin(&sm.g_min[par][0][gid], ord);
@@ -634,12 +651,9 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                 if (!done) {
                     const uint32_t mA = min(sm.g_min[par][0][gid], cnt);
                     const uint32_t mB = min(sm.g_min[par][1][gid], cnt);
-                    const unsigned long long pbase = sm.g_pbase[gid];
                     uint32_t newpos;
-                    bool mine = false;     // am I finalised this round?
-                    bool store = false;    // do I publish the new row state?
+                    bool mine = false, store = false;
                     uint32_t dirty = 0;
-                    uint32_t fl = RL_NONE_U32;
                     uint64_t* rem = nullptr;
                     uint64_t* ttl = nullptr;
                     if (MODE == 0 && lc && write_out) {
@@ -647,26 +661,34 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                         if (B.out_remaining) rem = B.out_remaining + ob;
                         if (B.out_ttl) ttl = B.out_ttl + ob;
                     }
-                    if (mA > pos) {  // run of denied requests: state untouched
+                    if (mA > pos) {  // run of denied requests: state untouched, fl from the evaluation
                         newpos = mA;
                         if (ord < mA) {
                             mine = true;
-                            fl = rl_walk_check_single<CELLS>(st, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                            if (lc && write_out) {  // remaining / ttl of every counter
+                                fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, true, rem, ttl);
+                                dirty = 0;
+                            }
                         }
-                    } else if (mB > pos) {  // run of allowed requests: values accumulate
+                    } else if (mB > pos) {  // run of allowed requests with equal deltas: values accumulate
                         newpos = mB;
                         if (ord < mB) {
                             mine = true;
-                            rl_advance_run<CELLS>(st, acc.cells, p_prev - pbase);
-                            if (MODE == 0)
-                                fl = rl_walk_check_single<CELLS>(st, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
-                            else
-                                rl_walk_update<CELLS>(st, dirty, desc, acc.cells, delta, now);
+                            fl = RL_NONE_U32;
                             store = (ord == mB - 1);
-                            if (store) dirty = 0;
-                            if (store) {
-                                const uint32_t n = rl_cells_n(acc.cells);
-                                for (uint32_t k = 0; k < n; k++) dirty |= 1u << rl_cells_at(acc.cells, k);
+                            if ((MODE == 0 && lc && write_out) || store) {
+                                if (!lc) {  // only the run's last member gets here: it is the sole writer of S
+#pragma unroll
+                                    for (int c = 0; c < CELLS; c++) {
+                                        loc.value[c] = sv[c];
+                                        loc.expiry[c] = se[c];
+                                    }
+                                }
+                                rl_advance_run<CELLS>(loc, acc.cells, (uint64_t)(ord - pos) * delta);
+                                if (MODE == 0)
+                                    fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                                else
+                                    rl_walk_update<CELLS>(loc, dirty, desc, acc.cells, delta, now);
                             }
                         }
                     } else {  // the request at `pos` is applied alone, sequential rule
@@ -674,13 +696,20 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                         if (ord == pos) {
                             mine = true;
                             store = true;
+                            if (!lc) {
+#pragma unroll
+                                for (int c = 0; c < CELLS; c++) {
+                                    loc.value[c] = sv[c];
+                                    loc.expiry[c] = se[c];
+                                }
+                            }
                             if (MODE == 2) {
-                                rl_walk_update<CELLS>(st, dirty, desc, acc.cells, delta, now);
+                                rl_walk_update<CELLS>(loc, dirty, desc, acc.cells, delta, now);
                             } else if (!multi) {
-                                fl = rl_walk_check_single<CELLS>(st, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                                fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
                             } else {
                                 const uint32_t fl_in = B.fl_prev[acc.req];
-                                const uint32_t local = rl_walk_check_multi<CELLS>(st, dirty, desc, acc.cells, acc.posorig,
+                                const uint32_t local = rl_walk_check_multi<CELLS>(loc, dirty, desc, acc.cells, acc.posorig,
                                                                                  delta, now, lc, fl_in, rem, ttl);
                                 if (!write_out && local != RL_NONE_U32) atomicMin(&B.fl_next[acc.req], local);
                                 fl = fl_in;
@@ -696,40 +725,41 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                                     B.out_first_limited[acc.req] = RL_NONE_U32;
                                 } else {
                                     // the access holding position fl names the limit
-                                    const uint32_t n = rl_cells_n(acc.cells);
-                                    for (uint32_t k = 0; k < n; k++)
-                                        if (rl_pos_at(acc.posorig, k) == fl)
+#pragma unroll
+                                    for (int k = 0; k < CELLS; k++)
+                                        if ((uint32_t)k < ncell && rl_pos_at(acc.posorig, k) == fl)
                                             B.out_first_limited[acc.req] = desc[rl_cells_at(acc.cells, k)].limit_id;
                                 }
                             }
                         }
-                        if (store && dirty) {
+                    }
+                    // the barrier between evaluation and this point ordered every read of S
+                    // before the publication of the new state
+                    if (store && dirty) {
 #pragma unroll
-                            for (int c = 0; c < CELLS; c++)
-                                if (dirty & (1u << c)) {
-                                    sm.s_val[gid * CELLS + c] = st.value[c];
-                                    sm.s_exp[gid * CELLS + c] = st.expiry[c];
-                                }
-                            atomicOr(&sm.g_dirty[gid], dirty);
-                        }
-                        if (ord == newpos - 1) {  // last finalised member re-arms the group
-                            sm.g_pbase[gid] = p_incl;
-                            sm.g_min[par ^ 1][0][gid] = 0xFFFFFFFFu;
-                            sm.g_min[par ^ 1][1][gid] = 0xFFFFFFFFu;
-                        }
+                        for (int c = 0; c < CELLS; c++)
+                            if (dirty & (1u << c)) {
+                                sm.s_val[gid * CELLS + c] = loc.value[c];
+                                sm.s_exp[gid * CELLS + c] = loc.expiry[c];
+                            }
+                        atomicOr(&sm.g_dirty[gid], dirty);
+                    }
+                    if (mine && ord == newpos - 1) {  // last finalised member re-arms the group
+                        sm.g_min[par ^ 1][0][gid] = 0xFFFFFFFFu;
+                        sm.g_min[par ^ 1][1][gid] = 0xFFFFFFFFu;
                     }
                     pos = newpos;
                 }
                 if (!__syncthreads_or(!done)) break;
             }
 
-            // ---- 5. write the dirty cells back ---------------------------------------------------
-            if (is_leader && row != nullptr && !snapshot) {
-                const uint32_t dirty = sm.g_dirty[gid];
+            // ---- 5. write the dirty cells back -------------------------------------------------------
+            if (is_rep && row != nullptr && !snapshot) {
+                const uint32_t dirty = sm.g_dirty[tid];
 #pragma unroll
                 for (int c = 0; c < CELLS; c++)
                     if (dirty & (1u << c))
-                        rl_st_cg(row + 16 + 16 * c, sm.s_val[gid * CELLS + c], sm.s_exp[gid * CELLS + c]);
+                        rl_st_cg(row + 16 + 16 * c, sm.s_val[tid * CELLS + c], sm.s_exp[tid * CELLS + c]);
             }
             __syncthreads();
         }

@@ -88,6 +88,9 @@ int emu_batch_csr(emu* e, int mode, uint32_t n, const uint32_t* off, const emu_c
                 P[i] = run;
             }
             const uint32_t lead_cells = acc[mem[0]].cells;
+            bool uniform = true;  // k_main: runs of allowed requests are closed-form only for equal deltas
+            for (uint32_t i = 1; i < n; i++)
+                if (delta[acc[mem[i]].req] != delta[acc[mem[0]].req] || acc[mem[i]].cells != lead_cells) uniform = false;
             uint32_t pos = 0;
             uint64_t pbase = 0;
             auto outputs = [&](const RlAccess& A, uint32_t fl) {
@@ -105,15 +108,14 @@ int emu_batch_csr(emu* e, int mode, uint32_t n, const uint32_t* off, const emu_c
                 uint32_t mA = n, mB = n;
                 for (uint32_t i = pos; i < n && (mA == n || mB == n); i++) {
                     const RlAccess& A = acc[mem[i]];
-                    const bool multi = rl_cells_multi(A.cells);
+                    const bool multi = mode == 0 && rl_cells_multi(A.cells);
                     bool aok = false, bok = false;
                     if (!multi) {
                         if (mode == 0) {
                             aok = rl_eval_deny_noeffect<RL_MAX_CELLS>(st, desc, A.cells, A.posorig, delta[A.req], now[A.req], lc != 0);
-                            bok = A.cells == lead_cells &&
-                                  rl_eval_allow_run<RL_MAX_CELLS>(st, desc, A.cells, P[i] - pbase, now[A.req]);
+                            bok = uniform && rl_eval_allow_run<RL_MAX_CELLS>(st, desc, A.cells, P[i] - pbase, now[A.req]);
                         } else {
-                            bok = A.cells == lead_cells && rl_eval_update_run<RL_MAX_CELLS>(st, A.cells, now[A.req]);
+                            bok = uniform && rl_eval_update_run<RL_MAX_CELLS>(st, A.cells, now[A.req]);
                         }
                     }
                     if (!aok && mA == n) mA = i;
