@@ -89,6 +89,8 @@ struct rl_engine {
     DevBuf<RlAccess> d_acc;
     DevBuf<uint64_t> d_delta, d_now;
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
+    DevBuf<uint4> d_items;
+    DevBuf<uint32_t> d_progress;
     DevBuf<uint8_t*> d_log_row;
     DevBuf<ulonglong2> d_log_state;
     // staging for RL_MEM_HOST calls
@@ -114,7 +116,7 @@ struct rl_engine {
 
 namespace {
 
-enum { MISC_ERR = 0, MISC_FLAGS = 1, MISC_SCANCTR = 2, MISC_CHANGED = 3, MISC_N = 8 };
+enum { MISC_ERR = 0, MISC_FLAGS = 1, MISC_SCANCTR = 2, MISC_CHANGED = 3, MISC_NITEMS = 4, MISC_N = 8 };
 
 int fail(rl_engine* e, int status, const char* fmt, ...) {
     char buf[512];
@@ -304,6 +306,11 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.fl_next = e->d_fl_next.p;
     B.phase = RL_PHASE_COMMIT;
     B.load_counters = lc;
+    B.items = e->d_items.p;
+    B.n_items = e->d_misc.p + MISC_NITEMS;
+    B.region_progress = e->d_progress.p;
+    B.chunk = RL_MAIN_THREADS;
+    B.heavy_len = 2 * RL_MAIN_THREADS;
     B.log_row = nullptr;
     B.log_state = nullptr;
     return B;
@@ -331,7 +338,9 @@ int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src&
         RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_set = true;
     }
-    kern<<<1u << e->log2P, RL_MAIN_THREADS, sizeof(Smem), e->stream>>>(D, B, src);
+    // upper bound of the work-item count: one per region + one per chunk of a heavy region
+    const uint32_t grid = (1u << e->log2P) + ceil_div(B.n_acc, RL_MAIN_THREADS);
+    kern<<<grid, RL_MAIN_THREADS, sizeof(Smem), e->stream>>>(D, B, src);
     return RL_OK;
 }
 
@@ -375,6 +384,7 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
                      int mode, int lc, const Outs& o) {
     RlDev D = make_dev(e);
     RlBatch B = make_batch(e, n_acc, n_req, o, lc);
+    if (mode == 0) B.heavy_len = 0xFFFFFFFFu;  // may hold coupled requests: regions stay sequential
     AccSrc src{e->d_acc.p, d_delta, d_now};
     int r = launch_partition(e, D, B, src);
     if (r) return r;
@@ -522,6 +532,8 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, cudaMemsetAsync(e->d_misc.p, 0, MISC_N * sizeof(uint32_t), e->stream));
     RL_CUDA(e, cudaMallocHost((void**)&e->h_misc, MISC_N * sizeof(uint32_t)));
     RL_CUDA(e, e->d_acc.reserve(maxA));
+    RL_CUDA(e, e->d_items.reserve((size_t)(1u << e->log2P) + maxA / RL_MAIN_THREADS + 2));
+    RL_CUDA(e, e->d_progress.reserve(1u << e->log2P));
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
     int r;
@@ -554,6 +566,8 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_now.release();
     e->d_fl_prev.release();
     e->d_fl_next.release();
+    e->d_items.release();
+    e->d_progress.release();
     e->d_log_row.release();
     e->d_log_state.release();
     e->d_in_recs.release();

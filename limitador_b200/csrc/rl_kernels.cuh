@@ -62,6 +62,14 @@ struct RlBatch {
     uint32_t* fl_next;
     int phase;          // RL_PHASE_*
     int load_counters;  // 0/1
+    // work items of k_main (built by k_colscan): x = region, y/z = [lo, hi) in part_idx,
+    // w = RL_NONE_U32 for a light region (its chunks run one after the other in one CTA) or the
+    // chunk's index inside a heavy region (one CTA per chunk, committed in order, see k_main)
+    uint4* items;
+    uint32_t* n_items;
+    uint32_t* region_progress;  // [P] chunks of a heavy region committed so far
+    uint32_t heavy_len;         // regions longer than this are chained; 0xFFFFFFFF disables
+    uint32_t chunk;             // accesses per chunk (= k_main block size)
     // undo log of the rows a coupled batch touches (RL_PHASE_SNAPSHOT / k_restore)
     uint8_t** log_row;     // [n_acc] row pointer logged at the partition position of a key's first access
     ulonglong2* log_state; // [n_acc][CELLS]
@@ -403,6 +411,41 @@ __global__ void __launch_bounds__(256) k_colscan(RlDev D, RlBatch B) {
         B.part_base[P1] = carry;
         *B.scan_ctr = 0;  // re-arm for the next batch
     }
+    __syncthreads();
+    // ---- work items for k_main: chunks of heavy regions first (they chain in launch order) ----
+    const uint32_t P = P1 - 1;
+    uint32_t hsum = 0, lsum = 0;
+    for (uint32_t q = threadIdx.x; q < P; q += 256) {
+        const uint32_t len = B.part_base[q + 1] - B.part_base[q];
+        if (len > B.heavy_len) hsum += (len + B.chunk - 1) / B.chunk;
+        else if (len) lsum += 1;
+    }
+    __shared__ uint32_t s_h[256], s_l[256];
+    s_h[threadIdx.x] = hsum;
+    s_l[threadIdx.x] = lsum;
+    __syncthreads();
+    uint32_t hb = 0, lb = 0, th = 0, tl = 0;
+    for (uint32_t t = 0; t < 256; t++) {
+        if (t < threadIdx.x) {
+            hb += s_h[t];
+            lb += s_l[t];
+        }
+        th += s_h[t];
+        tl += s_l[t];
+    }
+    for (uint32_t q = threadIdx.x; q < P; q += 256) {
+        const uint32_t lo = B.part_base[q], hi = B.part_base[q + 1];
+        const uint32_t len = hi - lo;
+        if (len > B.heavy_len) {
+            const uint32_t nc = (len + B.chunk - 1) / B.chunk;
+            for (uint32_t k = 0; k < nc; k++)
+                B.items[hb++] = make_uint4(q, lo + k * B.chunk, min(lo + (k + 1) * B.chunk, hi), k);
+            B.region_progress[q] = 0;
+        } else if (len) {
+            B.items[th + lb++] = make_uint4(q, lo, hi, RL_NONE_U32);
+        }
+    }
+    if (threadIdx.x == 0) *B.n_items = th + tl;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -488,14 +531,19 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
     Smem& sm = *reinterpret_cast<Smem*>(rl_smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t P = 1u << D.log2P;
     const bool lc = B.load_counters != 0;
     const bool write_out = (B.phase == RL_PHASE_COMMIT);
     const bool snapshot = (B.phase == RL_PHASE_SNAPSHOT);
 
-    for (uint32_t region = blockIdx.x; region < P; region += gridDim.x) {
-        const uint32_t lo = B.part_base[region], hi = B.part_base[region + 1];
-        if (lo >= hi) continue;
+    const uint32_t n_items = *B.n_items;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint4 it = B.items[item];
+        const uint32_t region = it.x, lo = it.y, hi = it.z;
+        // Heavy region: this CTA owns ONE chunk.  It replays the chunk speculatively against the
+        // rows as they are now, waits until the region's earlier chunks have committed, and
+        // commits if the rows it started from are unchanged (a hot saturated key: always);
+        // otherwise it replays the affected keys again from the committed state.
+        const bool chained = (it.w != RL_NONE_U32);
         // prefetch of the first chunk
         RlAccess nacc;
         uint64_t ndelta = 0, nnow = 0;
@@ -622,6 +670,7 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
             uint32_t pos = 0;
             const unsigned long long* sv = &sm.s_val[gid * CELLS];
             const unsigned long long* se = &sm.s_exp[gid * CELLS];
+            for (int attempt = 0;; attempt++) {
             for (uint32_t round = 0;; round++) {
                 const uint32_t par = round & 1;
                 uint32_t fl = RL_NONE_U32;
@@ -752,6 +801,41 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                 }
                 if (!__syncthreads_or(!done)) break;
             }
+            if (!chained || snapshot || attempt == 1) break;
+            // ---- commit point of a chained chunk: wait for the region's earlier chunks ---------------
+            if (tid == 0) {
+                volatile uint32_t* prog = B.region_progress + region;
+                while (*prog != it.w) __nanosleep(40);
+                __threadfence();
+            }
+            __syncthreads();
+            bool redo = false;
+            if (is_rep && row != nullptr) {
+                RlRow<CELLS> cur;
+                rl_row_load<CELLS>(row, CELLS, cur);
+                bool same = true;
+#pragma unroll
+                for (int c = 0; c < CELLS; c++) same = same && cur.value[c] == st.value[c] && cur.expiry[c] == st.expiry[c];
+                if (!same) {  // an earlier chunk changed this key: replay it from the committed state
+                    st = cur;
+#pragma unroll
+                    for (int c = 0; c < CELLS; c++) {
+                        sm.s_val[tid * CELLS + c] = cur.value[c];
+                        sm.s_exp[tid * CELLS + c] = cur.expiry[c];
+                    }
+                    sm.g_dirty[tid] = 0;
+                    sm.g_min[0][0][tid] = sm.g_min[0][1][tid] = 0xFFFFFFFFu;
+                    sm.g_min[1][0][tid] = sm.g_min[1][1][tid] = 0xFFFFFFFFu;
+                    sm.g_flags[tid] |= 4u;
+                    redo = true;
+                }
+            }
+            if (!__syncthreads_or(redo)) break;
+            if (valid && (sm.g_flags[gid] & 4u)) {
+                done = (gflags & 2u) != 0;
+                pos = 0;
+            }
+            }
 
             // ---- 5. write the dirty cells back -------------------------------------------------------
             if (is_rep && row != nullptr && !snapshot) {
@@ -760,8 +844,10 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                 for (int c = 0; c < CELLS; c++)
                     if (dirty & (1u << c))
                         rl_st_cg(row + 16 + 16 * c, sm.s_val[tid * CELLS + c], sm.s_exp[tid * CELLS + c]);
+                if (chained && dirty) __threadfence();
             }
             __syncthreads();
+            if (chained && !snapshot && tid == 0) atomicExch(B.region_progress + region, it.w + 1);
         }
     }
 }
