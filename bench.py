@@ -152,12 +152,16 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=65536, help="requests per GPU per step (C2: 65536)")
+    ap.add_argument("--batch", type=int, default=0, help="requests per GPU per step (C2: 65536, C3: 1048576)")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"],
+                    help="C2 = BASELINE.json configs[1] (the headline); C3 = configs[2], 16M uniform keys, 1 limit")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 256)")
     ap.add_argument("--cpu-sample-batches", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if not args.batch:
+        args.batch = 65536 if args.workload == "C2" else 1 << 20
 
     if args.impl == "reference":
         run_reference(args)
@@ -182,12 +186,16 @@ def main():
 
     K, W, batch = args.steps, args.warmup, args.batch
     Ke = args.e2e_steps or min(K, 256)
+    c3 = args.workload == "C3"
+    if c3 and world > 1:
+        raise SystemExit("--workload C3 is a single-GPU configuration")
     n_ns, n_rows = 64 * world, 1_000_000 * world
-    L = 4
-    limits = c2_limits(n_ns)
-    cap = (1 << 21) if world == 1 else (1 << 22)
+    L = 1 if c3 else 4
+    cells = 1 if c3 else 7
+    limits = streams.c3_uniform_1limit(batch=1, n_keys=16).limits if c3 else c2_limits(n_ns)
+    cap = (1 << 25) if c3 else ((1 << 21) if world == 1 else (1 << 22))
     max_batch = batch if world == 1 else 4 * batch
-    eng = Engine(capacity_rows=cap, cells_per_row=7, max_batch=max_batch, device=local_rank)
+    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank)
     eng.limits_set(limits)
     # a dedicated non-default stream: the engine launches on it and the CUDA events that time
     # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")
@@ -197,11 +205,16 @@ def main():
     assert eng.stream == stream.cuda_stream
 
     total = W + 2 * K + Ke
-    recs = streams.c2_device_stream(total, batch, dev, n_rows=n_rows, n_ns=n_ns,
-                                    first_batch=0, seed=streams.SEED + 1000 * rank)
+    t_gen = time.perf_counter()
+    if c3:
+        recs = streams.c3_device_stream(total, batch, dev, n_keys=16_000_000)
+    else:
+        recs = streams.c2_device_stream(total, batch, dev, n_rows=n_rows, n_ns=n_ns,
+                                        first_batch=0, seed=streams.SEED + 1000 * rank)
     out_lim = torch.zeros((total, batch), dtype=torch.uint8, device=dev)
     out_first = torch.zeros((total, batch), dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
+    print(f"[bench] generated {total} batches of {batch} in {time.perf_counter() - t_gen:.1f}s", file=sys.stderr)
 
     if world > 1:
         send_buf = torch.empty((batch, 4), dtype=torch.int64, device=dev)
@@ -214,7 +227,7 @@ def main():
         """One step with the batch resident in HBM."""
         if world == 1:
             eng.check_and_update_records_ptr(batch, recs[s].data_ptr(), out_lim[s].data_ptr(), MEM_DEVICE,
-                                             out_first_ptr=out_first[s].data_ptr(), stride=7)
+                                             out_first_ptr=out_first[s].data_ptr(), stride=cells)
             return
         # namespace-sharded: bucket by owner, scatter over NVLink (NCCL all-to-all), decide on the
         # owner, return the verdict bytes (SURVEY §8e; the only collective on the path)
@@ -228,7 +241,7 @@ def main():
             raise RuntimeError(f"rank {rank}: received {nrecv} > max_batch {max_batch}")
         dist.all_to_all_single(recv_buf[:nrecv], send_buf, rc, sc)
         if nrecv:
-            eng.check_and_update_records_ptr(nrecv, recv_buf.data_ptr(), v_recv.data_ptr(), MEM_DEVICE, stride=7)
+            eng.check_and_update_records_ptr(nrecv, recv_buf.data_ptr(), v_recv.data_ptr(), MEM_DEVICE, stride=cells)
         dist.all_to_all_single(v_back, v_recv[:nrecv], sc, rc)
         eng.unpermute_u8_ptr(batch, v_back.data_ptr(), src_idx.data_ptr(), out_lim[s].data_ptr())
 
@@ -253,9 +266,11 @@ def main():
         return ms
 
     # ---- warm-up -------------------------------------------------------------------------
+    t_w = time.perf_counter()
     for s in range(W):
         step_device(s)
     eng.sync()
+    print(f"[bench] warm-up {time.perf_counter() - t_w:.2f}s", file=sys.stderr)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -281,7 +296,7 @@ def main():
 
     def step_host(j: int):
         if world == 1:
-            eng.check_and_update_records_ptr(batch, h_recs[j].data_ptr(), h_lim[j].data_ptr(), MEM_HOST, stride=7)
+            eng.check_and_update_records_ptr(batch, h_recs[j].data_ptr(), h_lim[j].data_ptr(), MEM_HOST, stride=cells)
         else:
             s = W + 2 * K + j
             recs[s].copy_(h_recs[j], non_blocking=True)
@@ -299,6 +314,7 @@ def main():
 
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    print(f"[bench] passes: A {ms_a:.1f} ms, B {ms_b:.1f} ms, e2e {ms_e:.1f} ms (wall {wall_e:.1f})", file=sys.stderr)
 
     if rank != 0:
         if world > 1:
@@ -317,7 +333,7 @@ def main():
         per_launch = alg / main_launches
         avg_ms = main_ms / main_launches
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_main<7,RecordSrc,0>", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": f"k_main<{cells},RecordSrc,0,256>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                 "allowed_frac": float((lim_b == 0).mean()), "kernel_share_of_step": main_ms / ms_b}
@@ -332,15 +348,16 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import binding as ob
-        S = min(args.cpu_sample_batches, W + 2 * K)
+        S = max(1, min(args.cpu_sample_batches, W + 2 * K, (1 << 24) // batch))
         sample = recs[:S].cpu().numpy().view(RECORD_DTYPE).reshape(-1)
         ldesc = np.zeros(len(limits), dtype=ob.LIMIT_DESC_DTYPE)
         for f in ("limit_id", "ns_id", "max_value", "window_us", "qualified"):
             ldesc[f] = limits[f]
-        cores = os.cpu_count() or 1
-        mt = ob.OracleMT(ldesc, cores, 2 * n_rows)
+        cores = min(os.cpu_count() or 1, len(set(limits['ns_id'].tolist())))  # one owner thread per namespace
+        mt = ob.OracleMT(ldesc, cores, 2 * (16_000_000 if c3 else n_rows))
         t_cpu, v_cpu = mt.run(sample)
         mt.close()
+        print(f"[bench] cpu baseline {t_cpu:.2f}s", file=sys.stderr)
         v_gpu = out_lim[:S].cpu().numpy().reshape(-1)
         mism = int((v_cpu != v_gpu).sum())
         cpu = {"value": len(sample) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
@@ -352,11 +369,13 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_a / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={batch}/GPU, "
-                               f"delta=1, load_counters=false",
+        "config": {"workload": (f"C3: 1 limit (100/60s), 16000000 keys uniform, batch={batch}, delta=1, "
+                                f"load_counters=false, reference fixed-window semantics") if c3 else
+                               (f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={batch}/GPU, "
+                                f"delta=1, load_counters=false"),
                    "parallelism": "single GPU" if world == 1 else f"namespace-sharded x{world}, NCCL all-to-all",
                    "l2": "a distinct batch every step (inputs 2 MiB/step, never reused); table 256 MiB > L2",
-                   "table_rows": cap, "row_bytes": 128},
+                   "table_rows": cap, "row_bytes": 16 * (1 + cells)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * 32, "d2h_bytes_per_step": batch,
                 "steps": Ke, "ms_per_step": ms_e / Ke, "wall_ms_per_step": wall_e / Ke},
         "gpu_launches": int(launches),

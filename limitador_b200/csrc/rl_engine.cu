@@ -85,7 +85,7 @@ struct rl_engine {
     uint32_t limits_cap = 0, ns_cap = 0;
 
     // workspace
-    DevBuf<uint32_t> d_tile_cnt, d_region_total, d_part_base, d_part_idx, d_misc;  // misc: err, flags, scan_ctr, changed
+    DevBuf<uint32_t> d_tile_cnt, d_region_total, d_part_base, d_part_idx, d_part_row, d_misc;  // misc: err, flags, scan_ctr, changed
     DevBuf<RlAccess> d_acc;
     DevBuf<uint64_t> d_delta, d_now;
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
@@ -291,6 +291,7 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.region_total = e->d_region_total.p;
     B.part_base = e->d_part_base.p;
     B.part_idx = e->d_part_idx.p;
+    B.part_row = e->d_part_row.p;
     B.scan_ctr = e->d_misc.p + MISC_SCANCTR;
     uint32_t tile = ceil_div(n_acc, kMaxTiles);
     tile = std::max<uint32_t>(512, ((tile + 255) / 256) * 256);
@@ -310,23 +311,39 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.n_items = e->d_misc.p + MISC_NITEMS;
     B.region_progress = e->d_progress.p;
     B.chunk = RL_MAIN_THREADS;
-    B.heavy_len = 2 * RL_MAIN_THREADS;
+    // a region is split into chained chunks only when it is far heavier than the average one
+    B.heavy_len = std::max<uint32_t>(2 * RL_MAIN_THREADS, 4 * ceil_div(n_acc, 1u << e->log2P));
     B.log_row = nullptr;
     B.log_state = nullptr;
     return B;
 }
 
-template <class Src>
-int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+template <int CELLS, class Src>
+int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
     const uint32_t P1 = (1u << e->log2P) + 1;
     const size_t smem = (size_t)RL_PART_WARPS * P1 * sizeof(uint32_t);
-    k_part<Src, false><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        RL_CUDA(e, cudaFuncSetAttribute(k_part<CELLS, Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_CUDA(e, cudaFuncSetAttribute(k_part<CELLS, Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_part<CELLS, Src, false><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
     RL_LAUNCH_CHECK(e);
     k_colscan<<<ceil_div(P1, 32), 256, 0, e->stream>>>(D, B);
     RL_LAUNCH_CHECK(e);
-    k_part<Src, true><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
+    k_part<CELLS, Src, true><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
     RL_LAUNCH_CHECK(e);
     return RL_OK;
+}
+
+template <class Src>
+int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+    switch (e->cells) {
+        case 1: return launch_partition_cells<1, Src>(e, D, B, src);
+        case 3: return launch_partition_cells<3, Src>(e, D, B, src);
+        default: return launch_partition_cells<7, Src>(e, D, B, src);
+    }
 }
 
 template <int CELLS, class Src, int MODE>
@@ -363,17 +380,6 @@ int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) 
     if (e->profiling) {
         RL_CUDA(e, cudaEventRecord(ev1, e->stream));
         e->prof_events.emplace_back(ev0, ev1);
-    }
-    return RL_OK;
-}
-
-template <class Src>
-int set_part_smem(rl_engine* e) {
-    const uint32_t P1 = (1u << e->log2P) + 1;
-    const int smem = (int)(RL_PART_WARPS * P1 * sizeof(uint32_t));
-    if (smem > 48 * 1024) {
-        RL_CUDA(e, cudaFuncSetAttribute(k_part<Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        RL_CUDA(e, cudaFuncSetAttribute(k_part<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     return RL_OK;
 }
@@ -528,6 +534,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_region_total.reserve(P1 + 1));
     RL_CUDA(e, e->d_part_base.reserve(P1 + 2));
     RL_CUDA(e, e->d_part_idx.reserve(maxA));
+    RL_CUDA(e, e->d_part_row.reserve(maxA));
     RL_CUDA(e, e->d_misc.reserve(MISC_N));
     RL_CUDA(e, cudaMemsetAsync(e->d_misc.p, 0, MISC_N * sizeof(uint32_t), e->stream));
     RL_CUDA(e, cudaMallocHost((void**)&e->h_misc, MISC_N * sizeof(uint32_t)));
@@ -536,9 +543,6 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_progress.reserve(1u << e->log2P));
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
-    int r;
-    if ((r = set_part_smem<RecordSrc>(e))) return r;
-    if ((r = set_part_smem<AccSrc>(e))) return r;
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->stats.capacity_rows = e->capacity;
     e->stats.regions = 1u << e->log2P;
@@ -560,6 +564,7 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_region_total.release();
     e->d_part_base.release();
     e->d_part_idx.release();
+    e->d_part_row.release();
     e->d_misc.release();
     e->d_acc.release();
     e->d_delta.release();

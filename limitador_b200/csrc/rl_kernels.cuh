@@ -47,6 +47,7 @@ struct RlBatch {
     uint32_t* region_total;  // [P+1]
     uint32_t* part_base;     // [P+2]
     uint32_t* part_idx;      // [n_acc]
+    uint32_t* part_row;      // [n_acc] table row (index) of the access, probed / claimed by k_part
     uint32_t* scan_ctr;      // last-block-done counter of k_colscan
     uint32_t tile;           // accesses per tile (multiple of 256)
     uint32_t num_tiles;
@@ -267,7 +268,10 @@ struct AccSrc {
 // Tile = B.tile consecutive accesses; warp w of the CTA owns the w-th contiguous slice, so
 // stream order == (tile, warp, step, lane) and a stable rank is
 //   region base + (accesses of earlier tiles) + (accesses of earlier warps) + rank in slice.
-template <class Src, bool SCATTER>
+// The SCATTER pass also probes (and, for a new key, claims) the table row of every access and
+// records its index: the random HBM access of the batch happens here, in a kernel with
+// thousands of independent loads in flight per SM, and k_main later finds the row in L2.
+template <int CELLS, class Src, bool SCATTER>
 __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Src src) {
     extern __shared__ uint32_t wcnt[];  // [RL_PART_WARPS][P+1]
     const uint32_t P1 = (1u << D.log2P) + 1;
@@ -328,9 +332,15 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
         const uint32_t a = b + lane;
         const bool valid = a < s1;
         uint32_t r = P1 - 1;
+        uint32_t rowidx = 0xFFFFFFFFu;
         if (valid) {
             uint64_t klo, hhi;
-            if (src.ident(D, a, klo, hhi)) r = (uint32_t)rl_region_of(D, rl_row_hash(klo, hhi));
+            if (src.ident(D, a, klo, hhi)) {
+                const uint64_t h = rl_row_hash(klo, hhi);
+                r = (uint32_t)rl_region_of(D, h);
+                const uint8_t* row = rl_probe<CELLS>(D, h, klo, hhi, true);
+                if (row) rowidx = (uint32_t)((size_t)(row - D.rows) / RlGeom<CELLS>::ROW_BYTES);
+            }
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -342,7 +352,9 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
                 mycnt[r] = basepos + __popc(m);
             }
             basepos = __shfl_sync(m, basepos, leader);
-            B.part_idx[basepos + __popc(m & ((1u << lane) - 1))] = a;
+            const uint32_t mypos = basepos + __popc(m & ((1u << lane) - 1));
+            B.part_idx[mypos] = a;
+            B.part_row[mypos] = rowidx;
             if (Src::kAccessIsRequest && r == P1 - 1 && B.out_limited) {
                 // request without any applicable limit: not limited (lib.rs:434-440)
                 B.out_limited[a] = 0;
@@ -523,7 +535,7 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
 }
 
 template <int CELLS, class Src, int MODE, int CH>
-__global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
+__global__ void __launch_bounds__(CH, 3) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
     constexpr int PW = Smem::PW;
@@ -547,8 +559,12 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
         // prefetch of the first chunk
         RlAccess nacc;
         uint64_t ndelta = 0, nnow = 0;
+        uint32_t nrow = 0xFFFFFFFFu;
         nacc.key_lo = 0; nacc.hdr_hi = 0; nacc.req = 0; nacc.cells = 0; nacc.posorig = 0;
-        if (lo + tid < hi) src.full(D, B.part_idx[lo + tid], nacc, ndelta, nnow);
+        if (lo + tid < hi) {
+            nrow = B.part_row[lo + tid];
+            src.full(D, B.part_idx[lo + tid], nacc, ndelta, nnow);
+        }
 
         for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
             for (uint32_t i = tid; i < GT; i += CH) sm.g_tag[i] = 0ull;
@@ -559,7 +575,11 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
             const bool valid = p < hi;
             const RlAccess acc = nacc;
             const uint64_t delta = ndelta, now = nnow;
-            if (p + CH < hi) src.full(D, B.part_idx[p + CH], nacc, ndelta, nnow);
+            const uint32_t myrow = nrow;
+            if (p + CH < hi) {
+                nrow = B.part_row[p + CH];
+                src.full(D, B.part_idx[p + CH], nacc, ndelta, nnow);
+            }
             const uint64_t h = rl_row_hash(acc.key_lo, acc.hdr_hi);
             const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
             const RlCellDesc* desc = D.desc + (size_t)group * 8;
@@ -613,7 +633,8 @@ __global__ void __launch_bounds__(CH) k_main(RlDev D, RlBatch B, Src src) {
                         }
                         slot = s;
                         if (is_rep && row == nullptr) {
-                            row = rl_probe<CELLS>(D, h, acc.key_lo, acc.hdr_hi, true);
+                            // the row was located (or claimed) by k_part; its sectors are in L2
+                            if (myrow != 0xFFFFFFFFu) row = D.rows + (size_t)myrow * RlGeom<CELLS>::ROW_BYTES;
                             rl_row_load<CELLS>(row, CELLS, st);
                         }
                     }
