@@ -90,7 +90,7 @@ struct rl_engine {
     DevBuf<uint64_t> d_delta, d_now;
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
     DevBuf<uint4> d_items;
-    DevBuf<uint32_t> d_progress;
+    DevBuf<uint32_t> d_fallback, d_chain_status, d_chain_wcnt, d_chain_w;
     DevBuf<uint8_t*> d_log_row;
     DevBuf<ulonglong2> d_log_state;
     // staging for RL_MEM_HOST calls
@@ -309,7 +309,10 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.load_counters = lc;
     B.items = e->d_items.p;
     B.n_items = e->d_misc.p + MISC_NITEMS;
-    B.region_progress = e->d_progress.p;
+    B.region_fallback = e->d_fallback.p;
+    B.chain_status = e->d_chain_status.p;
+    B.chain_wcnt = e->d_chain_wcnt.p;
+    B.chain_w = e->d_chain_w.p;
     B.chunk = RL_MAIN_THREADS;
     // a region is split into chained chunks only when it is far heavier than the average one
     B.heavy_len = std::max<uint32_t>(2 * RL_MAIN_THREADS, 4 * ceil_div(n_acc, 1u << e->log2P));
@@ -540,7 +543,13 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, cudaMallocHost((void**)&e->h_misc, MISC_N * sizeof(uint32_t)));
     RL_CUDA(e, e->d_acc.reserve(maxA));
     RL_CUDA(e, e->d_items.reserve((size_t)(1u << e->log2P) + maxA / RL_MAIN_THREADS + 2));
-    RL_CUDA(e, e->d_progress.reserve(1u << e->log2P));
+    RL_CUDA(e, e->d_fallback.reserve(1u << e->log2P));
+    {
+        const size_t max_items = (size_t)(1u << e->log2P) + maxA / RL_MAIN_THREADS + 2;
+        RL_CUDA(e, e->d_chain_status.reserve(max_items));
+        RL_CUDA(e, e->d_chain_wcnt.reserve(max_items));
+        RL_CUDA(e, e->d_chain_w.reserve(max_items * RL_MAIN_THREADS));
+    }
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -572,7 +581,10 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_fl_prev.release();
     e->d_fl_next.release();
     e->d_items.release();
-    e->d_progress.release();
+    e->d_fallback.release();
+    e->d_chain_status.release();
+    e->d_chain_wcnt.release();
+    e->d_chain_w.release();
     e->d_log_row.release();
     e->d_log_state.release();
     e->d_in_recs.release();

@@ -68,7 +68,10 @@ struct RlBatch {
     // chunk's index inside a heavy region (one CTA per chunk, committed in order, see k_main)
     uint4* items;
     uint32_t* n_items;
-    uint32_t* region_progress;  // [P] chunks of a heavy region committed so far
+    uint32_t* region_fallback;  // [P] first chunk of a heavy region whose read set was written by an earlier chunk
+    uint32_t* chain_status;     // [items] 0 none, 1 write set published, 2 valid, 3 invalid, 4 committed
+    uint32_t* chain_wcnt;       // [items] size of the chunk's write set
+    uint32_t* chain_w;          // [items][chunk] rows the chunk writes
     uint32_t heavy_len;         // regions longer than this are chained; 0xFFFFFFFF disables
     uint32_t chunk;             // accesses per chunk (= k_main block size)
     // undo log of the rows a coupled batch touches (RL_PHASE_SNAPSHOT / k_restore)
@@ -450,9 +453,11 @@ __global__ void __launch_bounds__(256) k_colscan(RlDev D, RlBatch B) {
         const uint32_t len = hi - lo;
         if (len > B.heavy_len) {
             const uint32_t nc = (len + B.chunk - 1) / B.chunk;
-            for (uint32_t k = 0; k < nc; k++)
+            for (uint32_t k = 0; k < nc; k++) {
+                B.chain_status[hb] = 0;
                 B.items[hb++] = make_uint4(q, lo + k * B.chunk, min(lo + (k + 1) * B.chunk, hi), k);
-            B.region_progress[q] = 0;
+            }
+            B.region_fallback[q] = 0xFFFFFFFFu;
         } else if (len) {
             B.items[th + lb++] = make_uint4(q, lo, hi, RL_NONE_U32);
         }
@@ -496,6 +501,9 @@ struct RlMainSmem {
     uint32_t g_min[2][2][CH];  // [round parity][A|B][gid]
     uint32_t g_flags[CH];      // by gid: bit0 = members differ in delta or cell list
     uint32_t g_dirty[CH];
+    uint32_t rset[GT];         // chained chunks: rows this chunk read (its read set)
+    uint32_t w_cnt;
+    uint32_t bcast;
 };
 
 // Per-thread view of the limits its access touches, in the access's own cell order.
@@ -535,7 +543,7 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
 }
 
 template <int CELLS, class Src, int MODE, int CH>
-__global__ void __launch_bounds__(CH, 3) k_main(RlDev D, RlBatch B, Src src) {
+__global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
     constexpr int PW = Smem::PW;
@@ -551,10 +559,14 @@ __global__ void __launch_bounds__(CH, 3) k_main(RlDev D, RlBatch B, Src src) {
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint4 it = B.items[item];
         const uint32_t region = it.x, lo = it.y, hi = it.z;
-        // Heavy region: this CTA owns ONE chunk.  It replays the chunk speculatively against the
-        // rows as they are now, waits until the region's earlier chunks have committed, and
-        // commits if the rows it started from are unchanged (a hot saturated key: always);
-        // otherwise it replays the affected keys again from the committed state.
+        // Heavy region: this CTA owns ONE chunk and the region's chunks run concurrently under
+        // optimistic concurrency control.  A chunk replays its requests against the rows as they
+        // are (no row is written), publishes its WRITE set (rows it would change), and checks
+        // that no earlier chunk's write set meets its READ set.  If that holds for every chunk up
+        // to this one, all of them saw the state sequential execution would have shown them, and
+        // they commit in parallel — a saturated hot key is read by every chunk and written by
+        // none.  From the first chunk that fails the check on, chunks commit in order, re-reading
+        // their rows and replaying the keys whose state changed.
         const bool chained = (it.w != RL_NONE_U32);
         // prefetch of the first chunk
         RlAccess nacc;
@@ -823,13 +835,82 @@ __global__ void __launch_bounds__(CH, 3) k_main(RlDev D, RlBatch B, Src src) {
                 if (!__syncthreads_or(!done)) break;
             }
             if (!chained || snapshot || attempt == 1) break;
-            // ---- commit point of a chained chunk: wait for the region's earlier chunks ---------------
-            if (tid == 0) {
-                volatile uint32_t* prog = B.region_progress + region;
-                while (*prog != it.w) __nanosleep(40);
-                __threadfence();
+            const uint32_t base_item = item - it.w;  // first chunk of my region
+            // (b) publish the write set; remember the read set
+            for (uint32_t i = tid; i < GT; i += CH) sm.rset[i] = 0xFFFFFFFFu;
+            if (tid == 0) sm.w_cnt = 0;
+            __syncthreads();
+            if (is_rep && row != nullptr) {
+                uint32_t s2 = (myrow * 2654435761u) & (GT - 1);
+                for (;;) {
+                    const uint32_t old = atomicCAS(&sm.rset[s2], 0xFFFFFFFFu, myrow);
+                    if (old == 0xFFFFFFFFu || old == myrow) break;
+                    s2 = (s2 + 1) & (GT - 1);
+                }
+                if (sm.g_dirty[tid]) B.chain_w[(size_t)item * CH + atomicAdd(&sm.w_cnt, 1u)] = myrow;
             }
             __syncthreads();
+            if (tid == 0) {
+                B.chain_wcnt[item] = sm.w_cnt;
+                __threadfence();
+                atomicExch(B.chain_status + item, 1u);
+            }
+            // (c) wait until every earlier chunk of the region has published its write set
+            for (;;) {
+                bool ok = true;
+                for (uint32_t j = tid; j < it.w; j += CH)
+                    ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) >= 1u);
+                if (__syncthreads_and(ok)) break;
+                __nanosleep(100);
+            }
+            __threadfence();
+            // (d) does an earlier chunk write a row I read?  warp w scans chunks w, w+NW, ...
+            bool conflict = false;
+            for (uint32_t j = warp; j < it.w; j += Smem::NW) {
+                const uint32_t cj = __ldcg(B.chain_wcnt + base_item + j);
+                for (uint32_t i = lane; i < cj; i += 32) {
+                    const uint32_t w = __ldcg(B.chain_w + (size_t)(base_item + j) * CH + i);
+                    uint32_t s2 = (w * 2654435761u) & (GT - 1);
+                    for (;;) {
+                        const uint32_t x = sm.rset[s2];
+                        if (x == w) {
+                            conflict = true;
+                            break;
+                        }
+                        if (x == 0xFFFFFFFFu) break;
+                        s2 = (s2 + 1) & (GT - 1);
+                    }
+                }
+            }
+            conflict = __syncthreads_or(conflict);
+            if (tid == 0) {
+                if (conflict) atomicMin(B.region_fallback + region, it.w);
+                __threadfence();
+                atomicExch(B.chain_status + item, conflict ? 3u : 2u);
+            }
+            // (e) wait for the verdict of every earlier chunk, then learn where ordered commits start
+            for (;;) {
+                bool ok = true;
+                for (uint32_t j = tid; j < it.w; j += CH)
+                    ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) >= 2u);
+                if (__syncthreads_and(ok)) break;
+                __nanosleep(100);
+            }
+            if (tid == 0) {
+                __threadfence();
+                sm.bcast = *(volatile uint32_t*)(B.region_fallback + region);
+            }
+            __syncthreads();
+            if (it.w < sm.bcast) break;  // every chunk up to me validated: commit in parallel
+            // ---- ordered fallback: wait until all earlier chunks have committed -----------------------
+            for (;;) {
+                bool ok = true;
+                for (uint32_t j = tid; j < it.w; j += CH)
+                    ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) == 4u);
+                if (__syncthreads_and(ok)) break;
+                __nanosleep(100);
+            }
+            __threadfence();
             bool redo = false;
             if (is_rep && row != nullptr) {
                 RlRow<CELLS> cur;
@@ -868,7 +949,7 @@ __global__ void __launch_bounds__(CH, 3) k_main(RlDev D, RlBatch B, Src src) {
                 if (chained && dirty) __threadfence();
             }
             __syncthreads();
-            if (chained && !snapshot && tid == 0) atomicExch(B.region_progress + region, it.w + 1);
+            if (chained && !snapshot && tid == 0) atomicExch(B.chain_status + item, 4u);
         }
     }
 }
