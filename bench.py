@@ -314,6 +314,7 @@ def main():
 
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    print(f"[bench] engine stats {eng.stats()}", file=sys.stderr)
     print(f"[bench] passes: A {ms_a:.1f} ms, B {ms_b:.1f} ms, e2e {ms_e:.1f} ms (wall {wall_e:.1f})", file=sys.stderr)
 
     if rank != 0:

@@ -99,6 +99,11 @@ typedef struct rl_stats {
     uint32_t row_bytes;
     uint32_t fixed_point_rounds; /* speculative rounds run for multi-row requests (last batch) */
     uint32_t _pad;
+    uint64_t chunks;         /* k_main: chunks of <= 256 accesses replayed */
+    uint64_t replay_rounds;  /* k_main: run-length rounds summed over chunks */
+    uint64_t chained_chunks; /* chunks of heavy regions (optimistic concurrency control) */
+    uint64_t ordered_chunks; /* ... of which had to commit in order */
+    uint64_t phase_cycles[6]; /* k_main SM cycles summed over chunks: load, group, stage, replay, commit protocol, write-back */
 } rl_stats;
 
 int rl_engine_create(const rl_config *cfg, rl_engine **out);

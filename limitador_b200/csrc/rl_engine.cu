@@ -90,6 +90,8 @@ struct rl_engine {
     DevBuf<uint64_t> d_delta, d_now;
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
     DevBuf<uint4> d_items;
+    DevBuf<ulonglong2> d_part_acc;
+    DevBuf<unsigned long long> d_kstats;
     DevBuf<uint32_t> d_fallback, d_chain_status, d_chain_wcnt, d_chain_w;
     DevBuf<uint8_t*> d_log_row;
     DevBuf<ulonglong2> d_log_state;
@@ -164,6 +166,7 @@ RlDev make_dev(rl_engine* e) {
     D.err = e->d_misc.p + MISC_ERR;
     D.flags = e->d_misc.p + MISC_FLAGS;
     D.tag_mask = e->tag_mask;
+    D.kstats = e->d_kstats.p;
     return D;
 }
 
@@ -292,6 +295,7 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.part_base = e->d_part_base.p;
     B.part_idx = e->d_part_idx.p;
     B.part_row = e->d_part_row.p;
+    B.part_acc = e->d_part_acc.p;
     B.scan_ctr = e->d_misc.p + MISC_SCANCTR;
     uint32_t tile = ceil_div(n_acc, kMaxTiles);
     tile = std::max<uint32_t>(512, ((tile + 255) / 256) * 256);
@@ -538,10 +542,13 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_part_base.reserve(P1 + 2));
     RL_CUDA(e, e->d_part_idx.reserve(maxA));
     RL_CUDA(e, e->d_part_row.reserve(maxA));
+    RL_CUDA(e, e->d_part_acc.reserve(maxA * 3));
     RL_CUDA(e, e->d_misc.reserve(MISC_N));
     RL_CUDA(e, cudaMemsetAsync(e->d_misc.p, 0, MISC_N * sizeof(uint32_t), e->stream));
     RL_CUDA(e, cudaMallocHost((void**)&e->h_misc, MISC_N * sizeof(uint32_t)));
     RL_CUDA(e, e->d_acc.reserve(maxA));
+    RL_CUDA(e, e->d_kstats.reserve(16));
+    RL_CUDA(e, cudaMemsetAsync(e->d_kstats.p, 0, 16 * sizeof(unsigned long long), e->stream));
     RL_CUDA(e, e->d_items.reserve((size_t)(1u << e->log2P) + maxA / RL_MAIN_THREADS + 2));
     RL_CUDA(e, e->d_fallback.reserve(1u << e->log2P));
     {
@@ -574,6 +581,7 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_part_base.release();
     e->d_part_idx.release();
     e->d_part_row.release();
+    e->d_part_acc.release();
     e->d_misc.release();
     e->d_acc.release();
     e->d_delta.release();
@@ -581,6 +589,7 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_fl_prev.release();
     e->d_fl_next.release();
     e->d_items.release();
+    e->d_kstats.release();
     e->d_fallback.release();
     e->d_chain_status.release();
     e->d_chain_wcnt.release();
@@ -646,6 +655,15 @@ int rl_profile_end(rl_engine* e, double* out_main_ms, uint64_t* out_main_launche
 
 int rl_get_stats(rl_engine* e, rl_stats* out) {
     if (!e || !out) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    unsigned long long ks[16];
+    RL_CUDA(e, cudaMemcpyAsync(ks, e->d_kstats.p, sizeof ks, cudaMemcpyDeviceToHost, e->stream));
+    RL_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->stats.chunks = ks[0];
+    e->stats.replay_rounds = ks[1];
+    e->stats.chained_chunks = ks[2];
+    e->stats.ordered_chunks = ks[3];
+    for (int i = 0; i < 6; i++) e->stats.phase_cycles[i] = ks[8 + i];
     *out = e->stats;
     return RL_OK;
 }

@@ -37,6 +37,7 @@ struct RlDev {
     uint32_t* err;    // sticky max of RL_DEV_*
     uint32_t* flags;  // bit0: batch has multi-row requests
     unsigned long long tag_mask;  // ~0; tests narrow it to force in-CTA tag collisions
+    unsigned long long* kstats;   // [0] chunks, [1] replay rounds, [2] chained chunks, [3] ordered-fallback chunks
 };
 
 struct RlBatch {
@@ -48,6 +49,8 @@ struct RlBatch {
     uint32_t* part_base;     // [P+2]
     uint32_t* part_idx;      // [n_acc]
     uint32_t* part_row;      // [n_acc] table row (index) of the access, probed / claimed by k_part
+    ulonglong2* part_acc;    // [n_acc][3] the access itself, resolved, in partition order:
+                             //   {key_lo, hdr_hi} {req | cells<<32, posorig} {delta, now}
     uint32_t* scan_ctr;      // last-block-done counter of k_colscan
     uint32_t tile;           // accesses per tile (multiple of 256)
     uint32_t num_tiles;
@@ -336,6 +339,9 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
         const bool valid = a < s1;
         uint32_t r = P1 - 1;
         uint32_t rowidx = 0xFFFFFFFFu;
+        RlAccess racc;
+        uint64_t rdelta = 0, rnow = 0;
+        racc.key_lo = 0; racc.hdr_hi = 0; racc.req = 0; racc.cells = 0; racc.posorig = 0;
         if (valid) {
             uint64_t klo, hhi;
             if (src.ident(D, a, klo, hhi)) {
@@ -343,6 +349,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
                 r = (uint32_t)rl_region_of(D, h);
                 const uint8_t* row = rl_probe<CELLS>(D, h, klo, hhi, true);
                 if (row) rowidx = (uint32_t)((size_t)(row - D.rows) / RlGeom<CELLS>::ROW_BYTES);
+                src.full(D, a, racc, rdelta, rnow);
             }
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -358,6 +365,12 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
             const uint32_t mypos = basepos + __popc(m & ((1u << lane) - 1));
             B.part_idx[mypos] = a;
             B.part_row[mypos] = rowidx;
+            if (r != P1 - 1) {
+                ulonglong2* pa = B.part_acc + (size_t)mypos * 3;
+                pa[0] = make_ulonglong2(racc.key_lo, racc.hdr_hi);
+                pa[1] = make_ulonglong2((unsigned long long)racc.req | ((unsigned long long)racc.cells << 32), racc.posorig);
+                pa[2] = make_ulonglong2(rdelta, rnow);
+            }
             if (Src::kAccessIsRequest && r == P1 - 1 && B.out_limited) {
                 // request without any applicable limit: not limited (lib.rs:434-440)
                 B.out_limited[a] = 0;
@@ -542,6 +555,20 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
     b_ok = live_all && (within_all || !check_limit);
 }
 
+__device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAccess& acc, uint64_t& delta,
+                                             uint64_t& now, uint32_t& row) {
+    const ulonglong2* pa = B.part_acc + (size_t)p * 3;
+    const ulonglong2 a0 = __ldcs(pa), a1 = __ldcs(pa + 1), a2 = __ldcs(pa + 2);
+    row = __ldcs(B.part_row + p);
+    acc.key_lo = a0.x;
+    acc.hdr_hi = a0.y;
+    acc.req = (uint32_t)a1.x;
+    acc.cells = (uint32_t)(a1.x >> 32);
+    acc.posorig = a1.y;
+    delta = a2.x;
+    now = a2.y;
+}
+
 template <int CELLS, class Src, int MODE, int CH>
 __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
@@ -557,6 +584,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
 
     const uint32_t n_items = *B.n_items;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        long long tph = clock64();
         const uint4 it = B.items[item];
         const uint32_t region = it.x, lo = it.y, hi = it.z;
         // Heavy region: this CTA owns ONE chunk and the region's chunks run concurrently under
@@ -573,10 +601,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
         uint64_t ndelta = 0, nnow = 0;
         uint32_t nrow = 0xFFFFFFFFu;
         nacc.key_lo = 0; nacc.hdr_hi = 0; nacc.req = 0; nacc.cells = 0; nacc.posorig = 0;
-        if (lo + tid < hi) {
-            nrow = B.part_row[lo + tid];
-            src.full(D, B.part_idx[lo + tid], nacc, ndelta, nnow);
-        }
+        if (lo + tid < hi) rl_load_part(B, lo + tid, nacc, ndelta, nnow, nrow);
 
         for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
             for (uint32_t i = tid; i < GT; i += CH) sm.g_tag[i] = 0ull;
@@ -588,26 +613,28 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             const RlAccess acc = nacc;
             const uint64_t delta = ndelta, now = nnow;
             const uint32_t myrow = nrow;
-            if (p + CH < hi) {
-                nrow = B.part_row[p + CH];
-                src.full(D, B.part_idx[p + CH], nacc, ndelta, nnow);
-            }
+            if (p + CH < hi) rl_load_part(B, p + CH, nacc, ndelta, nnow, nrow);
             const uint64_t h = rl_row_hash(acc.key_lo, acc.hdr_hi);
             const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
-            const RlCellDesc* desc = D.desc + (size_t)group * 8;
+            const RlCellDesc* gdesc = D.desc + (size_t)group * 8;
             const uint32_t ncell = rl_cells_n(acc.cells);
             const bool multi = (MODE == 0) && rl_cells_multi(acc.cells);  // coupled to other rows (check only)
             RlMyLimits L;
             L.qmask = 0;
+            RlCellDesc mydesc[CELLS];  // the limits of the cells I touch, indexed by cell: kept in
+                                       // local memory (L1) so that no walk waits on global loads
 #pragma unroll
             for (int k = 0; k < CELLS; k++) {
                 L.mx[k] = 0;
                 if (valid && (uint32_t)k < ncell) {
-                    const RlCellDesc d = desc[rl_cells_at(acc.cells, k)];
+                    const uint32_t c = rl_cells_at(acc.cells, k);
+                    const RlCellDesc d = gdesc[c];
+                    mydesc[c] = d;
                     L.mx[k] = d.max_value;
                     L.qmask |= (d.qualified ? 1u : 0u) << k;
                 }
             }
+            const RlCellDesc* desc = mydesc;
             sm.key_lo[tid] = acc.key_lo;
             sm.key_hi[tid] = acc.hdr_hi;
             sm.d_arr[tid] = delta;
@@ -617,6 +644,13 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             sm.g_min[0][0][tid] = sm.g_min[0][1][tid] = 0xFFFFFFFFu;
             sm.g_min[1][0][tid] = sm.g_min[1][1][tid] = 0xFFFFFFFFu;
             __syncthreads();
+#define RL_PHASE_TICK(i)                                                         \
+    if (tid == 0) {                                                              \
+        const long long tnow = clock64();                                        \
+        atomicAdd(D.kstats + 8 + (i), (unsigned long long)(tnow - tph));         \
+        tph = tnow;                                                              \
+    }
+            RL_PHASE_TICK(0)  // item fetch + access load + init
 
             // ---- group by key; the claimer of a key probes its row right away ------------------
             uint32_t slot = 0, gid = tid;
@@ -660,6 +694,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                 }
             }
 
+            RL_PHASE_TICK(1)  // grouping (tag insert, verify)
             // ---- 2. stable ordinal: one packed add per (warp, key), one barrier ------------------
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             unsigned peers = 0;
@@ -697,6 +732,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             }
             const uint32_t gflags = valid ? sm.g_flags[gid] : 0;
             const bool uniform = !(gflags & 1u);
+            RL_PHASE_TICK(2)  // ordinals + row state staged
 
             // ---- 4. lock-step run-length replay -----------------------------------------------------
             bool done = !valid || snapshot || (gflags & 2u);
@@ -704,7 +740,9 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             const unsigned long long* sv = &sm.s_val[gid * CELLS];
             const unsigned long long* se = &sm.s_exp[gid * CELLS];
             for (int attempt = 0;; attempt++) {
+            uint32_t nrounds = 0;
             for (uint32_t round = 0;; round++) {
+                nrounds++;
                 const uint32_t par = round & 1;
                 uint32_t fl = RL_NONE_U32;
                 RlRow<CELLS> loc;
@@ -834,7 +872,13 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                 }
                 if (!__syncthreads_or(!done)) break;
             }
+            if (tid == 0) {
+                atomicAdd(D.kstats + 0, 1ull);
+                atomicAdd(D.kstats + 1, (unsigned long long)nrounds);
+            }
+            RL_PHASE_TICK(3)  // replay rounds
             if (!chained || snapshot || attempt == 1) break;
+            if (tid == 0) atomicAdd(D.kstats + 2, 1ull);
             const uint32_t base_item = item - it.w;  // first chunk of my region
             // (b) publish the write set; remember the read set
             for (uint32_t i = tid; i < GT; i += CH) sm.rset[i] = 0xFFFFFFFFu;
@@ -902,6 +946,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             }
             __syncthreads();
             if (it.w < sm.bcast) break;  // every chunk up to me validated: commit in parallel
+            if (tid == 0) atomicAdd(D.kstats + 3, 1ull);
             // ---- ordered fallback: wait until all earlier chunks have committed -----------------------
             for (;;) {
                 bool ok = true;
@@ -939,6 +984,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             }
             }
 
+            RL_PHASE_TICK(4)  // optimistic-commit protocol (chained chunks)
             // ---- 5. write the dirty cells back -------------------------------------------------------
             if (is_rep && row != nullptr && !snapshot) {
                 const uint32_t dirty = sm.g_dirty[tid];
@@ -950,6 +996,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             }
             __syncthreads();
             if (chained && !snapshot && tid == 0) atomicExch(B.chain_status + item, 4u);
+            RL_PHASE_TICK(5)  // write-back
         }
     }
 }

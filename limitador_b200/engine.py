@@ -50,6 +50,8 @@ class RlStats(C.Structure):
         ("kernel_launches", C.c_uint64), ("batches", C.c_uint64), ("requests", C.c_uint64),
         ("capacity_rows", C.c_uint64), ("regions", C.c_uint32), ("row_bytes", C.c_uint32),
         ("fixed_point_rounds", C.c_uint32), ("_pad", C.c_uint32),
+        ("chunks", C.c_uint64), ("replay_rounds", C.c_uint64), ("chained_chunks", C.c_uint64),
+        ("ordered_chunks", C.c_uint64), ("phase_cycles", C.c_uint64 * 6),
     ]
 
 
@@ -167,7 +169,9 @@ class Engine:
     def stats(self) -> dict:
         s = RlStats()
         self._check(self._lib.rl_get_stats(self._h, C.byref(s)))
-        return {f[0]: getattr(s, f[0]) for f in RlStats._fields_ if not f[0].startswith("_")}
+        d = {f[0]: getattr(s, f[0]) for f in RlStats._fields_ if not f[0].startswith("_")}
+        d["phase_cycles"] = list(d["phase_cycles"])
+        return d
 
     def profile_begin(self):
         self._check(self._lib.rl_profile_begin(self._h))
