@@ -555,6 +555,70 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
     b_ok = live_all && (within_all || !check_limit);
 }
 
+// The sequential rule applied by ONE thread directly on the staged row state (shared
+// memory) — the default path (single-row request, load_counters off).  Same arithmetic as
+// rl_walk_check_single / rl_walk_update (rl_core.h), without a private copy of the row.
+//   in_memory.rs:122-127 (insert on lookup), :110-112,130-132 (early return), :146-153 (update)
+template <int CELLS>
+__device__ __forceinline__ uint32_t rl_apply_check_smem(unsigned long long* sv, unsigned long long* se,
+                                                        const RlMyLimits& L, const RlCellDesc* gdesc, uint32_t cells,
+                                                        uint64_t posorig, uint64_t delta, uint64_t now,
+                                                        uint32_t& dirty) {
+    const uint32_t n = rl_cells_n(cells);
+    uint32_t fl = RL_NONE_U32;
+#pragma unroll
+    for (int k = 0; k < CELLS; k++) {
+        if ((uint32_t)k < n && fl == RL_NONE_U32) {
+            const uint32_t c = rl_cells_at(cells, k);
+            uint64_t v = sv[c], e = se[c];
+            if (((L.qmask >> k) & 1u) && e == 0) {
+                e = now + gdesc[c].window_us;
+                v = 0;
+                sv[c] = 0;
+                se[c] = e;
+                dirty |= 1u << c;
+            }
+            const uint64_t vv = (e <= now) ? 0 : v;
+            if (vv + delta > L.mx[k]) fl = rl_pos_at(posorig, k);
+        }
+    }
+    if (fl != RL_NONE_U32) return fl;
+#pragma unroll
+    for (int k = 0; k < CELLS; k++) {
+        if ((uint32_t)k < n) {
+            const uint32_t c = rl_cells_at(cells, k);
+            if (se[c] <= now) {
+                se[c] = now + gdesc[c].window_us;
+                sv[c] = delta;
+            } else {
+                sv[c] += delta;
+            }
+            dirty |= 1u << c;
+        }
+    }
+    return RL_NONE_U32;
+}
+
+template <int CELLS>
+__device__ __forceinline__ void rl_apply_update_smem(unsigned long long* sv, unsigned long long* se,
+                                                     const RlCellDesc* gdesc, uint32_t cells, uint64_t delta,
+                                                     uint64_t now, uint32_t& dirty) {
+    const uint32_t n = rl_cells_n(cells);
+#pragma unroll
+    for (int k = 0; k < CELLS; k++) {
+        if ((uint32_t)k < n) {
+            const uint32_t c = rl_cells_at(cells, k);
+            if (se[c] <= now) {
+                se[c] = now + gdesc[c].window_us;
+                sv[c] = delta;
+            } else {
+                sv[c] += delta;
+            }
+            dirty |= 1u << c;
+        }
+    }
+}
+
 __device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAccess& acc, uint64_t& delta,
                                              uint64_t& now, uint32_t& row) {
     const ulonglong2* pa = B.part_acc + (size_t)p * 3;
@@ -582,10 +646,13 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
     const bool write_out = (B.phase == RL_PHASE_COMMIT);
     const bool snapshot = (B.phase == RL_PHASE_SNAPSHOT);
 
+    // the work-item array is allocated for the launch's full grid: fetch my item together with
+    // the item count instead of after it
+    uint4 it0 = B.items[blockIdx.x];
     const uint32_t n_items = *B.n_items;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         long long tph = clock64();
-        const uint4 it = B.items[item];
+        const uint4 it = (item == blockIdx.x) ? it0 : B.items[item];
         const uint32_t region = it.x, lo = it.y, hi = it.z;
         // Heavy region: this CTA owns ONE chunk and the region's chunks run concurrently under
         // optimistic concurrency control.  A chunk replays its requests against the rows as they
@@ -772,7 +839,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                     const uint32_t mA = min(sm.g_min[par][0][gid], cnt);
                     const uint32_t mB = min(sm.g_min[par][1][gid], cnt);
                     uint32_t newpos;
-                    bool mine = false, store = false;
+                    bool mine = false, store = false, fast_store = false;
                     uint32_t dirty = 0;
                     uint64_t* rem = nullptr;
                     uint64_t* ttl = nullptr;
@@ -796,19 +863,22 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                             mine = true;
                             fl = RL_NONE_U32;
                             store = (ord == mB - 1);
-                            if ((MODE == 0 && lc && write_out) || store) {
-                                if (!lc) {  // only the run's last member gets here: it is the sole writer of S
-#pragma unroll
-                                    for (int c = 0; c < CELLS; c++) {
-                                        loc.value[c] = sv[c];
-                                        loc.expiry[c] = se[c];
-                                    }
-                                }
+                            if (MODE == 0 && lc && write_out) {
                                 rl_advance_run<CELLS>(loc, acc.cells, (uint64_t)(ord - pos) * delta);
-                                if (MODE == 0)
-                                    fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
-                                else
-                                    rl_walk_update<CELLS>(loc, dirty, desc, acc.cells, delta, now);
+                                fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                                fast_store = false;
+                            } else if (store) {
+                                // the run's last member is the sole writer of S (nobody reads it until
+                                // the next barrier): add the run's deltas in place
+                                const uint64_t add = (uint64_t)(mB - pos) * delta;
+#pragma unroll
+                                for (int k = 0; k < CELLS; k++)
+                                    if ((uint32_t)k < ncell) {
+                                        const uint32_t c = rl_cells_at(acc.cells, k);
+                                        sm.s_val[gid * CELLS + c] += add;
+                                        dirty |= 1u << c;
+                                    }
+                                fast_store = true;
                             }
                         }
                     } else {  // the request at `pos` is applied alone, sequential rule
@@ -816,23 +886,33 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                         if (ord == pos) {
                             mine = true;
                             store = true;
-                            if (!lc) {
-#pragma unroll
-                                for (int c = 0; c < CELLS; c++) {
-                                    loc.value[c] = sv[c];
-                                    loc.expiry[c] = se[c];
-                                }
-                            }
-                            if (MODE == 2) {
-                                rl_walk_update<CELLS>(loc, dirty, desc, acc.cells, delta, now);
-                            } else if (!multi) {
-                                fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                            if (!lc && !multi) {
+                                fast_store = true;  // operate on the staged state in place
+                                if (MODE == 2)
+                                    rl_apply_update_smem<CELLS>(&sm.s_val[gid * CELLS], &sm.s_exp[gid * CELLS], gdesc, acc.cells,
+                                                                delta, now, dirty);
+                                else
+                                    fl = rl_apply_check_smem<CELLS>(&sm.s_val[gid * CELLS], &sm.s_exp[gid * CELLS], L, gdesc,
+                                                                    acc.cells, acc.posorig, delta, now, dirty);
                             } else {
-                                const uint32_t fl_in = B.fl_prev[acc.req];
-                                const uint32_t local = rl_walk_check_multi<CELLS>(loc, dirty, desc, acc.cells, acc.posorig,
-                                                                                 delta, now, lc, fl_in, rem, ttl);
-                                if (!write_out && local != RL_NONE_U32) atomicMin(&B.fl_next[acc.req], local);
-                                fl = fl_in;
+                                if (!lc) {
+#pragma unroll
+                                    for (int c = 0; c < CELLS; c++) {
+                                        loc.value[c] = sv[c];
+                                        loc.expiry[c] = se[c];
+                                    }
+                                }
+                                if (MODE == 2) {
+                                    rl_walk_update<CELLS>(loc, dirty, desc, acc.cells, delta, now);
+                                } else if (!multi) {
+                                    fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                                } else {
+                                    const uint32_t fl_in = B.fl_prev[acc.req];
+                                    const uint32_t local = rl_walk_check_multi<CELLS>(loc, dirty, desc, acc.cells, acc.posorig,
+                                                                                     delta, now, lc, fl_in, rem, ttl);
+                                    if (!write_out && local != RL_NONE_U32) atomicMin(&B.fl_next[acc.req], local);
+                                    fl = fl_in;
+                                }
                             }
                         }
                     }
@@ -856,12 +936,14 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                     // the barrier between evaluation and this point ordered every read of S
                     // before the publication of the new state
                     if (store && dirty) {
+                        if (!fast_store) {
 #pragma unroll
-                        for (int c = 0; c < CELLS; c++)
-                            if (dirty & (1u << c)) {
-                                sm.s_val[gid * CELLS + c] = loc.value[c];
-                                sm.s_exp[gid * CELLS + c] = loc.expiry[c];
-                            }
+                            for (int c = 0; c < CELLS; c++)
+                                if (dirty & (1u << c)) {
+                                    sm.s_val[gid * CELLS + c] = loc.value[c];
+                                    sm.s_exp[gid * CELLS + c] = loc.expiry[c];
+                                }
+                        }
                         atomicOr(&sm.g_dirty[gid], dirty);
                     }
                     if (mine && ord == newpos - 1) {  // last finalised member re-arms the group
