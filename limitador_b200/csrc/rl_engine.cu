@@ -525,6 +525,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     e->log2P = log2_ceil(regions);
     e->log2R = lg - e->log2P;
     if (e->log2R > 31) return fail(e, RL_FATAL, "rows per region exceeds 2^31; raise regions");
+    if (lg > 31) return fail(e, RL_FATAL, "capacity_rows must not exceed 2^31");
     e->max_batch = std::max<uint32_t>(cfg->max_batch, 1);
     e->max_counters = cfg->max_counters ? cfg->max_counters : 4 * e->max_batch;
     e->max_counters = std::max(e->max_counters, e->max_batch);

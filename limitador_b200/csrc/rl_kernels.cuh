@@ -515,6 +515,8 @@ struct RlMainSmem {
     uint32_t g_flags[CH];      // by gid: bit0 = members differ in delta or cell list
     uint32_t g_dirty[CH];
     uint32_t rset[GT];         // chained chunks: rows this chunk read (its read set)
+    uint32_t rflag[GT];        // ... row is written by an earlier chunk
+    uint32_t need_bits[64];    // earlier chunks (bit per chunk) whose commit I must wait for
     uint32_t w_cnt;
     uint32_t bcast;
 };
@@ -655,13 +657,14 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
         const uint4 it = (item == blockIdx.x) ? it0 : B.items[item];
         const uint32_t region = it.x, lo = it.y, hi = it.z;
         // Heavy region: this CTA owns ONE chunk and the region's chunks run concurrently under
-        // optimistic concurrency control.  A chunk replays its requests against the rows as they
-        // are (no row is written), publishes its WRITE set (rows it would change), and checks
-        // that no earlier chunk's write set meets its READ set.  If that holds for every chunk up
-        // to this one, all of them saw the state sequential execution would have shown them, and
-        // they commit in parallel — a saturated hot key is read by every chunk and written by
-        // none.  From the first chunk that fails the check on, chunks commit in order, re-reading
-        // their rows and replaying the keys whose state changed.
+        // optimistic concurrency control, row by row.  A chunk replays its requests against the
+        // rows as they are (no row is written) and publishes the rows it read, each tagged with
+        // whether its replay changes it.  Requests of different keys never interact, so a row's
+        // history inside the batch is the sequence of chunks that read it: if none of the earlier
+        // ones writes it, the state this chunk saw is the one sequential execution shows it (a
+        // saturated hot key is read by every chunk and written by none) and the chunk commits at
+        // once.  Otherwise it waits for exactly the earlier chunks touching such a row, re-reads
+        // its rows and replays the keys whose state changed.
         const bool chained = (it.w != RL_NONE_U32);
         // prefetch of the first chunk
         RlAccess nacc;
@@ -962,8 +965,12 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             if (!chained || snapshot || attempt == 1) break;
             if (tid == 0) atomicAdd(D.kstats + 2, 1ull);
             const uint32_t base_item = item - it.w;  // first chunk of my region
-            // (b) publish the write set; remember the read set
-            for (uint32_t i = tid; i < GT; i += CH) sm.rset[i] = 0xFFFFFFFFu;
+            // (b) publish my read set, each row tagged with "I write it" (under my speculation)
+            for (uint32_t i = tid; i < GT; i += CH) {
+                sm.rset[i] = 0xFFFFFFFFu;
+                sm.rflag[i] = 0;
+            }
+            for (uint32_t i = tid; i < 64; i += CH) sm.need_bits[i] = 0;
             if (tid == 0) sm.w_cnt = 0;
             __syncthreads();
             if (is_rep && row != nullptr) {
@@ -973,7 +980,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                     if (old == 0xFFFFFFFFu || old == myrow) break;
                     s2 = (s2 + 1) & (GT - 1);
                 }
-                if (sm.g_dirty[tid]) B.chain_w[(size_t)item * CH + atomicAdd(&sm.w_cnt, 1u)] = myrow;
+                B.chain_w[(size_t)item * CH + atomicAdd(&sm.w_cnt, 1u)] = (myrow << 1) | (sm.g_dirty[tid] ? 1u : 0u);
             }
             __syncthreads();
             if (tid == 0) {
@@ -981,7 +988,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                 __threadfence();
                 atomicExch(B.chain_status + item, 1u);
             }
-            // (c) wait until every earlier chunk of the region has published its write set
+            // (c) wait until every earlier chunk of the region has published its set
             for (;;) {
                 bool ok = true;
                 for (uint32_t j = tid; j < it.w; j += CH)
@@ -990,50 +997,54 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                 __nanosleep(100);
             }
             __threadfence();
-            // (d) does an earlier chunk write a row I read?  warp w scans chunks w, w+NW, ...
-            bool conflict = false;
-            for (uint32_t j = warp; j < it.w; j += Smem::NW) {
-                const uint32_t cj = __ldcg(B.chain_wcnt + base_item + j);
-                for (uint32_t i = lane; i < cj; i += 32) {
-                    const uint32_t w = __ldcg(B.chain_w + (size_t)(base_item + j) * CH + i);
-                    uint32_t s2 = (w * 2654435761u) & (GT - 1);
-                    for (;;) {
-                        const uint32_t x = sm.rset[s2];
-                        if (x == w) {
-                            conflict = true;
-                            break;
+            // (d) rows I read that some earlier chunk writes: their history must be replayed in order.
+            //     Pass 1 flags those rows, pass 2 collects every earlier chunk that touches one of them
+            //     (a chunk that only READS such a row may turn into a writer once it re-validates).
+            bool any_dep = false;
+            for (int pass = 0; pass < 2; pass++) {
+                for (uint32_t j = warp; j < it.w; j += Smem::NW) {
+                    const uint32_t cj = __ldcg(B.chain_wcnt + base_item + j);
+                    bool hit = false;
+                    for (uint32_t i = lane; i < cj; i += 32) {
+                        const uint32_t e = __ldcg(B.chain_w + (size_t)(base_item + j) * CH + i);
+                        const uint32_t w = e >> 1;
+                        uint32_t s2 = (w * 2654435761u) & (GT - 1);
+                        for (;;) {
+                            const uint32_t x = sm.rset[s2];
+                            if (x == w) {
+                                if (pass == 0) {
+                                    if (e & 1u) sm.rflag[s2] = 1;
+                                } else if (sm.rflag[s2]) {
+                                    hit = true;
+                                }
+                                break;
+                            }
+                            if (x == 0xFFFFFFFFu) break;
+                            s2 = (s2 + 1) & (GT - 1);
                         }
-                        if (x == 0xFFFFFFFFu) break;
-                        s2 = (s2 + 1) & (GT - 1);
+                    }
+                    if (pass == 1 && __any_sync(0xffffffffu, hit)) {
+                        any_dep = true;
+                        if (lane == 0) atomicOr(&sm.need_bits[(j >> 5) & 63], (j < 2048) ? (1u << (j & 31)) : 0u);
                     }
                 }
+                any_dep = __syncthreads_or(any_dep);
+                if (pass == 0 && !any_dep) {
+                    // no flagged row yet is not conclusive for pass 0 (flags only set there): check them
+                    bool f = false;
+                    for (uint32_t i = tid; i < GT; i += CH) f = f || sm.rflag[i];
+                    if (!__syncthreads_or(f)) break;
+                }
             }
-            conflict = __syncthreads_or(conflict);
-            if (tid == 0) {
-                if (conflict) atomicMin(B.region_fallback + region, it.w);
-                __threadfence();
-                atomicExch(B.chain_status + item, conflict ? 3u : 2u);
-            }
-            // (e) wait for the verdict of every earlier chunk, then learn where ordered commits start
-            for (;;) {
-                bool ok = true;
-                for (uint32_t j = tid; j < it.w; j += CH)
-                    ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) >= 2u);
-                if (__syncthreads_and(ok)) break;
-                __nanosleep(100);
-            }
-            if (tid == 0) {
-                __threadfence();
-                sm.bcast = *(volatile uint32_t*)(B.region_fallback + region);
-            }
-            __syncthreads();
-            if (it.w < sm.bcast) break;  // every chunk up to me validated: commit in parallel
+            if (!any_dep) break;  // nothing I read is written before me: commit now, in parallel
             if (tid == 0) atomicAdd(D.kstats + 3, 1ull);
-            // ---- ordered fallback: wait until all earlier chunks have committed -----------------------
+            // (e) wait for the chunks my rows depend on to commit, then re-validate
             for (;;) {
                 bool ok = true;
-                for (uint32_t j = tid; j < it.w; j += CH)
-                    ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) == 4u);
+                for (uint32_t j = tid; j < it.w; j += CH) {
+                    const bool need = (j >= 2048) || ((sm.need_bits[j >> 5] >> (j & 31)) & 1u);
+                    if (need) ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) == 4u);
+                }
                 if (__syncthreads_and(ok)) break;
                 __nanosleep(100);
             }
