@@ -75,6 +75,7 @@ struct rl_engine {
     bool tables_dirty = true;
     bool any_multi_ns = false;
     uint32_t max_ns_limits = 0;
+    uint32_t max_cells_used = 1;  // highest cell index + 1 over all row groups
 
     // device tables
     DevBuf<RlCellDesc> d_desc;
@@ -182,11 +183,13 @@ int upload_tables(rl_engine* e) {
         d.limit_id = RL_NONE_U32;
         d.qualified = 0;
     }
+    e->max_cells_used = 1;
     for (size_t g = 1; g < ngroups; g++) {
         group_ns[g] = e->groups[g].ns;
         for (uint32_t c = 0; c < RL_MAX_CELLS; c++) {
             const uint32_t lid = e->groups[g].limit_of_cell[c];
             if (lid == RL_NONE_U32) continue;
+            e->max_cells_used = std::max(e->max_cells_used, c + 1);
             const HostLimit& l = e->limits[lid];
             RlCellDesc& d = desc[g * 8 + c];
             d.max_value = l.max_value;
@@ -353,10 +356,10 @@ int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& 
     }
 }
 
-template <int CELLS, class Src, int MODE>
+template <int GEO, int CELLS, class Src, int MODE, bool LC>
 int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
     using Smem = RlMainSmem<CELLS, RL_MAIN_THREADS>;
-    auto kern = k_main<CELLS, Src, MODE, RL_MAIN_THREADS>;
+    auto kern = k_main<GEO, CELLS, Src, MODE, RL_MAIN_THREADS, LC>;
     static bool attr_set = false;  // one per instantiation
     if (!attr_set) {
         RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
@@ -377,11 +380,14 @@ int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) 
         RL_CUDA(e, cudaEventRecord(ev0, e->stream));
     }
     int r;
-    switch (e->cells) {
-        case 1: r = launch_main_cells<1, Src, MODE>(e, D, B, src); break;
-        case 3: r = launch_main_cells<3, Src, MODE>(e, D, B, src); break;
-        default: r = launch_main_cells<7, Src, MODE>(e, D, B, src); break;
-    }
+    const bool lc = (MODE == 0) && B.load_counters;
+#define RL_MAIN_CASE(G, A) \
+    r = lc ? launch_main_cells<G, A, Src, MODE, MODE == 0>(e, D, B, src) : launch_main_cells<G, A, Src, MODE, false>(e, D, B, src)
+    if (e->cells == 1) RL_MAIN_CASE(1, 1);
+    else if (e->cells == 3) RL_MAIN_CASE(3, 3);
+    else if (e->max_cells_used <= 4) RL_MAIN_CASE(7, 4);  // 128-B rows of which at most 4 cells are in use
+    else RL_MAIN_CASE(7, 7);
+#undef RL_MAIN_CASE
     if (r) return r;
     RL_LAUNCH_CHECK(e);
     if (e->profiling) {
@@ -432,9 +438,9 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
             r = launch_main<AccSrc, 0>(e, D, B, src);
             if (r) return r;
             switch (e->cells) {
-                case 1: k_restore<1><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, B.log_row, B.log_state); break;
-                case 3: k_restore<3><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, B.log_row, B.log_state); break;
-                default: k_restore<7><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, B.log_row, B.log_state); break;
+                case 1: k_restore<1><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, 1, B.log_row, B.log_state); break;
+                case 3: k_restore<3><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, 3, B.log_row, B.log_state); break;
+                default: k_restore<7><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, e->max_cells_used <= 4 ? 4 : 7, B.log_row, B.log_state); break;
             }
             RL_LAUNCH_CHECK(e);
             k_fl_step<<<ceil_div(n_req, 256), 256, 0, e->stream>>>(n_req, B.fl_prev, B.fl_next,

@@ -206,6 +206,7 @@ __device__ __forceinline__ void rl_row_store(uint8_t* row, uint32_t dirty, const
 // written by a resolve kernel (general CSR form, or records of multi-row namespaces).
 struct RecordSrc {
     static constexpr bool kAccessIsRequest = true;
+    static constexpr bool kCanBeMulti = false;  // every namespace maps to one row
     const rl_record* recs;
     // identity of access a: false => no row (namespace without limits)
     __device__ __forceinline__ bool ident(const RlDev& D, uint32_t a, uint64_t& key_lo, uint64_t& hdr_hi) const {
@@ -246,6 +247,7 @@ struct RecordSrc {
 
 struct AccSrc {
     static constexpr bool kAccessIsRequest = false;
+    static constexpr bool kCanBeMulti = true;
     const RlAccess* acc;
     const uint64_t* delta;  // per request
     const uint64_t* now;    // per request
@@ -635,8 +637,10 @@ __device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAcc
     now = a2.y;
 }
 
-template <int CELLS, class Src, int MODE, int CH>
-__global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBatch B, Src src) {
+// GEO = cells per row of the table layout (row bytes), CELLS = cells any row group actually
+// uses (<= GEO): loops, registers and shared memory are sized by the latter.
+template <int GEO, int CELLS, class Src, int MODE, int CH, bool LC>
+__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2))) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
     constexpr int PW = Smem::PW;
@@ -644,9 +648,9 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
     Smem& sm = *reinterpret_cast<Smem*>(rl_smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool lc = B.load_counters != 0;
+    constexpr bool lc = LC;  // load_counters: compile-time, so the default kernel carries none of it
     const bool write_out = (B.phase == RL_PHASE_COMMIT);
-    const bool snapshot = (B.phase == RL_PHASE_SNAPSHOT);
+    const bool snapshot = Src::kCanBeMulti && (B.phase == RL_PHASE_SNAPSHOT);
 
     // the work-item array is allocated for the launch's full grid: fetch my item together with
     // the item count instead of after it
@@ -688,23 +692,24 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
             const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
             const RlCellDesc* gdesc = D.desc + (size_t)group * 8;
             const uint32_t ncell = rl_cells_n(acc.cells);
-            const bool multi = (MODE == 0) && rl_cells_multi(acc.cells);  // coupled to other rows (check only)
+            const bool multi = Src::kCanBeMulti && (MODE == 0) && rl_cells_multi(acc.cells);  // coupled to other rows
             RlMyLimits L;
             L.qmask = 0;
-            RlCellDesc mydesc[CELLS];  // the limits of the cells I touch, indexed by cell: kept in
-                                       // local memory (L1) so that no walk waits on global loads
+            constexpr bool kGeneric = LC || Src::kCanBeMulti;
+            RlCellDesc mydesc[kGeneric ? CELLS : 1];  // generic variants: the limits of the cells I touch,
+                                                      // indexed by cell, in local memory (L1) for the walks
 #pragma unroll
             for (int k = 0; k < CELLS; k++) {
                 L.mx[k] = 0;
                 if (valid && (uint32_t)k < ncell) {
                     const uint32_t c = rl_cells_at(acc.cells, k);
                     const RlCellDesc d = gdesc[c];
-                    mydesc[c] = d;
+                    if (kGeneric) mydesc[kGeneric ? c : 0] = d;
                     L.mx[k] = d.max_value;
                     L.qmask |= (d.qualified ? 1u : 0u) << k;
                 }
             }
-            const RlCellDesc* desc = mydesc;
+            const RlCellDesc* desc = kGeneric ? mydesc : gdesc;
             sm.key_lo[tid] = acc.key_lo;
             sm.key_hi[tid] = acc.hdr_hi;
             sm.d_arr[tid] = delta;
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                         slot = s;
                         if (is_rep && row == nullptr) {
                             // the row was located (or claimed) by k_part; its sectors are in L2
-                            if (myrow != 0xFFFFFFFFu) row = D.rows + (size_t)myrow * RlGeom<CELLS>::ROW_BYTES;
+                            if (myrow != 0xFFFFFFFFu) row = D.rows + (size_t)myrow * RlGeom<GEO>::ROW_BYTES;
                             rl_row_load<CELLS>(row, CELLS, st);
                         }
                     }
@@ -786,7 +791,7 @@ __global__ void __launch_bounds__(CH, (CELLS == 1 ? 3 : 2)) k_main(RlDev D, RlBa
                     B.log_row[p] = row;
 #pragma unroll
                     for (int c = 0; c < CELLS; c++)
-                        B.log_state[(size_t)p * CELLS + c] = make_ulonglong2(st.value[c], st.expiry[c]);
+                        B.log_state[(size_t)p * GEO + c] = make_ulonglong2(st.value[c], st.expiry[c]);
                 }
             }
             __syncthreads();
@@ -1204,7 +1209,7 @@ __global__ void k_resolve_records(RlDev D, uint32_t n, const rl_record* __restri
 
 // Undo a speculative round: put every logged row back to its state at batch start.
 template <int CELLS>
-__global__ void k_restore(uint32_t n_acc, uint8_t* const* __restrict__ log_row,
+__global__ void k_restore(uint32_t n_acc, uint32_t act, uint8_t* const* __restrict__ log_row,
                           const ulonglong2* __restrict__ log_state) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_acc) return;
@@ -1212,6 +1217,7 @@ __global__ void k_restore(uint32_t n_acc, uint8_t* const* __restrict__ log_row,
     if (!row) return;
 #pragma unroll
     for (int c = 0; c < CELLS; c++) {
+        if ((uint32_t)c >= act) break;  // only the cells in use were logged
         const ulonglong2 v = log_state[(size_t)p * CELLS + c];
         rl_st_cg(row + 16 + 16 * c, v.x, v.y);
     }
