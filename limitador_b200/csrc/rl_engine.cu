@@ -86,7 +86,7 @@ struct rl_engine {
     uint32_t limits_cap = 0, ns_cap = 0;
 
     // workspace
-    DevBuf<uint32_t> d_tile_cnt, d_region_total, d_part_base, d_part_idx, d_part_row, d_misc;  // misc: err, flags, scan_ctr, changed
+    DevBuf<uint32_t> d_tile_cnt, d_region_total, d_part_base, d_part_idx, d_part_row, d_reg_of, d_row_of, d_misc;  // misc: err, flags, scan_ctr, changed
     DevBuf<RlAccess> d_acc;
     DevBuf<uint64_t> d_delta, d_now;
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
@@ -297,6 +297,8 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.region_total = e->d_region_total.p;
     B.part_base = e->d_part_base.p;
     B.part_idx = e->d_part_idx.p;
+    B.reg_of = e->d_reg_of.p;
+    B.row_of = e->d_row_of.p;
     B.part_row = e->d_part_row.p;
     B.part_acc = e->d_part_acc.p;
     B.scan_ctr = e->d_misc.p + MISC_SCANCTR;
@@ -334,15 +336,14 @@ int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const
     const size_t smem = (size_t)RL_PART_WARPS * P1 * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-        RL_CUDA(e, cudaFuncSetAttribute(k_part<CELLS, Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_CUDA(e, cudaFuncSetAttribute(k_part<CELLS, Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_CUDA(e, cudaFuncSetAttribute(k_part<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_part<CELLS, Src, false><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
+    k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), e->stream>>>(D, B, src);
     RL_LAUNCH_CHECK(e);
     k_colscan<<<ceil_div(P1, 32), 256, 0, e->stream>>>(D, B);
     RL_LAUNCH_CHECK(e);
-    k_part<CELLS, Src, true><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
+    k_part<Src><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
     RL_LAUNCH_CHECK(e);
     return RL_OK;
 }
@@ -548,6 +549,8 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_region_total.reserve(P1 + 1));
     RL_CUDA(e, e->d_part_base.reserve(P1 + 2));
     RL_CUDA(e, e->d_part_idx.reserve(maxA));
+    RL_CUDA(e, e->d_reg_of.reserve(maxA));
+    RL_CUDA(e, e->d_row_of.reserve(maxA));
     RL_CUDA(e, e->d_part_row.reserve(maxA));
     RL_CUDA(e, e->d_part_acc.reserve(maxA * 3));
     RL_CUDA(e, e->d_misc.reserve(MISC_N));
@@ -587,6 +590,8 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_region_total.release();
     e->d_part_base.release();
     e->d_part_idx.release();
+    e->d_reg_of.release();
+    e->d_row_of.release();
     e->d_part_row.release();
     e->d_part_acc.release();
     e->d_misc.release();

@@ -47,6 +47,8 @@ struct RlBatch {
     uint32_t* tile_cnt;      // [num_tiles][P+1]; after k_colscan: exclusive prefix over tiles
     uint32_t* region_total;  // [P+1]
     uint32_t* part_base;     // [P+2]
+    uint32_t* reg_of;        // [n_acc] region of access a (P = "no row"), written by k_probe_count
+    uint32_t* row_of;        // [n_acc] table row (index) of access a, probed / claimed by k_probe_count
     uint32_t* part_idx;      // [n_acc]
     uint32_t* part_row;      // [n_acc] table row (index) of the access, probed / claimed by k_part
     ulonglong2* part_acc;    // [n_acc][3] the access itself, resolved, in partition order:
@@ -276,10 +278,65 @@ struct AccSrc {
 // Tile = B.tile consecutive accesses; warp w of the CTA owns the w-th contiguous slice, so
 // stream order == (tile, warp, step, lane) and a stable rank is
 //   region base + (accesses of earlier tiles) + (accesses of earlier warps) + rank in slice.
-// The SCATTER pass also probes (and, for a new key, claims) the table row of every access and
-// records its index: the random HBM access of the batch happens here, in a kernel with
-// thousands of independent loads in flight per SM, and k_main later finds the row in L2.
-template <int CELLS, class Src, bool SCATTER>
+// Probe + count.  One pass over the batch with as many independent loads in flight as the SM
+// can hold: every access finds (or, for a new key, claims) its table row — the one random HBM
+// access of the batch — and the per-tile histogram over the table regions is taken on the way.
+template <int CELLS, class Src>
+__global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src src) {
+    extern __shared__ uint32_t rcnt[];  // [P+1]
+    constexpr uint32_t RB = RlGeom<CELLS>::ROW_BYTES;
+    constexpr int U = 4;
+    const uint32_t P1 = (1u << D.log2P) + 1;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t t0 = tile * B.tile;
+    const uint32_t t1 = min(t0 + B.tile, B.n_acc);
+    for (uint32_t i = tid; i < P1; i += 1024) rcnt[i] = 0;
+    __syncthreads();
+    const uint32_t R = 1u << D.log2R;
+    for (uint32_t base = t0 + tid; base < t1; base += 1024 * U) {
+        uint64_t klo[U], hhi[U], h[U];
+        bool ok[U];
+        uint8_t* home[U];
+        ulonglong2 hdr[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t a = base + u * 1024;
+            klo[u] = hhi[u] = 0;
+            ok[u] = (a < t1) && src.ident(D, a, klo[u], hhi[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            h[u] = rl_row_hash(klo[u], hhi[u]);
+            home[u] = D.rows + ((rl_region_of(D, h[u]) << D.log2R) + ((uint32_t)h[u] & (R - 1))) * RB;
+            if (ok[u]) hdr[u] = rl_ld_cg(home[u]);  // the home rows of U accesses are fetched together
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t a = base + u * 1024;
+            if (a >= t1) continue;
+            uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
+            if (ok[u]) {
+                r = (uint32_t)rl_region_of(D, h[u]);
+                const uint8_t* row = (hdr[u].x == klo[u] && hdr[u].y == hhi[u])
+                                         ? home[u]
+                                         : rl_probe<CELLS>(D, h[u], klo[u], hhi[u], true);  // collision chain / insert
+                if (row) rowidx = (uint32_t)((size_t)(row - D.rows) / RB);
+            }
+            B.reg_of[a] = r;
+            B.row_of[a] = rowidx;
+            atomicAdd(&rcnt[r], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t r = tid; r < P1; r += 1024) B.tile_cnt[(size_t)tile * P1 + r] = rcnt[r];
+}
+
+// Stable scatter.  Tile = B.tile consecutive accesses; warp w of the CTA owns the w-th
+// contiguous slice, so stream order == (tile, warp, step, lane) and the stable rank of an
+// access is  region base + (accesses of earlier tiles) + (of earlier warps) + rank in slice.
+// Each access is written out resolved (part_acc) so that k_main reads its chunk coalesced.
+template <class Src>
 __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Src src) {
     extern __shared__ uint32_t wcnt[];  // [RL_PART_WARPS][P+1]
     const uint32_t P1 = (1u << D.log2P) + 1;
@@ -299,11 +356,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
     for (uint32_t b = s0; b < s1; b += 32) {
         const uint32_t a = b + lane;
         const bool valid = a < s1;
-        uint32_t r = P1 - 1;  // dummy region for accesses without a row
-        if (valid) {
-            uint64_t klo, hhi;
-            if (src.ident(D, a, klo, hhi)) r = (uint32_t)rl_region_of(D, rl_row_hash(klo, hhi));
-        }
+        const uint32_t r = valid ? __ldcg(B.reg_of + a) : P1 - 1;
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
             const unsigned m = __match_any_sync(vmask, r);
@@ -312,16 +365,6 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
         __syncwarp();
     }
     __syncthreads();
-
-    if (!SCATTER) {
-        for (uint32_t r = tid; r < P1; r += RL_PART_THREADS) {
-            uint32_t tot = 0;
-#pragma unroll
-            for (int w = 0; w < RL_PART_WARPS; w++) tot += wcnt[w * P1 + r];
-            B.tile_cnt[(size_t)tile * P1 + r] = tot;
-        }
-        return;
-    }
 
     // bases: region base + earlier tiles + earlier warps of this tile
     for (uint32_t r = tid; r < P1; r += RL_PART_THREADS) {
@@ -339,20 +382,14 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
     for (uint32_t b = s0; b < s1; b += 32) {
         const uint32_t a = b + lane;
         const bool valid = a < s1;
-        uint32_t r = P1 - 1;
-        uint32_t rowidx = 0xFFFFFFFFu;
+        uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
         RlAccess racc;
         uint64_t rdelta = 0, rnow = 0;
         racc.key_lo = 0; racc.hdr_hi = 0; racc.req = 0; racc.cells = 0; racc.posorig = 0;
         if (valid) {
-            uint64_t klo, hhi;
-            if (src.ident(D, a, klo, hhi)) {
-                const uint64_t h = rl_row_hash(klo, hhi);
-                r = (uint32_t)rl_region_of(D, h);
-                const uint8_t* row = rl_probe<CELLS>(D, h, klo, hhi, true);
-                if (row) rowidx = (uint32_t)((size_t)(row - D.rows) / RlGeom<CELLS>::ROW_BYTES);
-                src.full(D, a, racc, rdelta, rnow);
-            }
+            r = __ldcg(B.reg_of + a);
+            rowidx = __ldcg(B.row_of + a);
+            if (r != P1 - 1) src.full(D, a, racc, rdelta, rnow);
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -450,18 +487,29 @@ __global__ void __launch_bounds__(256) k_colscan(RlDev D, RlBatch B) {
         if (len > B.heavy_len) hsum += (len + B.chunk - 1) / B.chunk;
         else if (len) lsum += 1;
     }
-    __shared__ uint32_t s_h[256], s_l[256];
-    s_h[threadIdx.x] = hsum;
-    s_l[threadIdx.x] = lsum;
-    __syncthreads();
-    uint32_t hb = 0, lb = 0, th = 0, tl = 0;
-    for (uint32_t t = 0; t < 256; t++) {
-        if (t < threadIdx.x) {
-            hb += s_h[t];
-            lb += s_l[t];
+    __shared__ uint32_t s_hw[8], s_lw[8];
+    uint32_t hx = hsum, lx = lsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t hy = __shfl_up_sync(0xffffffffu, hx, o), ly = __shfl_up_sync(0xffffffffu, lx, o);
+        if ((int)lane >= o) {
+            hx += hy;
+            lx += ly;
         }
-        th += s_h[t];
-        tl += s_l[t];
+    }
+    if (lane == 31) {
+        s_hw[warp] = hx;
+        s_lw[warp] = lx;
+    }
+    __syncthreads();
+    uint32_t hb = hx - hsum, lb = lx - lsum, th = 0, tl = 0;
+    for (uint32_t w = 0; w < 8; w++) {
+        if (w < warp) {
+            hb += s_hw[w];
+            lb += s_lw[w];
+        }
+        th += s_hw[w];
+        tl += s_lw[w];
     }
     for (uint32_t q = threadIdx.x; q < P; q += 256) {
         const uint32_t lo = B.part_base[q], hi = B.part_base[q + 1];
