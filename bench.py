@@ -169,7 +169,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from limitador_b200 import Engine, streams
+    from limitador_b200 import Engine, exchange, streams
     from limitador_b200.engine import MEM_DEVICE, MEM_HOST, RECORD_DTYPE
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,19 +231,20 @@ def main():
             return
         # namespace-sharded: bucket by owner, scatter over NVLink (NCCL all-to-all), decide on the
         # owner, return the verdict bytes (the only collective on the path)
-        counts = eng.bucket_by_owner_ptr(batch, recs[s].data_ptr(), world, send_buf.data_ptr(), src_idx.data_ptr())
-        send_counts = torch.from_numpy(counts.astype(np.int64)).to(dev)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts)
-        sc, rc = counts.astype(np.int64).tolist(), recv_counts.cpu().tolist()
-        nrecv = int(sum(rc))
-        if nrecv > max_batch:
-            raise RuntimeError(f"rank {rank}: received {nrecv} > max_batch {max_batch}")
-        dist.all_to_all_single(recv_buf[:nrecv], send_buf, rc, sc)
-        if nrecv:
-            eng.check_and_update_records_ptr(nrecv, recv_buf.data_ptr(), v_recv.data_ptr(), MEM_DEVICE, stride=cells)
-        dist.all_to_all_single(v_back, v_recv[:nrecv], sc, rc)
-        eng.unpermute_u8_ptr(batch, v_back.data_ptr(), src_idx.data_ptr(), out_lim[s].data_ptr())
+        def bucket(t):
+            counts = eng.bucket_by_owner_ptr(batch, t.data_ptr(), world, send_buf.data_ptr(), src_idx.data_ptr())
+            return send_buf, src_idx, counts.astype(np.int64).tolist()
+
+        def decide(buf, m, verdict):
+            if m > max_batch:
+                raise RuntimeError(f"rank {rank}: received {m} > max_batch {max_batch}")
+            eng.check_and_update_records_ptr(m, buf.data_ptr(), verdict.data_ptr(), MEM_DEVICE, stride=cells)
+
+        def unpermute(vb, src, out):
+            eng.unpermute_u8_ptr(batch, vb.data_ptr(), src.data_ptr(), out.data_ptr())
+
+        exchange.sharded_step(recs[s], world, dist, bucket, decide, unpermute, out_lim[s],
+                              recv_buf=recv_buf, verdict_recv=v_recv, verdict_back=v_back)
 
     def barrier():
         if world > 1:

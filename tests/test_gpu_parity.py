@@ -300,3 +300,34 @@ def test_full_size_c2_properties():
     e.is_within_limits_records(recs)
     lid2, lo2, hi2, val2, exp2 = e.dump_arrays()
     assert int(val2.sum()) == int(val.sum()) and len(lid2) == len(lid)
+
+
+def test_bucket_by_owner_is_stable_and_matches_host_function():
+    """Multi-GPU exchange helpers: rl_bucket_by_owner == a stable sort by rl_owner_of(ns_id)."""
+    import torch
+    from limitador_b200 import exchange, owner_of
+    descs = np.array([(0, 0, 1, 1, 10, 60 * S)], dtype=LIMIT_DESC_DTYPE)
+    e = engine_with_limits(descs, 1)
+    rng = np.random.default_rng(7)
+    n = 50000
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    recs["ns_id"] = rng.integers(0, 300, size=n)
+    recs["key_lo"] = np.arange(n)
+    for world in (2, 8):
+        d_in = torch.from_numpy(recs.view(np.int64).reshape(-1, 4).copy()).cuda()
+        d_out = torch.empty_like(d_in)
+        d_src = torch.empty(n, dtype=torch.int32, device="cuda")
+        counts = e.bucket_by_owner_ptr(n, d_in.data_ptr(), world, d_out.data_ptr(), d_src.data_ptr())
+        e.sync()
+        owners = np.array([owner_of(int(ns), world) for ns in recs["ns_id"]])
+        perm, src, want_counts = exchange.stable_bucket_numpy(recs.view(np.int64).reshape(-1, 4), owners, world)
+        assert counts.tolist() == want_counts
+        assert np.array_equal(d_src.cpu().numpy(), src)
+        assert np.array_equal(d_out.cpu().numpy(), perm)
+        v_in = torch.from_numpy((np.arange(n) % 251).astype(np.uint8)).cuda()
+        v_out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        e.unpermute_u8_ptr(n, v_in.data_ptr(), d_src.data_ptr(), v_out.data_ptr())
+        e.sync()
+        want = np.zeros(n, dtype=np.uint8)
+        want[src] = (np.arange(n) % 251).astype(np.uint8)
+        assert np.array_equal(v_out.cpu().numpy(), want)
