@@ -189,6 +189,15 @@ int rl_profile_end(rl_engine *e, double *out_main_ms, uint64_t *out_main_launche
  * to h_counts[world] (host).  All d_* pointers are device memory. */
 int rl_bucket_by_owner(rl_engine *e, uint64_t n, const rl_record *d_recs, uint32_t world,
                        rl_record *d_out_recs, uint32_t *d_out_src, uint64_t *h_counts);
+/* Sync-free variant for fixed-size exchanges: owner o's records go to d_out_recs[o*slot_cap ...]
+ * (stable, at most slot_cap of them; the caller pre-fills d_out_recs[world*slot_cap] with 0xFF
+ * bytes = records of a namespace without limits, which the engine ignores).  d_out_pos[i] = slot
+ * of record i (or ~0 when its block overflowed, in which case *d_overflow |= 1).  Enqueued on
+ * the engine's stream; nothing is copied to the host. */
+int rl_bucket_by_owner_padded(rl_engine *e, uint64_t n, const rl_record *d_recs, uint32_t world, uint32_t slot_cap,
+                              rl_record *d_out_recs, uint32_t *d_out_pos, uint32_t *d_overflow);
+/* out[i] = in[pos[i]] (0 where pos[i] == ~0), device pointers. */
+int rl_gather_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *d_pos, uint8_t *d_out);
 /* out[src[i]] = in[i] for i < n (device pointers): return verdict bytes to request order. */
 int rl_unpermute_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *d_src, uint8_t *d_out);
 uint32_t rl_owner_of(uint32_t ns_id, uint32_t world);

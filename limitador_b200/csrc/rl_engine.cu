@@ -1207,18 +1207,52 @@ int rl_bucket_by_owner(rl_engine* e, uint64_t n, const rl_record* d_recs, uint32
     uint32_t* tile_cnt = e->d_bucket.p;
     uint32_t* owner_base = e->d_bucket.p + (size_t)(kMaxTiles + 1) * 32;
     k_bucket<false><<<num_tiles, RL_PART_THREADS, 0, e->stream>>>(d_recs, (uint32_t)n, world, tile, tile_cnt, owner_base,
-                                                                  d_out_recs, d_out_src);
+                                                                  d_out_recs, d_out_src, 0, nullptr);
     RL_LAUNCH_CHECK(e);
-    k_bucket_scan<<<1, 32, 0, e->stream>>>(num_tiles, world, tile_cnt, owner_base, e->d_bucket_counts.p);
+    k_bucket_scan<<<1, 32, 0, e->stream>>>(num_tiles, world, tile_cnt, owner_base, e->d_bucket_counts.p, 0, nullptr);
     RL_LAUNCH_CHECK(e);
     k_bucket<true><<<num_tiles, RL_PART_THREADS, 0, e->stream>>>(d_recs, (uint32_t)n, world, tile, tile_cnt, owner_base,
-                                                                 d_out_recs, d_out_src);
+                                                                 d_out_recs, d_out_src, 0, nullptr);
     RL_LAUNCH_CHECK(e);
     unsigned long long counts[32];
     RL_CUDA(e, cudaMemcpyAsync(counts, e->d_bucket_counts.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                e->stream));
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     for (uint32_t w = 0; w < world; w++) h_counts[w] = counts[w];
+    return RL_OK;
+}
+
+int rl_bucket_by_owner_padded(rl_engine* e, uint64_t n, const rl_record* d_recs, uint32_t world, uint32_t slot_cap,
+                              rl_record* d_out_recs, uint32_t* d_out_pos, uint32_t* d_overflow) {
+    if (!e) return RL_FATAL;
+    if (world == 0 || world > 32 || slot_cap == 0) return fail(e, RL_FATAL, "world must be 1..32 and slot_cap > 0");
+    RL_CUDA(e, cudaSetDevice(e->device));
+    if (n == 0) return RL_OK;
+    uint32_t tile = ceil_div(n, kMaxTiles);
+    tile = std::max<uint32_t>(512, ((tile + 255) / 256) * 256);
+    const uint32_t num_tiles = ceil_div(n, tile);
+    RL_CUDA(e, e->d_bucket.reserve((size_t)(kMaxTiles + 1) * 32 + 32));
+    RL_CUDA(e, e->d_bucket_counts.reserve(32));
+    uint32_t* tile_cnt = e->d_bucket.p;
+    uint32_t* owner_base = e->d_bucket.p + (size_t)(kMaxTiles + 1) * 32;
+    k_bucket<false><<<num_tiles, RL_PART_THREADS, 0, e->stream>>>(d_recs, (uint32_t)n, world, tile, tile_cnt, owner_base,
+                                                                  d_out_recs, nullptr, slot_cap, d_out_pos);
+    RL_LAUNCH_CHECK(e);
+    k_bucket_scan<<<1, 32, 0, e->stream>>>(num_tiles, world, tile_cnt, owner_base, e->d_bucket_counts.p, slot_cap,
+                                           d_overflow);
+    RL_LAUNCH_CHECK(e);
+    k_bucket<true><<<num_tiles, RL_PART_THREADS, 0, e->stream>>>(d_recs, (uint32_t)n, world, tile, tile_cnt, owner_base,
+                                                                 d_out_recs, nullptr, slot_cap, d_out_pos);
+    RL_LAUNCH_CHECK(e);
+    return RL_OK;
+}
+
+int rl_gather_u8(rl_engine* e, uint64_t n, const uint8_t* d_in, const uint32_t* d_pos, uint8_t* d_out) {
+    if (!e) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    if (n == 0) return RL_OK;
+    k_gather_u8<<<ceil_div(n, 256), 256, 0, e->stream>>>((uint32_t)n, d_in, d_pos, d_out);
+    RL_LAUNCH_CHECK(e);
     return RL_OK;
 }
 

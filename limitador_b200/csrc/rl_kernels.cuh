@@ -1452,11 +1452,15 @@ __device__ __forceinline__ uint32_t rl_owner_dev(uint32_t ns_id, uint32_t world)
     return (uint32_t)(rl_mix64((uint64_t)ns_id + 0x51ed270b0a1fULL) % world);
 }
 
+// slot_cap == 0: compact output (owner o's records at owner_base[o]...), out_src[pos] = a.
+// slot_cap  > 0: fixed-size blocks (owner o's records at o*slot_cap..., at most slot_cap of them;
+//                the caller pre-fills the buffer with no-op records), out_pos[a] = pos or ~0.
 template <bool SCATTER>
 __global__ void __launch_bounds__(RL_PART_THREADS) k_bucket(const rl_record* __restrict__ recs, uint32_t n,
                                                            uint32_t world, uint32_t tile, uint32_t* tile_cnt,
                                                            const uint32_t* __restrict__ owner_base,
-                                                           rl_record* out_recs, uint32_t* out_src) {
+                                                           rl_record* out_recs, uint32_t* out_src, uint32_t slot_cap,
+                                                           uint32_t* out_pos) {
     __shared__ uint32_t wcnt[RL_PART_WARPS][32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t t0 = blockIdx.x * tile, t1 = min(t0 + tile, n);
@@ -1513,8 +1517,15 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_bucket(const rl_record* __r
             }
             basepos = __shfl_sync(m, basepos, leader);
             const uint32_t pos = basepos + __popc(m & ((1u << lane) - 1));
-            out_recs[pos] = rec;
-            out_src[pos] = a;
+            if (slot_cap == 0) {
+                out_recs[pos] = rec;
+                out_src[pos] = a;
+            } else if (pos - o * slot_cap < slot_cap) {
+                out_recs[pos] = rec;
+                out_pos[a] = pos;
+            } else {
+                out_pos[a] = 0xFFFFFFFFu;  // block overflow (flagged by k_bucket_scan)
+            }
         }
         __syncwarp();
     }
@@ -1522,7 +1533,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_bucket(const rl_record* __r
 
 // single CTA: tile_cnt[t][o] -> exclusive prefix over tiles; owner totals -> owner_base
 __global__ void k_bucket_scan(uint32_t num_tiles, uint32_t world, uint32_t* tile_cnt, uint32_t* owner_base,
-                              unsigned long long* counts_out) {
+                              unsigned long long* counts_out, uint32_t slot_cap, uint32_t* overflow) {
     __shared__ uint32_t tot[32];
     const uint32_t o = threadIdx.x;
     if (o < 32) {
@@ -1539,11 +1550,18 @@ __global__ void k_bucket_scan(uint32_t num_tiles, uint32_t world, uint32_t* tile
     if (o == 0) {
         uint32_t run = 0;
         for (uint32_t w = 0; w < world; w++) {
-            owner_base[w] = run;
+            owner_base[w] = slot_cap ? w * slot_cap : run;
             counts_out[w] = tot[w];
             run += tot[w];
+            if (slot_cap && tot[w] > slot_cap && overflow) atomicOr(overflow, 1u);
         }
     }
+}
+
+__global__ void k_gather_u8(uint32_t n, const uint8_t* __restrict__ in, const uint32_t* __restrict__ pos,
+                            uint8_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (pos[i] != 0xFFFFFFFFu) ? in[pos[i]] : 0;
 }
 
 __global__ void k_unpermute_u8(uint32_t n, const uint8_t* __restrict__ in, const uint32_t* __restrict__ src,

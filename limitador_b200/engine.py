@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "rl_check_and_update_batch", "rl_is_within_limits_batch", "rl_is_within_limits_records",
     "rl_update_batch", "rl_update_records", "rl_get_counters", "rl_delete_counters", "rl_clear",
     "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
-    "rl_profile_begin", "rl_profile_end",
+    "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8",
 ]
 
 
@@ -102,6 +102,8 @@ def load_library(path: str | None = None):
     L.rl_dump_table.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
     L.rl_bucket_by_owner.argtypes = [vp, u64, vp, u32, vp, vp, vp]
     L.rl_unpermute_u8.argtypes = [vp, u64, vp, vp, vp]
+    L.rl_bucket_by_owner_padded.argtypes = [vp, u64, vp, u32, u32, vp, vp, vp]
+    L.rl_gather_u8.argtypes = [vp, u64, vp, vp, vp]
     L.rl_profile_begin.argtypes = [vp]
     L.rl_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.rl_owner_of.argtypes = [u32, u32]
@@ -266,6 +268,14 @@ class Engine:
         self._check(self._lib.rl_bucket_by_owner(self._h, n, C.c_void_p(recs_ptr), world,
                                                  C.c_void_p(out_recs_ptr), C.c_void_p(out_src_ptr), _p(counts)))
         return counts
+
+    def bucket_by_owner_padded_ptr(self, n, recs_ptr, world, slot_cap, out_recs_ptr, out_pos_ptr, overflow_ptr):
+        self._check(self._lib.rl_bucket_by_owner_padded(self._h, n, C.c_void_p(recs_ptr), world, slot_cap,
+                                                        C.c_void_p(out_recs_ptr), C.c_void_p(out_pos_ptr),
+                                                        C.c_void_p(overflow_ptr)))
+
+    def gather_u8_ptr(self, n, in_ptr, pos_ptr, out_ptr):
+        self._check(self._lib.rl_gather_u8(self._h, n, C.c_void_p(in_ptr), C.c_void_p(pos_ptr), C.c_void_p(out_ptr)))
 
     def unpermute_u8_ptr(self, n, in_ptr, src_ptr, out_ptr):
         self._check(self._lib.rl_unpermute_u8(self._h, n, C.c_void_p(in_ptr), C.c_void_p(src_ptr), C.c_void_p(out_ptr)))

@@ -331,3 +331,35 @@ def test_bucket_by_owner_is_stable_and_matches_host_function():
         want = np.zeros(n, dtype=np.uint8)
         want[src] = (np.arange(n) % 251).astype(np.uint8)
         assert np.array_equal(v_out.cpu().numpy(), want)
+
+
+def test_padded_bucket_exchange_roundtrip_single_process():
+    """The sync-free exchange used by bench.py at N>1, folded onto one GPU: bucket into fixed
+    blocks (no-op padding), run the engine over ALL blocks in (owner, slot) order, gather back —
+    equals running the oracle over the same permuted stream."""
+    import torch
+    descs = single_row_limits(3, n_ns=40, seed=5)
+    e = engine_with_limits(descs, 3, max_batch=1 << 17)
+    o = H.oracle_with_limits(descs)
+    world, n = 4, 20000
+    slot_cap = 8192
+    recs = H.random_records(descs, n, 99, n_keys=50)
+    d_in = torch.from_numpy(recs.view(np.int64).reshape(-1, 4).copy()).cuda()
+    send = torch.full((world * slot_cap, 4), -1, dtype=torch.int64, device="cuda")
+    pos = torch.empty(n, dtype=torch.int32, device="cuda")
+    ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    e.bucket_by_owner_padded_ptr(n, d_in.data_ptr(), world, slot_cap, send.data_ptr(), pos.data_ptr(), ovf.data_ptr())
+    verdict = torch.zeros(world * slot_cap, dtype=torch.uint8, device="cuda")
+    e.check_and_update_records_ptr(world * slot_cap, send.data_ptr(), verdict.data_ptr(), 1, stride=3)
+    out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    e.gather_u8_ptr(n, verdict.data_ptr(), pos.data_ptr(), out.data_ptr())
+    e.sync()
+    assert int(ovf.item()) == 0
+    from limitador_b200 import owner_of
+    owners = np.array([owner_of(int(ns), world) for ns in recs["ns_id"]])
+    order = np.argsort(owners, kind="stable")
+    lim, _, _, _ = o.batch_records(0, recs[order])
+    want = np.zeros(n, dtype=np.uint8)
+    want[order] = lim
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert_tables_equal(e, o, descs)
