@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -113,6 +114,8 @@ struct rl_engine {
     std::string last_error = "";
     // rl_profile_begin/end
     unsigned long long tag_mask = ~0ull;
+    uint32_t chunk = RL_MAIN_THREADS;  // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
+    uint32_t heavy_mult = 4;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
@@ -322,9 +325,9 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.chain_status = e->d_chain_status.p;
     B.chain_wcnt = e->d_chain_wcnt.p;
     B.chain_w = e->d_chain_w.p;
-    B.chunk = RL_MAIN_THREADS;
+    B.chunk = e->chunk;
     // a region is split into chained chunks only when it is far heavier than the average one
-    B.heavy_len = std::max<uint32_t>(2 * RL_MAIN_THREADS, 4 * ceil_div(n_acc, 1u << e->log2P));
+    B.heavy_len = e->heavy_mult ? std::max<uint32_t>(2 * e->chunk, e->heavy_mult * ceil_div(n_acc, 1u << e->log2P)) : 0xFFFFFFFFu;
     B.log_row = nullptr;
     B.log_state = nullptr;
     return B;
@@ -357,19 +360,25 @@ int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& 
     }
 }
 
-template <int GEO, int CELLS, class Src, int MODE, bool LC>
-int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
-    using Smem = RlMainSmem<CELLS, RL_MAIN_THREADS>;
-    auto kern = k_main<GEO, CELLS, Src, MODE, RL_MAIN_THREADS, LC>;
+template <int GEO, int CELLS, class Src, int MODE, bool LC, int CH>
+int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+    using Smem = RlMainSmem<CELLS, CH>;
+    auto kern = k_main<GEO, CELLS, Src, MODE, CH, LC>;
     static bool attr_set = false;  // one per instantiation
     if (!attr_set) {
         RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_set = true;
     }
     // upper bound of the work-item count: one per region + one per chunk of a heavy region
-    const uint32_t grid = (1u << e->log2P) + ceil_div(B.n_acc, RL_MAIN_THREADS);
-    kern<<<grid, RL_MAIN_THREADS, sizeof(Smem), e->stream>>>(D, B, src);
+    const uint32_t grid = (1u << e->log2P) + ceil_div(B.n_acc, CH);
+    kern<<<grid, CH, sizeof(Smem), e->stream>>>(D, B, src);
     return RL_OK;
+}
+
+template <int GEO, int CELLS, class Src, int MODE, bool LC>
+int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+    return e->chunk == 128 ? launch_main_ch<GEO, CELLS, Src, MODE, LC, 128>(e, D, B, src)
+                           : launch_main_ch<GEO, CELLS, Src, MODE, LC, 256>(e, D, B, src);
 }
 
 template <class Src, int MODE>
@@ -537,6 +546,8 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     e->max_counters = cfg->max_counters ? cfg->max_counters : 4 * e->max_batch;
     e->max_counters = std::max(e->max_counters, e->max_batch);
     e->groups.resize(1);
+    if (const char* v = getenv("RL_CHUNK")) e->chunk = (atoi(v) == 128) ? 128 : 256;
+    if (const char* v = getenv("RL_HEAVY_MULT")) e->heavy_mult = (uint32_t)atoi(v);
     if (cfg->flags & 1u) e->tag_mask = 0xFull << 24;  // RL_FLAG_DEBUG_WEAK_TAGS: 8 distinct tags per salt level
 
     const size_t bytes = (size_t)e->capacity * e->row_bytes;
@@ -559,13 +570,13 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_acc.reserve(maxA));
     RL_CUDA(e, e->d_kstats.reserve(16));
     RL_CUDA(e, cudaMemsetAsync(e->d_kstats.p, 0, 16 * sizeof(unsigned long long), e->stream));
-    RL_CUDA(e, e->d_items.reserve((size_t)(1u << e->log2P) + maxA / RL_MAIN_THREADS + 2));
+    RL_CUDA(e, e->d_items.reserve((size_t)(1u << e->log2P) + maxA / 128 + 2));
     RL_CUDA(e, e->d_fallback.reserve(1u << e->log2P));
     {
-        const size_t max_items = (size_t)(1u << e->log2P) + maxA / RL_MAIN_THREADS + 2;
+        const size_t max_items = (size_t)(1u << e->log2P) + maxA / 128 + 2;
         RL_CUDA(e, e->d_chain_status.reserve(max_items));
         RL_CUDA(e, e->d_chain_wcnt.reserve(max_items));
-        RL_CUDA(e, e->d_chain_w.reserve(max_items * RL_MAIN_THREADS));
+        RL_CUDA(e, e->d_chain_w.reserve(max_items * 256));
     }
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));

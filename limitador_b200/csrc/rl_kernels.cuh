@@ -688,7 +688,7 @@ __device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAcc
 // GEO = cells per row of the table layout (row bytes), CELLS = cells any row group actually
 // uses (<= GEO): loops, registers and shared memory are sized by the latter.
 template <int GEO, int CELLS, class Src, int MODE, int CH, bool LC>
-__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2))) k_main(RlDev D, RlBatch B, Src src) {
+__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * (256 / CH)) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
     constexpr int PW = Smem::PW;
