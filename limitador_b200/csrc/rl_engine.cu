@@ -114,7 +114,7 @@ struct rl_engine {
     std::string last_error = "";
     // rl_profile_begin/end
     unsigned long long tag_mask = ~0ull;
-    uint32_t chunk = RL_MAIN_THREADS;  // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
+    uint32_t chunk = 128;              // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
     uint32_t heavy_mult = 4;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
