@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 256)")
     ap.add_argument("--cpu-sample-batches", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="disable the engine's two-stream step pipelining")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not args.batch:
@@ -199,7 +200,9 @@ def main():
     # exchange blocks: each rank sends `slot_cap` record slots to every owner (3x the mean share)
     slot_cap = min(batch, ((3 * batch // world) + 255) // 256 * 256)
     max_batch = batch if world == 1 else world * slot_cap
-    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank)
+    # RL_FLAG_PIPELINE (2): the partition of step s+1 overlaps the replay of step s on the device
+    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank,
+                 flags=(2 if (world == 1 and not args.no_pipeline) else 0))
     eng.limits_set(limits)
     # a dedicated non-default stream: the engine launches on it and the CUDA events that time
     # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")
@@ -257,6 +260,7 @@ def main():
         e0.record(stream)
         for s in range(first, first + n):
             fn(s)
+        eng.fence()  # pipelined calls: order their completion before the closing event
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -377,7 +381,8 @@ def main():
                                 f"load_counters=false, reference fixed-window semantics") if c3 else
                                (f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={batch}/GPU, "
                                 f"delta=1, load_counters=false"),
-                   "parallelism": "single GPU" if world == 1 else
+                   "parallelism": ("single GPU, steps software-pipelined over 2 streams" if not args.no_pipeline else "single GPU")
+                   if world == 1 else
                    f"namespace-sharded x{world}, NCCL all-to-all of fixed {slot_cap}-record blocks per peer",
                    "l2": "a distinct batch every step (inputs 2 MiB/step, never reused); table 256 MiB > L2",
                    "table_rows": cap, "row_bytes": 16 * (1 + cells)},

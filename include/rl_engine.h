@@ -45,6 +45,10 @@ enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1 };
 /* test aid: narrow the in-kernel grouping tag so that distinct keys collide and the
  * collision path (salted re-insertion) is exercised */
 #define RL_FLAG_DEBUG_WEAK_TAGS 1u
+/* RL_MEM_DEVICE record calls are software-pipelined over two internal streams: the partition
+ * (probe / scan / scatter) of call s+1 overlaps the replay of call s.  Results are the same;
+ * outputs of such calls are ordered on the caller's stream only after rl_fence() (or rl_sync). */
+#define RL_FLAG_PIPELINE 2u
 
 typedef struct rl_config {
     uint32_t struct_size;    /* sizeof(rl_config) */
@@ -114,6 +118,9 @@ const char *rl_last_error(rl_engine *e);
  * engine's own stream.  rl_engine_stream returns the stream in use. */
 int rl_engine_set_stream(rl_engine *e, void *cuda_stream);
 void *rl_engine_stream(rl_engine *e);
+/* Make the engine's stream wait for every pipelined call issued so far (RL_FLAG_PIPELINE);
+ * a no-op otherwise.  Does not block the host. */
+int rl_fence(rl_engine *e);
 /* Wait for all enqueued work; returns and clears any deferred device-side error. */
 int rl_sync(rl_engine *e);
 int rl_get_stats(rl_engine *e, rl_stats *out);

@@ -60,6 +60,20 @@ struct DevBuf {
 
 }  // namespace
 
+// A second copy of the per-batch workspace: with RL_FLAG_PIPELINE the partition kernels of
+// batch s+1 run (on their own stream) while k_main of batch s is still replaying.
+struct WorkSet {
+    DevBuf<uint32_t> tile_cnt, region_total, part_base, part_idx, part_row, reg_of, row_of, fallback, chain_status,
+        chain_wcnt, chain_w, small;  // small: [0] scan counter, [1] item count
+    DevBuf<ulonglong2> part_acc;
+    DevBuf<uint4> items;
+    void release() {
+        tile_cnt.release(); region_total.release(); part_base.release(); part_idx.release(); part_row.release();
+        reg_of.release(); row_of.release(); fallback.release(); chain_status.release(); chain_wcnt.release();
+        chain_w.release(); small.release(); part_acc.release(); items.release();
+    }
+};
+
 struct rl_engine {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -113,6 +127,13 @@ struct rl_engine {
     rl_stats stats{};
     std::string last_error = "";
     // rl_profile_begin/end
+    // RL_FLAG_PIPELINE
+    bool pipeline = false;
+    WorkSet ws1;
+    cudaStream_t sp = nullptr, sm = nullptr;  // partition / replay streams
+    cudaEvent_t ev_in = nullptr, ev_part[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr};
+    uint64_t pipe_seq = 0;
+    bool pipe_pending = false;
     unsigned long long tag_mask = ~0ull;
     uint32_t chunk = 128;              // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
     uint32_t heavy_mult = 4;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
@@ -133,6 +154,8 @@ int fail(rl_engine* e, int status, const char* fmt, ...) {
     if (e) e->last_error = buf;
     return status;
 }
+
+int pipe_fence(rl_engine* e);
 
 #define RL_CUDA(e, call)                                                                          \
     do {                                                                                          \
@@ -263,6 +286,10 @@ int upload_tables(rl_engine* e) {
 
 // Translate the sticky device error (if any) into a status; clears it.
 int check_device_error(rl_engine* e) {
+    {
+        int rf = pipe_fence(e);
+        if (rf) return rf;
+    }
     RL_CUDA(e, cudaMemcpyAsync(e->h_misc, e->d_misc.p, MISC_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     const uint32_t code = e->h_misc[MISC_ERR];
@@ -292,7 +319,7 @@ struct Outs {
     uint32_t stride = 0;
 };
 
-RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, int lc) {
+RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, int lc, int set = 0) {
     RlBatch B;
     B.n_acc = n_acc;
     B.n_req = n_req;
@@ -330,11 +357,29 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.heavy_len = e->heavy_mult ? std::max<uint32_t>(2 * e->chunk, e->heavy_mult * ceil_div(n_acc, 1u << e->log2P)) : 0xFFFFFFFFu;
     B.log_row = nullptr;
     B.log_state = nullptr;
+    if (set == 1) {
+        WorkSet& w = e->ws1;
+        B.tile_cnt = w.tile_cnt.p;
+        B.region_total = w.region_total.p;
+        B.part_base = w.part_base.p;
+        B.part_idx = w.part_idx.p;
+        B.reg_of = w.reg_of.p;
+        B.row_of = w.row_of.p;
+        B.part_row = w.part_row.p;
+        B.part_acc = w.part_acc.p;
+        B.scan_ctr = w.small.p + 0;
+        B.items = w.items.p;
+        B.n_items = w.small.p + 1;
+        B.region_fallback = w.fallback.p;
+        B.chain_status = w.chain_status.p;
+        B.chain_wcnt = w.chain_wcnt.p;
+        B.chain_w = w.chain_w.p;
+    }
     return B;
 }
 
 template <int CELLS, class Src>
-int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
     const uint32_t P1 = (1u << e->log2P) + 1;
     const size_t smem = (size_t)RL_PART_WARPS * P1 * sizeof(uint32_t);
     static bool attr_set = false;
@@ -342,26 +387,27 @@ int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const
         RL_CUDA(e, cudaFuncSetAttribute(k_part<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), e->stream>>>(D, B, src);
+    k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), st>>>(D, B, src);
     RL_LAUNCH_CHECK(e);
-    k_colscan<<<ceil_div(P1, 32), 256, 0, e->stream>>>(D, B);
+    k_colscan<<<ceil_div(P1, 32), 256, 0, st>>>(D, B);
     RL_LAUNCH_CHECK(e);
-    k_part<Src><<<B.num_tiles, RL_PART_THREADS, smem, e->stream>>>(D, B, src);
+    k_part<Src><<<B.num_tiles, RL_PART_THREADS, smem, st>>>(D, B, src);
     RL_LAUNCH_CHECK(e);
     return RL_OK;
 }
 
 template <class Src>
-int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st = nullptr) {
+    if (!st) st = e->stream;
     switch (e->cells) {
-        case 1: return launch_partition_cells<1, Src>(e, D, B, src);
-        case 3: return launch_partition_cells<3, Src>(e, D, B, src);
-        default: return launch_partition_cells<7, Src>(e, D, B, src);
+        case 1: return launch_partition_cells<1, Src>(e, D, B, src, st);
+        case 3: return launch_partition_cells<3, Src>(e, D, B, src, st);
+        default: return launch_partition_cells<7, Src>(e, D, B, src, st);
     }
 }
 
 template <int GEO, int CELLS, class Src, int MODE, bool LC, int CH>
-int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
     using Smem = RlMainSmem<CELLS, CH>;
     auto kern = k_main<GEO, CELLS, Src, MODE, CH, LC>;
     static bool attr_set = false;  // one per instantiation
@@ -371,28 +417,29 @@ int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& sr
     }
     // upper bound of the work-item count: one per region + one per chunk of a heavy region
     const uint32_t grid = (1u << e->log2P) + ceil_div(B.n_acc, CH);
-    kern<<<grid, CH, sizeof(Smem), e->stream>>>(D, B, src);
+    kern<<<grid, CH, sizeof(Smem), st>>>(D, B, src);
     return RL_OK;
 }
 
 template <int GEO, int CELLS, class Src, int MODE, bool LC>
-int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
-    return e->chunk == 128 ? launch_main_ch<GEO, CELLS, Src, MODE, LC, 128>(e, D, B, src)
-                           : launch_main_ch<GEO, CELLS, Src, MODE, LC, 256>(e, D, B, src);
+int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
+    return e->chunk == 128 ? launch_main_ch<GEO, CELLS, Src, MODE, LC, 128>(e, D, B, src, st)
+                           : launch_main_ch<GEO, CELLS, Src, MODE, LC, 256>(e, D, B, src, st);
 }
 
 template <class Src, int MODE>
-int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) {
+int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st = nullptr) {
+    if (!st) st = e->stream;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->profiling) {
         RL_CUDA(e, cudaEventCreate(&ev0));
         RL_CUDA(e, cudaEventCreate(&ev1));
-        RL_CUDA(e, cudaEventRecord(ev0, e->stream));
+        RL_CUDA(e, cudaEventRecord(ev0, st));
     }
     int r;
     const bool lc = (MODE == 0) && B.load_counters;
 #define RL_MAIN_CASE(G, A) \
-    r = lc ? launch_main_cells<G, A, Src, MODE, MODE == 0>(e, D, B, src) : launch_main_cells<G, A, Src, MODE, false>(e, D, B, src)
+    r = lc ? launch_main_cells<G, A, Src, MODE, MODE == 0>(e, D, B, src, st) : launch_main_cells<G, A, Src, MODE, false>(e, D, B, src, st)
     if (e->cells == 1) RL_MAIN_CASE(1, 1);
     else if (e->cells == 3) RL_MAIN_CASE(3, 3);
     else if (e->max_cells_used <= 4) RL_MAIN_CASE(7, 4);  // 128-B rows of which at most 4 cells are in use
@@ -401,9 +448,18 @@ int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src) 
     if (r) return r;
     RL_LAUNCH_CHECK(e);
     if (e->profiling) {
-        RL_CUDA(e, cudaEventRecord(ev1, e->stream));
+        RL_CUDA(e, cudaEventRecord(ev1, st));
         e->prof_events.emplace_back(ev0, ev1);
     }
+    return RL_OK;
+}
+
+// Make the caller's stream wait for everything the pipeline still has in flight.
+int pipe_fence(rl_engine* e) {
+    if (!e->pipe_pending) return RL_OK;
+    const int last = (int)((e->pipe_seq - 1) & 1);
+    RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_main[last], 0));
+    e->pipe_pending = false;
     return RL_OK;
 }
 
@@ -467,8 +523,35 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
     return launch_main<AccSrc, 0>(e, D, B, src);
 }
 
-int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int mode, int lc, const Outs& o) {
+int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int mode, int lc, const Outs& o,
+                        bool may_pipeline = false) {
     RlDev D = make_dev(e);
+    if (may_pipeline && e->pipeline && !e->any_multi_ns) {
+        // Two-stage software pipeline over successive calls: partition (probe, scan, scatter) of this
+        // batch on `sp` overlaps the replay of the previous batch on `sm`.  The probe only reads row
+        // headers and claims empty rows; the replay only touches the cells of rows found by ITS
+        // probe, and replays stay in call order on `sm`, so the table sees the batches in order.
+        const int k = (int)(e->pipe_seq & 1);
+        RlBatch B = make_batch(e, n, n, o, lc, k);
+        RecordSrc src{d_recs};
+        RL_CUDA(e, cudaEventRecord(e->ev_in, e->stream));  // inputs: whatever the caller enqueued so far
+        RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_in, 0));
+        if (e->pipe_seq >= 2) RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_main[k], 0));  // workspace set k is free
+        int r = launch_partition(e, D, B, src, e->sp);
+        if (r) return r;
+        RL_CUDA(e, cudaEventRecord(e->ev_part[k], e->sp));
+        RL_CUDA(e, cudaStreamWaitEvent(e->sm, e->ev_part[k], 0));
+        r = mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src, e->sm) : launch_main<RecordSrc, 0>(e, D, B, src, e->sm);
+        if (r) return r;
+        RL_CUDA(e, cudaEventRecord(e->ev_main[k], e->sm));
+        e->pipe_seq++;
+        e->pipe_pending = true;
+        return RL_OK;
+    }
+    {
+        int r = pipe_fence(e);
+        if (r) return r;
+    }
     if (!e->any_multi_ns) {
         RlBatch B = make_batch(e, n, n, o, lc);
         RecordSrc src{d_recs};
@@ -489,10 +572,20 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
     return run_acc_pipeline(e, (uint32_t)n_acc, n, e->d_delta.p, e->d_now.p, mode, lc, o);
 }
 
-int ensure_ready(rl_engine* e, uint64_t n) {
+int ensure_ready(rl_engine* e, uint64_t n, bool fence = true) {
     if (!e) return RL_FATAL;
+    if (fence) {
+        int rf = pipe_fence(e);
+        if (rf) return rf;
+    }
     if (n > e->max_batch) return fail(e, RL_FATAL, "batch of %llu exceeds max_batch=%u", (unsigned long long)n, e->max_batch);
     RL_CUDA(e, cudaSetDevice(e->device));
+    if (e->tables_dirty && e->pipeline) {
+        int r = pipe_fence(e);
+        if (r) return r;
+        RL_CUDA(e, cudaStreamSynchronize(e->sp));
+        RL_CUDA(e, cudaStreamSynchronize(e->sm));
+    }
     return upload_tables(e);
 }
 
@@ -580,6 +673,33 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     }
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
+    if (cfg->flags & 2u) {  // RL_FLAG_PIPELINE
+        e->pipeline = true;
+        RL_CUDA(e, cudaStreamCreateWithFlags(&e->sp, cudaStreamNonBlocking));
+        RL_CUDA(e, cudaStreamCreateWithFlags(&e->sm, cudaStreamNonBlocking));
+        RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) {
+            RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_part[k], cudaEventDisableTiming));
+            RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_main[k], cudaEventDisableTiming));
+        }
+        WorkSet& w = e->ws1;
+        const size_t max_items = (size_t)(1u << e->log2P) + maxA / 128 + 2;
+        RL_CUDA(e, w.tile_cnt.reserve((size_t)(kMaxTiles + 1) * P1));
+        RL_CUDA(e, w.region_total.reserve(P1 + 1));
+        RL_CUDA(e, w.part_base.reserve(P1 + 2));
+        RL_CUDA(e, w.part_idx.reserve(maxA));
+        RL_CUDA(e, w.part_row.reserve(maxA));
+        RL_CUDA(e, w.reg_of.reserve(maxA));
+        RL_CUDA(e, w.row_of.reserve(maxA));
+        RL_CUDA(e, w.part_acc.reserve(maxA * 3));
+        RL_CUDA(e, w.items.reserve(max_items));
+        RL_CUDA(e, w.fallback.reserve(1u << e->log2P));
+        RL_CUDA(e, w.chain_status.reserve(max_items));
+        RL_CUDA(e, w.chain_wcnt.reserve(max_items));
+        RL_CUDA(e, w.chain_w.reserve(max_items * 256));
+        RL_CUDA(e, w.small.reserve(8));
+        RL_CUDA(e, cudaMemsetAsync(w.small.p, 0, 8 * sizeof(uint32_t), e->stream));
+    }
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->stats.capacity_rows = e->capacity;
     e->stats.regions = 1u << e->log2P;
@@ -590,7 +710,17 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
 void rl_engine_destroy(rl_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->sp) cudaStreamSynchronize(e->sp);
+    if (e->sm) cudaStreamSynchronize(e->sm);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    e->ws1.release();
+    if (e->ev_in) cudaEventDestroy(e->ev_in);
+    for (int k = 0; k < 2; k++) {
+        if (e->ev_part[k]) cudaEventDestroy(e->ev_part[k]);
+        if (e->ev_main[k]) cudaEventDestroy(e->ev_main[k]);
+    }
+    if (e->sp) cudaStreamDestroy(e->sp);
+    if (e->sm) cudaStreamDestroy(e->sm);
     if (e->d_rows) cudaFree(e->d_rows);
     e->d_desc.release();
     e->d_limits.release();
@@ -638,6 +768,10 @@ void rl_engine_destroy(rl_engine* e) {
 int rl_engine_set_stream(rl_engine* e, void* cuda_stream) {
     if (!e) return RL_FATAL;
     RL_CUDA(e, cudaSetDevice(e->device));
+    {
+        int rf = pipe_fence(e);
+        if (rf) return rf;
+    }
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return RL_OK;
@@ -651,6 +785,12 @@ int rl_sync(rl_engine* e) {
     return check_device_error(e);
 }
 
+int rl_fence(rl_engine* e) {
+    if (!e) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    return pipe_fence(e);
+}
+
 int rl_profile_begin(rl_engine* e) {
     if (!e) return RL_FATAL;
     e->profiling = true;
@@ -661,6 +801,10 @@ int rl_profile_end(rl_engine* e, double* out_main_ms, uint64_t* out_main_launche
     if (!e) return RL_FATAL;
     RL_CUDA(e, cudaSetDevice(e->device));
     e->profiling = false;
+    {
+        int rf = pipe_fence(e);
+        if (rf) return rf;
+    }
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     double ms = 0;
     for (auto& pr : e->prof_events) {
@@ -679,6 +823,10 @@ int rl_profile_end(rl_engine* e, double* out_main_ms, uint64_t* out_main_launche
 int rl_get_stats(rl_engine* e, rl_stats* out) {
     if (!e || !out) return RL_FATAL;
     RL_CUDA(e, cudaSetDevice(e->device));
+    {
+        int rf = pipe_fence(e);
+        if (rf) return rf;
+    }
     unsigned long long ks[16];
     RL_CUDA(e, cudaMemcpyAsync(ks, e->d_kstats.p, sizeof ks, cudaMemcpyDeviceToHost, e->stream));
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -754,7 +902,9 @@ int rl_limits_set(rl_engine* e, const rl_limit_desc* limits, uint32_t n) {
 }
 
 static int reset_selected(rl_engine* e, const std::vector<uint8_t>& sel) {
-    int r = upload_tables(e);
+    int r = pipe_fence(e);
+    if (r) return r;
+    r = upload_tables(e);
     if (r) return r;
     DevBuf<uint8_t> d_sel;
     RL_CUDA(e, d_sel.reserve(std::max<size_t>(sel.size(), 1)));
@@ -822,7 +972,9 @@ int rl_clear(rl_engine* e) {
 int rl_sweep(rl_engine* e, uint64_t now_us, uint64_t* out_invalidated) {
     if (!e) return RL_FATAL;
     RL_CUDA(e, cudaSetDevice(e->device));
-    int r = upload_tables(e);
+    int r = pipe_fence(e);
+    if (r) return r;
+    r = upload_tables(e);
     if (r) return r;
     DevBuf<unsigned long long> d_cnt;
     RL_CUDA(e, d_cnt.reserve(1));
@@ -847,7 +999,9 @@ int rl_sweep(rl_engine* e, uint64_t now_us, uint64_t* out_invalidated) {
 static int scan_table(rl_engine* e, int mode, uint64_t now_us, const std::vector<uint8_t>& ns_sel, uint64_t cap,
                       uint32_t* out_limit_id, uint64_t* out_key_lo, uint64_t* out_key_hi, uint64_t* out_a,
                       uint64_t* out_b, uint64_t* out_count) {
-    int r = upload_tables(e);
+    int r = pipe_fence(e);
+    if (r) return r;
+    r = upload_tables(e);
     if (r) return r;
     // device capacity: every live cell could match; bound by cap + unqualified fix-ups
     const uint64_t dcap = std::max<uint64_t>(cap, 1);
@@ -971,7 +1125,7 @@ static int stage_outs(rl_engine* e, uint64_t n, uint64_t n_ctr_out, bool want_fi
 int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs, int load_counters, int mem,
                                 uint8_t* out_limited, uint32_t* out_first_limited, uint64_t* out_remaining,
                                 uint64_t* out_ttl_us, uint32_t out_stride) {
-    int r = ensure_ready(e, n);
+    int r = ensure_ready(e, n, mem != RL_MEM_DEVICE);
     if (r) return r;
     if (n == 0) return RL_OK;
     if (!recs || !out_limited) return fail(e, RL_FATAL, "null recs/out_limited");
@@ -987,7 +1141,7 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
         o.rem = lc ? out_remaining : nullptr;
         o.ttl = lc ? out_ttl_us : nullptr;
         o.stride = out_stride;
-        return run_record_pipeline(e, (uint32_t)n, recs, 0, load_counters ? 1 : 0, o);
+        return run_record_pipeline(e, (uint32_t)n, recs, 0, load_counters ? 1 : 0, o, true);
     }
     RL_CUDA(e, e->d_in_recs.reserve(e->max_batch));
     RL_CUDA(e, cudaMemcpyAsync(e->d_in_recs.p, recs, n * sizeof(rl_record), cudaMemcpyHostToDevice, e->stream));
@@ -1117,7 +1271,7 @@ int rl_update_batch(rl_engine* e, uint64_t n, const uint32_t* ctr_off, const rl_
 }
 
 int rl_update_records(rl_engine* e, uint64_t n, const rl_record* recs, int mem) {
-    int r = ensure_ready(e, n);
+    int r = ensure_ready(e, n, mem != RL_MEM_DEVICE);
     if (r) return r;
     if (n == 0) return RL_OK;
     if (!recs) return fail(e, RL_FATAL, "null recs");
@@ -1130,7 +1284,7 @@ int rl_update_records(rl_engine* e, uint64_t n, const rl_record* recs, int mem) 
         d_recs = e->d_in_recs.p;
     }
     Outs o;
-    if ((r = run_record_pipeline(e, (uint32_t)n, d_recs, 2, 0, o))) return r;
+    if ((r = run_record_pipeline(e, (uint32_t)n, d_recs, 2, 0, o, mem == RL_MEM_DEVICE))) return r;
     if (mem == RL_MEM_HOST) return check_device_error(e);
     return RL_OK;
 }

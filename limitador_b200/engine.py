@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "rl_check_and_update_batch", "rl_is_within_limits_batch", "rl_is_within_limits_records",
     "rl_update_batch", "rl_update_records", "rl_get_counters", "rl_delete_counters", "rl_clear",
     "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
-    "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8",
+    "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8", "rl_fence",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library(path: str | None = None):
     L.rl_engine_stream.argtypes = [vp]
     L.rl_engine_stream.restype = vp
     L.rl_sync.argtypes = [vp]
+    L.rl_fence.argtypes = [vp]
     L.rl_get_stats.argtypes = [vp, C.POINTER(RlStats)]
     L.rl_limits_set.argtypes = [vp, vp, u32]
     L.rl_limits_delete.argtypes = [vp, vp, u32]
@@ -160,6 +161,10 @@ class Engine:
 
     def sync(self):
         self._check(self._lib.rl_sync(self._h))
+
+    def fence(self):
+        """Order every pipelined call issued so far before later work on the engine's stream."""
+        self._check(self._lib.rl_fence(self._h))
 
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._lib.rl_engine_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))

@@ -363,3 +363,35 @@ def test_padded_bucket_exchange_roundtrip_single_process():
     want[order] = lim
     assert np.array_equal(out.cpu().numpy(), want)
     assert_tables_equal(e, o, descs)
+
+
+def test_pipelined_device_calls_match_oracle():
+    """RL_FLAG_PIPELINE: back-to-back device-memory calls overlap (partition of call s+1 with the
+    replay of call s); after rl_fence/rl_sync the verdicts and the table equal the sequential ones."""
+    import torch
+    w = streams.WORKLOADS["C2"](batch=16384, n_rows=20000, n_ns=32)
+    e = Engine(capacity_rows=w.capacity_rows, cells_per_row=w.cells_per_row, max_batch=w.batch, flags=2)
+    e.limits_set(w.limits)
+    o = H.oracle_with_limits(w.limits, 1 << 16)
+    nb = 12
+    recs = [w.batch_records(b) for b in range(nb)]
+    d_recs = [torch.from_numpy(r.view(np.int64).reshape(-1, 4).copy()).cuda() for r in recs]
+    d_lim = [torch.zeros(w.batch, dtype=torch.uint8, device="cuda") for _ in range(nb)]
+    d_first = [torch.zeros(w.batch, dtype=torch.int32, device="cuda") for _ in range(nb)]
+    torch.cuda.synchronize()
+    for b in range(nb):
+        e.check_and_update_records_ptr(w.batch, d_recs[b].data_ptr(), d_lim[b].data_ptr(), 1,
+                                       out_first_ptr=d_first[b].data_ptr(), stride=w.cells_per_row)
+    e.fence()
+    e.sync()
+    for b in range(nb):
+        want = o.batch_records(0, recs[b])
+        assert np.array_equal(d_lim[b].cpu().numpy(), want[0]), f"batch {b}"
+        assert np.array_equal(d_first[b].cpu().numpy().astype(np.uint32), want[1])
+    assert_tables_equal(e, o, w.limits)
+    # a host-memory call after pipelined ones is ordered behind them
+    r = w.batch_records(nb)
+    got = e.check_and_update_records(r, False, stride=w.cells_per_row)
+    want = o.batch_records(0, r)
+    assert np.array_equal(got[0], want[0])
+    assert_tables_equal(e, o, w.limits)
