@@ -171,7 +171,7 @@ def main():
     import torch
     import torch.distributed as dist
     from limitador_b200 import Engine, exchange, streams
-    from limitador_b200.engine import MEM_DEVICE, MEM_HOST, RECORD_DTYPE
+    from limitador_b200.engine import MEM_DEVICE, MEM_HOST, MEM_HOST_ASYNC, RECORD_DTYPE
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -301,7 +301,10 @@ def main():
 
     def step_host(j: int):
         if world == 1:
-            eng.check_and_update_records_ptr(batch, h_recs[j].data_ptr(), h_lim[j].data_ptr(), MEM_HOST, stride=cells)
+            # pinned host buffers; with the pipelined engine the call only enqueues (H2D, kernels, D2H)
+            # and the copies of step j overlap the kernels of its neighbours; timed() fences at the end
+            eng.check_and_update_records_ptr(batch, h_recs[j].data_ptr(), h_lim[j].data_ptr(),
+                                             MEM_HOST if args.no_pipeline else MEM_HOST_ASYNC, stride=cells)
         else:
             s = W + 2 * K + j
             recs[s].copy_(h_recs[j], non_blocking=True)

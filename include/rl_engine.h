@@ -40,7 +40,11 @@ extern "C" {
 typedef struct rl_engine rl_engine;
 
 enum { RL_OK = 0, RL_TRANSIENT = 1, RL_FATAL = 2 };
-enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1 };
+enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1,
+       /* pinned host buffers that stay valid until rl_sync(): rl_check_and_update_records returns after
+        * ENQUEUEING the H2D copy, the kernels and the D2H copy of the verdicts (needs RL_FLAG_PIPELINE;
+        * otherwise, or with load_counters outputs, it behaves like RL_MEM_HOST) */
+       RL_MEM_HOST_ASYNC = 2 };
 #define RL_NONE 0xFFFFFFFFu
 /* test aid: narrow the in-kernel grouping tag so that distinct keys collide and the
  * collision path (salted re-insertion) is exercised */

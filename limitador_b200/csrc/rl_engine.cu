@@ -134,6 +134,16 @@ struct rl_engine {
     cudaEvent_t ev_in = nullptr, ev_part[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr};
     uint64_t pipe_seq = 0;
     bool pipe_pending = false;
+    // RL_MEM_HOST_ASYNC: ring of device staging slots; copies overlap the kernels of other calls
+    static constexpr int kRing = 4;
+    DevBuf<rl_record> ring_recs[kRing];
+    DevBuf<uint8_t> ring_lim[kRing];
+    DevBuf<uint32_t> ring_first[kRing];
+    cudaEvent_t ev_slot[kRing] = {nullptr, nullptr, nullptr, nullptr};  // slot's D2H done
+    cudaStream_t sd = nullptr;                                          // D2H stream
+    uint64_t ring_seq = 0;
+    bool d2h_pending = false;
+    int d2h_last = 0;
     unsigned long long tag_mask = ~0ull;
     uint32_t chunk = 128;              // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
     uint32_t heavy_mult = 4;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
@@ -459,6 +469,8 @@ int pipe_fence(rl_engine* e) {
     if (!e->pipe_pending) return RL_OK;
     const int last = (int)((e->pipe_seq - 1) & 1);
     RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_main[last], 0));
+    if (e->d2h_pending) RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_slot[e->d2h_last], 0));
+    e->d2h_pending = false;
     e->pipe_pending = false;
     return RL_OK;
 }
@@ -585,6 +597,7 @@ int ensure_ready(rl_engine* e, uint64_t n, bool fence = true) {
         if (r) return r;
         RL_CUDA(e, cudaStreamSynchronize(e->sp));
         RL_CUDA(e, cudaStreamSynchronize(e->sm));
+        RL_CUDA(e, cudaStreamSynchronize(e->sd));
     }
     return upload_tables(e);
 }
@@ -677,6 +690,8 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
         e->pipeline = true;
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sp, cudaStreamNonBlocking));
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sm, cudaStreamNonBlocking));
+        RL_CUDA(e, cudaStreamCreateWithFlags(&e->sd, cudaStreamNonBlocking));
+        for (int k = 0; k < rl_engine::kRing; k++) RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_slot[k], cudaEventDisableTiming));
         RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
         for (int k = 0; k < 2; k++) {
             RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_part[k], cudaEventDisableTiming));
@@ -712,6 +727,14 @@ void rl_engine_destroy(rl_engine* e) {
     cudaSetDevice(e->device);
     if (e->sp) cudaStreamSynchronize(e->sp);
     if (e->sm) cudaStreamSynchronize(e->sm);
+    if (e->sd) cudaStreamSynchronize(e->sd);
+    for (int k = 0; k < rl_engine::kRing; k++) {
+        e->ring_recs[k].release();
+        e->ring_lim[k].release();
+        e->ring_first[k].release();
+        if (e->ev_slot[k]) cudaEventDestroy(e->ev_slot[k]);
+    }
+    if (e->sd) cudaStreamDestroy(e->sd);
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->ws1.release();
     if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -1125,7 +1148,10 @@ static int stage_outs(rl_engine* e, uint64_t n, uint64_t n_ctr_out, bool want_fi
 int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs, int load_counters, int mem,
                                 uint8_t* out_limited, uint32_t* out_first_limited, uint64_t* out_remaining,
                                 uint64_t* out_ttl_us, uint32_t out_stride) {
-    int r = ensure_ready(e, n, mem != RL_MEM_DEVICE);
+    const bool host_async = (mem == RL_MEM_HOST_ASYNC) && e && e->pipeline && !e->any_multi_ns &&
+                            !(load_counters && (out_remaining || out_ttl_us));
+    if (mem == RL_MEM_HOST_ASYNC && !host_async) mem = RL_MEM_HOST;  // not available: plain synchronous call
+    int r = ensure_ready(e, n, mem == RL_MEM_HOST);
     if (r) return r;
     if (n == 0) return RL_OK;
     if (!recs || !out_limited) return fail(e, RL_FATAL, "null recs/out_limited");
@@ -1142,6 +1168,32 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
         o.ttl = lc ? out_ttl_us : nullptr;
         o.stride = out_stride;
         return run_record_pipeline(e, (uint32_t)n, recs, 0, load_counters ? 1 : 0, o, true);
+    }
+    if (host_async) {
+        // H2D on the caller's stream (which carries nothing else of ours), kernels on the pipeline
+        // streams, D2H on `sd`: the copies of one call overlap the kernels of its neighbours.
+        const int slot = (int)(e->ring_seq % rl_engine::kRing);
+        RL_CUDA(e, e->ring_recs[slot].reserve(e->max_batch));
+        RL_CUDA(e, e->ring_lim[slot].reserve(e->max_batch));
+        if (out_first_limited) RL_CUDA(e, e->ring_first[slot].reserve(e->max_batch));
+        if (e->ring_seq >= (uint64_t)rl_engine::kRing)
+            RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_slot[slot], 0));  // slot drained (its D2H done)
+        RL_CUDA(e, cudaMemcpyAsync(e->ring_recs[slot].p, recs, n * sizeof(rl_record), cudaMemcpyHostToDevice, e->stream));
+        Outs o;
+        o.limited = e->ring_lim[slot].p;
+        o.first = out_first_limited ? e->ring_first[slot].p : nullptr;
+        o.stride = out_stride;
+        if ((r = run_record_pipeline(e, (uint32_t)n, e->ring_recs[slot].p, 0, load_counters ? 1 : 0, o, true))) return r;
+        const int k = (int)((e->pipe_seq - 1) & 1);
+        RL_CUDA(e, cudaStreamWaitEvent(e->sd, e->ev_main[k], 0));
+        RL_CUDA(e, cudaMemcpyAsync(out_limited, o.limited, n, cudaMemcpyDeviceToHost, e->sd));
+        if (out_first_limited)
+            RL_CUDA(e, cudaMemcpyAsync(out_first_limited, o.first, n * 4, cudaMemcpyDeviceToHost, e->sd));
+        RL_CUDA(e, cudaEventRecord(e->ev_slot[slot], e->sd));
+        e->d2h_pending = true;
+        e->d2h_last = slot;
+        e->ring_seq++;
+        return RL_OK;
     }
     RL_CUDA(e, e->d_in_recs.reserve(e->max_batch));
     RL_CUDA(e, cudaMemcpyAsync(e->d_in_recs.p, recs, n * sizeof(rl_record), cudaMemcpyHostToDevice, e->stream));

@@ -14,7 +14,7 @@ import numpy as np
 from . import build as _build
 
 RL_OK, RL_TRANSIENT, RL_FATAL = 0, 1, 2
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
 NONE = 0xFFFFFFFF
 
 RECORD_DTYPE = np.dtype(

@@ -395,3 +395,27 @@ def test_pipelined_device_calls_match_oracle():
     want = o.batch_records(0, r)
     assert np.array_equal(got[0], want[0])
     assert_tables_equal(e, o, w.limits)
+
+
+def test_async_host_calls_match_oracle():
+    """RL_MEM_HOST_ASYNC: pinned host buffers, calls only enqueue H2D + kernels + D2H; after
+    rl_sync the verdicts in host memory equal the sequential ones (more calls than ring slots)."""
+    import torch
+    w = streams.WORKLOADS["C2"](batch=8192, n_rows=20000, n_ns=32)
+    e = Engine(capacity_rows=w.capacity_rows, cells_per_row=w.cells_per_row, max_batch=w.batch, flags=2)
+    e.limits_set(w.limits)
+    o = H.oracle_with_limits(w.limits, 1 << 16)
+    nb = 11
+    recs = [w.batch_records(b) for b in range(nb)]
+    h_recs = torch.stack([torch.from_numpy(r.view(np.int64).reshape(-1, 4).copy()) for r in recs]).pin_memory()
+    h_lim = torch.zeros((nb, w.batch), dtype=torch.uint8).pin_memory()
+    h_first = torch.zeros((nb, w.batch), dtype=torch.int32).pin_memory()
+    for b in range(nb):
+        e.check_and_update_records_ptr(w.batch, h_recs[b].data_ptr(), h_lim[b].data_ptr(), 2,
+                                       out_first_ptr=h_first[b].data_ptr(), stride=w.cells_per_row)
+    e.sync()
+    for b in range(nb):
+        want = o.batch_records(0, recs[b])
+        assert np.array_equal(h_lim[b].numpy(), want[0]), f"batch {b}"
+        assert np.array_equal(h_first[b].numpy().astype(np.uint32), want[1])
+    assert_tables_equal(e, o, w.limits)
