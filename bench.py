@@ -202,7 +202,7 @@ def main():
     max_batch = batch if world == 1 else world * slot_cap
     # RL_FLAG_PIPELINE (2): the partition of step s+1 overlaps the replay of step s on the device
     eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank,
-                 flags=(2 if (world == 1 and not args.no_pipeline) else 0))
+                 flags=(0 if args.no_pipeline else 2))
     eng.limits_set(limits)
     # a dedicated non-default stream: the engine launches on it and the CUDA events that time
     # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")
@@ -224,12 +224,12 @@ def main():
     print(f"[bench] generated {total} batches of {batch} in {time.perf_counter() - t_gen:.1f}s", file=sys.stderr)
 
     if world > 1:
-        send_buf = torch.empty((world * slot_cap, 4), dtype=torch.int64, device=dev)
-        pos_idx = torch.empty(batch, dtype=torch.int32, device=dev)
+        send_buf = [torch.empty((world * slot_cap, 4), dtype=torch.int64, device=dev) for _ in range(2)]
+        pos_idx = [torch.empty(batch, dtype=torch.int32, device=dev) for _ in range(2)]
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        recv_buf = torch.empty((world * slot_cap, 4), dtype=torch.int64, device=dev)
-        v_recv = torch.zeros(world * slot_cap, dtype=torch.uint8, device=dev)
-        v_back = torch.empty(world * slot_cap, dtype=torch.uint8, device=dev)
+        recv_buf = [torch.empty((world * slot_cap, 4), dtype=torch.int64, device=dev) for _ in range(2)]
+        v_recv = [torch.zeros(world * slot_cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+        v_back = [torch.empty(world * slot_cap, dtype=torch.uint8, device=dev) for _ in range(2)]
 
     def step_device(s: int):
         """One step with the batch resident in HBM."""
@@ -241,13 +241,30 @@ def main():
         # all-to-all of the 32-B records over NVLink, decide on the owner, one all-to-all of the
         # verdict bytes back, gather into request order.  No host round trip inside a step: unused
         # slots carry no-op records (a namespace without limits) that the engine ignores.
-        send_buf.fill_(-1)
-        eng.bucket_by_owner_padded_ptr(batch, recs[s].data_ptr(), world, slot_cap, send_buf.data_ptr(),
-                                       pos_idx.data_ptr(), overflow.data_ptr())
-        dist.all_to_all_single(recv_buf, send_buf)
-        eng.check_and_update_records_ptr(world * slot_cap, recv_buf.data_ptr(), v_recv.data_ptr(), MEM_DEVICE, stride=cells)
-        dist.all_to_all_single(v_back, v_recv)
-        eng.gather_u8_ptr(batch, v_back.data_ptr(), pos_idx.data_ptr(), out_lim[s].data_ptr())
+        # Steps are software-pipelined: the verdicts of step s travel back while step s+1 is
+        # already being exchanged and decided (double-buffered exchange buffers).
+        b = s & 1
+        send_buf[b].fill_(-1)
+        eng.bucket_by_owner_padded_ptr(batch, recs[s].data_ptr(), world, slot_cap, send_buf[b].data_ptr(),
+                                       pos_idx[b].data_ptr(), overflow.data_ptr())
+        dist.all_to_all_single(recv_buf[b], send_buf[b])
+        eng.check_and_update_records_ptr(world * slot_cap, recv_buf[b].data_ptr(), v_recv[b].data_ptr(), MEM_DEVICE,
+                                         stride=cells)
+        pending.append(s)
+        if len(pending) > 1:
+            finish_step(pending.pop(0), 1)
+
+    pending = []
+
+    def finish_step(s: int, age: int):
+        b = s & 1
+        eng.fence_call(age)  # the decisions of step s are done (step s+1 may still be running)
+        dist.all_to_all_single(v_back[b], v_recv[b])
+        eng.gather_u8_ptr(batch, v_back[b].data_ptr(), pos_idx[b].data_ptr(), out_lim[s].data_ptr())
+
+    def drain():
+        while pending:
+            finish_step(pending.pop(0), 0)
 
     def barrier():
         if world > 1:
@@ -260,6 +277,8 @@ def main():
         e0.record(stream)
         for s in range(first, first + n):
             fn(s)
+        if world > 1:
+            drain()  # the last step's verdicts are still on their way back
         eng.fence()  # pipelined calls: order their completion before the closing event
         e1.record(stream)
         barrier()
@@ -274,6 +293,8 @@ def main():
     t_w = time.perf_counter()
     for s in range(W):
         step_device(s)
+    if world > 1:
+        drain()
     eng.sync()
     print(f"[bench] warm-up {time.perf_counter() - t_w:.2f}s", file=sys.stderr)
 
@@ -309,11 +330,11 @@ def main():
             s = W + 2 * K + j
             recs[s].copy_(h_recs[j], non_blocking=True)
             step_device(s)
+            drain()
+            eng.fence()
             h_lim[j].copy_(out_lim[s], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
-    for j in range(min(3, Ke)):
-        pass  # table and clocks are already warm; the first e2e steps are part of the measurement
     t0 = time.perf_counter()
     ms_e = timed(step_host, 0, Ke)
     wall_e = (time.perf_counter() - t0) * 1e3

@@ -125,6 +125,9 @@ void *rl_engine_stream(rl_engine *e);
 /* Make the engine's stream wait for every pipelined call issued so far (RL_FLAG_PIPELINE);
  * a no-op otherwise.  Does not block the host. */
 int rl_fence(rl_engine *e);
+/* Same for one call only: age 0 = the last pipelined call, 1 = the one before it (later calls keep
+ * running).  Lets a caller overlap the post-processing of call s with the kernels of call s+1. */
+int rl_fence_call(rl_engine *e, uint32_t age);
 /* Wait for all enqueued work; returns and clears any deferred device-side error. */
 int rl_sync(rl_engine *e);
 int rl_get_stats(rl_engine *e, rl_stats *out);

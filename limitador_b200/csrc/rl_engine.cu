@@ -814,6 +814,17 @@ int rl_fence(rl_engine* e) {
     return pipe_fence(e);
 }
 
+int rl_fence_call(rl_engine* e, uint32_t age) {
+    if (!e) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    if (!e->pipeline || e->pipe_seq == 0) return RL_OK;
+    if (age == 0) return pipe_fence(e);
+    if (age > 1 || e->pipe_seq < 2) return age > 1 ? fail(e, RL_FATAL, "rl_fence_call: age must be 0 or 1") : RL_OK;
+    // the call before the last one: its replay event is still the one recorded for it
+    RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_main[(e->pipe_seq - 2) & 1], 0));
+    return RL_OK;
+}
+
 int rl_profile_begin(rl_engine* e) {
     if (!e) return RL_FATAL;
     e->profiling = true;

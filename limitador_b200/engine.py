@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "rl_check_and_update_batch", "rl_is_within_limits_batch", "rl_is_within_limits_records",
     "rl_update_batch", "rl_update_records", "rl_get_counters", "rl_delete_counters", "rl_clear",
     "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
-    "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8", "rl_fence",
+    "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8", "rl_fence", "rl_fence_call",
 ]
 
 
@@ -87,6 +87,7 @@ def load_library(path: str | None = None):
     L.rl_engine_stream.restype = vp
     L.rl_sync.argtypes = [vp]
     L.rl_fence.argtypes = [vp]
+    L.rl_fence_call.argtypes = [vp, u32]
     L.rl_get_stats.argtypes = [vp, C.POINTER(RlStats)]
     L.rl_limits_set.argtypes = [vp, vp, u32]
     L.rl_limits_delete.argtypes = [vp, vp, u32]
@@ -179,6 +180,10 @@ class Engine:
         d = {f[0]: getattr(s, f[0]) for f in RlStats._fields_ if not f[0].startswith("_")}
         d["phase_cycles"] = list(d["phase_cycles"])
         return d
+
+    def fence_call(self, age: int):
+        """Order only the pipelined call issued `age` calls ago (0 = last, 1 = the one before)."""
+        self._check(self._lib.rl_fence_call(self._h, age))
 
     def profile_begin(self):
         self._check(self._lib.rl_profile_begin(self._h))
