@@ -364,7 +364,16 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.chain_w = e->d_chain_w.p;
     B.chunk = e->chunk;
     // a region is split into chained chunks only when it is far heavier than the average one
-    B.heavy_len = e->heavy_mult ? std::max<uint32_t>(2 * e->chunk, e->heavy_mult * ceil_div(n_acc, 1u << e->log2P)) : 0xFFFFFFFFu;
+    // partition granularity: about one k_main chunk per partition, never finer than the table's regions
+    {
+        uint32_t want = std::max<uint32_t>(64, ceil_div(n_acc, e->chunk));
+        uint32_t lp = 0;
+        while ((1u << (lp + 1)) <= want) lp++;
+        lp = std::min<uint32_t>(lp, e->log2P);
+        B.part_shift = e->log2P - lp;
+        B.nparts = 1u << lp;
+    }
+    B.heavy_len = e->heavy_mult ? std::max<uint32_t>(2 * e->chunk, e->heavy_mult * ceil_div(n_acc, B.nparts)) : 0xFFFFFFFFu;
     B.log_row = nullptr;
     B.log_state = nullptr;
     if (set == 1) {
@@ -390,11 +399,12 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
 
 template <int CELLS, class Src>
 int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
-    const uint32_t P1 = (1u << e->log2P) + 1;
+    const uint32_t P1 = B.nparts + 1;
     const size_t smem = (size_t)RL_PART_WARPS * P1 * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-        RL_CUDA(e, cudaFuncSetAttribute(k_part<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int max_smem = (int)((size_t)RL_PART_WARPS * ((1u << e->log2P) + 1) * sizeof(uint32_t));
+        RL_CUDA(e, cudaFuncSetAttribute(k_part<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
     k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), st>>>(D, B, src);
@@ -426,7 +436,7 @@ int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& sr
         attr_set = true;
     }
     // upper bound of the work-item count: one per region + one per chunk of a heavy region
-    const uint32_t grid = (1u << e->log2P) + ceil_div(B.n_acc, CH);
+    const uint32_t grid = B.nparts + ceil_div(B.n_acc, CH);
     kern<<<grid, CH, sizeof(Smem), st>>>(D, B, src);
     return RL_OK;
 }

@@ -54,6 +54,8 @@ struct RlBatch {
     ulonglong2* part_acc;    // [n_acc][3] the access itself, resolved, in partition order:
                              //   {key_lo, hdr_hi} {req | cells<<32, posorig} {delta, now}
     uint32_t* scan_ctr;      // last-block-done counter of k_colscan
+    uint32_t nparts;         // partitions of this batch: table regions merged 2^part_shift at a time, so
+    uint32_t part_shift;     //   that a small batch still fills its k_main chunks (nparts = P >> part_shift)
     uint32_t tile;           // accesses per tile (multiple of 256)
     uint32_t num_tiles;
     // outputs (device)
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src sr
     extern __shared__ uint32_t rcnt[];  // [P+1]
     constexpr uint32_t RB = RlGeom<CELLS>::ROW_BYTES;
     constexpr int U = 4;
-    const uint32_t P1 = (1u << D.log2P) + 1;
+    const uint32_t P1 = B.nparts + 1;
     const uint32_t tid = threadIdx.x;
     const uint32_t tile = blockIdx.x;
     const uint32_t t0 = tile * B.tile;
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src sr
             if (a >= t1) continue;
             uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
             if (ok[u]) {
-                r = (uint32_t)rl_region_of(D, h[u]);
+                r = (uint32_t)rl_region_of(D, h[u]) >> B.part_shift;
                 const uint8_t* row = (hdr[u].x == klo[u] && hdr[u].y == hhi[u])
                                          ? home[u]
                                          : rl_probe<CELLS>(D, h[u], klo[u], hhi[u], true);  // collision chain / insert
@@ -338,8 +340,8 @@ __global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src sr
 // Each access is written out resolved (part_acc) so that k_main reads its chunk coalesced.
 template <class Src>
 __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Src src) {
-    extern __shared__ uint32_t wcnt[];  // [RL_PART_WARPS][P+1]
-    const uint32_t P1 = (1u << D.log2P) + 1;
+    extern __shared__ uint32_t wcnt[];  // [RL_PART_WARPS][nparts+1]
+    const uint32_t P1 = B.nparts + 1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
     const uint32_t t0 = tile * B.tile;
@@ -426,24 +428,33 @@ __global__ void __launch_bounds__(256) k_colscan(RlDev D, RlBatch B) {
     __shared__ uint32_t part[8][32];
     __shared__ uint32_t s_last;
     __shared__ uint32_t s_warp[8];
-    const uint32_t P1 = (1u << D.log2P) + 1;
+    const uint32_t P1 = B.nparts + 1;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * 32 + lane;
     const uint32_t nt = B.num_tiles;
     const uint32_t per = (nt + 7) / 8;
     const uint32_t a0 = min(warp * per, nt), a1 = min(a0 + per, nt);
+    // at most 32 tiles per warp (256 tiles / 8 warps): keep them in registers so that all the
+    // loads of a column slice are in flight together instead of one dependent load per tile
+    uint32_t cnt[32];
     uint32_t sum = 0;
-    if (r < P1)
-        for (uint32_t t = a0; t < a1; t++) sum += B.tile_cnt[(size_t)t * P1 + r];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const uint32_t t = a0 + i;
+        cnt[i] = (r < P1 && t < a1) ? __ldcg(&B.tile_cnt[(size_t)t * P1 + r]) : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) sum += cnt[i];
     part[warp][lane] = sum;
     __syncthreads();
     uint32_t run = 0;
     for (uint32_t w = 0; w < warp; w++) run += part[w][lane];
     if (r < P1) {
-        for (uint32_t t = a0; t < a1; t++) {
-            const uint32_t c = B.tile_cnt[(size_t)t * P1 + r];
-            B.tile_cnt[(size_t)t * P1 + r] = run;
-            run += c;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const uint32_t t = a0 + i;
+            if (t < a1) B.tile_cnt[(size_t)t * P1 + r] = run;
+            run += cnt[i];
         }
         if (warp == 7) B.region_total[r] = run;  // warp 7 ends with the full column sum
     }
