@@ -146,6 +146,7 @@ struct rl_engine {
     int d2h_last = 0;
     unsigned long long tag_mask = ~0ull;
     uint32_t chunk = 128;              // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
+    uint32_t part_target = 128;        // accesses per partition aimed at (RL_PART_TARGET)
     uint32_t heavy_mult = 4;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -366,7 +367,7 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     // a region is split into chained chunks only when it is far heavier than the average one
     // partition granularity: about one k_main chunk per partition, never finer than the table's regions
     {
-        uint32_t want = std::max<uint32_t>(64, ceil_div(n_acc, e->chunk));
+        uint32_t want = std::max<uint32_t>(64, ceil_div(n_acc, e->part_target));
         uint32_t lp = 0;
         while ((1u << (lp + 1)) <= want) lp++;
         lp = std::min<uint32_t>(lp, e->log2P);
@@ -664,6 +665,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     e->groups.resize(1);
     if (const char* v = getenv("RL_CHUNK")) e->chunk = (atoi(v) == 128) ? 128 : 256;
     if (const char* v = getenv("RL_HEAVY_MULT")) e->heavy_mult = (uint32_t)atoi(v);
+    if (const char* v = getenv("RL_PART_TARGET")) e->part_target = std::max(16, atoi(v));
     if (cfg->flags & 1u) e->tag_mask = 0xFull << 24;  // RL_FLAG_DEBUG_WEAK_TAGS: 8 distinct tags per salt level
 
     const size_t bytes = (size_t)e->capacity * e->row_bytes;
