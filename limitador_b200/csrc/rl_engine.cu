@@ -147,7 +147,7 @@ struct rl_engine {
     unsigned long long tag_mask = ~0ull;
     uint32_t chunk = 128;              // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
     uint32_t part_target = 128;        // accesses per partition aimed at (RL_PART_TARGET)
-    uint32_t heavy_mult = 4;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
+    uint32_t heavy_mult = 2;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
