@@ -216,6 +216,21 @@ int rl_gather_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *
 int rl_unpermute_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *d_src, uint8_t *d_out);
 uint32_t rl_owner_of(uint32_t ns_id, uint32_t world);
 
+/* ---- Batching front (SURVEY §8b threading row) ---------------------------------------------
+ * Thread-safe, blocking, one request per call: concurrent callers are coalesced by a dispatcher
+ * thread into batches of at most max_batch requests (waiting at most max_delay_us for company)
+ * and shipped through rl_check_and_update_batch.  The drain order is the stream order that
+ * defines the result; *out_seq returns the caller's position in it.  now_us == 0 = the front
+ * stamps the batch with the wall clock when it drains it.  While a front exists, it owns the
+ * engine's request path (maintenance calls must be serialised by the caller). */
+typedef struct rl_front rl_front;
+int rl_front_create(rl_engine *e, uint32_t max_batch, uint32_t max_delay_us, rl_front **out);
+void rl_front_destroy(rl_front *f);
+int rl_front_check_and_update(rl_front *f, const rl_counter *ctrs, uint32_t m, uint64_t delta, uint64_t now_us,
+                              int load_counters, uint8_t *out_limited, uint32_t *out_first_limited,
+                              uint64_t *out_remaining, uint64_t *out_ttl_us, uint64_t *out_seq);
+int rl_front_stats(rl_front *f, uint64_t *out_batches, uint64_t *out_requests);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,8 +1,8 @@
 """limitador_b200 — B200-native batched rate-limit engine for Kuadrant/limitador's
 check_rate_limited_and_update hot path."""
-from .engine import Engine, EngineError, owner_of, RECORD_DTYPE, COUNTER_DTYPE, LIMIT_DESC_DTYPE, NONE  # noqa: F401
+from .engine import Engine, EngineError, Front, owner_of, RECORD_DTYPE, COUNTER_DTYPE, LIMIT_DESC_DTYPE, NONE  # noqa: F401
 from .limiter import (Authorization, CheckResult, Context, Counter, GpuCounterStorage, Limit,  # noqa: F401
                       RateLimiter)
 
-__all__ = ["Engine", "EngineError", "owner_of", "RateLimiter", "Limit", "Counter", "Context", "CheckResult",
+__all__ = ["Engine", "EngineError", "Front", "owner_of", "RateLimiter", "Limit", "Counter", "Context", "CheckResult",
            "Authorization", "GpuCounterStorage", "RECORD_DTYPE", "COUNTER_DTYPE", "LIMIT_DESC_DTYPE", "NONE"]

@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "rl_update_batch", "rl_update_records", "rl_get_counters", "rl_delete_counters", "rl_clear",
     "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
     "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8", "rl_fence", "rl_fence_call",
+    "rl_front_create", "rl_front_destroy", "rl_front_check_and_update", "rl_front_stats",
 ]
 
 
@@ -108,6 +109,11 @@ def load_library(path: str | None = None):
     L.rl_gather_u8.argtypes = [vp, u64, vp, vp, vp]
     L.rl_profile_begin.argtypes = [vp]
     L.rl_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.rl_front_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
+    L.rl_front_destroy.argtypes = [vp]
+    L.rl_front_destroy.restype = None
+    L.rl_front_check_and_update.argtypes = [vp, vp, u32, u64, u64, i32, vp, vp, vp, vp, vp]
+    L.rl_front_stats.argtypes = [vp, vp, vp]
     L.rl_owner_of.argtypes = [u32, u32]
     L.rl_owner_of.restype = u32
     if path == _build.LIB_PATH:
@@ -337,3 +343,45 @@ class Engine:
 
 def owner_of(ns_id: int, world: int) -> int:
     return int(load_library().rl_owner_of(ns_id, world))
+
+
+class Front:
+    """The batching front: blocking, thread-safe single-request calls over one Engine."""
+
+    def __init__(self, engine: Engine, max_batch: int = 1024, max_delay_us: int = 50):
+        self._lib = load_library()
+        self._engine = engine  # keep alive
+        self._h = C.c_void_p()
+        st = self._lib.rl_front_create(engine._h, max_batch, max_delay_us, C.byref(self._h))
+        if st != RL_OK:
+            raise EngineError(st, "rl_front_create failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rl_front_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check_and_update(self, ctrs, delta: int, now_us: int = 0, load_counters: bool = False):
+        """ctrs: COUNTER_DTYPE array.  Returns (limited, first_limited_id|None, seq, remaining, ttl)."""
+        ctrs = np.ascontiguousarray(ctrs, dtype=COUNTER_DTYPE)
+        m = len(ctrs)
+        lim, first, seq = C.c_uint8(0), C.c_uint32(NONE), C.c_uint64(0)
+        rem = np.zeros(max(m, 1), dtype=np.uint64)
+        ttl = np.zeros(max(m, 1), dtype=np.uint64)
+        st = self._lib.rl_front_check_and_update(self._h, _p(ctrs), m, delta, now_us, int(load_counters),
+                                                 C.addressof(lim), C.addressof(first), _p(rem), _p(ttl),
+                                                 C.addressof(seq))
+        if st != RL_OK:
+            raise EngineError(st, self._lib.rl_last_error(self._engine._h).decode())
+        return bool(lim.value), (None if first.value == NONE else first.value), seq.value, rem[:m], ttl[:m]
+
+    def stats(self):
+        b, r = C.c_uint64(0), C.c_uint64(0)
+        self._lib.rl_front_stats(self._h, C.addressof(b), C.addressof(r))
+        return {"batches": b.value, "requests": r.value}

@@ -419,3 +419,48 @@ def test_async_host_calls_match_oracle():
         assert np.array_equal(h_lim[b].numpy(), want[0]), f"batch {b}"
         assert np.array_equal(h_first[b].numpy().astype(np.uint32), want[1])
     assert_tables_equal(e, o, w.limits)
+
+
+def test_batching_front_concurrent_callers_linearise():
+    """rl_front: 8 threads issue single requests concurrently; the front coalesces them into
+    batches.  Replaying the requests through the oracle in the front's drain order (out_seq)
+    must reproduce every verdict, remaining and ttl — a valid linearisation, like concurrent
+    callers of InMemoryStorage."""
+    import threading
+    from limitador_b200 import Front
+    descs = H.mixed_limits(n_ns=12, seed=8)
+    e = engine_with_limits(descs, 3, max_batch=4096)
+    o = H.oracle_with_limits(descs)
+    front = Front(e, max_batch=256, max_delay_us=200)
+    n_threads, per_thread = 8, 300
+    results = [[] for _ in range(n_threads)]
+
+    def worker(t):
+        off, ctrs, delta, now = H.random_csr_stream(descs, per_thread, 4000 + t, n_keys=5)
+        for i in range(per_thread):
+            c = ctrs[off[i]:off[i + 1]]
+            # one clock for all threads would be the wall clock; use a fixed stamp per request so the
+            # oracle replay is deterministic whatever the interleaving
+            lim, first, seq, rem, ttl = front.check_and_update(c, int(delta[i]), now_us=H.T0 + 1, load_counters=True)
+            results[t].append((seq, c.copy(), int(delta[i]), lim, first, rem.copy(), ttl.copy()))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    st = front.stats()
+    front.close()
+    allr = sorted([r for rs in results for r in rs], key=lambda r: r[0])
+    assert [r[0] for r in allr if len(r[1])] == sorted(r[0] for r in allr if len(r[1]))
+    assert st["requests"] == sum(1 for r in allr if len(r[1]))
+    assert st["batches"] < st["requests"], "requests were never coalesced"
+    for seq, c, d, lim, first, rem, ttl in allr:
+        if len(c) == 0:
+            assert lim is False
+            continue
+        wl, widx, wrem, wttl = o.check_and_update(c, d, True, H.T0 + 1)
+        assert lim == wl, seq
+        assert first == (None if widx is None else int(c[widx]["limit_id"]))
+        assert rem.tolist() == wrem.tolist() and ttl.tolist() == wttl.tolist()
+    assert_tables_equal(e, o, descs)
