@@ -578,6 +578,8 @@ struct RlMainSmem {
     uint32_t rset[GT];         // chained chunks: rows this chunk read (its read set)
     uint32_t rflag[GT];        // ... row is written by an earlier chunk
     uint32_t need_bits[64];    // earlier chunks (bit per chunk) whose commit I must wait for
+    uint32_t scan_off[CH];     // dependency scan: offsets of the earlier chunks' sets, CH chunks at a time
+    uint32_t scan_w[NW];
     uint32_t w_cnt;
     uint32_t bcast;
 };
@@ -1064,40 +1066,67 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
             // (d) rows I read that some earlier chunk writes: their history must be replayed in order.
             //     Pass 1 flags those rows, pass 2 collects every earlier chunk that touches one of them
             //     (a chunk that only READS such a row may turn into a writer once it re-validates).
+            //     The earlier chunks' sets are scanned CH chunks at a time, flattened: thread t fetches
+            //     the size of chunk blk*CH+t, a block scan turns sizes into offsets, and the threads then
+            //     stride over all the entries of those chunks at once (independent loads, not one
+            //     dependent round trip per earlier chunk).
             bool any_dep = false;
             for (int pass = 0; pass < 2; pass++) {
-                for (uint32_t j = warp; j < it.w; j += Smem::NW) {
-                    const uint32_t cj = __ldcg(B.chain_wcnt + base_item + j);
-                    bool hit = false;
-                    for (uint32_t i = lane; i < cj; i += 32) {
-                        const uint32_t e = __ldcg(B.chain_w + (size_t)(base_item + j) * CH + i);
+                bool flagged = false;
+                for (uint32_t blk = 0; blk < it.w; blk += CH) {
+                    const uint32_t jn = min((uint32_t)CH, it.w - blk);  // chunks in this block
+                    const uint32_t myc = (tid < jn) ? __ldcg(B.chain_wcnt + base_item + blk + tid) : 0;
+                    uint32_t x = myc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                        if ((int)lane >= o) x += y;
+                    }
+                    if (lane == 31) sm.scan_w[warp] = x;
+                    __syncthreads();
+                    uint32_t woff = 0, total = 0;
+                    for (uint32_t w = 0; w < Smem::NW; w++) {
+                        if (w < warp) woff += sm.scan_w[w];
+                        total += sm.scan_w[w];
+                    }
+                    sm.scan_off[tid] = woff + x - myc;  // exclusive offset of chunk blk+tid
+                    __syncthreads();
+                    for (uint32_t q = tid; q < total; q += CH) {
+                        // chunk holding flattened entry q: last j with scan_off[j] <= q
+                        uint32_t lo = 0, hi = jn - 1;
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi + 1) >> 1;
+                            if (sm.scan_off[mid] <= q) lo = mid;
+                            else hi = mid - 1;
+                        }
+                        const uint32_t j = blk + lo;
+                        const uint32_t e = __ldcg(B.chain_w + (size_t)(base_item + j) * CH + (q - sm.scan_off[lo]));
                         const uint32_t w = e >> 1;
                         uint32_t s2 = (w * 2654435761u) & (GT - 1);
                         for (;;) {
-                            const uint32_t x = sm.rset[s2];
-                            if (x == w) {
+                            const uint32_t xs = sm.rset[s2];
+                            if (xs == w) {
                                 if (pass == 0) {
-                                    if (e & 1u) sm.rflag[s2] = 1;
+                                    if (e & 1u) {
+                                        sm.rflag[s2] = 1;
+                                        flagged = true;
+                                    }
                                 } else if (sm.rflag[s2]) {
-                                    hit = true;
+                                    any_dep = true;
+                                    atomicOr(&sm.need_bits[(j >> 5) & 63], (j < 2048) ? (1u << (j & 31)) : 0u);
                                 }
                                 break;
                             }
-                            if (x == 0xFFFFFFFFu) break;
+                            if (xs == 0xFFFFFFFFu) break;
                             s2 = (s2 + 1) & (GT - 1);
                         }
                     }
-                    if (pass == 1 && __any_sync(0xffffffffu, hit)) {
-                        any_dep = true;
-                        if (lane == 0) atomicOr(&sm.need_bits[(j >> 5) & 63], (j < 2048) ? (1u << (j & 31)) : 0u);
-                    }
+                    __syncthreads();  // scan_off / scan_w are reused by the next block
                 }
-                any_dep = __syncthreads_or(any_dep);
-                if (pass == 0 && !any_dep) {
-                    // no flagged row yet is not conclusive for pass 0 (flags only set there): check them
-                    bool f = false;
-                    for (uint32_t i = tid; i < GT; i += CH) f = f || sm.rflag[i];
-                    if (!__syncthreads_or(f)) break;
+                if (pass == 0) {
+                    if (!__syncthreads_or(flagged)) break;  // no row of mine is written earlier
+                } else {
+                    any_dep = __syncthreads_or(any_dep);
                 }
             }
             if (!any_dep) break;  // nothing I read is written before me: commit now, in parallel
