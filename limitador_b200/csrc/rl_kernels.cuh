@@ -1047,6 +1047,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
                     s2 = (s2 + 1) & (GT - 1);
                 }
                 B.chain_w[(size_t)item * CH + atomicAdd(&sm.w_cnt, 1u)] = (myrow << 1) | (sm.g_dirty[tid] ? 1u : 0u);
+                __threadfence();  // my entry is visible device-wide before the status word says so
             }
             __syncthreads();
             if (tid == 0) {
