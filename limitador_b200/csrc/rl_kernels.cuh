@@ -97,9 +97,6 @@ struct RlBatch {
 // ---------------------------------------------------------------------------------------
 // memory helpers: table traffic bypasses L1 (.cg) — rows have no L1 reuse and .cg keeps the
 // CTA's own earlier writes (previous chunk) visible without relying on L1 invalidation.
-struct __align__(16) RlU128 {
-    unsigned long long x, y;
-};
 __device__ __forceinline__ ulonglong2 rl_ld_cg(const void* p) {
     return __ldcg(reinterpret_cast<const ulonglong2*>(p));
 }
@@ -620,6 +617,15 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
     b_ok = live_all && (within_all || !check_limit);
 }
 
+// k_main accounts its SM cycles per phase (thread 0, one clock64 and one atomic per phase and
+// chunk): rl_stats.phase_cycles, the numbers DESIGN.md §10 quotes.
+#define RL_PHASE_TICK(i)                                                         \
+    if (tid == 0) {                                                              \
+        const long long tnow = clock64();                                        \
+        atomicAdd(D.kstats + 8 + (i), (unsigned long long)(tnow - tph));         \
+        tph = tnow;                                                              \
+    }
+
 // The sequential rule applied by ONE thread directly on the staged row state (shared
 // memory) — the default path (single-row request, load_counters off).  Same arithmetic as
 // rl_walk_check_single / rl_walk_update (rl_core.h), without a private copy of the row.
@@ -725,11 +731,13 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
         // optimistic concurrency control, row by row.  A chunk replays its requests against the
         // rows as they are (no row is written) and publishes the rows it read, each tagged with
         // whether its replay changes it.  Requests of different keys never interact, so a row's
-        // history inside the batch is the sequence of chunks that read it: if none of the earlier
-        // ones writes it, the state this chunk saw is the one sequential execution shows it (a
-        // saturated hot key is read by every chunk and written by none) and the chunk commits at
-        // once.  Otherwise it waits for exactly the earlier chunks touching such a row, re-reads
-        // its rows and replays the keys whose state changed.
+        // history inside the batch is the sequence of chunks that touch it.  A row is "ordered"
+        // for this chunk if an earlier chunk writes it (my read may be stale) or if I write it (an
+        // earlier chunk may still have to read it).  With no ordered row the state this chunk saw
+        // is the one sequential execution shows it and nobody before it can be disturbed by its
+        // writes (a saturated hot key is read by every chunk and written by none): it commits at
+        // once.  Otherwise it waits for exactly the earlier chunks touching an ordered row,
+        // re-reads its rows and replays the keys whose state changed.
         const bool chained = (it.w != RL_NONE_U32);
         // prefetch of the first chunk
         RlAccess nacc;
@@ -780,12 +788,6 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
             sm.g_min[0][0][tid] = sm.g_min[0][1][tid] = 0xFFFFFFFFu;
             sm.g_min[1][0][tid] = sm.g_min[1][1][tid] = 0xFFFFFFFFu;
             __syncthreads();
-#define RL_PHASE_TICK(i)                                                         \
-    if (tid == 0) {                                                              \
-        const long long tnow = clock64();                                        \
-        atomicAdd(D.kstats + 8 + (i), (unsigned long long)(tnow - tph));         \
-        tph = tnow;                                                              \
-    }
             RL_PHASE_TICK(0)  // item fetch + access load + init
 
             // ---- group by key; the claimer of a key probes its row right away ------------------
@@ -1046,6 +1048,8 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
                     if (old == 0xFFFFFFFFu || old == myrow) break;
                     s2 = (s2 + 1) & (GT - 1);
                 }
+                // a row I WRITE is ordered too: no earlier chunk may still be reading it when I commit
+                if (sm.g_dirty[tid]) sm.rflag[s2] = 1;
                 B.chain_w[(size_t)item * CH + atomicAdd(&sm.w_cnt, 1u)] = (myrow << 1) | (sm.g_dirty[tid] ? 1u : 0u);
                 __threadfence();  // my entry is visible device-wide before the status word says so
             }
@@ -1073,7 +1077,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
             //     dependent round trip per earlier chunk).
             bool any_dep = false;
             for (int pass = 0; pass < 2; pass++) {
-                bool flagged = false;
+                bool flagged = is_rep && row != nullptr && sm.g_dirty[tid] != 0;
                 for (uint32_t blk = 0; blk < it.w; blk += CH) {
                     const uint32_t jn = min((uint32_t)CH, it.w - blk);  // chunks in this block
                     const uint32_t myc = (tid < jn) ? __ldcg(B.chain_wcnt + base_item + blk + tid) : 0;
@@ -1125,7 +1129,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
                     __syncthreads();  // scan_off / scan_w are reused by the next block
                 }
                 if (pass == 0) {
-                    if (!__syncthreads_or(flagged)) break;  // no row of mine is written earlier
+                    if (!__syncthreads_or(flagged)) break;  // no ordered row
                 } else {
                     any_dep = __syncthreads_or(any_dep);
                 }

@@ -71,7 +71,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIB_PATH
+    path = path or os.environ.get("RL_ENGINE_LIB") or _build.LIB_PATH
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build it with `python -m limitador_b200.build` "
