@@ -464,3 +464,37 @@ def test_batching_front_concurrent_callers_linearise():
         assert first == (None if widx is None else int(c[widx]["limit_id"]))
         assert rem.tolist() == wrem.tolist() and ttl.tolist() == wttl.tolist()
     assert_tables_equal(e, o, descs)
+
+
+@pytest.mark.parametrize("chunk,mult", [(128, 1), (256, 1), (128, 2)])
+def test_chained_commit_stress(monkeypatch, chunk, mult):
+    """Optimistic-commit protocol under stress: RL_HEAVY_MULT=1 chains every partition above the
+    average, and a tiny key space makes the chunks of a partition share written rows in every
+    direction (earlier writer -> later reader AND later writer -> earlier reader, the case a
+    round-1 bug missed).  Records and CSR forms, both load_counters values."""
+    monkeypatch.setenv("RL_CHUNK", str(chunk))
+    monkeypatch.setenv("RL_HEAVY_MULT", str(mult))
+    for cells in (1, 3):
+        descs = single_row_limits(cells, seed=20 + cells)
+        e = engine_with_limits(descs, cells, regions=4)
+        o = H.oracle_with_limits(descs)
+        for b in range(4):
+            recs = H.random_records(descs, 6000, 300 + 10 * cells + b, n_keys=25, monotone=(b % 2 == 0))
+            lc = bool(b & 1)
+            got = e.check_and_update_records(recs, lc, stride=cells)
+            want = o.batch_records(0, recs, lc, cells)
+            assert got[0].tolist() == want[0].tolist(), (cells, b)
+            assert got[1].tolist() == want[1].tolist()
+            if lc:
+                assert got[2].tolist() == want[2].tolist() and got[3].tolist() == want[3].tolist()
+            assert_tables_equal(e, o, descs)
+        assert e.stats()["chained_chunks"] > 0 and e.stats()["ordered_chunks"] > 0
+    # update_counters through the same chained path
+    descs = single_row_limits(3, seed=31)
+    e = engine_with_limits(descs, 3, regions=4)
+    o = H.oracle_with_limits(descs)
+    for b in range(3):
+        recs = H.random_records(descs, 5000, 700 + b, n_keys=25)
+        e.update_records(recs)
+        o.batch_records(2, recs)
+        assert_tables_equal(e, o, descs)
