@@ -306,12 +306,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_enqueue_us = []  # CPU time to enqueue one step, per timed pass (launch-bound check)
+
     def timed(fn, first: int, n: int) -> float:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        t_host = time.perf_counter()
         for s in range(first, first + n):
             fn(s)
+        host_enqueue_us.append((time.perf_counter() - t_host) * 1e6 / max(n, 1))
         if world > 1:
             drain()  # the last step's verdicts are still on their way back
         eng.fence()  # pipelined calls: order their completion before the closing event
@@ -381,6 +385,7 @@ def main():
     if world > 1 and int(overflow.item()) != 0:
         raise RuntimeError("an exchange block overflowed (namespace skew beyond 2x): rerun with a larger slot_cap")
     print(f"[bench] engine stats {eng.stats()}", file=sys.stderr)
+    print(f"[bench] host enqueue us/step per pass: {[round(x, 1) for x in host_enqueue_us]}", file=sys.stderr)
     print(f"[bench] passes: A {ms_a:.1f} ms, B {ms_b:.1f} ms, e2e {ms_e:.1f} ms (wall {wall_e:.1f})", file=sys.stderr)
 
     if rank != 0:
