@@ -410,7 +410,7 @@ def main():
                 "alg_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                 "allowed_frac": float((lim_b == 0).mean()), "kernel_share_of_step": main_ms / ms_b}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and not c3:
             try:
                 roof["traffic"] = json.load(open(tp)).get("k_main_dram_bytes_per_launch")
             except Exception:

@@ -488,7 +488,8 @@ def test_chained_commit_stress(monkeypatch, chunk, mult):
             if lc:
                 assert got[2].tolist() == want[2].tolist() and got[3].tolist() == want[3].tolist()
             assert_tables_equal(e, o, descs)
-        assert e.stats()["chained_chunks"] > 0 and e.stats()["ordered_chunks"] > 0
+        if mult == 1:  # every partition above the average is chained
+            assert e.stats()["chained_chunks"] > 0 and e.stats()["ordered_chunks"] > 0
     # update_counters through the same chained path
     descs = single_row_limits(3, seed=31)
     e = engine_with_limits(descs, 3, regions=4)
