@@ -129,9 +129,12 @@ struct rl_engine {
     // rl_profile_begin/end
     // RL_FLAG_PIPELINE
     bool pipeline = false;
-    WorkSet ws1;
+    static constexpr int kSets = 3;  // workspace sets = pipeline depth (probe | scan+scatter | replay)
+    WorkSet wsx[2];                  // sets 1 and 2 (set 0 = the engine's own members)
+    cudaStream_t sq = nullptr;       // scan + scatter stream
     cudaStream_t sp = nullptr, sm = nullptr;  // partition / replay streams
-    cudaEvent_t ev_in = nullptr, ev_part[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr, ev_probe[3] = {nullptr, nullptr, nullptr}, ev_part[3] = {nullptr, nullptr, nullptr},
+                ev_main[3] = {nullptr, nullptr, nullptr};
     uint64_t pipe_seq = 0;
     bool pipe_pending = false;
     // RL_MEM_HOST_ASYNC: ring of device staging slots; copies overlap the kernels of other calls
@@ -377,8 +380,8 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.heavy_len = e->heavy_mult ? std::max<uint32_t>(2 * e->chunk, e->heavy_mult * ceil_div(n_acc, B.nparts)) : 0xFFFFFFFFu;
     B.log_row = nullptr;
     B.log_state = nullptr;
-    if (set == 1) {
-        WorkSet& w = e->ws1;
+    if (set >= 1) {
+        WorkSet& w = e->wsx[set - 1];
         B.tile_cnt = w.tile_cnt.p;
         B.region_total = w.region_total.p;
         B.part_base = w.part_base.p;
@@ -399,7 +402,7 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
 }
 
 template <int CELLS, class Src>
-int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
+int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st, int stage) {
     const uint32_t P1 = B.nparts + 1;
     const size_t smem = (size_t)RL_PART_WARPS * P1 * sizeof(uint32_t);
     static bool attr_set = false;
@@ -408,22 +411,28 @@ int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const
         RL_CUDA(e, cudaFuncSetAttribute(k_part<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
-    k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), st>>>(D, B, src);
-    RL_LAUNCH_CHECK(e);
-    k_colscan<<<ceil_div(P1, 32), 256, 0, st>>>(D, B);
-    RL_LAUNCH_CHECK(e);
-    k_part<Src><<<B.num_tiles, RL_PART_THREADS, smem, st>>>(D, B, src);
-    RL_LAUNCH_CHECK(e);
+    if (stage & 1) {
+        k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), st>>>(D, B, src);
+        RL_LAUNCH_CHECK(e);
+    }
+    if (stage & 2) {
+        k_colscan<<<ceil_div(P1, 32), 256, 0, st>>>(D, B);
+        RL_LAUNCH_CHECK(e);
+        k_part<Src><<<B.num_tiles, RL_PART_THREADS, smem, st>>>(D, B, src);
+        RL_LAUNCH_CHECK(e);
+    }
     return RL_OK;
 }
 
+// stage: 1 = probe + count, 2 = scan + scatter, 3 = both
 template <class Src>
-int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st = nullptr) {
+int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st = nullptr,
+                     int stage = 3) {
     if (!st) st = e->stream;
     switch (e->cells) {
-        case 1: return launch_partition_cells<1, Src>(e, D, B, src, st);
-        case 3: return launch_partition_cells<3, Src>(e, D, B, src, st);
-        default: return launch_partition_cells<7, Src>(e, D, B, src, st);
+        case 1: return launch_partition_cells<1, Src>(e, D, B, src, st, stage);
+        case 3: return launch_partition_cells<3, Src>(e, D, B, src, st, stage);
+        default: return launch_partition_cells<7, Src>(e, D, B, src, st, stage);
     }
 }
 
@@ -478,7 +487,7 @@ int launch_main(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, 
 // Make the caller's stream wait for everything the pipeline still has in flight.
 int pipe_fence(rl_engine* e) {
     if (!e->pipe_pending) return RL_OK;
-    const int last = (int)((e->pipe_seq - 1) & 1);
+    const int last = (int)((e->pipe_seq - 1) % rl_engine::kSets);
     RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_main[last], 0));
     if (e->d2h_pending) RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_slot[e->d2h_last], 0));
     e->d2h_pending = false;
@@ -550,19 +559,24 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
                         bool may_pipeline = false) {
     RlDev D = make_dev(e);
     if (may_pipeline && e->pipeline && !e->any_multi_ns) {
-        // Two-stage software pipeline over successive calls: partition (probe, scan, scatter) of this
-        // batch on `sp` overlaps the replay of the previous batch on `sm`.  The probe only reads row
-        // headers and claims empty rows; the replay only touches the cells of rows found by ITS
+        // Three-stage software pipeline over successive calls: probe+count of batch s+2 (`sp`) and
+        // scan+scatter of batch s+1 (`sq`) overlap the replay of batch s (`sm`).  The probe only reads
+        // row headers and claims empty rows; the replay only touches the cells of rows found by ITS
         // probe, and replays stay in call order on `sm`, so the table sees the batches in order.
-        const int k = (int)(e->pipe_seq & 1);
+        const int k = (int)(e->pipe_seq % rl_engine::kSets);
         RlBatch B = make_batch(e, n, n, o, lc, k);
         RecordSrc src{d_recs};
         RL_CUDA(e, cudaEventRecord(e->ev_in, e->stream));  // inputs: whatever the caller enqueued so far
         RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_in, 0));
-        if (e->pipe_seq >= 2) RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_main[k], 0));  // workspace set k is free
-        int r = launch_partition(e, D, B, src, e->sp);
+        if (e->pipe_seq >= (uint64_t)rl_engine::kSets)
+            RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_main[k], 0));  // workspace set k is free again
+        int r = launch_partition(e, D, B, src, e->sp, 1);
         if (r) return r;
-        RL_CUDA(e, cudaEventRecord(e->ev_part[k], e->sp));
+        RL_CUDA(e, cudaEventRecord(e->ev_probe[k], e->sp));
+        RL_CUDA(e, cudaStreamWaitEvent(e->sq, e->ev_probe[k], 0));
+        r = launch_partition(e, D, B, src, e->sq, 2);
+        if (r) return r;
+        RL_CUDA(e, cudaEventRecord(e->ev_part[k], e->sq));
         RL_CUDA(e, cudaStreamWaitEvent(e->sm, e->ev_part[k], 0));
         r = mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src, e->sm) : launch_main<RecordSrc, 0>(e, D, B, src, e->sm);
         if (r) return r;
@@ -607,6 +621,7 @@ int ensure_ready(rl_engine* e, uint64_t n, bool fence = true) {
         int r = pipe_fence(e);
         if (r) return r;
         RL_CUDA(e, cudaStreamSynchronize(e->sp));
+        RL_CUDA(e, cudaStreamSynchronize(e->sq));
         RL_CUDA(e, cudaStreamSynchronize(e->sm));
         RL_CUDA(e, cudaStreamSynchronize(e->sd));
     }
@@ -705,12 +720,15 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sd, cudaStreamNonBlocking));
         for (int k = 0; k < rl_engine::kRing; k++) RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_slot[k], cudaEventDisableTiming));
         RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
-        for (int k = 0; k < 2; k++) {
+        RL_CUDA(e, cudaStreamCreateWithFlags(&e->sq, cudaStreamNonBlocking));
+        for (int k = 0; k < rl_engine::kSets; k++) {
+            RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_probe[k], cudaEventDisableTiming));
             RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_part[k], cudaEventDisableTiming));
             RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_main[k], cudaEventDisableTiming));
         }
-        WorkSet& w = e->ws1;
         const size_t max_items = (size_t)(1u << e->log2P) + maxA / 128 + 2;
+        for (int wi = 0; wi < rl_engine::kSets - 1; wi++) {
+        WorkSet& w = e->wsx[wi];
         RL_CUDA(e, w.tile_cnt.reserve((size_t)(kMaxTiles + 1) * P1));
         RL_CUDA(e, w.region_total.reserve(P1 + 1));
         RL_CUDA(e, w.part_base.reserve(P1 + 2));
@@ -726,6 +744,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
         RL_CUDA(e, w.chain_w.reserve(max_items * 256));
         RL_CUDA(e, w.small.reserve(8));
         RL_CUDA(e, cudaMemsetAsync(w.small.p, 0, 8 * sizeof(uint32_t), e->stream));
+        }
     }
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->stats.capacity_rows = e->capacity;
@@ -748,12 +767,16 @@ void rl_engine_destroy(rl_engine* e) {
     }
     if (e->sd) cudaStreamDestroy(e->sd);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->ws1.release();
+    e->wsx[0].release();
+    e->wsx[1].release();
+    if (e->sq) cudaStreamSynchronize(e->sq);
     if (e->ev_in) cudaEventDestroy(e->ev_in);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < rl_engine::kSets; k++) {
+        if (e->ev_probe[k]) cudaEventDestroy(e->ev_probe[k]);
         if (e->ev_part[k]) cudaEventDestroy(e->ev_part[k]);
         if (e->ev_main[k]) cudaEventDestroy(e->ev_main[k]);
     }
+    if (e->sq) cudaStreamDestroy(e->sq);
     if (e->sp) cudaStreamDestroy(e->sp);
     if (e->sm) cudaStreamDestroy(e->sm);
     if (e->d_rows) cudaFree(e->d_rows);
@@ -831,9 +854,10 @@ int rl_fence_call(rl_engine* e, uint32_t age) {
     RL_CUDA(e, cudaSetDevice(e->device));
     if (!e->pipeline || e->pipe_seq == 0) return RL_OK;
     if (age == 0) return pipe_fence(e);
-    if (age > 1 || e->pipe_seq < 2) return age > 1 ? fail(e, RL_FATAL, "rl_fence_call: age must be 0 or 1") : RL_OK;
-    // the call before the last one: its replay event is still the one recorded for it
-    RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_main[(e->pipe_seq - 2) & 1], 0));
+    if (age >= (uint32_t)rl_engine::kSets) return fail(e, RL_FATAL, "rl_fence_call: age must be < %d", rl_engine::kSets);
+    if (e->pipe_seq <= age) return RL_OK;
+    // an earlier call: its replay event is still the one recorded for it
+    RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_main[(e->pipe_seq - 1 - age) % rl_engine::kSets], 0));
     return RL_OK;
 }
 
@@ -1207,7 +1231,7 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
         o.first = out_first_limited ? e->ring_first[slot].p : nullptr;
         o.stride = out_stride;
         if ((r = run_record_pipeline(e, (uint32_t)n, e->ring_recs[slot].p, 0, load_counters ? 1 : 0, o, true))) return r;
-        const int k = (int)((e->pipe_seq - 1) & 1);
+        const int k = (int)((e->pipe_seq - 1) % rl_engine::kSets);
         RL_CUDA(e, cudaStreamWaitEvent(e->sd, e->ev_main[k], 0));
         RL_CUDA(e, cudaMemcpyAsync(out_limited, o.limited, n, cudaMemcpyDeviceToHost, e->sd));
         if (out_first_limited)
