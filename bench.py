@@ -411,7 +411,8 @@ def main():
         per_launch = alg / main_launches
         avg_ms = main_ms / main_launches
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": f"k_main<{cells},RecordSrc,0,256>", "achieved": achieved, "peak": peak,
+        act = 4 if (cells == 7 and L <= 4) else cells  # cells in use (rl_engine.cu: max_cells_used)
+        roof = {"bound": "hbm", "kernel": f"k_main<{cells},{act},RecordSrc,0,{os.environ.get('RL_CHUNK', '128')},false>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                 "allowed_frac": float((lim_b == 0).mean()), "kernel_share_of_step": main_ms / ms_b}
