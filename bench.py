@@ -285,7 +285,6 @@ def main():
         # Steps are software-pipelined: the verdicts of step s travel back while step s+1 is
         # already being exchanged and decided (double-buffered exchange buffers).
         b = s & 1
-        send_buf[b].fill_(-1)
         eng.bucket_by_owner_padded_ptr(batch, recs[s].data_ptr(), world, slot_cap, send_buf[b].data_ptr(),
                                        pos_idx[b].data_ptr(), overflow.data_ptr())
         dist.all_to_all_single(recv_buf[b], send_buf[b])

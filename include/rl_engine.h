@@ -204,8 +204,8 @@ int rl_profile_end(rl_engine *e, double *out_main_ms, uint64_t *out_main_launche
 int rl_bucket_by_owner(rl_engine *e, uint64_t n, const rl_record *d_recs, uint32_t world,
                        rl_record *d_out_recs, uint32_t *d_out_src, uint64_t *h_counts);
 /* Sync-free variant for fixed-size exchanges: owner o's records go to d_out_recs[o*slot_cap ...]
- * (stable, at most slot_cap of them; the caller pre-fills d_out_recs[world*slot_cap] with 0xFF
- * bytes = records of a namespace without limits, which the engine ignores).  d_out_pos[i] = slot
+ * (stable, at most slot_cap of them; the unused slots of d_out_recs[world*slot_cap] are filled with
+ * 0xFF bytes = records of a namespace without limits, which the engine ignores).  d_out_pos[i] = slot
  * of record i (or ~0 when its block overflowed, in which case *d_overflow |= 1).  Enqueued on
  * the engine's stream; nothing is copied to the host. */
 int rl_bucket_by_owner_padded(rl_engine *e, uint64_t n, const rl_record *d_recs, uint32_t world, uint32_t slot_cap,

@@ -1499,6 +1499,8 @@ int rl_bucket_by_owner_padded(rl_engine* e, uint64_t n, const rl_record* d_recs,
     RL_CUDA(e, e->d_bucket_counts.reserve(32));
     uint32_t* tile_cnt = e->d_bucket.p;
     uint32_t* owner_base = e->d_bucket.p + (size_t)(kMaxTiles + 1) * 32;
+    // unused slots = no-op records (ns_id 0xFFFFFFFF: a namespace without limits)
+    RL_CUDA(e, cudaMemsetAsync(d_out_recs, 0xFF, (size_t)world * slot_cap * sizeof(rl_record), e->stream));
     k_bucket<false><<<num_tiles, RL_PART_THREADS, 0, e->stream>>>(d_recs, (uint32_t)n, world, tile, tile_cnt, owner_base,
                                                                   d_out_recs, nullptr, slot_cap, d_out_pos);
     RL_LAUNCH_CHECK(e);
