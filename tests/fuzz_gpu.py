@@ -1,0 +1,109 @@
+"""Randomised parity fuzzing on a GPU box (not collected by pytest; run as
+`python tests/fuzz_gpu.py --seconds 120`).  Every round draws a limits table, an engine
+geometry, the chained-commit knobs and a stream with a tiny key space, runs it through the
+C-ABI in one of the call styles (records / CSR, host / pipelined device / async host,
+check / update) and compares verdicts, outputs and the full table with the oracle."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from limitador_b200 import Engine  # noqa: E402
+from tests import helpers as H  # noqa: E402
+from tests.test_gpu_parity import single_row_limits  # noqa: E402
+
+
+def one_round(seed: int) -> str:
+    import torch
+    rng = np.random.default_rng(seed)
+    cells = int(rng.choice([1, 3, 7]))
+    os.environ["RL_CHUNK"] = str(int(rng.choice([128, 256])))
+    os.environ["RL_HEAVY_MULT"] = str(int(rng.choice([1, 1, 2, 4])))
+    os.environ["RL_PART_TARGET"] = str(int(rng.choice([32, 128, 512])))
+    style = str(rng.choice(["rec_host", "rec_dev_pipe", "rec_host_async", "csr_host", "rec_update"]))
+    regions = int(rng.choice([1, 2, 4, 16]))
+    n_keys = int(rng.choice([3, 10, 40, 400]))
+    n = int(rng.choice([700, 3000, 9000]))
+    lc = bool(rng.integers(0, 2))
+    flags = 2 if style in ("rec_dev_pipe", "rec_host_async") else 0
+    if style == "csr_host":
+        descs = H.mixed_limits(n_ns=12, seed=seed)
+    else:
+        descs = single_row_limits(cells, n_ns=int(rng.choice([2, 9])), seed=seed)
+    e = Engine(capacity_rows=1 << 14, cells_per_row=cells, max_batch=1 << 14, regions=regions, flags=flags)
+    e.limits_set(descs)
+    o = H.oracle_with_limits(descs)
+    tag = f"seed={seed} style={style} cells={cells} chunk={os.environ['RL_CHUNK']} mult={os.environ['RL_HEAVY_MULT']} " \
+          f"pt={os.environ['RL_PART_TARGET']} regions={regions} keys={n_keys} n={n} lc={lc}"
+    nb = 5
+    if style == "csr_host":
+        for b in range(nb):
+            off, ctrs, delta, now = H.random_csr_stream(descs, n // 3, seed * 100 + b, n_keys=max(2, n_keys // 4),
+                                                        monotone=bool(b & 1))
+            got = e.check_and_update_batch(off, ctrs, delta, now, lc)
+            want = o.batch_csr(0, off, ctrs, delta, now, lc)
+            for k in range(4 if lc else 2):
+                assert np.array_equal(got[k], want[k]), f"{tag} batch {b} output {k}"
+    elif style == "rec_update":
+        for b in range(nb):
+            recs = H.random_records(descs, n, seed * 100 + b, n_keys=n_keys, monotone=bool(b & 1))
+            e.update_records(recs)
+            o.batch_records(2, recs)
+    else:
+        batches = [H.random_records(descs, n, seed * 100 + b, n_keys=n_keys, monotone=bool(b & 1)) for b in range(nb)]
+        if style == "rec_host":
+            for b, recs in enumerate(batches):
+                got = e.check_and_update_records(recs, lc, stride=cells)
+                want = o.batch_records(0, recs, lc, cells)
+                for k in range(4 if lc else 2):
+                    assert np.array_equal(got[k], want[k]), f"{tag} batch {b} output {k}"
+        else:
+            host = torch.stack([torch.from_numpy(r.view(np.int64).reshape(-1, 4).copy()) for r in batches])
+            if style == "rec_dev_pipe":
+                src = host.cuda()
+                lim = torch.zeros((nb, n), dtype=torch.uint8, device="cuda")
+                first = torch.zeros((nb, n), dtype=torch.int32, device="cuda")
+                mem = 1
+            else:
+                src = host.pin_memory()
+                lim = torch.zeros((nb, n), dtype=torch.uint8).pin_memory()
+                first = torch.zeros((nb, n), dtype=torch.int32).pin_memory()
+                mem = 2
+            torch.cuda.synchronize()
+            for b in range(nb):
+                e.check_and_update_records_ptr(n, src[b].data_ptr(), lim[b].data_ptr(), mem,
+                                               out_first_ptr=first[b].data_ptr(), stride=cells)
+            e.sync()
+            for b, recs in enumerate(batches):
+                want = o.batch_records(0, recs)
+                assert np.array_equal(lim[b].cpu().numpy(), want[0]), f"{tag} batch {b} verdicts"
+                assert np.array_equal(first[b].cpu().numpy().astype(np.uint32), want[1]), f"{tag} batch {b} first"
+    assert H.normalise_dump(e.dump(), descs) == H.normalise_dump(o.dump(), descs), f"{tag} table"
+    e.close()
+    return tag
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=60)
+    ap.add_argument("--first-seed", type=int, default=1)
+    args = ap.parse_args()
+    t0, seed, done = time.time(), args.first_seed, 0
+    while time.time() - t0 < args.seconds:
+        try:
+            one_round(seed)
+        except AssertionError as ex:
+            print("FUZZ MISMATCH:", ex)
+            sys.exit(1)
+        seed += 1
+        done += 1
+    print(f"fuzz ok: {done} rounds, seeds {args.first_seed}..{seed - 1}")
+
+
+if __name__ == "__main__":
+    main()
