@@ -345,7 +345,6 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.row_of = e->d_row_of.p;
     B.part_row = e->d_part_row.p;
     B.part_acc = e->d_part_acc.p;
-    B.embed_mx = (e->max_cells_used <= 4) ? 1u : 0u;
     B.scan_ctr = e->d_misc.p + MISC_SCANCTR;
     uint32_t tile = ceil_div(n_acc, kMaxTiles);
     tile = std::max<uint32_t>(512, ((tile + 255) / 256) * 256);
@@ -697,7 +696,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_reg_of.reserve(maxA));
     RL_CUDA(e, e->d_row_of.reserve(maxA));
     RL_CUDA(e, e->d_part_row.reserve(maxA));
-    RL_CUDA(e, e->d_part_acc.reserve(maxA * 5));
+    RL_CUDA(e, e->d_part_acc.reserve(maxA * 3));
     RL_CUDA(e, e->d_misc.reserve(MISC_N));
     RL_CUDA(e, cudaMemsetAsync(e->d_misc.p, 0, MISC_N * sizeof(uint32_t), e->stream));
     RL_CUDA(e, cudaMallocHost((void**)&e->h_misc, MISC_N * sizeof(uint32_t)));
@@ -737,7 +736,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
         RL_CUDA(e, w.part_row.reserve(maxA));
         RL_CUDA(e, w.reg_of.reserve(maxA));
         RL_CUDA(e, w.row_of.reserve(maxA));
-        RL_CUDA(e, w.part_acc.reserve(maxA * 5));
+        RL_CUDA(e, w.part_acc.reserve(maxA * 3));
         RL_CUDA(e, w.items.reserve(max_items));
         RL_CUDA(e, w.fallback.reserve(1u << e->log2P));
         RL_CUDA(e, w.chain_status.reserve(max_items));

@@ -51,11 +51,8 @@ struct RlBatch {
     uint32_t* row_of;        // [n_acc] table row (index) of access a, probed / claimed by k_probe_count
     uint32_t* part_idx;      // [n_acc]
     uint32_t* part_row;      // [n_acc] table row (index) of the access, probed / claimed by k_part
-    ulonglong2* part_acc;    // [n_acc][5] the access itself, resolved, in partition order:
-                             //   {key_lo, hdr_hi} {req | cells<<32, posorig} {delta, now} and, when no row
-                             //   group uses more than 4 cells (embed_mx), {max0, max1} {max2, max3}: the limits
-                             //   of the touched cells, with their "qualified" bits in posorig[28..31]
-    uint32_t embed_mx;
+    ulonglong2* part_acc;    // [n_acc][3] the access itself, resolved, in partition order:
+                             //   {key_lo, hdr_hi} {req | cells<<32, posorig} {delta, now}
     uint32_t* scan_ctr;      // last-block-done counter of k_colscan
     uint32_t nparts;         // partitions of this batch: table regions merged 2^part_shift at a time, so
     uint32_t part_shift;     //   that a small batch still fills its k_main chunks (nparts = P >> part_shift)
@@ -407,27 +404,9 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
             B.part_idx[mypos] = a;
             B.part_row[mypos] = rowidx;
             if (r != P1 - 1) {
-                ulonglong2* pa = B.part_acc + (size_t)mypos * 5;
-                unsigned long long posorig = racc.posorig;
-                if (B.embed_mx) {
-                    // carry the limits along: k_main then needs no dependent load of the descriptor table
-                    const RlCellDesc* gd = D.desc + (size_t)(racc.hdr_hi >> 32) * 8;
-                    const uint32_t nc = rl_cells_n(racc.cells);
-                    unsigned long long mx[4] = {0, 0, 0, 0};
-                    unsigned long long qm = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if ((uint32_t)k < nc) {
-                            const RlCellDesc d = gd[rl_cells_at(racc.cells, k)];
-                            mx[k] = d.max_value;
-                            qm |= (unsigned long long)(d.qualified ? 1u : 0u) << k;
-                        }
-                    posorig |= qm << 28;
-                    pa[3] = make_ulonglong2(mx[0], mx[1]);
-                    pa[4] = make_ulonglong2(mx[2], mx[3]);
-                }
+                ulonglong2* pa = B.part_acc + (size_t)mypos * 3;
                 pa[0] = make_ulonglong2(racc.key_lo, racc.hdr_hi);
-                pa[1] = make_ulonglong2((unsigned long long)racc.req | ((unsigned long long)racc.cells << 32), posorig);
+                pa[1] = make_ulonglong2((unsigned long long)racc.req | ((unsigned long long)racc.cells << 32), racc.posorig);
                 pa[2] = make_ulonglong2(rdelta, rnow);
             }
             if (Src::kAccessIsRequest && r == P1 - 1 && B.out_limited) {
@@ -712,13 +691,9 @@ __device__ __forceinline__ void rl_apply_update_smem(unsigned long long* sv, uns
 }
 
 __device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAccess& acc, uint64_t& delta,
-                                             uint64_t& now, uint32_t& row, ulonglong2& m01, ulonglong2& m23) {
-    const ulonglong2* pa = B.part_acc + (size_t)p * 5;
+                                             uint64_t& now, uint32_t& row) {
+    const ulonglong2* pa = B.part_acc + (size_t)p * 3;
     const ulonglong2 a0 = __ldcs(pa), a1 = __ldcs(pa + 1), a2 = __ldcs(pa + 2);
-    if (B.embed_mx) {
-        m01 = __ldcs(pa + 3);
-        m23 = __ldcs(pa + 4);
-    }
     row = __ldcs(B.part_row + p);
     acc.key_lo = a0.x;
     acc.hdr_hi = a0.y;
@@ -769,8 +744,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
         uint64_t ndelta = 0, nnow = 0;
         uint32_t nrow = 0xFFFFFFFFu;
         nacc.key_lo = 0; nacc.hdr_hi = 0; nacc.req = 0; nacc.cells = 0; nacc.posorig = 0;
-        ulonglong2 nm01 = make_ulonglong2(0, 0), nm23 = make_ulonglong2(0, 0);
-        if (lo + tid < hi) rl_load_part(B, lo + tid, nacc, ndelta, nnow, nrow, nm01, nm23);
+        if (lo + tid < hi) rl_load_part(B, lo + tid, nacc, ndelta, nnow, nrow);
 
         for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
             for (uint32_t i = tid; i < GT; i += CH) sm.g_tag[i] = 0ull;
@@ -782,8 +756,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
             const RlAccess acc = nacc;
             const uint64_t delta = ndelta, now = nnow;
             const uint32_t myrow = nrow;
-            const ulonglong2 m01 = nm01, m23 = nm23;
-            if (p + CH < hi) rl_load_part(B, p + CH, nacc, ndelta, nnow, nrow, nm01, nm23);
+            if (p + CH < hi) rl_load_part(B, p + CH, nacc, ndelta, nnow, nrow);
             const uint64_t h = rl_row_hash(acc.key_lo, acc.hdr_hi);
             const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
             const RlCellDesc* gdesc = D.desc + (size_t)group * 8;
@@ -794,23 +767,15 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
             constexpr bool kGeneric = LC || Src::kCanBeMulti;
             RlCellDesc mydesc[kGeneric ? CELLS : 1];  // generic variants: the limits of the cells I touch,
                                                       // indexed by cell, in local memory (L1) for the walks
-            if (!kGeneric && CELLS <= 4 && B.embed_mx) {
-                // the limits travelled with the access (k_part): no dependent descriptor loads here
-                const unsigned long long em[4] = {m01.x, m01.y, m23.x, m23.y};
 #pragma unroll
-                for (int k = 0; k < CELLS; k++) L.mx[k] = em[k];
-                L.qmask = (uint32_t)(acc.posorig >> 28) & 0xFu;
-            } else {
-#pragma unroll
-                for (int k = 0; k < CELLS; k++) {
-                    L.mx[k] = 0;
-                    if (valid && (uint32_t)k < ncell) {
-                        const uint32_t c = rl_cells_at(acc.cells, k);
-                        const RlCellDesc d = gdesc[c];
-                        if (kGeneric) mydesc[kGeneric ? c : 0] = d;
-                        L.mx[k] = d.max_value;
-                        L.qmask |= (d.qualified ? 1u : 0u) << k;
-                    }
+            for (int k = 0; k < CELLS; k++) {
+                L.mx[k] = 0;
+                if (valid && (uint32_t)k < ncell) {
+                    const uint32_t c = rl_cells_at(acc.cells, k);
+                    const RlCellDesc d = gdesc[c];
+                    if (kGeneric) mydesc[kGeneric ? c : 0] = d;
+                    L.mx[k] = d.max_value;
+                    L.qmask |= (d.qualified ? 1u : 0u) << k;
                 }
             }
             const RlCellDesc* desc = kGeneric ? mydesc : gdesc;
