@@ -235,7 +235,8 @@ def main():
     eng.set_stream(stream.cuda_stream)
     assert eng.stream == stream.cuda_stream
 
-    total = W + 2 * K + Ke
+    E_WARM = 3  # untimed e2e steps before the timed ones: staging slots, pinned pages, copy engines
+    total = W + 2 * K + E_WARM + Ke
     # every step consumes its own batch; if the driver asks for more steps than ~48 GB of stream can
     # hold, the pool is cycled (timestamps then repeat; said so in config.l2)
     pool = min(total, max(W + 8, int(48e9 // (batch * 37))))
@@ -264,47 +265,54 @@ def main():
     torch.cuda.synchronize()
     print(f"[bench] generated {total} batches of {batch} in {time.perf_counter() - t_gen:.1f}s", file=sys.stderr)
 
+    ex = None
     if world > 1:
-        send_buf = [torch.empty((world * slot_cap, 4), dtype=torch.int64, device=dev) for _ in range(2)]
-        pos_idx = [torch.empty(batch, dtype=torch.int32, device=dev) for _ in range(2)]
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        recv_buf = [torch.empty((world * slot_cap, 4), dtype=torch.int64, device=dev) for _ in range(2)]
-        v_recv = [torch.zeros(world * slot_cap, dtype=torch.uint8, device=dev) for _ in range(2)]
-        v_back = [torch.empty(world * slot_cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+
+        class _EngineOps:
+            """exchange.LanePipelinedExchange's device work: the engine's kernels on this rank's stream"""
+            @staticmethod
+            def fence(age):
+                if age == 0:
+                    eng.fence()
+                else:
+                    eng.fence_call(age)
+
+            @staticmethod
+            def bucket(r, send, pos):
+                eng.bucket_by_owner_padded_ptr(batch, r.data_ptr(), world, slot_cap, send.data_ptr(), pos.data_ptr(),
+                                               overflow.data_ptr())
+
+            @staticmethod
+            def lane_put(send, lane):
+                eng.record_lane_put_ptr(world * slot_cap, send.data_ptr(), lane.data_ptr())
+
+            @staticmethod
+            def decide(recv, verdict):
+                eng.check_and_update_records_ptr(world * slot_cap, recv.data_ptr(), verdict.data_ptr(), MEM_DEVICE,
+                                                 stride=cells)
+
+            @staticmethod
+            def lane_gather(recv, pos, out):
+                eng.record_lane_gather_ptr(batch, recv.data_ptr(), pos.data_ptr(), out.data_ptr())
+
+        ex = exchange.LanePipelinedExchange(world, batch, slot_cap, dist, _EngineOps, dev)
 
     def step_device(s: int):
         """One step with the batch resident in HBM."""
         if world == 1:
             eng.check_and_update_records_ptr(batch, recs[s].data_ptr(), out_lim[s].data_ptr(), MEM_DEVICE,
                                              out_first_ptr=out_first[s].data_ptr(), stride=cells)
-            return
-        # namespace-sharded (SURVEY §8e): bucket my slice by owner into fixed-size blocks, one NCCL
-        # all-to-all of the 32-B records over NVLink, decide on the owner, one all-to-all of the
-        # verdict bytes back, gather into request order.  No host round trip inside a step: unused
-        # slots carry no-op records (a namespace without limits) that the engine ignores.
-        # Steps are software-pipelined: the verdicts of step s travel back while step s+1 is
-        # already being exchanged and decided (double-buffered exchange buffers).
-        b = s & 1
-        eng.bucket_by_owner_padded_ptr(batch, recs[s].data_ptr(), world, slot_cap, send_buf[b].data_ptr(),
-                                       pos_idx[b].data_ptr(), overflow.data_ptr())
-        dist.all_to_all_single(recv_buf[b], send_buf[b])
-        eng.check_and_update_records_ptr(world * slot_cap, recv_buf[b].data_ptr(), v_recv[b].data_ptr(), MEM_DEVICE,
-                                         stride=cells)
-        pending.append(s)
-        if len(pending) > 1:
-            finish_step(pending.pop(0), 1)
-
-    pending = []
-
-    def finish_step(s: int, age: int):
-        b = s & 1
-        eng.fence_call(age)  # the decisions of step s are done (step s+1 may still be running)
-        dist.all_to_all_single(v_back[b], v_recv[b])
-        eng.gather_u8_ptr(batch, v_back[b].data_ptr(), pos_idx[b].data_ptr(), out_lim[s].data_ptr())
+            return None
+        # namespace-sharded (SURVEY §8e): bucket my slice by owner into fixed-size blocks, ONE NCCL
+        # all-to-all of the 32-B records over NVLink, decide on the owner.  The verdict bytes of step
+        # s-2 ride back in the lane byte of step s's records (exchange.LanePipelinedExchange), so there
+        # is no reverse collective and no host round trip; unused slots carry no-op records (a
+        # namespace without limits) that the engine ignores.  Returns the output completed by this step.
+        return ex.step(recs[s], out_lim[s])
 
     def drain():
-        while pending:
-            finish_step(pending.pop(0), 0)
+        return ex.flush() if ex is not None else []
 
     def barrier():
         if world > 1:
@@ -313,7 +321,7 @@ def main():
 
     host_enqueue_us = []  # CPU time to enqueue one step, per timed pass (launch-bound check)
 
-    def timed(fn, first: int, n: int) -> float:
+    def timed(fn, first: int, n: int, deliver=None) -> float:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -321,8 +329,9 @@ def main():
         for s in range(first, first + n):
             fn(s)
         host_enqueue_us.append((time.perf_counter() - t_host) * 1e6 / max(n, 1))
-        if world > 1:
-            drain()  # the last step's verdicts are still on their way back
+        for t in drain():  # N>1: the last two steps' verdicts are still on their way back
+            if deliver:
+                deliver(t)
         eng.fence()  # pipelined calls: order their completion before the closing event
         e1.record(stream)
         barrier()
@@ -337,8 +346,7 @@ def main():
     t_w = time.perf_counter()
     for s in range(W):
         step_device(s)
-    if world > 1:
-        drain()
+    drain()
     eng.sync()
     print(f"[bench] warm-up {time.perf_counter() - t_w:.2f}s", file=sys.stderr)
 
@@ -359,10 +367,29 @@ def main():
     eng.sync()
 
     # ---- e2e: HOST buffers through the C-ABI (H2D + kernels + D2H per step) ----------------
-    h_recs = torch.empty((Ke, batch, 4), dtype=torch.int64).pin_memory()
-    h_recs.copy_(recs[W + 2 * K:W + 2 * K + Ke])
-    h_lim = torch.empty((Ke, batch), dtype=torch.uint8).pin_memory()
+    # The pinned buffers are allocated (and the enqueuing thread runs) on the CPUs NVML names as
+    # local to this GPU, as a NUMA-aware server would: a remote socket halves the PCIe rate.
+    cpus_before = os.sched_getaffinity(0)
+    try:
+        sampler.nv.nvmlDeviceSetCpuAffinity(sampler.h)
+    except Exception as ex:  # restricted cpuset, no NVML: measure as placed
+        print(f"[bench] GPU-local CPU affinity not applied: {ex}", file=sys.stderr)
+    Kh = E_WARM + Ke
+    h_recs = torch.empty((Kh, batch, 4), dtype=torch.int64).pin_memory()
+    h_recs.copy_(recs[W + 2 * K:W + 2 * K + Kh])
+    h_lim = torch.empty((Kh, batch), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize()
+    # the copy roofline of this box for the e2e number: a plain pinned H2D of the same bytes
+    d_probe = torch.empty_like(h_recs, device=dev)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_probe.copy_(h_recs, non_blocking=True)
+    pe0.record(stream)
+    for _ in range(3):
+        d_probe.copy_(h_recs, non_blocking=True)
+    pe1.record(stream)
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * h_recs.numel() * 8 / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+    del d_probe
 
     def step_host(j: int):
         if world == 1:
@@ -371,22 +398,35 @@ def main():
             eng.check_and_update_records_ptr(batch, h_recs[j].data_ptr(), h_lim[j].data_ptr(),
                                              MEM_HOST if args.no_pipeline else MEM_HOST_ASYNC, stride=cells)
         else:
+            # same pipelining through the exchange: H2D of this step's records, the step, and the D2H
+            # of whichever step's verdicts this exchange delivered (timed() flushes the last two)
             s = W + 2 * K + j
             recs[s].copy_(h_recs[j], non_blocking=True)
-            step_device(s)
-            drain()
-            eng.fence()
-            h_lim[j].copy_(out_lim[s], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            done = step_device(s)
+            if done is not None:
+                e2e_deliver(done)
+
+    def e2e_deliver(t):
+        j = e2e_slot[t.data_ptr()]
+        h_lim[j].copy_(t, non_blocking=True)
+
+    e2e_slot = {out_lim[W + 2 * K + j].data_ptr(): j for j in range(Kh)} if world > 1 else {}
+    for j in range(E_WARM):
+        step_host(j)
+    for t in drain():
+        e2e_deliver(t)
+    eng.sync()
+    torch.cuda.synchronize()
 
     t0 = time.perf_counter()
-    ms_e = timed(step_host, 0, Ke)
+    ms_e = timed(step_host, E_WARM, Ke, deliver=e2e_deliver)
     wall_e = (time.perf_counter() - t0) * 1e3
     ms_e = max(ms_e, 0.0)
     e2e_value = world * batch * Ke / (max(ms_e, 1e-9) * 1e-3)
 
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    os.sched_setaffinity(0, cpus_before)  # the CPU baseline below gets every host core again
     if world > 1 and int(overflow.item()) != 0:
         raise RuntimeError("an exchange block overflowed (namespace skew beyond 2x): rerun with a larger slot_cap")
     print(f"[bench] engine stats {eng.stats()}", file=sys.stderr)
@@ -453,12 +493,15 @@ def main():
                                 f"delta=1, load_counters=false"),
                    "parallelism": ("single GPU, steps software-pipelined over 2 streams" if not args.no_pipeline else "single GPU")
                    if world == 1 else
-                   f"namespace-sharded x{world}, NCCL all-to-all of fixed {slot_cap}-record blocks per peer",
+                   f"namespace-sharded x{world}, one NCCL all-to-all of fixed {slot_cap}-record blocks per peer and step "
+                   f"(verdicts return in the records' lane byte two steps later)",
                    "l2": ("a distinct batch every step (never reused); table > L2" if pool == total else
                           f"{pool} distinct batches cycled (timestamps repeat); table > L2"),
                    "table_rows": cap, "row_bytes": 16 * (1 + cells)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * 32, "d2h_bytes_per_step": batch,
-                "steps": Ke, "ms_per_step": ms_e / Ke, "wall_ms_per_step": wall_e / Ke},
+                "steps": Ke, "ms_per_step": ms_e / Ke, "wall_ms_per_step": wall_e / Ke,
+                # what bounds it: this box's pinned H2D copy rate, and the fraction of it the step stream reached
+                "h2d_copy_gbps": h2d_gbps, "h2d_frac_of_copy_rate": (batch * 32 * Ke / (max(ms_e, 1e-9) * 1e-3) / 1e9) / h2d_gbps},
         "gpu_launches": int(launches),
         "clocks": sampler.result(),
     }

@@ -86,9 +86,12 @@ typedef struct rl_record {
     uint32_t ns_id;
     uint32_t hits_addend; /* RLS uint32 hits_addend (envoy_rls/server.rs:131-135), used as delta */
     uint64_t key_lo;
-    uint64_t key_hi;
+    uint64_t key_hi;      /* bits 0..31: digest bits 64..95; bits 32..55: must be 0; bits 56..63: the lane
+                             byte, opaque to every decision call (rl_record_lane_put/_gather use it) */
     uint64_t now_us;
 } rl_record;
+#define RL_RECORD_LANE_BYTE 23 /* byte offset of the lane byte inside rl_record */
+#define RL_RECORD_KEY_HI_MASK 0x00FFFFFFFFFFFFFFull
 
 /* One counter of a request in the general (CSR) form: Counter = limit + set_variables. */
 typedef struct rl_counter {
@@ -212,6 +215,12 @@ int rl_bucket_by_owner_padded(rl_engine *e, uint64_t n, const rl_record *d_recs,
                               rl_record *d_out_recs, uint32_t *d_out_pos, uint32_t *d_overflow);
 /* out[i] = in[pos[i]] (0 where pos[i] == ~0), device pointers. */
 int rl_gather_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *d_pos, uint8_t *d_out);
+/* Pipelined exchange: the verdict bytes of an earlier step travel back in the lane byte of this
+ * step's records, so a sharded step costs one all-to-all instead of two.
+ *   rl_record_lane_put   : lane byte of d_recs[i] = d_lane[i], i < n_slots (after rl_bucket_by_owner_padded)
+ *   rl_record_lane_gather: d_out[i] = lane byte of d_recs[d_pos[i]] (0 where d_pos[i] == ~0) */
+int rl_record_lane_put(rl_engine *e, uint64_t n_slots, rl_record *d_recs, const uint8_t *d_lane);
+int rl_record_lane_gather(rl_engine *e, uint64_t n, const rl_record *d_recs, const uint32_t *d_pos, uint8_t *d_out);
 /* out[src[i]] = in[i] for i < n (device pointers): return verdict bytes to request order. */
 int rl_unpermute_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *d_src, uint8_t *d_out);
 uint32_t rl_owner_of(uint32_t ns_id, uint32_t world);

@@ -316,7 +316,7 @@ int check_device_error(rl_engine* e) {
         case RL_DEV_UNKNOWN_LIMIT:
             return fail(e, RL_FATAL, "request names a limit_id that was never registered with rl_limits_set");
         case RL_DEV_KEY_RANGE:
-            return fail(e, RL_FATAL, "key_hi must be < 2^32 (counter identity is a 96-bit digest)");
+            return fail(e, RL_FATAL, "key_hi bits 32..55 must be zero (counter identity is a 96-bit digest)");
         case RL_DEV_TOO_MANY_COUNTERS:
             return fail(e, RL_FATAL, "a request has more than %d counters", RL_MAX_CTRS_PER_REQ);
         default:
@@ -1518,6 +1518,24 @@ int rl_gather_u8(rl_engine* e, uint64_t n, const uint8_t* d_in, const uint32_t* 
     RL_CUDA(e, cudaSetDevice(e->device));
     if (n == 0) return RL_OK;
     k_gather_u8<<<ceil_div(n, 256), 256, 0, e->stream>>>((uint32_t)n, d_in, d_pos, d_out);
+    RL_LAUNCH_CHECK(e);
+    return RL_OK;
+}
+
+int rl_record_lane_put(rl_engine* e, uint64_t n_slots, rl_record* d_recs, const uint8_t* d_lane) {
+    if (!e) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    if (n_slots == 0) return RL_OK;
+    k_lane_put<<<ceil_div(n_slots, 256), 256, 0, e->stream>>>((uint32_t)n_slots, d_recs, d_lane);
+    RL_LAUNCH_CHECK(e);
+    return RL_OK;
+}
+
+int rl_record_lane_gather(rl_engine* e, uint64_t n, const rl_record* d_recs, const uint32_t* d_pos, uint8_t* d_out) {
+    if (!e) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    if (n == 0) return RL_OK;
+    k_lane_gather<<<ceil_div(n, 256), 256, 0, e->stream>>>((uint32_t)n, d_recs, d_pos, d_out);
     RL_LAUNCH_CHECK(e);
     return RL_OK;
 }

@@ -217,7 +217,8 @@ struct RecordSrc {
         const RlNsDev ns = D.ns[ns_id];
         if (ns.mode != 1) return false;
         if (ns.qualified_row) {
-            const unsigned long long key_hi = __ldcs(reinterpret_cast<const unsigned long long*>(&recs[a]) + 2);
+            const unsigned long long key_hi =
+                __ldcs(reinterpret_cast<const unsigned long long*>(&recs[a]) + 2) & RL_RECORD_KEY_HI_MASK;
             if (key_hi >> 32) {
                 rl_set_err(D, RL_DEV_KEY_RANGE);
                 return false;
@@ -237,7 +238,7 @@ struct RecordSrc {
         const uint32_t ns_id = (uint32_t)w0.x;
         const RlNsDev ns = D.ns[ns_id];
         acc.key_lo = ns.qualified_row ? w0.y : 0;
-        acc.hdr_hi = ((uint64_t)ns.group << 32) | (ns.qualified_row ? w1.x : 0);
+        acc.hdr_hi = ((uint64_t)ns.group << 32) | (ns.qualified_row ? (w1.x & RL_RECORD_KEY_HI_MASK) : 0);
         acc.req = a;
         acc.cells = ns.cells;
         acc.posorig = RL_IDENT_POSORIG;
@@ -1285,7 +1286,7 @@ __global__ void k_resolve_records(RlDev D, uint32_t n, const rl_record* __restri
         RlCtrIn r;
         r.limit_id = D.ns_limit_ids[lim_off + j];
         r.key_lo = rec.key_lo;
-        r.key_hi = rec.key_hi;
+        r.key_hi = rec.key_hi & RL_RECORD_KEY_HI_MASK;
         return r;
     };
     RlAccess tmp[RL_MAX_CTRS_PER_REQ];
@@ -1390,7 +1391,7 @@ __global__ void k_query_records(RlDev D, uint32_t n, const rl_record* __restrict
         for (uint32_t j = 0; j < ns.lim_cnt; j++) {
             const uint32_t lid = D.ns_limit_ids[ns.lim_off + j];
             bool err = false;
-            if (rl_query_counter<CELLS>(D, lid, rec.key_lo, rec.key_hi, rec.hits_addend, rec.now_us, err)) {
+            if (rl_query_counter<CELLS>(D, lid, rec.key_lo, rec.key_hi & RL_RECORD_KEY_HI_MASK, rec.hits_addend, rec.now_us, err)) {
                 first = lid;
                 break;
             }
@@ -1607,6 +1608,19 @@ __global__ void k_gather_u8(uint32_t n, const uint8_t* __restrict__ in, const ui
                             uint8_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (pos[i] != 0xFFFFFFFFu) ? in[pos[i]] : 0;
+}
+
+// The lane byte of rl_record (top byte of key_hi) is opaque to the engine: the pipelined exchange
+// returns the verdicts of an earlier step in it, so a step costs ONE all-to-all instead of two.
+__global__ void k_lane_put(uint32_t n_slots, rl_record* recs, const uint8_t* __restrict__ lane_in) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots) reinterpret_cast<uint8_t*>(recs + i)[RL_RECORD_LANE_BYTE] = lane_in[i];
+}
+
+__global__ void k_lane_gather(uint32_t n, const rl_record* __restrict__ recs, const uint32_t* __restrict__ pos,
+                              uint8_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (pos[i] != 0xFFFFFFFFu) ? reinterpret_cast<const uint8_t*>(recs + pos[i])[RL_RECORD_LANE_BYTE] : 0;
 }
 
 __global__ void k_unpermute_u8(uint32_t n, const uint8_t* __restrict__ in, const uint32_t* __restrict__ src,

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "rl_check_and_update_batch", "rl_is_within_limits_batch", "rl_is_within_limits_records",
     "rl_update_batch", "rl_update_records", "rl_get_counters", "rl_delete_counters", "rl_clear",
     "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
-    "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8", "rl_fence", "rl_fence_call",
+    "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8", "rl_record_lane_put", "rl_record_lane_gather", "rl_fence", "rl_fence_call",
     "rl_front_create", "rl_front_destroy", "rl_front_check_and_update", "rl_front_stats",
 ]
 
@@ -107,6 +107,8 @@ def load_library(path: str | None = None):
     L.rl_unpermute_u8.argtypes = [vp, u64, vp, vp, vp]
     L.rl_bucket_by_owner_padded.argtypes = [vp, u64, vp, u32, u32, vp, vp, vp]
     L.rl_gather_u8.argtypes = [vp, u64, vp, vp, vp]
+    L.rl_record_lane_put.argtypes = [vp, u64, vp, vp]
+    L.rl_record_lane_gather.argtypes = [vp, u64, vp, vp, vp]
     L.rl_profile_begin.argtypes = [vp]
     L.rl_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.rl_front_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
@@ -292,6 +294,13 @@ class Engine:
 
     def gather_u8_ptr(self, n, in_ptr, pos_ptr, out_ptr):
         self._check(self._lib.rl_gather_u8(self._h, n, C.c_void_p(in_ptr), C.c_void_p(pos_ptr), C.c_void_p(out_ptr)))
+
+    def record_lane_put_ptr(self, n_slots, recs_ptr, lane_ptr):
+        self._check(self._lib.rl_record_lane_put(self._h, n_slots, C.c_void_p(recs_ptr), C.c_void_p(lane_ptr)))
+
+    def record_lane_gather_ptr(self, n, recs_ptr, pos_ptr, out_ptr):
+        self._check(self._lib.rl_record_lane_gather(self._h, n, C.c_void_p(recs_ptr), C.c_void_p(pos_ptr),
+                                                    C.c_void_p(out_ptr)))
 
     def unpermute_u8_ptr(self, n, in_ptr, src_ptr, out_ptr):
         self._check(self._lib.rl_unpermute_u8(self._h, n, C.c_void_p(in_ptr), C.c_void_p(src_ptr), C.c_void_p(out_ptr)))

@@ -7,6 +7,8 @@ Every counter a request touches belongs to the request's namespace
   ->  decide locally (stream order = source rank, source index)  ->  all-to-all of the verdict
   bytes back  ->  restore request order.
 The only collective on the path is that personalised all-to-all (NCCL over NVLink on GPUs).
+`sharded_step` is the plain two-collective form; `LanePipelinedExchange` is the pipelined form
+bench.py runs (fixed-size blocks, one all-to-all per step, no host synchronisation).
 The orchestration is backend-agnostic: bench.py plugs in the engine's kernels on GPU tensors,
 tests/test_exchange_gloo.py plugs in numpy + the oracle on CPU tensors over gloo.
 """
@@ -55,3 +57,73 @@ def stable_bucket_numpy(recs_np: np.ndarray, owners: np.ndarray, world: int):
     order = np.argsort(owners, kind="stable")
     counts = np.bincount(owners, minlength=world).astype(np.int64)
     return recs_np[order], order.astype(np.int32), counts.tolist()
+
+
+class LanePipelinedExchange:
+    """Sharded steps with ONE all-to-all each (include/rl_engine.h: rl_record_lane_put/_gather).
+
+    Blocks are fixed-size (`slot_cap` record slots per peer, unused slots are no-op records), so no
+    counts travel and nothing synchronises with the host.  The verdict byte of the record that sat in
+    slot (p, k) of step s-2 rides back in the lane byte of slot (p, k) of step s: the reverse
+    all-to-all of the two-collective scheme disappears, and the decisions of step s-1 overlap the
+    exchange of step s.  A step's verdicts are therefore delivered two steps later (`step` returns
+    the output tensor that has just been completed); `flush` delivers what is still in flight with
+    lane-only exchanges.
+
+    `ops` supplies the device work (bench.py: the engine's kernels on CUDA tensors; the gloo test:
+    numpy + the oracle):
+      bucket(recs, send, pos)        send[world*slot_cap, 4] <- recs bucketed by owner (+ padding), pos[n] <- slot
+      lane_put(send, lane)           lane byte of send[i] <- lane[i]
+      decide(recv, verdict)          check_and_update over every slot of recv, verdict[i] <- limited (may be asynchronous)
+      lane_gather(recv, pos, out)    out[i] <- lane byte of recv[pos[i]]
+      fence(age)                     order the current stream after the decide call `age` calls back (0 = the last)
+    """
+
+    DEPTH = 3
+
+    def __init__(self, world: int, batch: int, slot_cap: int, dist, ops, device):
+        import torch
+        self.world, self.batch, self.slot_cap, self.dist, self.ops = world, batch, slot_cap, dist, ops
+        slots = world * slot_cap
+        self.send = torch.empty((slots, 4), dtype=torch.int64, device=device)
+        self.recv = [torch.empty((slots, 4), dtype=torch.int64, device=device) for _ in range(self.DEPTH)]
+        self.pos = [torch.zeros(batch, dtype=torch.int32, device=device) for _ in range(self.DEPTH)]
+        self.verdict = [torch.zeros(slots, dtype=torch.uint8, device=device) for _ in range(self.DEPTH)]
+        self.outs = [None] * self.DEPTH  # output tensor of the step that used buffer set b, until delivered
+        self.seq = 0
+
+    def step(self, recs, out_limited):
+        """Enqueue one step for `recs` ([batch, 4] int64 = rl_record[batch]); its verdicts land in
+        `out_limited` two steps (or a flush) later.  Returns the output tensor completed by this
+        step's exchange, or None."""
+        ops, s = self.ops, self.seq
+        b, b2 = s % self.DEPTH, (s - 2) % self.DEPTH
+        ops.fence(1)  # the decisions of step s-2 are final (step s-1 may still be running)
+        ops.bucket(recs, self.send, self.pos[b])
+        ops.lane_put(self.send, self.verdict[b2])
+        self.dist.all_to_all_single(self.recv[b], self.send)
+        ops.decide(self.recv[b], self.verdict[b])
+        done = self.outs[b2] if s >= 2 else None
+        if done is not None:
+            ops.lane_gather(self.recv[b], self.pos[b2], done)
+            self.outs[b2] = None
+        self.outs[b] = out_limited
+        self.seq += 1
+        return done
+
+    def flush(self):
+        """Deliver the verdicts of the (up to two) steps still in flight; returns their outputs."""
+        ops, done = self.ops, []
+        ops.fence(0)  # every decide call so far
+        for back in (2, 1):
+            b = (self.seq - back) % self.DEPTH
+            if self.seq < back or self.outs[b] is None:
+                continue
+            self.send.fill_(-1)  # no records, only lanes
+            ops.lane_put(self.send, self.verdict[b])
+            spare = self.recv[(self.seq + back) % self.DEPTH]  # no decide call is reading any of them now
+            self.dist.all_to_all_single(spare, self.send)
+            ops.lane_gather(spare, self.pos[b], self.outs[b])
+            done.append(self.outs[b])
+            self.outs[b] = None
+        return done

@@ -137,6 +137,12 @@ static lo_slot *q_find(lo_oracle *o, uint32_t limit_id, uint64_t lo, uint64_t hi
     }
 }
 
+/* Room for `extra` more entries without growing: callers that keep entry pointers across several
+ * q_get_or_insert calls (one request's counters) reserve first, so no pointer outlives a rehash. */
+static void q_reserve(lo_oracle *o, uint64_t extra) {
+    while ((o->nfull + extra) * 2 > o->nslots) grow_table(o);
+}
+
 /* moka get_with / get_with_by_ref (in_memory.rs:51-56,122-127): insert-if-missing. */
 static lo_slot *q_get_or_insert(lo_oracle *o, uint32_t limit_id, uint64_t lo, uint64_t hi,
                                 lo_entry init) {
@@ -280,6 +286,7 @@ int lo_check_and_update(lo_oracle *o, const lo_counter *ctrs, uint32_t m, uint64
     if (m > MAXC) return -2;
     for (uint32_t i = 0; i < m; i++)
         if (!get_limit(o, ctrs[i].limit_id)) return -1;
+    q_reserve(o, (uint64_t)m + 1); /* touched[] points into the table until the updates below */
 
     /* in_memory.rs:105 (simple counters first) then :121 (qualified counters). */
     for (int pass = 0; pass < 2; pass++) {
@@ -420,7 +427,7 @@ int lo_batch_records(lo_oracle *o, int mode, uint64_t n, const lo_record *recs, 
             c[k].limit_id = o->ns_limits[r->ns_id][k];
             int q = o->limits[c[k].limit_id].qualified;
             c[k].key_lo = q ? r->key_lo : 0;
-            c[k].key_hi = q ? r->key_hi : 0;
+            c[k].key_hi = q ? (r->key_hi & LO_RECORD_KEY_HI_MASK) : 0; /* top byte: opaque lane */
         }
         uint32_t fl = LO_NONE;
         int res = 0;
@@ -593,7 +600,7 @@ static void *mt_worker(void *p) {
             c[k].limit_id = o->ns_limits[r->ns_id][k];
             int q = o->limits[c[k].limit_id].qualified;
             c[k].key_lo = q ? r->key_lo : 0;
-            c[k].key_hi = q ? r->key_hi : 0;
+            c[k].key_hi = q ? (r->key_hi & LO_RECORD_KEY_HI_MASK) : 0; /* top byte: opaque lane */
         }
         int res = m ? lo_check_and_update(o, c, m, r->hits_addend, 0, r->now_us, NULL, NULL, NULL) : 0;
         a->out_limited[i] = (uint8_t)(res > 0);

@@ -47,6 +47,9 @@ typedef struct {
     uint64_t key_hi;
     uint64_t now_us;
 } lo_record;
+/* top byte of lo_record.key_hi: opaque "lane" byte, not part of the counter identity
+ * (include/rl_engine.h, rl_record) */
+#define LO_RECORD_KEY_HI_MASK 0x00FFFFFFFFFFFFFFull
 
 #define LO_NONE 0xFFFFFFFFu
 

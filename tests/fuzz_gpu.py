@@ -18,18 +18,37 @@ from tests import helpers as H  # noqa: E402
 from tests.test_gpu_parity import single_row_limits  # noqa: E402
 
 
-def one_round(seed: int) -> str:
+def explain(tag, b, k, got, want, recs):
+    """Mismatch diagnostics: where, how many, and the request's place among those of its key."""
+    bad = np.flatnonzero(got != want)
+    lines = [f"{tag} batch {b} output {k}: {len(bad)} of {len(got)} differ"]
+    per = len(got) // len(recs)
+    for j in bad[:8]:
+        i = int(j) // per
+        same = np.flatnonzero((recs["ns_id"][:i + 1] == recs["ns_id"][i]) & (recs["key_lo"][:i + 1] == recs["key_lo"][i]) &
+                              (recs["key_hi"][:i + 1] == recs["key_hi"][i]))
+        lines.append(f"  idx {int(j)} (request {i}, slot {int(j) % per}): got {int(got[j])} want {int(want[j])}; ns {int(recs['ns_id'][i])} "
+                     f"delta {int(recs['hits_addend'][i])} now {int(recs['now_us'][i])}; {len(same)}-th request of its key "
+                     f"(previous at {same[-2] if len(same) > 1 else None})")
+    return "\n".join(lines)
+
+
+def one_round(seed: int, override=None) -> str:
     import torch
     rng = np.random.default_rng(seed)
     cells = int(rng.choice([1, 3, 7]))
-    os.environ["RL_CHUNK"] = str(int(rng.choice([128, 256])))
-    os.environ["RL_HEAVY_MULT"] = str(int(rng.choice([1, 1, 2, 4])))
-    os.environ["RL_PART_TARGET"] = str(int(rng.choice([32, 128, 512])))
+    chunk = int(rng.choice([128, 256]))
+    mult = int(rng.choice([1, 1, 2, 4]))
+    pt = int(rng.choice([32, 128, 512]))
     style = str(rng.choice(["rec_host", "rec_dev_pipe", "rec_host_async", "csr_host", "rec_update"]))
     regions = int(rng.choice([1, 2, 4, 16]))
     n_keys = int(rng.choice([3, 10, 40, 400]))
     n = int(rng.choice([700, 3000, 9000]))
     lc = bool(rng.integers(0, 2))
+    ov = override or {}
+    chunk, mult, pt = int(ov.get("chunk", chunk)), int(ov.get("mult", mult)), int(ov.get("pt", pt))
+    regions, lc = int(ov.get("regions", regions)), bool(int(ov.get("lc", lc)))
+    os.environ["RL_CHUNK"], os.environ["RL_HEAVY_MULT"], os.environ["RL_PART_TARGET"] = str(chunk), str(mult), str(pt)
     flags = 2 if style in ("rec_dev_pipe", "rec_host_async") else 0
     if style == "csr_host":
         descs = H.mixed_limits(n_ns=12, seed=seed)
@@ -38,8 +57,7 @@ def one_round(seed: int) -> str:
     e = Engine(capacity_rows=1 << 14, cells_per_row=cells, max_batch=1 << 14, regions=regions, flags=flags)
     e.limits_set(descs)
     o = H.oracle_with_limits(descs)
-    tag = f"seed={seed} style={style} cells={cells} chunk={os.environ['RL_CHUNK']} mult={os.environ['RL_HEAVY_MULT']} " \
-          f"pt={os.environ['RL_PART_TARGET']} regions={regions} keys={n_keys} n={n} lc={lc}"
+    tag = f"seed={seed} style={style} cells={cells} chunk={chunk} mult={mult} pt={pt} regions={regions} keys={n_keys} n={n} lc={lc}"
     nb = 5
     if style == "csr_host":
         for b in range(nb):
@@ -61,7 +79,7 @@ def one_round(seed: int) -> str:
                 got = e.check_and_update_records(recs, lc, stride=cells)
                 want = o.batch_records(0, recs, lc, cells)
                 for k in range(4 if lc else 2):
-                    assert np.array_equal(got[k], want[k]), f"{tag} batch {b} output {k}"
+                    assert np.array_equal(got[k], want[k]), explain(tag, b, k, got[k], want[k], recs)
         else:
             host = torch.stack([torch.from_numpy(r.view(np.int64).reshape(-1, 4).copy()) for r in batches])
             if style == "rec_dev_pipe":
@@ -92,17 +110,31 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60)
     ap.add_argument("--first-seed", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=0, help="run this one seed only")
+    ap.add_argument("--set", action="append", default=[], help="override a drawn knob: chunk|mult|pt|regions|lc=VALUE")
+    ap.add_argument("--keep-going", action="store_true")
     args = ap.parse_args()
-    t0, seed, done = time.time(), args.first_seed, 0
-    while time.time() - t0 < args.seconds:
+    override = dict(kv.split("=", 1) for kv in args.set)
+    if args.seed:
         try:
-            one_round(seed)
+            print("ok:", one_round(args.seed, override))
         except AssertionError as ex:
             print("FUZZ MISMATCH:", ex)
             sys.exit(1)
+        return
+    t0, seed, done, bad = time.time(), args.first_seed, 0, 0
+    while time.time() - t0 < args.seconds:
+        try:
+            one_round(seed, override)
+        except AssertionError as ex:
+            print("FUZZ MISMATCH:", ex)
+            bad += 1
+            if not args.keep_going:
+                sys.exit(1)
         seed += 1
         done += 1
-    print(f"fuzz ok: {done} rounds, seeds {args.first_seed}..{seed - 1}")
+    print(f"fuzz {'ok' if not bad else 'FAILED'}: {done} rounds, {bad} mismatching, seeds {args.first_seed}..{seed - 1}")
+    sys.exit(1 if bad else 0)
 
 
 if __name__ == "__main__":

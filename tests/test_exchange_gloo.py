@@ -24,11 +24,11 @@ N_BATCHES = 3
 BATCH = 4096
 
 
-def make_stream(rank):
+def make_stream(rank, n_batches=N_BATCHES):
     w = streams.c2_zipf_4limits(batch=BATCH, n_rows=3000, n_ns=16)
     rng = np.random.default_rng(100 + rank)
     out = []
-    for b in range(N_BATCHES):
+    for b in range(n_batches):
         r = w.batch_records(b * WORLD + rank)
         r["hits_addend"] = rng.choice([1, 1, 2], size=BATCH)
         out.append(r)
@@ -69,6 +69,94 @@ def _worker(rank, port, ret):
     ret[rank] = np.concatenate(verdicts)
     dist.barrier()
     dist.destroy_process_group()
+
+
+class _NumpyOps:
+    """LanePipelinedExchange's device work on CPU tensors: numpy bucketing, the oracle as decider."""
+
+    def __init__(self, lib, orc, rank, slot_cap):
+        self.lib, self.orc, self.rank, self.slot_cap = lib, orc, rank, slot_cap
+        self.decided = 0
+
+    def fence(self, age):
+        pass
+
+    def bucket(self, recs, send, pos):
+        a = recs.numpy().view(RECORD_DTYPE).reshape(-1)
+        owners = np.array([self.lib.rl_owner_of(int(ns), WORLD) for ns in a["ns_id"]], dtype=np.int64)
+        out = send.numpy()
+        out[:] = -1
+        p = pos.numpy()
+        for o in range(WORLD):
+            idx = np.flatnonzero(owners == o)
+            assert len(idx) <= self.slot_cap
+            out[o * self.slot_cap:o * self.slot_cap + len(idx)] = recs.numpy()[idx]
+            p[idx] = o * self.slot_cap + np.arange(len(idx))
+
+    def lane_put(self, send, lane):
+        send.numpy().view(np.uint8).reshape(-1, 32)[:, 23] = lane.numpy()
+
+    def decide(self, recv, verdict):
+        a = recv.numpy().view(RECORD_DTYPE).reshape(-1)
+        real = a["ns_id"] != 0xFFFFFFFF
+        assert all(self.lib.rl_owner_of(int(ns), WORLD) == self.rank for ns in np.unique(a["ns_id"][real]))
+        lim, _, _, _ = self.orc.batch_records(0, a)  # padding = a namespace without limits: never limited
+        verdict[:] = torch.from_numpy(lim)
+        self.decided += int(real.sum())
+
+    def lane_gather(self, recv, pos, out):
+        out[:] = torch.from_numpy(recv.numpy().view(np.uint8).reshape(-1, 32)[pos.numpy().astype(np.int64), 23].copy())
+
+
+def _lane_worker(rank, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    lib = load_library()
+    w, batches = make_stream(rank, n_batches=5)
+    orc = ob.Oracle(1 << 14)
+    for d in w.limits:
+        orc.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    slot_cap = BATCH  # worst case: every record of a rank has the same owner
+    ops = _NumpyOps(lib, orc, rank, slot_cap)
+    ex = exchange.LanePipelinedExchange(WORLD, BATCH, slot_cap, dist, ops, "cpu")
+    outs = [torch.full((BATCH,), 7, dtype=torch.uint8) for _ in batches]
+    delivered = []
+    for recs_np, out in zip(batches[:3], outs[:3]):
+        d = ex.step(torch.from_numpy(recs_np.view(np.int64).reshape(-1, 4).copy()), out)
+        delivered.append(d is not None)
+    assert delivered == [False, False, True]
+    assert len(ex.flush()) == 2  # mid-stream flush, then the pipeline refills
+    for recs_np, out in zip(batches[3:], outs[3:]):
+        assert ex.step(torch.from_numpy(recs_np.view(np.int64).reshape(-1, 4).copy()), out) is None
+    assert len(ex.flush()) == 2 and ex.flush() == []
+    ret[rank] = np.concatenate([o.numpy() for o in outs])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_lane_pipelined_exchange_matches_global_oracle():
+    """One all-to-all per step, verdicts returned two steps later in the records' lane byte."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_lane_worker, args=(port, ret), nprocs=WORLD, join=True)
+    w, b0 = make_stream(0, n_batches=5)
+    _, b1 = make_stream(1, n_batches=5)
+    orc = ob.Oracle(1 << 14)
+    for d in w.limits:
+        orc.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    want0, want1 = [], []
+    for s0, s1 in zip(b0, b1):
+        lim, _, _, _ = orc.batch_records(0, np.concatenate([s0, s1]))
+        want0.append(lim[:BATCH])
+        want1.append(lim[BATCH:])
+    assert np.array_equal(ret[0], np.concatenate(want0))
+    assert np.array_equal(ret[1], np.concatenate(want1))
+    assert 0 < int(ret[0].sum()) < len(ret[0])
 
 
 def test_two_rank_sharded_step_matches_global_oracle():

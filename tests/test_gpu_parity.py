@@ -365,6 +365,52 @@ def test_padded_bucket_exchange_roundtrip_single_process():
     assert_tables_equal(e, o, descs)
 
 
+def test_record_lane_byte_is_opaque_and_round_trips():
+    """rl_record_lane_put/_gather (the one-collective exchange): the lane byte travels in the records,
+    the decision calls ignore it, and gathering through the bucket positions restores request order."""
+    import torch
+    descs = single_row_limits(3, n_ns=40, seed=6)
+    e = engine_with_limits(descs, 3, max_batch=1 << 17)
+    o = H.oracle_with_limits(descs)
+    world, n, slot_cap = 4, 20000, 8192
+    recs = H.random_records(descs, n, 77, n_keys=50)
+    d_in = torch.from_numpy(recs.view(np.int64).reshape(-1, 4).copy()).cuda()
+    send = torch.empty((world * slot_cap, 4), dtype=torch.int64, device="cuda")
+    pos = torch.empty(n, dtype=torch.int32, device="cuda")
+    ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lane = torch.randint(0, 256, (world * slot_cap,), dtype=torch.uint8, device="cuda")
+    e.bucket_by_owner_padded_ptr(n, d_in.data_ptr(), world, slot_cap, send.data_ptr(), pos.data_ptr(), ovf.data_ptr())
+    e.record_lane_put_ptr(world * slot_cap, send.data_ptr(), lane.data_ptr())
+    verdict = torch.zeros(world * slot_cap, dtype=torch.uint8, device="cuda")
+    e.check_and_update_records_ptr(world * slot_cap, send.data_ptr(), verdict.data_ptr(), 1, stride=3)
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    e.record_lane_gather_ptr(n, send.data_ptr(), pos.data_ptr(), back.data_ptr())
+    e.sync()
+    assert int(ovf.item()) == 0
+    # the lane bytes came back in request order ...
+    assert np.array_equal(back.cpu().numpy(), lane.cpu().numpy()[pos.cpu().numpy().astype(np.int64)])
+    # ... and did not change a single decision: same verdicts and table as the oracle on the clean records
+    from limitador_b200 import owner_of
+    owners = np.array([owner_of(int(ns), world) for ns in recs["ns_id"]])
+    order = np.argsort(owners, kind="stable")
+    lim, _, _, _ = o.batch_records(0, recs[order])
+    got = verdict.cpu().numpy()[pos.cpu().numpy().astype(np.int64)]
+    want = np.zeros(n, dtype=np.uint8)
+    want[order] = lim
+    assert np.array_equal(got, want)
+    assert_tables_equal(e, o, descs)
+    # the oracle ignores the lane byte too (it checks the exchanged stream in the gloo test)
+    o2 = H.oracle_with_limits(descs)
+    laned = send.cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+    lim2, _, _, _ = o2.batch_records(0, laned)
+    assert np.array_equal(lim2, verdict.cpu().numpy())
+    # a set bit between the digest and the lane byte is still a key-range error
+    bad = recs[recs["ns_id"] % 4 != 3][:8].copy()  # namespaces with qualified limits (single_row_limits)
+    bad["key_hi"] |= np.uint64(1 << 40)
+    with pytest.raises(EngineError):
+        e.check_and_update_records(bad, False, stride=3)
+
+
 def test_pipelined_device_calls_match_oracle():
     """RL_FLAG_PIPELINE: back-to-back device-memory calls overlap (partition of call s+1 with the
     replay of call s); after rl_fence/rl_sync the verdicts and the table equal the sequential ones."""

@@ -352,3 +352,26 @@ def test_mt_baseline_matches_single_thread():
     for threads in (1, 3):
         _, got = ob.bench_records_mt(descs, recs, threads, 1024)
         assert got.tolist() == want.tolist()
+
+
+def test_results_do_not_depend_on_table_growth():
+    """The oracle's own hash table is an implementation detail: a run that starts from a tiny table
+    (and rehashes many times, also in the middle of a request that already holds counters) must give
+    the outputs and the final state of a run that never grows.  (Regression: entry pointers kept
+    across a rehash lost updates.)"""
+    from tests import helpers as H
+    from tests.test_gpu_parity import single_row_limits
+    for seed, cells in ((9, 3), (3, 7), (5, 1)):
+        descs = single_row_limits(cells, n_ns=9, seed=seed)
+        runs = []
+        for cap in (16, 1 << 17):
+            o = H.oracle_with_limits(descs, cap)
+            outs = []
+            for b in range(3):
+                recs = H.random_records(descs, 4000, seed * 100 + b, n_keys=400, monotone=bool(b & 1))
+                outs.append([x.copy() for x in o.batch_records(0, recs, True, cells)])
+            runs.append((outs, H.normalise_dump(o.dump(), descs)))
+        assert runs[0][1] == runs[1][1]
+        for a, b in zip(runs[0][0], runs[1][0]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
