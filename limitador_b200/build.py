@@ -54,5 +54,16 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(name: str, defines) -> str:
+    """An A/B build with extra -D flags into limitador_b200/variants/ (load it with RL_ENGINE_LIB=<path>);
+    the product library is always the plain build above."""
+    out_dir = os.path.join(_PKG, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"librl_engine_{name}.so")
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(_ROOT, "include"), "-o", out, *sources()]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build_engine(force=True, verbose=True))

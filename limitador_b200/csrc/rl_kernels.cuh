@@ -620,12 +620,27 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
 
 // k_main accounts its SM cycles per phase (thread 0, one clock64 and one atomic per phase and
 // chunk): rl_stats.phase_cycles, the numbers DESIGN.md §10 quotes.
+#ifndef RL_MINB_MID
+#define RL_MINB_MID 3  // resident 256-thread CTA equivalents per SM asked of the compiler for 3..4-cell rows
+#endif
+#ifndef RL_WAIT_NS
+#define RL_WAIT_NS 100  // back-off of the chained-commit wait loops
+#endif
+#ifndef RL_KSTATS
+#define RL_KSTATS 1  // build with -DRL_KSTATS=0 to compile the accounting out (A/B of its cost)
+#endif
+#if RL_KSTATS
 #define RL_PHASE_TICK(i)                                                         \
     if (tid == 0) {                                                              \
         const long long tnow = clock64();                                        \
         atomicAdd(D.kstats + 8 + (i), (unsigned long long)(tnow - tph));         \
         tph = tnow;                                                              \
     }
+#define RL_KSTAT_ADD(i, v) atomicAdd(D.kstats + (i), (unsigned long long)(v))
+#else
+#define RL_PHASE_TICK(i)
+#define RL_KSTAT_ADD(i, v)
+#endif
 
 // The sequential rule applied by ONE thread directly on the staged row state (shared
 // memory) — the default path (single-row request, load_counters off).  Same arithmetic as
@@ -708,7 +723,7 @@ __device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAcc
 // GEO = cells per row of the table layout (row bytes), CELLS = cells any row group actually
 // uses (<= GEO): loops, registers and shared memory are sized by the latter.
 template <int GEO, int CELLS, class Src, int MODE, int CH, bool LC>
-__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * (256 / CH)) k_main(RlDev D, RlBatch B, Src src) {
+__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? RL_MINB_MID : 2)) * (256 / CH)) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
     constexpr int PW = Smem::PW;
@@ -1027,12 +1042,12 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
                 if (!__syncthreads_or(!done)) break;
             }
             if (tid == 0) {
-                atomicAdd(D.kstats + 0, 1ull);
-                atomicAdd(D.kstats + 1, (unsigned long long)nrounds);
+                RL_KSTAT_ADD(0, 1);
+                RL_KSTAT_ADD(1, nrounds);
             }
             RL_PHASE_TICK(3)  // replay rounds
             if (!chained || snapshot || attempt == 1) break;
-            if (tid == 0) atomicAdd(D.kstats + 2, 1ull);
+            if (tid == 0) RL_KSTAT_ADD(2, 1);
             const uint32_t base_item = item - it.w;  // first chunk of my region
             // (b) publish my read set, each row tagged with "I write it" (under my speculation)
             for (uint32_t i = tid; i < GT; i += CH) {
@@ -1066,7 +1081,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
                 for (uint32_t j = tid; j < it.w; j += CH)
                     ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) >= 1u);
                 if (__syncthreads_and(ok)) break;
-                __nanosleep(100);
+                __nanosleep(RL_WAIT_NS);
             }
             __threadfence();
             // (d) rows I read that some earlier chunk writes: their history must be replayed in order.
@@ -1136,7 +1151,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
                 }
             }
             if (!any_dep) break;  // nothing I read is written before me: commit now, in parallel
-            if (tid == 0) atomicAdd(D.kstats + 3, 1ull);
+            if (tid == 0) RL_KSTAT_ADD(3, 1);
             // (e) wait for the chunks my rows depend on to commit, then re-validate
             for (;;) {
                 bool ok = true;
@@ -1145,7 +1160,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? 3 : 2)) * 
                     if (need) ok = ok && (*(volatile uint32_t*)(B.chain_status + base_item + j) == 4u);
                 }
                 if (__syncthreads_and(ok)) break;
-                __nanosleep(100);
+                __nanosleep(RL_WAIT_NS);
             }
             __threadfence();
             bool redo = false;
