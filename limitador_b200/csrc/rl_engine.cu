@@ -18,6 +18,13 @@
 
 #include "rl_kernels.cuh"
 
+#ifndef RL_SETS
+#define RL_SETS 3  // RL_FLAG_PIPELINE: calls in flight on the device (>= 3: one per pipeline stage)
+#endif
+#ifndef RL_RING
+#define RL_RING 4  // RL_MEM_HOST_ASYNC: staging slots (H2D of call i+RL_RING waits for the D2H of call i)
+#endif
+
 namespace {
 
 constexpr uint32_t kMaxTiles = 256;
@@ -129,21 +136,20 @@ struct rl_engine {
     // rl_profile_begin/end
     // RL_FLAG_PIPELINE
     bool pipeline = false;
-    static constexpr int kSets = 3;  // workspace sets = pipeline depth (probe | scan+scatter | replay)
-    WorkSet wsx[2];                  // sets 1 and 2 (set 0 = the engine's own members)
+    static constexpr int kSets = RL_SETS;  // workspace sets = calls in flight (probe | scan+scatter | replay)
+    WorkSet wsx[kSets - 1];                // sets 1.. (set 0 = the engine's own members)
     cudaStream_t sq = nullptr;       // scan + scatter stream
     cudaStream_t sp = nullptr, sm = nullptr;  // partition / replay streams
-    cudaEvent_t ev_in = nullptr, ev_probe[3] = {nullptr, nullptr, nullptr}, ev_part[3] = {nullptr, nullptr, nullptr},
-                ev_main[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr, ev_probe[kSets] = {}, ev_part[kSets] = {}, ev_main[kSets] = {};
     uint64_t pipe_seq = 0;
     bool pipe_pending = false;
     // RL_MEM_HOST_ASYNC: ring of device staging slots; copies overlap the kernels of other calls
-    static constexpr int kRing = 4;
+    static constexpr int kRing = RL_RING;
     DevBuf<rl_record> ring_recs[kRing];
     DevBuf<uint8_t> ring_lim[kRing];
     DevBuf<uint32_t> ring_first[kRing];
-    cudaEvent_t ev_slot[kRing] = {nullptr, nullptr, nullptr, nullptr};  // slot's D2H done
-    cudaStream_t sd = nullptr;                                          // D2H stream
+    cudaEvent_t ev_slot[kRing] = {};  // slot's D2H done
+    cudaStream_t sd = nullptr;        // D2H stream
     uint64_t ring_seq = 0;
     bool d2h_pending = false;
     int d2h_last = 0;
@@ -767,8 +773,7 @@ void rl_engine_destroy(rl_engine* e) {
     }
     if (e->sd) cudaStreamDestroy(e->sd);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->wsx[0].release();
-    e->wsx[1].release();
+    for (int k = 0; k < rl_engine::kSets - 1; k++) e->wsx[k].release();
     if (e->sq) cudaStreamSynchronize(e->sq);
     if (e->ev_in) cudaEventDestroy(e->ev_in);
     for (int k = 0; k < rl_engine::kSets; k++) {
