@@ -411,11 +411,12 @@ template <int CELLS, class Src>
 int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st, int stage) {
     const uint32_t P1 = B.nparts + 1;
     const size_t smem = (size_t)RL_PART_WARPS * P1 * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    static int smem_limit[64] = {};  // per instantiation and device: raised as engines with more regions appear
+    const int dv = e->device & 63;
+    if (smem > 48 * 1024 && (int)smem > smem_limit[dv]) {
         const int max_smem = (int)((size_t)RL_PART_WARPS * ((1u << e->log2P) + 1) * sizeof(uint32_t));
         RL_CUDA(e, cudaFuncSetAttribute(k_part<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
+        smem_limit[dv] = max_smem;
     }
     if (stage & 1) {
         k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), st>>>(D, B, src);
@@ -446,10 +447,11 @@ template <int GEO, int CELLS, class Src, int MODE, bool LC, int CH>
 int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
     using Smem = RlMainSmem<CELLS, CH>;
     auto kern = k_main<GEO, CELLS, Src, MODE, CH, LC>;
-    static bool attr_set = false;  // one per instantiation
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // per instantiation and device (function attributes are per device)
+    const int dv = e->device & 63;
+    if (!attr_set[dv]) {
         RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        attr_set = true;
+        attr_set[dv] = true;
     }
     // upper bound of the work-item count: one per region + one per chunk of a heavy region
     const uint32_t grid = B.nparts + ceil_div(B.n_acc, CH);
