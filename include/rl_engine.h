@@ -53,6 +53,9 @@ enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1,
  * (probe / scan / scatter) of call s+1 overlaps the replay of call s.  Results are the same;
  * outputs of such calls are ordered on the caller's stream only after rl_fence() (or rl_sync). */
 #define RL_FLAG_PIPELINE 2u
+/* rl_stats.chunks / replay_rounds / chained_chunks / ordered_chunks / phase_cycles are accounted by the
+ * replay kernel (a few atomics per chunk, ~7 % of a 65536-request step); without the flag they stay 0. */
+#define RL_FLAG_KERNEL_STATS 4u
 
 typedef struct rl_config {
     uint32_t struct_size;    /* sizeof(rl_config) */
@@ -110,7 +113,7 @@ typedef struct rl_stats {
     uint32_t row_bytes;
     uint32_t fixed_point_rounds; /* speculative rounds run for multi-row requests (last batch) */
     uint32_t _pad;
-    uint64_t chunks;         /* k_main: chunks of <= 256 accesses replayed */
+    uint64_t chunks;         /* (RL_FLAG_KERNEL_STATS) k_main: chunks of <= 256 accesses replayed */
     uint64_t replay_rounds;  /* k_main: run-length rounds summed over chunks */
     uint64_t chained_chunks; /* chunks of heavy regions (optimistic concurrency control) */
     uint64_t ordered_chunks; /* ... of which had to commit in order */

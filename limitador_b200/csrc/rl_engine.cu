@@ -21,6 +21,9 @@
 #ifndef RL_SETS
 #define RL_SETS 3  // RL_FLAG_PIPELINE: calls in flight on the device (>= 3: one per pipeline stage)
 #endif
+#ifndef RL_D2H_ON_SM
+#define RL_D2H_ON_SM 0
+#endif
 #ifndef RL_RING
 #define RL_RING 4  // RL_MEM_HOST_ASYNC: staging slots (H2D of call i+RL_RING waits for the D2H of call i)
 #endif
@@ -136,6 +139,7 @@ struct rl_engine {
     // rl_profile_begin/end
     // RL_FLAG_PIPELINE
     bool pipeline = false;
+    bool kernel_stats = false;  // RL_FLAG_KERNEL_STATS
     static constexpr int kSets = RL_SETS;  // workspace sets = calls in flight (probe | scan+scatter | replay)
     WorkSet wsx[kSets - 1];                // sets 1.. (set 0 = the engine's own members)
     cudaStream_t sq = nullptr;       // scan + scatter stream
@@ -213,7 +217,7 @@ RlDev make_dev(rl_engine* e) {
     D.err = e->d_misc.p + MISC_ERR;
     D.flags = e->d_misc.p + MISC_FLAGS;
     D.tag_mask = e->tag_mask;
-    D.kstats = e->d_kstats.p;
+    D.kstats = e->kernel_stats ? e->d_kstats.p : nullptr;
     return D;
 }
 
@@ -721,6 +725,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     }
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
+    e->kernel_stats = (cfg->flags & RL_FLAG_KERNEL_STATS) != 0;
     if (cfg->flags & 2u) {  // RL_FLAG_PIPELINE
         e->pipeline = true;
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sp, cudaStreamNonBlocking));
@@ -1238,12 +1243,19 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
         o.first = out_first_limited ? e->ring_first[slot].p : nullptr;
         o.stride = out_stride;
         if ((r = run_record_pipeline(e, (uint32_t)n, e->ring_recs[slot].p, 0, load_counters ? 1 : 0, o, true))) return r;
+#if RL_D2H_ON_SM
+        // the verdicts leave on the replay stream itself, right behind their k_main: no stream of ours
+        // ever parks on a cross-stream wait in front of a copy (hardware-queue aliasing)
+        cudaStream_t sd = e->sm;
+#else
+        cudaStream_t sd = e->sd;
         const int k = (int)((e->pipe_seq - 1) % rl_engine::kSets);
-        RL_CUDA(e, cudaStreamWaitEvent(e->sd, e->ev_main[k], 0));
-        RL_CUDA(e, cudaMemcpyAsync(out_limited, o.limited, n, cudaMemcpyDeviceToHost, e->sd));
+        RL_CUDA(e, cudaStreamWaitEvent(sd, e->ev_main[k], 0));
+#endif
+        RL_CUDA(e, cudaMemcpyAsync(out_limited, o.limited, n, cudaMemcpyDeviceToHost, sd));
         if (out_first_limited)
-            RL_CUDA(e, cudaMemcpyAsync(out_first_limited, o.first, n * 4, cudaMemcpyDeviceToHost, e->sd));
-        RL_CUDA(e, cudaEventRecord(e->ev_slot[slot], e->sd));
+            RL_CUDA(e, cudaMemcpyAsync(out_first_limited, o.first, n * 4, cudaMemcpyDeviceToHost, sd));
+        RL_CUDA(e, cudaEventRecord(e->ev_slot[slot], sd));
         e->d2h_pending = true;
         e->d2h_last = slot;
         e->ring_seq++;

@@ -37,7 +37,7 @@ struct RlDev {
     uint32_t* err;    // sticky max of RL_DEV_*
     uint32_t* flags;  // bit0: batch has multi-row requests
     unsigned long long tag_mask;  // ~0; tests narrow it to force in-CTA tag collisions
-    unsigned long long* kstats;   // [0] chunks, [1] replay rounds, [2] chained chunks, [3] ordered-fallback chunks
+    unsigned long long* kstats;   // nullptr = no accounting; [0] chunks, [1] replay rounds, [2] chained chunks, [3] ordered-fallback chunks
 };
 
 struct RlBatch {
@@ -618,8 +618,9 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
     b_ok = live_all && (within_all || !check_limit);
 }
 
-// k_main accounts its SM cycles per phase (thread 0, one clock64 and one atomic per phase and
-// chunk): rl_stats.phase_cycles, the numbers DESIGN.md §10 quotes.
+// With RL_FLAG_KERNEL_STATS (D.kstats != nullptr) k_main accounts its chunks, rounds and SM cycles per
+// phase (thread 0, one clock64 and one atomic per phase and chunk): rl_stats.phase_cycles, the numbers
+// DESIGN.md §10 quotes.  It costs ~7 % of the C2 step (600 chunks x 8 atomics on nine words), hence opt-in.
 #ifndef RL_MINB_MID
 #define RL_MINB_MID 3  // resident 256-thread CTA equivalents per SM asked of the compiler for 3..4-cell rows
 #endif
@@ -631,12 +632,13 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
 #endif
 #if RL_KSTATS
 #define RL_PHASE_TICK(i)                                                         \
-    if (tid == 0) {                                                              \
+    if (D.kstats != nullptr && tid == 0) {                                       \
         const long long tnow = clock64();                                        \
         atomicAdd(D.kstats + 8 + (i), (unsigned long long)(tnow - tph));         \
         tph = tnow;                                                              \
     }
-#define RL_KSTAT_ADD(i, v) atomicAdd(D.kstats + (i), (unsigned long long)(v))
+#define RL_KSTAT_ADD(i, v) \
+    if (D.kstats != nullptr) atomicAdd(D.kstats + (i), (unsigned long long)(v))
 #else
 #define RL_PHASE_TICK(i)
 #define RL_KSTAT_ADD(i, v)
@@ -740,7 +742,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? RL_MINB_MI
     uint4 it0 = B.items[blockIdx.x];
     const uint32_t n_items = *B.n_items;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        long long tph = clock64();
+        long long tph = D.kstats != nullptr ? clock64() : 0;
         const uint4 it = (item == blockIdx.x) ? it0 : B.items[item];
         const uint32_t region = it.x, lo = it.y, hi = it.z;
         // Heavy region: this CTA owns ONE chunk and the region's chunks run concurrently under

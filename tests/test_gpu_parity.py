@@ -12,8 +12,8 @@ pytestmark = pytest.mark.gpu
 S = 1_000_000
 
 
-def engine_with_limits(descs, cells, capacity=1 << 14, max_batch=1 << 16, regions=0):
-    e = Engine(capacity_rows=capacity, cells_per_row=cells, max_batch=max_batch, regions=regions)
+def engine_with_limits(descs, cells, capacity=1 << 14, max_batch=1 << 16, regions=0, flags=0):
+    e = Engine(capacity_rows=capacity, cells_per_row=cells, max_batch=max_batch, regions=regions, flags=flags)
     e.limits_set(descs)
     return e
 
@@ -522,7 +522,7 @@ def test_chained_commit_stress(monkeypatch, chunk, mult):
     monkeypatch.setenv("RL_HEAVY_MULT", str(mult))
     for cells in (1, 3):
         descs = single_row_limits(cells, seed=20 + cells)
-        e = engine_with_limits(descs, cells, regions=4)
+        e = engine_with_limits(descs, cells, regions=4, flags=4)  # RL_FLAG_KERNEL_STATS: chunk accounting on
         o = H.oracle_with_limits(descs)
         for b in range(4):
             recs = H.random_records(descs, 6000, 300 + 10 * cells + b, n_keys=25, monotone=(b % 2 == 0))
