@@ -21,9 +21,6 @@
 #ifndef RL_SETS
 #define RL_SETS 3  // RL_FLAG_PIPELINE: calls in flight on the device (>= 3: one per pipeline stage)
 #endif
-#ifndef RL_D2H_ON_SM
-#define RL_D2H_ON_SM 0
-#endif
 #ifndef RL_RING
 #define RL_RING 4  // RL_MEM_HOST_ASYNC: staging slots (H2D of call i+RL_RING waits for the D2H of call i)
 #endif
@@ -153,7 +150,6 @@ struct rl_engine {
     DevBuf<uint8_t> ring_lim[kRing];
     DevBuf<uint32_t> ring_first[kRing];
     cudaEvent_t ev_slot[kRing] = {};  // slot's D2H done
-    cudaStream_t sd = nullptr;        // D2H stream
     uint64_t ring_seq = 0;
     bool d2h_pending = false;
     int d2h_last = 0;
@@ -635,7 +631,6 @@ int ensure_ready(rl_engine* e, uint64_t n, bool fence = true) {
         RL_CUDA(e, cudaStreamSynchronize(e->sp));
         RL_CUDA(e, cudaStreamSynchronize(e->sq));
         RL_CUDA(e, cudaStreamSynchronize(e->sm));
-        RL_CUDA(e, cudaStreamSynchronize(e->sd));
     }
     return upload_tables(e);
 }
@@ -730,7 +725,6 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
         e->pipeline = true;
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sp, cudaStreamNonBlocking));
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sm, cudaStreamNonBlocking));
-        RL_CUDA(e, cudaStreamCreateWithFlags(&e->sd, cudaStreamNonBlocking));
         for (int k = 0; k < rl_engine::kRing; k++) RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_slot[k], cudaEventDisableTiming));
         RL_CUDA(e, cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sq, cudaStreamNonBlocking));
@@ -771,14 +765,12 @@ void rl_engine_destroy(rl_engine* e) {
     cudaSetDevice(e->device);
     if (e->sp) cudaStreamSynchronize(e->sp);
     if (e->sm) cudaStreamSynchronize(e->sm);
-    if (e->sd) cudaStreamSynchronize(e->sd);
     for (int k = 0; k < rl_engine::kRing; k++) {
         e->ring_recs[k].release();
         e->ring_lim[k].release();
         e->ring_first[k].release();
         if (e->ev_slot[k]) cudaEventDestroy(e->ev_slot[k]);
     }
-    if (e->sd) cudaStreamDestroy(e->sd);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (int k = 0; k < rl_engine::kSets - 1; k++) e->wsx[k].release();
     if (e->sq) cudaStreamSynchronize(e->sq);
@@ -1230,7 +1222,7 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
     }
     if (host_async) {
         // H2D on the caller's stream (which carries nothing else of ours), kernels on the pipeline
-        // streams, D2H on `sd`: the copies of one call overlap the kernels of its neighbours.
+        // streams, D2H behind the replay: the copies of one call overlap the kernels of its neighbours.
         const int slot = (int)(e->ring_seq % rl_engine::kRing);
         RL_CUDA(e, e->ring_recs[slot].reserve(e->max_batch));
         RL_CUDA(e, e->ring_lim[slot].reserve(e->max_batch));
@@ -1243,15 +1235,11 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
         o.first = out_first_limited ? e->ring_first[slot].p : nullptr;
         o.stride = out_stride;
         if ((r = run_record_pipeline(e, (uint32_t)n, e->ring_recs[slot].p, 0, load_counters ? 1 : 0, o, true))) return r;
-#if RL_D2H_ON_SM
-        // the verdicts leave on the replay stream itself, right behind their k_main: no stream of ours
-        // ever parks on a cross-stream wait in front of a copy (hardware-queue aliasing)
+        // The verdicts leave on the replay stream itself, right behind their k_main.  A dedicated copy
+        // stream parked on "replay done" looked cleaner, but streams share hardware queues: whenever
+        // it landed on the queue of the stream carrying the next H2D, that copy waited for the replay
+        // too and the whole pipeline serialised (e2e 0.4 instead of 1.1 G decisions/s, one run in three).
         cudaStream_t sd = e->sm;
-#else
-        cudaStream_t sd = e->sd;
-        const int k = (int)((e->pipe_seq - 1) % rl_engine::kSets);
-        RL_CUDA(e, cudaStreamWaitEvent(sd, e->ev_main[k], 0));
-#endif
         RL_CUDA(e, cudaMemcpyAsync(out_limited, o.limited, n, cudaMemcpyDeviceToHost, sd));
         if (out_first_limited)
             RL_CUDA(e, cudaMemcpyAsync(out_first_limited, o.first, n * 4, cudaMemcpyDeviceToHost, sd));
