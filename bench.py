@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 256)")
     ap.add_argument("--cpu-sample-batches", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange-lag", type=int, default=3,
+                    help="N>1: verdicts return in the records of the step this many steps later (1..3)")
     ap.add_argument("--no-pipeline", action="store_true", help="disable the engine's two-stream step pipelining")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -296,7 +298,7 @@ def main():
             def lane_gather(recv, pos, out):
                 eng.record_lane_gather_ptr(batch, recv.data_ptr(), pos.data_ptr(), out.data_ptr())
 
-        ex = exchange.LanePipelinedExchange(world, batch, slot_cap, dist, _EngineOps, dev)
+        ex = exchange.LanePipelinedExchange(world, batch, slot_cap, dist, _EngineOps, dev, lag=args.exchange_lag)
 
     def step_device(s: int):
         """One step with the batch resident in HBM."""
@@ -306,7 +308,7 @@ def main():
             return None
         # namespace-sharded: bucket my slice by owner into fixed-size blocks, ONE NCCL
         # all-to-all of the 32-B records over NVLink, decide on the owner.  The verdict bytes of step
-        # s-2 ride back in the lane byte of step s's records (exchange.LanePipelinedExchange), so there
+        # s-lag ride back in the lane byte of step s's records (exchange.LanePipelinedExchange), so there
         # is no reverse collective and no host round trip; unused slots carry no-op records (a
         # namespace without limits) that the engine ignores.  Returns the output completed by this step.
         return ex.step(recs[s], out_lim[s])
@@ -329,7 +331,7 @@ def main():
         for s in range(first, first + n):
             fn(s)
         host_enqueue_us.append((time.perf_counter() - t_host) * 1e6 / max(n, 1))
-        for t in drain():  # N>1: the last two steps' verdicts are still on their way back
+        for t in drain():  # N>1: the last steps' verdicts are still on their way back
             if deliver:
                 deliver(t)
         eng.fence()  # pipelined calls: order their completion before the closing event
@@ -496,7 +498,7 @@ def main():
                    "parallelism": ("single GPU, steps software-pipelined over 2 streams" if not args.no_pipeline else "single GPU")
                    if world == 1 else
                    f"namespace-sharded x{world}, one NCCL all-to-all of fixed {slot_cap}-record blocks per peer and step "
-                   f"(verdicts return in the records' lane byte two steps later)",
+                   f"(verdicts return in the records' lane byte {args.exchange_lag} steps later)",
                    "l2": ("a distinct batch every step (never reused); table > L2" if pool == total else
                           f"{pool} distinct batches cycled (timestamps repeat); table > L2"),
                    "table_rows": cap, "row_bytes": 16 * (1 + cells)},

@@ -64,9 +64,10 @@ class LanePipelinedExchange:
 
     Blocks are fixed-size (`slot_cap` record slots per peer, unused slots are no-op records), so no
     counts travel and nothing synchronises with the host.  The verdict byte of the record that sat in
-    slot (p, k) of step s-2 rides back in the lane byte of slot (p, k) of step s: the reverse
-    all-to-all of the two-collective scheme disappears, and the decisions of step s-1 overlap the
-    exchange of step s.  A step's verdicts are therefore delivered two steps later (`step` returns
+    slot (p, k) of step s-lag rides back in the lane byte of slot (p, k) of step s: the reverse
+    all-to-all of the two-collective scheme disappears, and the decisions of the last lag-1 steps
+    overlap the exchange of step s (a step's period is bounded by (decision latency + exchange) / lag,
+    not by their sum).  A step's verdicts are therefore delivered `lag` steps later (`step` returns
     the output tensor that has just been completed); `flush` delivers what is still in flight with
     lane-only exchanges.
 
@@ -79,49 +80,49 @@ class LanePipelinedExchange:
       fence(age)                     order the current stream after the decide call `age` calls back (0 = the last)
     """
 
-    DEPTH = 3
-
-    def __init__(self, world: int, batch: int, slot_cap: int, dist, ops, device):
+    def __init__(self, world: int, batch: int, slot_cap: int, dist, ops, device, lag: int = 2):
         import torch
-        self.world, self.batch, self.slot_cap, self.dist, self.ops = world, batch, slot_cap, dist, ops
+        assert lag >= 1
+        self.world, self.batch, self.slot_cap, self.dist, self.ops, self.lag = world, batch, slot_cap, dist, ops, lag
+        self.depth = depth = lag + 1  # buffer sets: a set is reused lag+1 steps later
         slots = world * slot_cap
         self.send = torch.empty((slots, 4), dtype=torch.int64, device=device)
-        self.recv = [torch.empty((slots, 4), dtype=torch.int64, device=device) for _ in range(self.DEPTH)]
-        self.pos = [torch.zeros(batch, dtype=torch.int32, device=device) for _ in range(self.DEPTH)]
-        self.verdict = [torch.zeros(slots, dtype=torch.uint8, device=device) for _ in range(self.DEPTH)]
-        self.outs = [None] * self.DEPTH  # output tensor of the step that used buffer set b, until delivered
+        self.recv = [torch.empty((slots, 4), dtype=torch.int64, device=device) for _ in range(depth)]
+        self.pos = [torch.zeros(batch, dtype=torch.int32, device=device) for _ in range(depth)]
+        self.verdict = [torch.zeros(slots, dtype=torch.uint8, device=device) for _ in range(depth)]
+        self.outs = [None] * depth  # output tensor of the step that used buffer set b, until delivered
         self.seq = 0
 
     def step(self, recs, out_limited):
         """Enqueue one step for `recs` ([batch, 4] int64 = rl_record[batch]); its verdicts land in
-        `out_limited` two steps (or a flush) later.  Returns the output tensor completed by this
+        `out_limited` `lag` steps (or a flush) later.  Returns the output tensor completed by this
         step's exchange, or None."""
-        ops, s = self.ops, self.seq
-        b, b2 = s % self.DEPTH, (s - 2) % self.DEPTH
-        ops.fence(1)  # the decisions of step s-2 are final (step s-1 may still be running)
-        ops.bucket(recs, self.send, self.pos[b])
-        ops.lane_put(self.send, self.verdict[b2])
+        ops, s, lag = self.ops, self.seq, self.lag
+        b, bl = s % self.depth, (s - lag) % self.depth
+        ops.bucket(recs, self.send, self.pos[b])  # independent of any decision: runs while they finish
+        ops.fence(lag - 1)  # the decisions of step s-lag are final (later steps may still be running)
+        ops.lane_put(self.send, self.verdict[bl])
         self.dist.all_to_all_single(self.recv[b], self.send)
         ops.decide(self.recv[b], self.verdict[b])
-        done = self.outs[b2] if s >= 2 else None
+        done = self.outs[bl] if s >= lag else None
         if done is not None:
-            ops.lane_gather(self.recv[b], self.pos[b2], done)
-            self.outs[b2] = None
+            ops.lane_gather(self.recv[b], self.pos[bl], done)
+            self.outs[bl] = None
         self.outs[b] = out_limited
         self.seq += 1
         return done
 
     def flush(self):
-        """Deliver the verdicts of the (up to two) steps still in flight; returns their outputs."""
+        """Deliver the verdicts of the (up to `lag`) steps still in flight; returns their outputs."""
         ops, done = self.ops, []
         ops.fence(0)  # every decide call so far
-        for back in (2, 1):
-            b = (self.seq - back) % self.DEPTH
+        for back in range(self.lag, 0, -1):
+            b = (self.seq - back) % self.depth
             if self.seq < back or self.outs[b] is None:
                 continue
             self.send.fill_(-1)  # no records, only lanes
             ops.lane_put(self.send, self.verdict[b])
-            spare = self.recv[(self.seq + back) % self.DEPTH]  # no decide call is reading any of them now
+            spare = self.recv[(self.seq + back) % self.depth]  # no decide call is reading any of them now
             self.dist.all_to_all_single(spare, self.send)
             ops.lane_gather(spare, self.pos[b], self.outs[b])
             done.append(self.outs[b])

@@ -108,44 +108,46 @@ class _NumpyOps:
         out[:] = torch.from_numpy(recv.numpy().view(np.uint8).reshape(-1, 32)[pos.numpy().astype(np.int64), 23].copy())
 
 
-def _lane_worker(rank, port, ret):
+def _lane_worker(rank, port, ret, lag):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     lib = load_library()
-    w, batches = make_stream(rank, n_batches=5)
+    w, batches = make_stream(rank, n_batches=6)
     orc = ob.Oracle(1 << 14)
     for d in w.limits:
         orc.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
     slot_cap = BATCH  # worst case: every record of a rank has the same owner
     ops = _NumpyOps(lib, orc, rank, slot_cap)
-    ex = exchange.LanePipelinedExchange(WORLD, BATCH, slot_cap, dist, ops, "cpu")
+    ex = exchange.LanePipelinedExchange(WORLD, BATCH, slot_cap, dist, ops, "cpu", lag=lag)
     outs = [torch.full((BATCH,), 7, dtype=torch.uint8) for _ in batches]
     delivered = []
-    for recs_np, out in zip(batches[:3], outs[:3]):
+    for recs_np, out in zip(batches[:4], outs[:4]):
         d = ex.step(torch.from_numpy(recs_np.view(np.int64).reshape(-1, 4).copy()), out)
         delivered.append(d is not None)
-    assert delivered == [False, False, True]
-    assert len(ex.flush()) == 2  # mid-stream flush, then the pipeline refills
-    for recs_np, out in zip(batches[3:], outs[3:]):
-        assert ex.step(torch.from_numpy(recs_np.view(np.int64).reshape(-1, 4).copy()), out) is None
-    assert len(ex.flush()) == 2 and ex.flush() == []
+    assert delivered == [i >= lag for i in range(4)]
+    assert len(ex.flush()) == min(lag, 4)  # mid-stream flush, then the pipeline refills
+    for i, (recs_np, out) in enumerate(zip(batches[4:], outs[4:])):
+        d = ex.step(torch.from_numpy(recs_np.view(np.int64).reshape(-1, 4).copy()), out)
+        assert (d is not None) == (i >= lag)
+    assert len(ex.flush()) == min(lag, 2) and ex.flush() == []
     ret[rank] = np.concatenate([o.numpy() for o in outs])
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_lane_pipelined_exchange_matches_global_oracle():
-    """One all-to-all per step, verdicts returned two steps later in the records' lane byte."""
+@pytest.mark.parametrize("lag", [1, 2, 3])
+def test_two_rank_lane_pipelined_exchange_matches_global_oracle(lag):
+    """One all-to-all per step, verdicts returned `lag` steps later in the records' lane byte."""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_lane_worker, args=(port, ret), nprocs=WORLD, join=True)
-    w, b0 = make_stream(0, n_batches=5)
-    _, b1 = make_stream(1, n_batches=5)
+    mp.spawn(_lane_worker, args=(port, ret, lag), nprocs=WORLD, join=True)
+    w, b0 = make_stream(0, n_batches=6)
+    _, b1 = make_stream(1, n_batches=6)
     orc = ob.Oracle(1 << 14)
     for d in w.limits:
         orc.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))

@@ -29,7 +29,7 @@ def make_stream(rank):
     return w, [w.batch_records(b * WORLD + rank) for b in range(N_STEPS)]
 
 
-def _worker(rank, port, ret):
+def _worker(rank, port, ret, lag):
     from limitador_b200 import Engine
     from limitador_b200.engine import MEM_DEVICE
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -69,7 +69,7 @@ def _worker(rank, port, ret):
         def lane_gather(recv, pos, out):
             eng.record_lane_gather_ptr(BATCH, recv.data_ptr(), pos.data_ptr(), out.data_ptr())
 
-    ex = exchange.LanePipelinedExchange(WORLD, BATCH, slot_cap, dist, Ops, dev)
+    ex = exchange.LanePipelinedExchange(WORLD, BATCH, slot_cap, dist, Ops, dev, lag=lag)
     d_recs = [torch.from_numpy(r.view(np.int64).reshape(-1, 4).copy()).to(dev) for r in batches]
     outs = [torch.full((BATCH,), 7, dtype=torch.uint8, device=dev) for _ in batches]
     torch.cuda.synchronize()
@@ -88,7 +88,8 @@ def _worker(rank, port, ret):
 
 
 @pytest.mark.gpu
-def test_two_gpu_lane_pipelined_exchange_matches_global_oracle():
+@pytest.mark.parametrize("lag", [2, 3])
+def test_two_gpu_lane_pipelined_exchange_matches_global_oracle(lag):
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs two GPUs")
     s = socket.socket()
@@ -97,7 +98,7 @@ def test_two_gpu_lane_pipelined_exchange_matches_global_oracle():
     s.close()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(port, ret), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(port, ret, lag), nprocs=WORLD, join=True)
     w, b0 = make_stream(0)
     _, b1 = make_stream(1)
     orc = ob.Oracle(1 << 16)
