@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 256)")
     ap.add_argument("--cpu-sample-batches", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange-lag", type=int, default=3,
+    ap.add_argument("--exchange-lag", type=int, default=2,
                     help="N>1: verdicts return in the records of the step this many steps later (1..3)")
     ap.add_argument("--no-pipeline", action="store_true", help="disable the engine's two-stream step pipelining")
     args = ap.parse_args()
