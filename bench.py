@@ -21,6 +21,13 @@ import time
 
 import numpy as np
 
+# The engine drives four streams (caller, probe, scan+scatter, replay) that wait on each other's events.
+# CUDA maps streams onto a small number of hardware queues (8 by default); two of ours on one queue
+# serialise the H2D copies behind kernel waits and the end-to-end pass drops from 1.1 to 0.4 G decisions/s
+# (profiles/r01_e2e_queue_aliasing.txt).  More queues make that unlikely; a deployment sets the same
+# variable before CUDA is initialised.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
