@@ -59,3 +59,13 @@ def test_long_dependency_chain_converges():
     now = np.full(n, H.T0, dtype=np.uint64)
     rounds = run_both(descs, 1, [(off, ctrs, delta, now)], False)
     assert rounds[0] > 2
+
+
+@pytest.mark.parametrize("cells,load_counters,seed", [(1, True, 11), (3, False, 12), (7, True, 13)])
+def test_wide_key_space_streams_match_oracle(cells, load_counters, seed):
+    """Many distinct keys with few requests each (state carried across batches, windows expiring
+    between them, the oracle's table growing under it) — the shape the GPU fuzzing found the oracle's
+    rehash bug with."""
+    descs = H.mixed_limits(n_ns=12, seed=seed)
+    batches = [H.random_csr_stream(descs, 2500, seed * 100 + b, n_keys=120, monotone=bool(b & 1)) for b in range(4)]
+    run_both(descs, cells, batches, load_counters)
