@@ -294,6 +294,9 @@ __global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src sr
     for (uint32_t i = tid; i < P1; i += 1024) rcnt[i] = 0;
     __syncthreads();
     const uint32_t R = 1u << D.log2R;
+#if RL_EXP_PAD_AGG
+    uint32_t npad = 0;
+#endif
     for (uint32_t base = t0 + tid; base < t1; base += 1024 * U) {
         uint64_t klo[U], hhi[U], h[U];
         bool ok[U];
@@ -325,9 +328,23 @@ __global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src sr
             }
             B.reg_of[a] = r;
             B.row_of[a] = rowidx;
+#if RL_EXP_PAD_AGG
+            if (r != P1 - 1) atomicAdd(&rcnt[r], 1u);
+            else npad++;
+#else
             atomicAdd(&rcnt[r], 1u);
+#endif
         }
     }
+#if RL_EXP_PAD_AGG
+    {
+        // accesses without limits (the padding of a fixed-size exchange block is thousands of them per
+        // tile) all count into one bucket: sum them per warp first
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npad += __shfl_xor_sync(0xffffffffu, npad, o);
+        if ((tid & 31) == 0 && npad) atomicAdd(&rcnt[P1 - 1], npad);
+    }
+#endif
     __syncthreads();
     for (uint32_t r = tid; r < P1; r += 1024) B.tile_cnt[(size_t)tile * P1 + r] = rcnt[r];
 }
@@ -621,6 +638,14 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
 // With RL_FLAG_KERNEL_STATS (D.kstats != nullptr) k_main accounts its chunks, rounds and SM cycles per
 // phase (thread 0, one clock64 and one atomic per phase and chunk): rl_stats.phase_cycles, the numbers
 // DESIGN.md §10 quotes.  It costs ~7 % of the C2 step (600 chunks x 8 atomics on nine words), hence opt-in.
+// Experiments prepared for the next round, off in the product build; measure with
+// build.build_variant(name, ["RL_EXP_...=1"]) + RL_ENGINE_LIB before flipping a default.
+#ifndef RL_EXP_PAD_AGG
+#define RL_EXP_PAD_AGG 0  // k_probe_count: one shared-memory add per warp for the no-limit bucket (exchange padding)
+#endif
+#ifndef RL_EXP_ROW_PREFETCH
+#define RL_EXP_ROW_PREFETCH 0  // k_main: every thread fetches its row state before the grouping, not only the reps after it
+#endif
 #ifndef RL_MINB_MID
 #define RL_MINB_MID 3  // resident 256-thread CTA equivalents per SM asked of the compiler for 3..4-cell rows
 #endif
@@ -813,6 +838,13 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? RL_MINB_MI
             uint8_t* row = nullptr;
             bool is_rep = false;
             RlRow<CELLS> st;
+#if RL_EXP_ROW_PREFETCH
+            // every thread fetches the state of its own row now (threads of one key hit the same sectors):
+            // the L2 round trip overlaps the grouping barriers; only the key's rep ends up using it.  The
+            // previous chunk of this CTA wrote its rows back before the barrier that ended it.
+            rl_row_load<CELLS>((valid && myrow != 0xFFFFFFFFu) ? D.rows + (size_t)myrow * RlGeom<GEO>::ROW_BYTES : nullptr,
+                               CELLS, st);
+#endif
             {
                 bool pending = valid;
                 uint32_t salt = 0;
@@ -837,7 +869,9 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? RL_MINB_MI
                         if (is_rep && row == nullptr) {
                             // the row was located (or claimed) by k_part; its sectors are in L2
                             if (myrow != 0xFFFFFFFFu) row = D.rows + (size_t)myrow * RlGeom<GEO>::ROW_BYTES;
+#if !RL_EXP_ROW_PREFETCH
                             rl_row_load<CELLS>(row, CELLS, st);
+#endif
                         }
                     }
                     __syncthreads();
