@@ -151,7 +151,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={batch}"},
+        # the same workload string as the GPU arm's (one step here = a bounded sample of it, see cpu_baseline.sample)
+        "config": {"workload": f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={args.batch}/GPU, "
+                               f"delta=1, load_counters=false",
+                   "parallelism": f"{cores} host threads, namespaces assigned to threads by load"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
