@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange-lag", type=int, default=2,
                     help="N>1: verdicts return in the records of the step this many steps later (1..3)")
-    ap.add_argument("--no-pipeline", action="store_true", help="disable the engine's two-stream step pipelining")
+    ap.add_argument("--no-pipeline", action="store_true", help="disable the pipelining of successive steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not args.batch:
@@ -505,7 +505,7 @@ def main():
                                 f"load_counters=false, reference fixed-window semantics") if c3 else
                                (f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={batch}/GPU, "
                                 f"delta=1, load_counters=false"),
-                   "parallelism": ("single GPU, steps software-pipelined over 2 streams" if not args.no_pipeline else "single GPU")
+                   "parallelism": ("single GPU, successive steps pipelined over 3 streams (probe | scan+scatter | replay)" if not args.no_pipeline else "single GPU")
                    if world == 1 else
                    f"namespace-sharded x{world}, one NCCL all-to-all of fixed {slot_cap}-record blocks per peer and step "
                    f"(verdicts return in the records' lane byte {args.exchange_lag} steps later)",
