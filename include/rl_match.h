@@ -1,0 +1,85 @@
+/* rl_match.h — CPU front of the engine: limits -> counters.
+ *
+ * Replaces, for a table-driven subset of the reference's CEL expressions,
+ *   RateLimiter::counters_that_apply          limitador/src/lib.rs:507-522
+ *     = Storage::get_limits                   limitador/src/storage/mod.rs:85-91
+ *     + Limit::applies                        limitador/src/limit.rs:157-174
+ *         (Predicate::test                    limitador/src/limit/cel.rs:314-334: a condition over an unbound
+ *                                             name or a missing key is false, never an error)
+ *     + Counter::new / resolve_variables      limitador/src/counter.rs:20-32, limit.rs:133-148 (a variable
+ *                                             without a value drops the counter)
+ *   and the interning a GPU-backed CounterStorage needs: Limit identity (limit.rs:177-214: namespace,
+ *   seconds, conditions, variables — max_value, name and id excluded) -> dense limit_id, namespace -> ns_id,
+ *   (namespace, variable set) -> varset_id, resolved variable values -> 96-bit counter key.
+ *
+ * Expressions accepted (anything else is refused at rl_matcher_add_limit with RL_FATAL, so that a deployment
+ * can keep such limits on the reference's interpreter):
+ *   operand   := IDENT ('.' IDENT)*                         a root binding, dots are part of the name
+ *              | 'descriptors[' N '].' IDENT                the Envoy descriptor list (cel.rs:102-114)
+ *              | 'descriptors[' N '][' QUOTED ']'
+ *   condition := operand ('==' | '!=') QUOTED               QUOTED = '...' or "..."
+ *   variable  := operand
+ *
+ * Output = exactly the inputs of rl_check_and_update_batch (include/rl_engine.h): a CSR of rl_counter.
+ * Counters come out in the limits' registration order (the reference iterates a HashSet: unspecified).
+ * Pure host code; no CUDA call is made by anything in this header.
+ */
+#ifndef RL_MATCH_H
+#define RL_MATCH_H
+
+#include <stdint.h>
+
+#include "rl_engine.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rl_matcher rl_matcher;
+
+#define RL_BIND_ROOT 0xFFFFFFFFu
+/* One (key, value) of a request's context: a root binding (Context::from(HashMap), cel.rs:156-160) or an
+ * entry of descriptors[descriptor] (Context::list_binding, cel.rs:102-114).  Strings are NUL-terminated
+ * UTF-8 owned by the caller. */
+typedef struct rl_binding {
+    uint32_t descriptor; /* index into the descriptor list, or RL_BIND_ROOT */
+    uint32_t _pad;
+    const char *key;
+    const char *value;
+} rl_binding;
+
+int rl_matcher_create(rl_matcher **out);
+void rl_matcher_destroy(rl_matcher *m);
+const char *rl_matcher_last_error(rl_matcher *m);
+
+/* Limit::new + Storage::add_limit / update_limit (storage/mod.rs:60-83).  A limit with a known identity keeps
+ * its limit_id and takes the new max_value / name.  *out_desc is what rl_limits_set needs. */
+int rl_matcher_add_limit(rl_matcher *m, const char *ns, uint64_t max_value, uint64_t seconds,
+                         const char *const *conditions, uint32_t n_cond, const char *const *variables,
+                         uint32_t n_var, const char *name /* nullable */, rl_limit_desc *out_desc);
+/* Storage::delete_limit (storage/mod.rs:93-117): the id is retired, never reused. */
+int rl_matcher_delete_limit(rl_matcher *m, uint32_t limit_id);
+/* RL_OK and *out_ns_id, or RL_FATAL if no limit was ever added for the namespace (no limits => allow,
+ * lib.rs:434-440: the caller skips the engine). */
+int rl_matcher_namespace_id(rl_matcher *m, const char *ns, uint32_t *out_ns_id);
+/* Name of a limit (Authorization::Limited(name)), or NULL. */
+const char *rl_matcher_limit_name(rl_matcher *m, uint32_t limit_id);
+
+/* counters_that_apply for one request: *out_n counters written to out_ctrs (RL_FATAL if more than cap). */
+int rl_matcher_counters(rl_matcher *m, uint32_t ns_id, const rl_binding *binds, uint32_t n_binds,
+                        rl_counter *out_ctrs, uint32_t cap, uint32_t *out_n);
+/* The same for n requests: request i owns binds[bind_off[i] .. bind_off[i+1]); fills out_ctr_off[0..n] and
+ * out_ctrs (capacity cap counters) — pass both straight to rl_check_and_update_batch.  Thread-safe against
+ * other matching calls; rl_matcher_add_limit / _delete_limit take the matcher exclusively. */
+int rl_matcher_counters_batch(rl_matcher *m, uint64_t n, const uint32_t *ns_id, const uint32_t *bind_off,
+                              const rl_binding *binds, uint32_t *out_ctr_off, rl_counter *out_ctrs, uint64_t cap);
+/* The 96-bit counter key of n (variable source, value) pairs (any order): key_lo = digest bits 0..63,
+ * key_hi = bits 64..95.  BLAKE2b-96 over the pairs sorted by source, each string length-prefixed (u32 LE).
+ * (0, 0) for n == 0 (unqualified counter). */
+void rl_counter_key(const char *const *sources, const char *const *values, uint32_t n, uint64_t *key_lo,
+                    uint64_t *key_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RL_MATCH_H */

@@ -30,7 +30,7 @@ def _nvcc() -> str:
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("rl_engine.cu", "rl_front.cu")]
+    return [os.path.join(CSRC, f) for f in ("rl_engine.cu", "rl_front.cu", "rl_match.cpp")]
 
 
 def _deps():

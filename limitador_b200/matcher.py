@@ -1,0 +1,155 @@
+"""ctypes binding of the native CPU front (include/rl_match.h, csrc/rl_match.cpp): limits -> counters.
+
+`Matcher` is the compiled counterpart of `limiter.RateLimiter.counters_that_apply` (lib.rs:507-522): it
+interns limits, namespaces and variable sets the same way `limiter.RateLimiter` does, matches a request's
+context against the namespace's limits and returns the CSR of `rl_counter` that
+`Engine.check_and_update_batch` takes.  No decision is computed here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine as _eng
+
+BIND_ROOT = 0xFFFFFFFF
+
+MATCH_SYMBOLS = (
+    "rl_matcher_create", "rl_matcher_destroy", "rl_matcher_last_error", "rl_matcher_add_limit",
+    "rl_matcher_delete_limit", "rl_matcher_namespace_id", "rl_matcher_limit_name", "rl_matcher_counters",
+    "rl_matcher_counters_batch", "rl_counter_key",
+)
+
+
+class RlBinding(C.Structure):
+    _fields_ = [("descriptor", C.c_uint32), ("_pad", C.c_uint32), ("key", C.c_char_p), ("value", C.c_char_p)]
+
+
+class MatcherError(RuntimeError):
+    pass
+
+
+def _lib():
+    L = _eng.load_library()
+    if getattr(L, "_rl_match_ready", False):
+        return L
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    L.rl_matcher_create.argtypes = [C.POINTER(vp)]
+    L.rl_matcher_destroy.argtypes = [vp]
+    L.rl_matcher_destroy.restype = None
+    L.rl_matcher_last_error.argtypes = [vp]
+    L.rl_matcher_last_error.restype = C.c_char_p
+    L.rl_matcher_add_limit.argtypes = [vp, C.c_char_p, u64, u64, C.POINTER(C.c_char_p), u32, C.POINTER(C.c_char_p), u32,
+                                       C.c_char_p, vp]
+    L.rl_matcher_delete_limit.argtypes = [vp, u32]
+    L.rl_matcher_namespace_id.argtypes = [vp, C.c_char_p, C.POINTER(u32)]
+    L.rl_matcher_limit_name.argtypes = [vp, u32]
+    L.rl_matcher_limit_name.restype = C.c_char_p
+    L.rl_matcher_counters.argtypes = [vp, u32, C.POINTER(RlBinding), u32, vp, u32, C.POINTER(u32)]
+    L.rl_matcher_counters_batch.argtypes = [vp, u64, vp, vp, C.POINTER(RlBinding), vp, vp, u64]
+    L.rl_counter_key.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u32, C.POINTER(u64), C.POINTER(u64)]
+    L.rl_counter_key.restype = None
+    L._rl_match_ready = True
+    return L
+
+
+def _strs(items: Sequence[str]):
+    arr = (C.c_char_p * max(len(items), 1))()
+    for i, s in enumerate(items):
+        arr[i] = s.encode()
+    return arr
+
+
+def counter_key(set_variables: Dict[str, str]) -> Tuple[int, int]:
+    """(key_lo, key_hi) of resolved variables: the digest `limiter.Counter.key` computes with hashlib."""
+    ks = list(set_variables)
+    lo, hi = C.c_uint64(), C.c_uint64()
+    _lib().rl_counter_key(_strs(ks), _strs([set_variables[k] for k in ks]), len(ks), C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def _bindings(root: Optional[Dict[str, str]], descriptors: Optional[List[Dict[str, str]]]):
+    flat = [(BIND_ROOT, k, v) for k, v in (root or {}).items()]
+    for i, d in enumerate(descriptors or []):
+        flat += [(i, k, v) for k, v in d.items()]
+    return flat
+
+
+class Matcher:
+    def __init__(self):
+        self._lib = _lib()
+        h = C.c_void_p()
+        if self._lib.rl_matcher_create(C.byref(h)) != 0:
+            raise MatcherError("rl_matcher_create failed")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._lib.rl_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status):
+        if status != 0:
+            raise MatcherError(self._lib.rl_matcher_last_error(self._h).decode())
+
+    def add_limit(self, namespace: str, max_value: int, seconds: int, conditions: Iterable[str] = (),
+                  variables: Iterable[str] = (), name: Optional[str] = None) -> np.void:
+        """-> one LIMIT_DESC_DTYPE row (limit_id, ns_id, varset_id, qualified, max_value, window_us)."""
+        conds, vars_ = list(conditions), list(variables)
+        desc = np.zeros(1, dtype=_eng.LIMIT_DESC_DTYPE)
+        self._check(self._lib.rl_matcher_add_limit(self._h, namespace.encode(), max_value, seconds, _strs(conds), len(conds),
+                                                   _strs(vars_), len(vars_), None if name is None else name.encode(),
+                                                   desc.ctypes.data))
+        return desc[0]
+
+    def delete_limit(self, limit_id: int):
+        self._check(self._lib.rl_matcher_delete_limit(self._h, limit_id))
+
+    def namespace_id(self, namespace: str) -> Optional[int]:
+        out = C.c_uint32()
+        return out.value if self._lib.rl_matcher_namespace_id(self._h, namespace.encode(), C.byref(out)) == 0 else None
+
+    def limit_name(self, limit_id: int) -> Optional[str]:
+        s = self._lib.rl_matcher_limit_name(self._h, limit_id)
+        return None if s is None else s.decode()
+
+    def counters(self, ns_id: int, root: Optional[Dict[str, str]] = None,
+                 descriptors: Optional[List[Dict[str, str]]] = None, cap: int = 64) -> np.ndarray:
+        """counters_that_apply for one request -> COUNTER_DTYPE array (registration order)."""
+        flat = _bindings(root, descriptors)
+        binds = (RlBinding * max(len(flat), 1))()
+        for i, (d, k, v) in enumerate(flat):
+            binds[i] = RlBinding(d, 0, k.encode(), v.encode())
+        out = np.zeros(cap, dtype=_eng.COUNTER_DTYPE)
+        n = C.c_uint32()
+        self._check(self._lib.rl_matcher_counters(self._h, ns_id, binds, len(flat), out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value]
+
+    def counters_batch(self, ns_ids: Sequence[int], contexts: Sequence[Tuple[Optional[dict], Optional[list]]],
+                       cap: Optional[int] = None):
+        """-> (ctr_off[n+1] uint32, ctrs COUNTER_DTYPE): the inputs of Engine.check_and_update_batch."""
+        n = len(ns_ids)
+        flats = [_bindings(r, d) for r, d in contexts]
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(f) for f in flats])
+        binds = (RlBinding * max(int(off[-1]), 1))()
+        j = 0
+        for f in flats:
+            for d, k, v in f:
+                binds[j] = RlBinding(d, 0, k.encode(), v.encode())
+                j += 1
+        cap = cap or 64 * max(n, 1)
+        ctr_off = np.zeros(n + 1, dtype=np.uint32)
+        ctrs = np.zeros(cap, dtype=_eng.COUNTER_DTYPE)
+        ids = np.ascontiguousarray(ns_ids, dtype=np.uint32)
+        self._check(self._lib.rl_matcher_counters_batch(self._h, n, ids.ctypes.data, off.ctypes.data, binds,
+                                                        ctr_off.ctypes.data, ctrs.ctypes.data, cap))
+        return ctr_off, ctrs[:int(ctr_off[-1])]

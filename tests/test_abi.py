@@ -12,8 +12,8 @@ from limitador_b200 import build, engine
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    hdr = open(os.path.join(ROOT, "include", "rl_engine.h")).read()
+def declared_functions(header="rl_engine.h"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(rl_[a-z0-9_]+)\s*\(", hdr)))
 
@@ -26,6 +26,12 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rl_engine.h but not exported"
     assert sorted(engine.ABI_SYMBOLS) == names
+    # the CPU front's header (limits -> counters)
+    from limitador_b200 import matcher
+    mnames = declared_functions("rl_match.h")
+    assert len(mnames) == 10 and sorted(matcher.MATCH_SYMBOLS) == mnames
+    for n in mnames:
+        assert hasattr(lib, n), f"{n} declared in include/rl_match.h but not exported"
 
 
 def test_binary_targets_sm_100a_only():

@@ -1,0 +1,287 @@
+"""The native CPU front (include/rl_match.h): limits -> counters.
+
+Pinned by the reference's own `Limit::applies` tests (limitador/src/limit.rs:239-348), restated for both
+the Python mirror (limitador_b200/limiter.py) and the compiled matcher, and by a randomised differential
+test of the two over the accepted expression subset (conditions on root bindings and on descriptors[i],
+== and !=, variables, unset names, shared variable sets, deletes and re-adds).  No GPU involved."""
+import threading
+
+import numpy as np
+import pytest
+
+from limitador_b200 import limiter as LM
+from limitador_b200 import matcher as MT
+from limitador_b200.engine import COUNTER_DTYPE
+
+
+def both_apply(conditions, variables, values):
+    """-> (python mirror says the limit applies, native matcher yields a counter)"""
+    lim = LM.Limit("test_namespace", 10, 60, conditions, variables)
+    py = lim.applies(LM.Context(values))
+    m = MT.Matcher()
+    d = m.add_limit("test_namespace", 10, 60, conditions, variables)
+    got = m.counters(int(d["ns_id"]), values)
+    assert len(got) in (0, 1)
+    return py, len(got) == 1
+
+
+# limit.rs:239-254, 256-271, 273-289, 291-306, 308-327, 329-348
+REFERENCE_KATS = [
+    ("limit_applies", ['x == "5"'], ["y"], {"x": "5", "y": "1"}, True),
+    ("limit_does_not_apply_when_cond_is_false", ['x == "5"'], ["y"], {"x": "1", "y": "1"}, False),
+    ("limit_does_not_apply_when_cond_var_is_not_set", ['x == "5"'], ["y"], {"a": "1", "y": "1"}, False),
+    ("limit_does_not_apply_when_var_not_set", ['x == "5"'], ["y"], {"x": "5"}, False),
+    ("limit_applies_when_all_its_conditions_apply", ['x == "5"', 'y == "2"'], ["z"], {"x": "5", "y": "2", "z": "1"}, True),
+    ("limit_does_not_apply_if_one_cond_doesnt", ['x == "5"', 'y == "2"'], ["z"], {"x": "3", "y": "2", "z": "1"}, False),
+]
+
+
+@pytest.mark.parametrize("name,conds,vars_,values,want", REFERENCE_KATS, ids=[k[0] for k in REFERENCE_KATS])
+def test_reference_applies_kats(name, conds, vars_, values, want):
+    py, native = both_apply(conds, vars_, values)
+    assert py == want and native == want
+
+
+def test_counter_key_is_blake2b_96_of_the_sorted_pairs():
+    for sv in ({"a": "1"}, {"descriptors[0].user": "alice", "z": ""}, {"k" * 200: "v" * 300, "b": "x"}, {"é": "ü"}):
+        c = LM.Counter(LM.Limit("ns", 1, 1), dict(sv))  # the digest covers the resolved (source, value) pairs only
+        assert MT.counter_key(sv) == c.key()
+    assert MT.counter_key({}) == (0, 0)
+
+
+def test_expressions_outside_the_subset_are_refused_and_change_nothing():
+    m = MT.Matcher()
+    d0 = m.add_limit("ns", 5, 60, ["a == 'x'"], ["u"])
+    for conds, vars_ in ((["foo.contains('bar')"], []), ([], ["int(x) * 3"]), (["a == b"], []), (["a == 'x' && b == 'y'"], []),
+                         (["descriptors[0] == 'x'"], []), (["limit.name == null"], [])):
+        with pytest.raises(MT.MatcherError) as ei:
+            m.add_limit("ns2", 5, 60, conds, vars_)
+        assert "unsupported" in str(ei.value)
+    assert m.namespace_id("ns2") is None
+    d1 = m.add_limit("ns", 7, 60, ["a == 'x'"], ["u"], name="renamed")  # same identity: update_limit
+    assert int(d1["limit_id"]) == int(d0["limit_id"]) and int(d1["max_value"]) == 7
+    assert m.limit_name(int(d0["limit_id"])) == "renamed"
+
+
+class _CaptureStorage:
+    """what RateLimiter._push_limit hands to the storage (the rl_limit_desc rows)"""
+
+    def __init__(self):
+        self.descs = {}
+
+    def set_limit(self, limit_id, ns_id, varset_id, qualified, max_value, window_us):
+        self.descs[limit_id] = (limit_id, ns_id, varset_id, int(qualified), max_value, window_us)
+
+    def forget_limit(self, limit_id):
+        pass
+
+    def delete_counters(self, ids):
+        pass
+
+
+def random_limit(rng, namespaces, keys, values):
+    def operand():
+        k = str(rng.choice(keys))
+        style = int(rng.integers(0, 4))
+        if style == 0:
+            return k
+        if style == 1:
+            return f"descriptors[{int(rng.integers(0, 2))}].{k}"
+        if style == 2:
+            return f"descriptors[{int(rng.integers(0, 2))}]['{k}']"
+        return f"req.{k}"
+    conds = []
+    for _ in range(int(rng.integers(0, 4))):
+        op = "==" if rng.random() < 0.7 else "!="
+        q = "'" if rng.random() < 0.5 else '"'
+        pad = " " * int(rng.integers(0, 3))
+        conds.append(f"{pad}{operand()} {op}{pad}{q}{rng.choice(values)}{q}{pad}")
+    vars_ = [operand() for _ in range(int(rng.integers(0, 3)))]
+    name = None if rng.random() < 0.5 else f"lim{int(rng.integers(0, 1000))}"
+    return LM.Limit(str(rng.choice(namespaces)), int(rng.integers(0, 100)), int(rng.choice([1, 60, 3600])), conds, vars_, name)
+
+
+def random_context(rng, keys, values):
+    root = {}
+    for k in keys:
+        if rng.random() < 0.5:
+            root[k] = str(rng.choice(values))
+        if rng.random() < 0.3:
+            root[f"req.{k}"] = str(rng.choice(values))
+    descriptors = []
+    for _ in range(int(rng.integers(0, 3))):
+        descriptors.append({k: str(rng.choice(values)) for k in keys if rng.random() < 0.5})
+    return root, descriptors
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_matcher_equals_the_python_mirror_on_random_limits_and_contexts(seed):
+    rng = np.random.default_rng(seed)
+    namespaces, keys, values = ["ns_a", "ns_b", "ns_c"], ["m", "u", "path", "k9"], ["GET", "POST", "alice", "", "x y"]
+    cap = _CaptureStorage()
+    rl = LM.RateLimiter(cap)
+    m = MT.Matcher()
+    live = []
+    for step in range(60):
+        r = rng.random()
+        if r < 0.75 or not live:
+            lim = random_limit(rng, namespaces, keys, values)
+            is_new = rl.add_limit(lim)
+            if not is_new:
+                rl.update_limit(lim)
+            d = m.add_limit(lim.namespace, lim.max_value, lim.seconds, lim.conditions, lim.variables, lim.name)
+            lid = int(d["limit_id"])
+            assert tuple(int(d[f]) for f in ("limit_id", "ns_id", "varset_id", "qualified", "max_value", "window_us")) == cap.descs[lid]
+            if is_new:
+                live.append(lim)
+        else:
+            lim = live.pop(int(rng.integers(0, len(live))))
+            lid = rl._limit_ids[lim.identity()]
+            rl.delete_limit(lim)
+            m.delete_limit(lid)
+        # a batch of requests against the current limits
+        reqs = [(str(rng.choice(namespaces + ["unknown_ns"])),) + random_context(rng, keys, values) for _ in range(25)]
+        want_off, want = [0], []
+        for ns, root, descs in reqs:
+            for c in rl.counters_that_apply(ns, LM.Context(root, descs)):
+                want.append((c.limit_id,) + c.key())
+            want_off.append(len(want))
+        ns_ids = [m.namespace_id(ns) if m.namespace_id(ns) is not None else 0xFFFFFF for ns, _, _ in reqs]
+        off, ctrs = m.counters_batch(ns_ids, [(root, descs) for _, root, descs in reqs])
+        assert off.tolist() == want_off, f"step {step}"
+        assert [(int(c["limit_id"]), int(c["key_lo"]), int(c["key_hi"])) for c in ctrs] == want, f"step {step}"
+        # the single-request call agrees with the batch
+        j = int(rng.integers(0, len(reqs)))
+        one = m.counters(ns_ids[j], reqs[j][1], reqs[j][2])
+        assert one.tobytes() == ctrs[off[j]:off[j + 1]].tobytes()
+    for lim in live:  # names follow update_limit on both sides
+        lid = rl._limit_ids[lim.identity()]
+        assert m.limit_name(lid) == rl._limits[lim.namespace][lim].name
+
+
+def test_limits_sharing_a_variable_set_share_the_counter_key_and_the_varset_id():
+    m = MT.Matcher()
+    a = m.add_limit("ns", 5, 60, [], ["descriptors[0].user"])
+    b = m.add_limit("ns", 50, 3600, ["descriptors[0].method == 'GET'"], ["descriptors[0].user"])
+    c = m.add_limit("ns", 9, 60, [], [])
+    assert int(a["varset_id"]) == int(b["varset_id"]) != 0 and int(c["varset_id"]) == 0 and int(c["qualified"]) == 0
+    got = m.counters(int(a["ns_id"]), None, [{"user": "bob", "method": "GET"}])
+    assert got["limit_id"].tolist() == [0, 1, 2]
+    assert got["key_lo"][0] == got["key_lo"][1] != 0 and got["key_lo"][2] == 0
+    assert (int(got["key_lo"][0]), int(got["key_hi"][0])) == MT.counter_key({"descriptors[0].user": "bob"})
+    got = m.counters(int(a["ns_id"]), None, [{"user": "bob", "method": "PUT"}])
+    assert got["limit_id"].tolist() == [0, 2]
+
+
+def test_too_many_counters_is_an_error_not_a_truncation():
+    m = MT.Matcher()
+    for i in range(5):
+        d = m.add_limit("ns", 5, 60 + i, [], [])
+    with pytest.raises(MT.MatcherError):
+        m.counters(int(d["ns_id"]), {}, None, cap=4)
+    assert len(m.counters(int(d["ns_id"]), {}, None, cap=5)) == 5
+
+
+def test_concurrent_matching_threads_agree():
+    rng = np.random.default_rng(3)
+    keys, values = ["m", "u", "path"], ["GET", "POST", "alice"]
+    m = MT.Matcher()
+    for _ in range(40):
+        lim = random_limit(rng, ["ns"], keys, values)
+        m.add_limit(lim.namespace, lim.max_value, lim.seconds, lim.conditions, lim.variables, lim.name)
+    ns = m.namespace_id("ns")
+    ctxs = [random_context(rng, keys, values) for _ in range(300)]
+    want = m.counters_batch([ns] * len(ctxs), ctxs)
+    results, errors = [None] * 4, []
+
+    def worker(i):
+        try:
+            for _ in range(5):
+                results[i] = m.counters_batch([ns] * len(ctxs), ctxs)
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors
+    for off, ctrs in results:
+        assert off.tolist() == want[0].tolist() and ctrs.tobytes() == want[1].tobytes()
+
+
+def _serving_scenario(seed, n_req=400):
+    """limits of an API gateway shape + a request stream of Envoy-like descriptors"""
+    rng = np.random.default_rng(seed)
+    limits = [
+        LM.Limit("api", 5, 60, ["descriptors[0].method == 'GET'"], ["descriptors[0].user"], name="get-per-user"),
+        LM.Limit("api", 3, 60, ["descriptors[0].method == 'POST'"], ["descriptors[0].user"], name="post-per-user"),
+        LM.Limit("api", 40, 3600, [], ["descriptors[0].user"], name="hourly-per-user"),
+        LM.Limit("api", 120, 60, ["descriptors[0].method != 'OPTIONS'"], [], name="global"),
+        LM.Limit("admin", 2, 10, [], ["descriptors[0].user", "descriptors[0].path"]),
+    ]
+    reqs = []
+    for i in range(n_req):
+        ns = "api" if rng.random() < 0.85 else ("admin" if rng.random() < 0.8 else "nobody")
+        d = {"method": str(rng.choice(["GET", "POST", "OPTIONS"])), "user": f"u{int(rng.integers(0, 6))}"}
+        if rng.random() < 0.7:
+            d["path"] = str(rng.choice(["/a", "/b"]))
+        reqs.append((ns, d, int(rng.choice([1, 1, 2])), 1_700_000_000_000_000 + i * 150_000))
+    return limits, reqs
+
+
+@pytest.mark.parametrize("load_counters", [False, True])
+def test_matcher_plus_batched_storage_equals_the_mirror_request_by_request(load_counters):
+    """End to end on the CPU: native matcher -> CSR -> the oracle's batched check_and_update gives the
+    verdicts, limit names, remaining and ttl of the RateLimiter mirror called one request at a time."""
+    from oracle import binding as ob
+    from tests import helpers as H
+    limits, reqs = _serving_scenario(1)
+    clock = {"t": 0}
+    rl = LM.RateLimiter(H.OracleStorage(), clock=lambda: clock["t"])
+    m = MT.Matcher()
+    o = ob.Oracle(64)
+    for lim in limits:
+        rl.add_limit(lim)
+        d = m.add_limit(lim.namespace, lim.max_value, lim.seconds, lim.conditions, lim.variables, lim.name)
+        o.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    want = []
+    for ns, d, delta, now in reqs:
+        clock["t"] = now
+        want.append(rl.check_rate_limited_and_update(ns, LM.Context({}, [d]), delta, load_counters))
+    ns_ids = [m.namespace_id(ns) if m.namespace_id(ns) is not None else 0xFFFFFF for ns, _, _, _ in reqs]
+    off, ctrs = m.counters_batch(ns_ids, [({}, [d]) for _, d, _, _ in reqs])
+    lim, fl, rem, ttl = o.batch_csr(0, off, ctrs, [r[2] for r in reqs], [r[3] for r in reqs], load_counters)
+    assert lim.tolist() == [int(w.limited) for w in want]
+    assert 0 < int(lim.sum()) < len(lim)
+    for i, w in enumerate(want):
+        if w.limited:
+            assert m.limit_name(int(fl[i])) == w.limit_name
+        if load_counters:
+            got = sorted((int(c["limit_id"]), int(rem[off[i] + j]), int(ttl[off[i] + j])) for j, c in enumerate(ctrs[off[i]:off[i + 1]]))
+            assert got == sorted((c.limit_id, c.remaining, c.expires_in_us) for c in w.counters)
+
+
+@pytest.mark.gpu
+def test_matcher_feeds_the_engine():
+    """The same stream through the native matcher and ONE rl_check_and_update_batch call on the GPU."""
+    from limitador_b200 import Engine
+    from tests import helpers as H
+    limits, reqs = _serving_scenario(2, n_req=3000)
+    clock = {"t": 0}
+    rl = LM.RateLimiter(H.OracleStorage(), clock=lambda: clock["t"])
+    m = MT.Matcher()
+    e = Engine(capacity_rows=1 << 12, cells_per_row=3, max_batch=4096)
+    descs = []
+    for lim in limits:
+        rl.add_limit(lim)
+        descs.append(m.add_limit(lim.namespace, lim.max_value, lim.seconds, lim.conditions, lim.variables, lim.name))
+    e.limits_set(np.array(descs))
+    want = []
+    for ns, d, delta, now in reqs:
+        clock["t"] = now
+        want.append(rl.check_rate_limited_and_update(ns, LM.Context({}, [d]), delta, False))
+    ns_ids = [m.namespace_id(ns) if m.namespace_id(ns) is not None else 0xFFFFFF for ns, _, _, _ in reqs]
+    off, ctrs = m.counters_batch(ns_ids, [({}, [d]) for _, d, _, _ in reqs])
+    lim, fl, _, _ = e.check_and_update_batch(off, ctrs, [r[2] for r in reqs], [r[3] for r in reqs], False)
+    assert lim.tolist() == [int(w.limited) for w in want]
+    assert [m.limit_name(int(f)) for f, w in zip(fl, want) if w.limited] == [w.limit_name for w in want if w.limited]
