@@ -14,7 +14,9 @@
  *
  * Parity pin: the reference cannot be built here (no rustc/cargo) and ships no golden
  * vector files; this oracle is pinned by porting the reference's own known-answer unit
- * and integration tests (tests/test_oracle_kats.py cites each one by file:line).
+ * and integration tests (tests/test_oracle_kats.py cites each one by file:line), and
+ * cross-checked on random streams against an independent Python restatement of the same
+ * reference files (tests/spec_model.py, tests/test_oracle_vs_spec.py).
  */
 #ifndef LIMITADOR_ORACLE_H
 #define LIMITADOR_ORACLE_H
