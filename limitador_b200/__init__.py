@@ -3,6 +3,8 @@ check_rate_limited_and_update hot path."""
 from .engine import Engine, EngineError, Front, owner_of, RECORD_DTYPE, COUNTER_DTYPE, LIMIT_DESC_DTYPE, NONE  # noqa: F401
 from .limiter import (Authorization, CheckResult, Context, Counter, GpuCounterStorage, Limit,  # noqa: F401
                       RateLimiter)
+from .matcher import Matcher, MatcherError, counter_key  # noqa: F401
 
 __all__ = ["Engine", "EngineError", "Front", "owner_of", "RateLimiter", "Limit", "Counter", "Context", "CheckResult",
-           "Authorization", "GpuCounterStorage", "RECORD_DTYPE", "COUNTER_DTYPE", "LIMIT_DESC_DTYPE", "NONE"]
+           "Authorization", "GpuCounterStorage", "Matcher", "MatcherError", "counter_key", "RECORD_DTYPE", "COUNTER_DTYPE",
+           "LIMIT_DESC_DTYPE", "NONE"]
