@@ -49,9 +49,9 @@ enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1,
 /* test aid: narrow the in-kernel grouping tag so that distinct keys collide and the
  * collision path (salted re-insertion) is exercised */
 #define RL_FLAG_DEBUG_WEAK_TAGS 1u
-/* RL_MEM_DEVICE record calls are software-pipelined over two internal streams: the partition
- * (probe / scan / scatter) of call s+1 overlaps the replay of call s.  Results are the same;
- * outputs of such calls are ordered on the caller's stream only after rl_fence() (or rl_sync). */
+/* Record calls with RL_MEM_DEVICE / RL_MEM_HOST_ASYNC buffers are software-pipelined over three internal
+ * streams: probe+count of call s+2 and scan+scatter of call s+1 overlap the replay of call s.  Results are
+ * the same; outputs of such calls are ordered on the caller's stream only after rl_fence() (or rl_sync). */
 #define RL_FLAG_PIPELINE 2u
 /* rl_stats.chunks / replay_rounds / chained_chunks / ordered_chunks / phase_cycles are accounted by the
  * replay kernel (a few atomics per chunk, ~7 % of a 65536-request step); without the flag they stay 0. */
