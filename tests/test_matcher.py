@@ -285,3 +285,25 @@ def test_matcher_feeds_the_engine():
     lim, fl, _, _ = e.check_and_update_batch(off, ctrs, [r[2] for r in reqs], [r[3] for r in reqs], False)
     assert lim.tolist() == [int(w.limited) for w in want]
     assert [m.limit_name(int(f)) for f, w in zip(fl, want) if w.limited] == [w.limit_name for w in want if w.limited]
+
+
+def test_expression_shapes_of_the_reference_docs_and_example_configs_are_accepted():
+    """The condition / variable shapes that appear in the reference's documentation and example limit files
+    (bracketed keys with dots, dotted member access, != on a path) all fall inside the subset."""
+    m = MT.Matcher()
+    lims = [
+        (["descriptors[0]['req.method'] == 'GET'", "descriptors[0]['req.path'] != '/json'"], []),
+        (["descriptors[0]['req.method'] == 'POST'", "descriptors[0]['req.path'] != '/json'"], ["descriptors[0]['user_id']"]),
+        (["descriptors[0].req_method == 'GET'"], ["descriptors[0].user_id"]),
+        (["descriptors[0].KEY_A == 'VALUE_A'", "descriptors[0].OTHER_KEY == 'WRONG_VALUE'"], []),
+    ]
+    ids = [int(m.add_limit("test_namespace", 5, 60 + i, c, v)["limit_id"]) for i, (c, v) in enumerate(lims)]
+    ns = m.namespace_id("test_namespace")
+    got = m.counters(ns, None, [{"req.method": "GET", "req.path": "/", "user_id": "7", "req_method": "GET", "KEY_A": "VALUE_A"}])
+    assert got["limit_id"].tolist() == [ids[0], ids[2]]
+    got = m.counters(ns, None, [{"req.method": "POST", "req.path": "/x", "user_id": "7"}])
+    assert got["limit_id"].tolist() == [ids[1]]
+    # descriptors[0].user_id and descriptors[0]['user_id'] are different identities reading the same entry
+    assert (int(got["key_lo"][0]), int(got["key_hi"][0])) == MT.counter_key({"descriptors[0]['user_id']": "7"})
+    got = m.counters(ns, None, [{"req.method": "GET", "req.path": "/json"}])
+    assert len(got) == 0
