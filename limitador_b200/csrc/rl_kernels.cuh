@@ -646,8 +646,8 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
 #ifndef RL_EXP_ROW_PREFETCH
 #define RL_EXP_ROW_PREFETCH 0  // k_main: every thread fetches its row state before the grouping, not only the reps after it
 #endif
-#ifndef RL_MINB_MID
-#define RL_MINB_MID 3  // resident 256-thread CTA equivalents per SM asked of the compiler for 3..4-cell rows
+#ifndef RL_MID_CTAS
+#define RL_MID_CTAS 6  // resident 128-thread k_main CTAs per SM asked of the compiler for 3..4-cell rows (registers = 512 / this)
 #endif
 #ifndef RL_WAIT_NS
 #define RL_WAIT_NS 100  // back-off of the chained-commit wait loops
@@ -750,7 +750,7 @@ __device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAcc
 // GEO = cells per row of the table layout (row bytes), CELLS = cells any row group actually
 // uses (<= GEO): loops, registers and shared memory are sized by the latter.
 template <int GEO, int CELLS, class Src, int MODE, int CH, bool LC>
-__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 4 : (CELLS <= 4 ? RL_MINB_MID : 2)) * (256 / CH)) k_main(RlDev D, RlBatch B, Src src) {
+__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTAS : 4)) * 128 / CH) k_main(RlDev D, RlBatch B, Src src) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
     constexpr int PW = Smem::PW;

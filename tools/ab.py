@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B of build-time variants of librl_engine.so on a GPU box.
 
-    python tools/ab.py build  name1:RL_EXP_PAD_AGG=1  name2:RL_MINB_MID=2,RL_EXP_ROW_PREFETCH=1 ...
+    python tools/ab.py build  name1:RL_EXP_PAD_AGG=1  name2:RL_MID_CTAS=5,RL_EXP_ROW_PREFETCH=1 ...
         builds limitador_b200/variants/librl_engine_<name>.so (they travel with the gpurun snapshot) and prints
         the shell snippet to run under gpurun: the default library first and last, every variant in between,
         each through `bench.py --no-cpu-baseline` with RL_ENGINE_LIB pointing at it.
