@@ -307,3 +307,41 @@ def test_expression_shapes_of_the_reference_docs_and_example_configs_are_accepte
     assert (int(got["key_lo"][0]), int(got["key_hi"][0])) == MT.counter_key({"descriptors[0]['user_id']": "7"})
     got = m.counters(ns, None, [{"req.method": "GET", "req.path": "/json"}])
     assert len(got) == 0
+
+
+def test_parser_accepts_exactly_what_the_python_mirror_accepts():
+    """Random strings over the grammar's alphabet: the native parser and the mirror's regular expressions
+    agree on accept / refuse for conditions and for variables (and nothing crashes)."""
+    rng = np.random.default_rng(11)
+    pieces = ["descriptors", "[", "]", "0", "12", ".", "'", '"', "==", "!=", " ", "a", "b_1", "req.path", "=", "!", "x y",
+              "descriptors[0]", "descriptors[1].k", "descriptors[0]['k.v']", "'lit'", '"lit"', "\t", "é", "9z", "_"]
+    m = MT.Matcher()
+    n_acc_c = n_acc_v = 0
+    operands = ["a", "b_1", "req.path", "descriptors[0].k", "descriptors[12]['k.v']", 'descriptors[1]["x"]', "descriptors[0]",
+                "descriptors[0].9", "descriptors[x].k", "descriptors[0]['']", "9z", "_u", "é", "descriptors", "a.b.c", "a b"]
+    ops = ["==", "!=", " == ", "\t!= ", "=", "!==", "<", ""]
+    lits = ["'lit'", '"lit"', "''", "'x y'", "'unterminated", "bare", "'a'b'", '"q\'q"', "'tail' x", ""]
+    for i in range(4000):
+        if rng.random() < 0.6:  # near-valid: operand op literal with optional padding
+            pad = [" ", "", "  ", "\t"]
+            s = str(rng.choice(pad)) + str(rng.choice(operands)) + str(rng.choice(ops)) + str(rng.choice(lits)) + str(rng.choice(pad))
+            if rng.random() < 0.3:
+                s = str(rng.choice(pad)) + str(rng.choice(operands)) + str(rng.choice(pad))
+        else:  # noise
+            s = "".join(str(rng.choice(pieces)) for _ in range(int(rng.integers(1, 7))))
+        want_c, want_v = LM._PRED.match(s) is not None, LM._VAR.match(s) is not None
+        try:
+            m.add_limit("fuzz", 1, 1 + i, [s], [])
+            got_c = True
+        except MT.MatcherError:
+            got_c = False
+        try:
+            m.add_limit("fuzz", 1, 100000 + i, [], [s])
+            got_v = True
+        except MT.MatcherError:
+            got_v = False
+        assert got_c == want_c, f"condition {s!r}: native {got_c}, mirror {want_c}"
+        assert got_v == want_v, f"variable {s!r}: native {got_v}, mirror {want_v}"
+        n_acc_c += got_c
+        n_acc_v += got_v
+    assert n_acc_c > 20 and n_acc_v > 50  # the generator does produce valid expressions
