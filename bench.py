@@ -233,20 +233,6 @@ def main():
     cells = 1 if c3 else 7
     limits = streams.c3_uniform_1limit(batch=1, n_keys=16).limits if c3 else c2_limits(n_ns)
     cap = (1 << 25) if c3 else ((1 << 21) if world == 1 else (1 << 22))
-    # exchange blocks: each rank sends `slot_cap` record slots to every owner (2x the mean share)
-    slot_cap = min(batch, ((2 * batch // world) + 255) // 256 * 256)
-    max_batch = batch if world == 1 else world * slot_cap
-    # RL_FLAG_PIPELINE (2): the partition of step s+1 overlaps the replay of step s on the device
-    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank,
-                 flags=(0 if args.no_pipeline else 2))
-    eng.limits_set(limits)
-    # a dedicated non-default stream: the engine launches on it and the CUDA events that time
-    # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
-    assert eng.stream == stream.cuda_stream
-
     E_WARM = 3  # untimed e2e steps before the timed ones: staging slots, pinned pages, copy engines
     total = W + 2 * K + E_WARM + Ke
     # every step consumes its own batch; if the driver asks for more steps than ~48 GB of stream can
@@ -260,6 +246,29 @@ def main():
                                              first_batch=0, seed=streams.SEED + 1000 * rank)
     out_lim_pool = torch.zeros((pool, batch), dtype=torch.uint8, device=dev)
     out_first_pool = torch.zeros((pool, batch), dtype=torch.int32, device=dev)
+
+    # exchange blocks: each rank sends `slot_cap` record slots to every owner.  Sized from the traffic itself,
+    # as a deployment would: the largest (rank -> owner) share seen in a sample of the stream, max over ranks,
+    # plus 20 % headroom (an overflow is detected and fails the run; 2x the mean share if nothing was sampled)
+    slot_cap = min(batch, ((2 * batch // world) + 255) // 256 * 256)
+    if world > 1:
+        lut = torch.tensor([exchange.owner_of(ns, world) for ns in range(n_ns)], dtype=torch.int64, device=dev)
+        seen = torch.tensor([exchange.observed_block_max(recs_pool[:min(pool, 64)], lut, world)], dtype=torch.int64, device=dev)
+        dist.all_reduce(seen, op=dist.ReduceOp.MAX)
+        slot_cap = exchange.slot_cap_for(int(seen.item()), batch)
+        print(f"[bench] largest exchange block in the sample: {int(seen.item())} records -> slot_cap {slot_cap}", file=sys.stderr)
+    max_batch = batch if world == 1 else world * slot_cap
+    # RL_FLAG_PIPELINE (2): the partition of step s+1 overlaps the replay of step s on the device
+    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank,
+                 flags=(0 if args.no_pipeline else 2))
+    eng.limits_set(limits)
+    # a dedicated non-default stream: the engine launches on it and the CUDA events that time
+    # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    assert eng.stream == stream.cuda_stream
 
     class _Cyc:
         """step index -> pooled batch (identity unless the pool had to be capped)"""
@@ -442,7 +451,8 @@ def main():
     sampler.join(timeout=2)
     os.sched_setaffinity(0, cpus_before)  # the CPU baseline below gets every host core again
     if world > 1 and int(overflow.item()) != 0:
-        raise RuntimeError("an exchange block overflowed (namespace skew beyond 2x): rerun with a larger slot_cap")
+        raise RuntimeError(f"an exchange block overflowed (more than {slot_cap} records for one owner): the sampled "
+                           f"headroom was too small")
     print(f"[bench] engine stats {eng.stats()}", file=sys.stderr)
     print(f"[bench] host enqueue us/step per pass: {[round(x, 1) for x in host_enqueue_us]}", file=sys.stderr)
     print(f"[bench] passes: A {ms_a:.1f} ms, B {ms_b:.1f} ms, e2e {ms_e:.1f} ms (wall {wall_e:.1f})", file=sys.stderr)
@@ -508,6 +518,7 @@ def main():
                    "parallelism": ("single GPU, successive steps pipelined over 3 streams (probe | scan+scatter | replay)" if not args.no_pipeline else "single GPU")
                    if world == 1 else
                    f"namespace-sharded x{world}, one NCCL all-to-all of fixed {slot_cap}-record blocks per peer and step "
+                   f"(block = 1.2 x the largest share sampled) "
                    f"(verdicts return in the records' lane byte {args.exchange_lag} steps later)",
                    "l2": ("a distinct batch every step (never reused); table > L2" if pool == total else
                           f"{pool} distinct batches cycled (timestamps repeat); table > L2"),

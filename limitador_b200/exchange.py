@@ -128,3 +128,26 @@ class LanePipelinedExchange:
             done.append(self.outs[b])
             self.outs[b] = None
         return done
+
+
+def owner_of(ns_id: int, world: int) -> int:
+    """rl_owner_of (include/rl_engine.h): the rank that owns a namespace."""
+    from . import engine as _eng
+    return int(_eng.load_library().rl_owner_of(int(ns_id), int(world)))
+
+
+def observed_block_max(recs, owner_lut, world: int) -> int:
+    """Largest number of records one step of `recs` ([steps, batch, 4] int64 = rl_record) sends to one owner.
+    `owner_lut[ns_id]` = owner rank (a tensor on the records' device)."""
+    import torch
+    worst = 0
+    for s in range(recs.shape[0]):
+        ns = recs[s, :, 0] & 0xFFFFFFFF  # rl_record word 0 = ns_id | hits_addend << 32
+        worst = max(worst, int(torch.bincount(owner_lut[ns], minlength=world).max().item()))
+    return worst
+
+
+def slot_cap_for(largest_block: int, batch: int, headroom: float = 1.2) -> int:
+    """Exchange block size (record slots per peer) for an observed largest block: headroom on top, a multiple
+    of 256, never more than a whole batch."""
+    return int(min(batch, (int(largest_block * headroom) + 255) // 256 * 256))

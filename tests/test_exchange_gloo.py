@@ -183,3 +183,20 @@ def test_two_rank_sharded_step_matches_global_oracle():
     assert np.array_equal(ret[0], np.concatenate(want0))
     assert np.array_equal(ret[1], np.concatenate(want1))
     assert 0 < int(ret[0].sum()) < len(ret[0])
+
+
+def test_exchange_blocks_are_sized_from_the_observed_traffic():
+    """bench.py sizes the fixed exchange blocks from a sample of the stream: largest (rank -> owner) share x 1.2."""
+    lib = load_library()
+    world, batch, steps = 4, 8192, 6
+    recs = streams.c2_device_stream(steps, batch, "cpu", n_rows=50000, n_ns=64 * world)
+    a = recs.numpy().view(RECORD_DTYPE).reshape(steps, batch)
+    owner = np.array([lib.rl_owner_of(ns, world) for ns in range(64 * world)])
+    want = max(int(np.bincount(owner[a["ns_id"][s]], minlength=world).max()) for s in range(steps))
+    lut = torch.tensor([exchange.owner_of(ns, world) for ns in range(64 * world)], dtype=torch.int64)
+    assert lut.tolist() == owner.tolist()
+    got = exchange.observed_block_max(recs, lut, world)
+    assert got == want and batch // world < got < batch
+    cap = exchange.slot_cap_for(got, batch)
+    assert cap % 256 == 0 and got * 1.2 <= cap + 255 and cap >= got and cap <= batch
+    assert exchange.slot_cap_for(batch, batch) == batch
