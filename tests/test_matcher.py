@@ -266,7 +266,7 @@ def test_matcher_feeds_the_engine():
     """The same stream through the native matcher and ONE rl_check_and_update_batch call on the GPU."""
     from limitador_b200 import Engine
     from tests import helpers as H
-    limits, reqs = _serving_scenario(2, n_req=3000)
+    limits, reqs = _serving_scenario(2, n_req=1500)
     clock = {"t": 0}
     rl = LM.RateLimiter(H.OracleStorage(), clock=lambda: clock["t"])
     m = MT.Matcher()
