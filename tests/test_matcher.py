@@ -345,3 +345,28 @@ def test_parser_accepts_exactly_what_the_python_mirror_accepts():
         n_acc_c += got_c
         n_acc_v += got_v
     assert n_acc_c > 20 and n_acc_v > 50  # the generator does produce valid expressions
+
+
+def test_matcher_csr_through_the_kernel_algorithm_emulation():
+    """The stream of the GPU test above through tests/emu (the kernels' batching algorithm on the host,
+    3 cells per row, coupled requests spanning the per-user row and the namespace's unqualified row)."""
+    from tests import helpers as H
+    limits, reqs = _serving_scenario(2, n_req=1500)
+    clock = {"t": 0}
+    rl = LM.RateLimiter(H.OracleStorage(), clock=lambda: clock["t"])
+    m = MT.Matcher()
+    descs = []
+    for lim in limits:
+        rl.add_limit(lim)
+        descs.append(m.add_limit(lim.namespace, lim.max_value, lim.seconds, lim.conditions, lim.variables, lim.name))
+    emu = H.Emu(np.array(descs), 3)
+    want = []
+    for ns, d, delta, now in reqs:
+        clock["t"] = now
+        want.append(rl.check_rate_limited_and_update(ns, LM.Context({}, [d]), delta, False))
+    ns_ids = [m.namespace_id(ns) if m.namespace_id(ns) is not None else 0xFFFFFF for ns, _, _, _ in reqs]
+    off, ctrs = m.counters_batch(ns_ids, [({}, [d]) for _, d, _, _ in reqs])
+    lim, fl, _, _ = emu.batch_csr(0, off, ctrs, [r[2] for r in reqs], [r[3] for r in reqs], False)
+    assert lim.tolist() == [int(w.limited) for w in want]
+    assert [m.limit_name(int(f)) for f, w in zip(fl, want) if w.limited] == [w.limit_name for w in want if w.limited]
+    assert emu.rounds >= 1  # coupled requests did go through the fixed-point rounds
