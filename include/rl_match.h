@@ -73,6 +73,17 @@ int rl_matcher_counters(rl_matcher *m, uint32_t ns_id, const rl_binding *binds, 
  * other matching calls; rl_matcher_add_limit / _delete_limit take the matcher exclusively. */
 int rl_matcher_counters_batch(rl_matcher *m, uint64_t n, const uint32_t *ns_id, const uint32_t *bind_off,
                               const rl_binding *binds, uint32_t *out_ctr_off, rl_counter *out_ctrs, uint64_t cap);
+/* CheckResult::response_header (lib.rs:235-275) for one request, from the load_counters outputs of
+ * rl_check_and_update_batch: the request's counters are ordered by remaining (stable), then
+ *   X-RateLimit-Limit     = "<max>, <max>;w=<seconds>[;name=\"<name>\"], ..."  (most restrictive first; a '"' in a
+ *                            name becomes '\'')
+ *   X-RateLimit-Remaining = remaining of the most restrictive counter
+ *   X-RateLimit-Reset     = its ttl in whole seconds
+ * max, seconds and name come from the matcher's limits.  Each buffer receives a NUL-terminated string (all
+ * empty when n == 0); RL_FATAL if one is too small or a limit_id is unknown. */
+int rl_matcher_response_headers(rl_matcher *m, const rl_counter *ctrs, const uint64_t *remaining,
+                                const uint64_t *ttl_us, uint32_t n, char *out_limit, uint32_t cap_limit,
+                                char *out_remaining, uint32_t cap_remaining, char *out_reset, uint32_t cap_reset);
 /* The 96-bit counter key of n (variable source, value) pairs (any order): key_lo = digest bits 0..63,
  * key_hi = bits 64..95.  BLAKE2b-96 over the pairs sorted by source, each string length-prefixed (u32 LE).
  * (0, 0) for n == 0 (unqualified counter). */

@@ -541,6 +541,44 @@ int rl_matcher_counters_batch(rl_matcher* m, uint64_t n, const uint32_t* ns_id, 
     return RL_OK;
 }
 
+int rl_matcher_response_headers(rl_matcher* m, const rl_counter* ctrs, const uint64_t* remaining, const uint64_t* ttl_us,
+                                uint32_t n, char* out_limit, uint32_t cap_limit, char* out_remaining, uint32_t cap_remaining,
+                                char* out_reset, uint32_t cap_reset) {
+    if (!m || !out_limit || !out_remaining || !out_reset || !cap_limit || !cap_remaining || !cap_reset ||
+        (n && (!ctrs || !remaining || !ttl_us)))
+        return RL_FATAL;
+    out_limit[0] = out_remaining[0] = out_reset[0] = 0;
+    if (n == 0) return RL_OK;
+    std::shared_lock<std::shared_mutex> lock(m->mu);
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (ctrs[i].limit_id >= m->limits.size()) return mfail(m, "unknown limit_id %u", ctrs[i].limit_id);
+        order[i] = i;
+    }
+    // sort by the remaining of the counters, most restrictive first (lib.rs:238-242; sort_by is stable)
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return remaining[a] < remaining[b]; });
+    std::string text;
+    for (const uint32_t i : order) {  // ", <max>;w=<secs>[;name=\"...\"]" for every counter (lib.rs:244-252)
+        const MLimit& L = m->limits[ctrs[i].limit_id];
+        text += ", " + std::to_string(L.max_value) + ";w=" + std::to_string(L.seconds);
+        if (L.has_name) {
+            std::string nm = L.name;
+            std::replace(nm.begin(), nm.end(), '"', '\'');
+            text += ";name=\"" + nm + "\"";
+        }
+    }
+    const uint32_t f = order[0];
+    const std::string lim = std::to_string(m->limits[ctrs[f].limit_id].max_value) + text;
+    const std::string rem = std::to_string(remaining[f]);
+    const std::string rst = std::to_string(ttl_us[f] / 1000000ull);  // Duration::as_secs (lib.rs:268-270)
+    if (lim.size() + 1 > cap_limit || rem.size() + 1 > cap_remaining || rst.size() + 1 > cap_reset)
+        return mfail(m, "header buffer too small (%zu bytes needed for X-RateLimit-Limit)", lim.size() + 1);
+    memcpy(out_limit, lim.c_str(), lim.size() + 1);
+    memcpy(out_remaining, rem.c_str(), rem.size() + 1);
+    memcpy(out_reset, rst.c_str(), rst.size() + 1);
+    return RL_OK;
+}
+
 void rl_counter_key(const char* const* sources, const char* const* values, uint32_t n, uint64_t* key_lo, uint64_t* key_hi) {
     *key_lo = *key_hi = 0;
     if (n == 0) return;

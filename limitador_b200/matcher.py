@@ -19,7 +19,7 @@ BIND_ROOT = 0xFFFFFFFF
 MATCH_SYMBOLS = (
     "rl_matcher_create", "rl_matcher_destroy", "rl_matcher_last_error", "rl_matcher_add_limit",
     "rl_matcher_delete_limit", "rl_matcher_namespace_id", "rl_matcher_limit_name", "rl_matcher_counters",
-    "rl_matcher_counters_batch", "rl_counter_key",
+    "rl_matcher_counters_batch", "rl_counter_key", "rl_matcher_response_headers",
 )
 
 
@@ -49,6 +49,7 @@ def _lib():
     L.rl_matcher_limit_name.restype = C.c_char_p
     L.rl_matcher_counters.argtypes = [vp, u32, C.POINTER(RlBinding), u32, vp, u32, C.POINTER(u32)]
     L.rl_matcher_counters_batch.argtypes = [vp, u64, vp, vp, C.POINTER(RlBinding), vp, vp, u64]
+    L.rl_matcher_response_headers.argtypes = [vp, vp, vp, vp, u32, C.c_char_p, u32, C.c_char_p, u32, C.c_char_p, u32]
     L.rl_counter_key.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u32, C.POINTER(u64), C.POINTER(u64)]
     L.rl_counter_key.restype = None
     L._rl_match_ready = True
@@ -132,6 +133,19 @@ class Matcher:
         n = C.c_uint32()
         self._check(self._lib.rl_matcher_counters(self._h, ns_id, binds, len(flat), out.ctypes.data, cap, C.byref(n)))
         return out[:n.value]
+
+    def response_headers(self, ctrs: np.ndarray, remaining, ttl_us) -> Dict[str, str]:
+        """CheckResult::response_header (lib.rs:235-275) of one request from its load_counters outputs."""
+        ctrs = np.ascontiguousarray(ctrs, dtype=_eng.COUNTER_DTYPE)
+        rem = np.ascontiguousarray(remaining, dtype=np.uint64)
+        ttl = np.ascontiguousarray(ttl_us, dtype=np.uint64)
+        bl, br, bs = C.create_string_buffer(64 + 96 * max(len(ctrs), 1) + 300 * len(ctrs)), C.create_string_buffer(32), C.create_string_buffer(32)
+        self._check(self._lib.rl_matcher_response_headers(self._h, ctrs.ctypes.data, rem.ctypes.data, ttl.ctypes.data, len(ctrs),
+                                                          bl, len(bl), br, len(br), bs, len(bs)))
+        if len(ctrs) == 0:
+            return {}
+        return {"X-RateLimit-Limit": bl.value.decode(), "X-RateLimit-Remaining": br.value.decode(),
+                "X-RateLimit-Reset": bs.value.decode()}
 
     def counters_batch(self, ns_ids: Sequence[int], contexts: Sequence[Tuple[Optional[dict], Optional[list]]],
                        cap: Optional[int] = None):

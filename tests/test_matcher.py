@@ -370,3 +370,35 @@ def test_matcher_csr_through_the_kernel_algorithm_emulation():
     assert lim.tolist() == [int(w.limited) for w in want]
     assert [m.limit_name(int(f)) for f, w in zip(fl, want) if w.limited] == [w.limit_name for w in want if w.limited]
     assert emu.rounds >= 1  # coupled requests did go through the fixed-point rounds
+
+
+def test_response_headers_render_the_reference_strings():
+    """CheckResult::response_header (lib.rs:235-275): the exact header strings of the reference's server tests
+    (envoy_rls/server.rs:337-426, 496-591, 593-680) and agreement with the Python mirror on random counters,
+    names with quotes included."""
+    m = MT.Matcher()
+    a = m.add_limit("ns", 1, 60, [], ["u"])
+    ctr = np.array([(int(a["limit_id"]), 0, 1, 0)], dtype=COUNTER_DTYPE)
+    assert m.response_headers(ctr, [0], [59_500_000]) == {"X-RateLimit-Limit": "1, 1;w=60", "X-RateLimit-Remaining": "0",
+                                                           "X-RateLimit-Reset": "59"}
+    b = m.add_limit("ns", 0, 60, [], ["v"])
+    c = m.add_limit("ns", 10, 60, [], ["w"])
+    two = np.array([(int(c["limit_id"]), 0, 1, 0), (int(b["limit_id"]), 0, 1, 0)], dtype=COUNTER_DTYPE)
+    assert m.response_headers(two, [10, 0], [60_000_000, 60_000_000])["X-RateLimit-Limit"] == "0, 0;w=60, 10;w=60"
+    assert m.response_headers(ctr[:0], [], []) == {}
+    assert m.response_headers(np.array([(int(c["limit_id"]), 0, 1, 0)], dtype=COUNTER_DTYPE), [4], [1])["X-RateLimit-Remaining"] == "4"
+    # random agreement with the mirror
+    rng = np.random.default_rng(5)
+    lims = []
+    for i in range(12):
+        name = None if i % 3 == 0 else f'lim "{i}" x'
+        L = LM.Limit("rnd", int(rng.integers(0, 1000)), int(rng.choice([1, 60, 3600])) + i, [], ["u"], name)
+        lims.append((L, int(m.add_limit(L.namespace, L.max_value, L.seconds, L.conditions, L.variables, L.name)["limit_id"])))
+    for _ in range(200):
+        pick = [lims[int(j)] for j in rng.choice(len(lims), size=int(rng.integers(1, 6)), replace=False)]
+        rem = [int(rng.integers(0, 5)) for _ in pick]  # ties exercise the stable order
+        ttl = [int(rng.integers(0, 4_000_000_000)) for _ in pick]
+        cs = [LM.Counter(L, {"u": "x"}, remaining=r, expires_in_us=t, limit_id=lid) for (L, lid), r, t in zip(pick, rem, ttl)]
+        want = LM.CheckResult(False, cs).response_header()
+        got = m.response_headers(np.array([(lid, 0, 1, 0) for _, lid in pick], dtype=COUNTER_DTYPE), rem, ttl)
+        assert got == want
