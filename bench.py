@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--exchange-lag", type=int, default=2,
                     help="N>1: verdicts return in the records of the step this many steps later (1..3)")
     ap.add_argument("--no-pipeline", action="store_true", help="disable the pipelining of successive steps")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads / legs reported under `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if not args.batch:

@@ -70,14 +70,13 @@ struct DevBuf {
 // A second copy of the per-batch workspace: with RL_FLAG_PIPELINE the partition kernels of
 // batch s+1 run (on their own stream) while k_main of batch s is still replaying.
 struct WorkSet {
-    DevBuf<uint32_t> tile_cnt, region_total, part_base, part_idx, part_row, reg_of, row_of, fallback, chain_status,
-        chain_wcnt, chain_w, small;  // small: [0] scan counter, [1] item count
-    DevBuf<ulonglong2> part_acc;
+    DevBuf<uint32_t> tile_cnt, part_base, part_idx, part_row, reg_of, row_of, chain_status,
+        chain_wcnt, chain_w, small;  // small: [0] blocks-done counter of the probe, [1] item count, [2] ticket, [3] exit counter
     DevBuf<uint4> items;
     void release() {
-        tile_cnt.release(); region_total.release(); part_base.release(); part_idx.release(); part_row.release();
-        reg_of.release(); row_of.release(); fallback.release(); chain_status.release(); chain_wcnt.release();
-        chain_w.release(); small.release(); part_acc.release(); items.release();
+        tile_cnt.release(); part_base.release(); part_idx.release(); part_row.release();
+        reg_of.release(); row_of.release(); chain_status.release(); chain_wcnt.release();
+        chain_w.release(); small.release(); items.release();
     }
 };
 
@@ -108,14 +107,13 @@ struct rl_engine {
     uint32_t limits_cap = 0, ns_cap = 0;
 
     // workspace
-    DevBuf<uint32_t> d_tile_cnt, d_region_total, d_part_base, d_part_idx, d_part_row, d_reg_of, d_row_of, d_misc;  // misc: err, flags, scan_ctr, changed
+    DevBuf<uint32_t> d_tile_cnt, d_part_base, d_part_idx, d_part_row, d_reg_of, d_row_of, d_misc;  // misc: err, flags, scan_ctr, changed, ...
     DevBuf<RlAccess> d_acc;
     DevBuf<uint64_t> d_delta, d_now;
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
     DevBuf<uint4> d_items;
-    DevBuf<ulonglong2> d_part_acc;
     DevBuf<unsigned long long> d_kstats;
-    DevBuf<uint32_t> d_fallback, d_chain_status, d_chain_wcnt, d_chain_w;
+    DevBuf<uint32_t> d_chain_status, d_chain_wcnt, d_chain_w;
     DevBuf<uint8_t*> d_log_row;
     DevBuf<ulonglong2> d_log_state;
     // staging for RL_MEM_HOST calls
@@ -153,9 +151,10 @@ struct rl_engine {
     uint64_t ring_seq = 0;
     bool d2h_pending = false;
     int d2h_last = 0;
-    unsigned long long tag_mask = ~0ull;
+    uint32_t weak_slots = 0;           // RL_FLAG_DEBUG_WEAK_TAGS
     uint32_t chunk = 128;              // accesses per k_main chunk (128 or 256; RL_CHUNK overrides)
     uint32_t part_target = 128;        // accesses per partition aimed at (RL_PART_TARGET)
+    uint32_t main_grid_cap = 148 * 16;  // k_main CTAs launched at most (SMs x 16)
     uint32_t heavy_mult = 2;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -163,7 +162,7 @@ struct rl_engine {
 
 namespace {
 
-enum { MISC_ERR = 0, MISC_FLAGS = 1, MISC_SCANCTR = 2, MISC_CHANGED = 3, MISC_NITEMS = 4, MISC_N = 8 };
+enum { MISC_ERR = 0, MISC_FLAGS = 1, MISC_SCANCTR = 2, MISC_CHANGED = 3, MISC_NITEMS = 4, MISC_TICKET = 5, MISC_EXITCTR = 6, MISC_N = 8 };
 
 int fail(rl_engine* e, int status, const char* fmt, ...) {
     char buf[512];
@@ -212,7 +211,6 @@ RlDev make_dev(rl_engine* e) {
     D.ns_limit_ids = e->d_ns_limit_ids.p;
     D.err = e->d_misc.p + MISC_ERR;
     D.flags = e->d_misc.p + MISC_FLAGS;
-    D.tag_mask = e->tag_mask;
     D.kstats = e->kernel_stats ? e->d_kstats.p : nullptr;
     return D;
 }
@@ -343,15 +341,16 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     RlBatch B;
     B.n_acc = n_acc;
     B.n_req = n_req;
+    B.n_dev = nullptr;
     B.tile_cnt = e->d_tile_cnt.p;
-    B.region_total = e->d_region_total.p;
     B.part_base = e->d_part_base.p;
     B.part_idx = e->d_part_idx.p;
     B.reg_of = e->d_reg_of.p;
     B.row_of = e->d_row_of.p;
     B.part_row = e->d_part_row.p;
-    B.part_acc = e->d_part_acc.p;
     B.scan_ctr = e->d_misc.p + MISC_SCANCTR;
+    B.ticket = e->d_misc.p + MISC_TICKET;
+    B.exit_ctr = e->d_misc.p + MISC_EXITCTR;
     uint32_t tile = ceil_div(n_acc, kMaxTiles);
     tile = std::max<uint32_t>(512, ((tile + 255) / 256) * 256);
     B.tile = tile;
@@ -368,7 +367,6 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.load_counters = lc;
     B.items = e->d_items.p;
     B.n_items = e->d_misc.p + MISC_NITEMS;
-    B.region_fallback = e->d_fallback.p;
     B.chain_status = e->d_chain_status.p;
     B.chain_wcnt = e->d_chain_wcnt.p;
     B.chain_w = e->d_chain_w.p;
@@ -389,17 +387,16 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     if (set >= 1) {
         WorkSet& w = e->wsx[set - 1];
         B.tile_cnt = w.tile_cnt.p;
-        B.region_total = w.region_total.p;
         B.part_base = w.part_base.p;
         B.part_idx = w.part_idx.p;
         B.reg_of = w.reg_of.p;
         B.row_of = w.row_of.p;
         B.part_row = w.part_row.p;
-        B.part_acc = w.part_acc.p;
         B.scan_ctr = w.small.p + 0;
         B.items = w.items.p;
         B.n_items = w.small.p + 1;
-        B.region_fallback = w.fallback.p;
+        B.ticket = w.small.p + 2;
+        B.exit_ctr = w.small.p + 3;
         B.chain_status = w.chain_status.p;
         B.chain_wcnt = w.chain_wcnt.p;
         B.chain_w = w.chain_w.p;
@@ -419,12 +416,10 @@ int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const
         smem_limit[dv] = max_smem;
     }
     if (stage & 1) {
-        k_probe_count<CELLS, Src><<<B.num_tiles, 1024, P1 * sizeof(uint32_t), st>>>(D, B, src);
+        k_probe_count<CELLS, Src><<<B.num_tiles, RL_PROBE_THREADS, (P1 + 1) * sizeof(uint32_t), st>>>(D, B, src);
         RL_LAUNCH_CHECK(e);
     }
     if (stage & 2) {
-        k_colscan<<<ceil_div(P1, 32), 256, 0, st>>>(D, B);
-        RL_LAUNCH_CHECK(e);
         k_part<Src><<<B.num_tiles, RL_PART_THREADS, smem, st>>>(D, B, src);
         RL_LAUNCH_CHECK(e);
     }
@@ -453,9 +448,10 @@ int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& sr
         RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_set[dv] = true;
     }
-    // upper bound of the work-item count: one per region + one per chunk of a heavy region
-    const uint32_t grid = B.nparts + ceil_div(B.n_acc, CH);
-    kern<<<grid, CH, sizeof(Smem), st>>>(D, B, src);
+    // upper bound of the work-item count: one per partition + one per chunk of a heavy partition; CTAs take
+    // items from a ticket, so a smaller grid only means that some CTAs take several
+    const uint32_t grid = std::min<uint32_t>(B.nparts + ceil_div(B.n_acc, CH), e->main_grid_cap);
+    kern<<<grid, CH, sizeof(Smem), st>>>(D, B, src, e->weak_slots);
     return RL_OK;
 }
 
@@ -663,6 +659,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     cudaDeviceProp prop;
     RL_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
     if (prop.major < 10) return fail(e, RL_FATAL, "device sm_%d%d is not sm_100a", prop.major, prop.minor);
+    e->main_grid_cap = (uint32_t)prop.multiProcessorCount * 16u;
     RL_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     e->cells = cfg->cells_per_row;
@@ -688,7 +685,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     if (const char* v = getenv("RL_CHUNK")) e->chunk = (atoi(v) == 128) ? 128 : 256;
     if (const char* v = getenv("RL_HEAVY_MULT")) e->heavy_mult = (uint32_t)atoi(v);
     if (const char* v = getenv("RL_PART_TARGET")) e->part_target = std::max(16, atoi(v));
-    if (cfg->flags & 1u) e->tag_mask = 0xFull << 24;  // RL_FLAG_DEBUG_WEAK_TAGS: 8 distinct tags per salt level
+    if (cfg->flags & 1u) e->weak_slots = 1;  // RL_FLAG_DEBUG_WEAK_TAGS: four home slots in the grouping table
 
     const size_t bytes = (size_t)e->capacity * e->row_bytes;
     RL_CUDA(e, cudaMalloc((void**)&e->d_rows, bytes));
@@ -697,13 +694,11 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     const uint32_t P1 = (1u << e->log2P) + 1;
     const size_t maxA = e->max_counters;
     RL_CUDA(e, e->d_tile_cnt.reserve((size_t)(kMaxTiles + 1) * P1));
-    RL_CUDA(e, e->d_region_total.reserve(P1 + 1));
     RL_CUDA(e, e->d_part_base.reserve(P1 + 2));
     RL_CUDA(e, e->d_part_idx.reserve(maxA));
     RL_CUDA(e, e->d_reg_of.reserve(maxA));
     RL_CUDA(e, e->d_row_of.reserve(maxA));
     RL_CUDA(e, e->d_part_row.reserve(maxA));
-    RL_CUDA(e, e->d_part_acc.reserve(maxA * 3));
     RL_CUDA(e, e->d_misc.reserve(MISC_N));
     RL_CUDA(e, cudaMemsetAsync(e->d_misc.p, 0, MISC_N * sizeof(uint32_t), e->stream));
     RL_CUDA(e, cudaMallocHost((void**)&e->h_misc, MISC_N * sizeof(uint32_t)));
@@ -711,7 +706,6 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_kstats.reserve(16));
     RL_CUDA(e, cudaMemsetAsync(e->d_kstats.p, 0, 16 * sizeof(unsigned long long), e->stream));
     RL_CUDA(e, e->d_items.reserve((size_t)(1u << e->log2P) + maxA / 128 + 2));
-    RL_CUDA(e, e->d_fallback.reserve(1u << e->log2P));
     {
         const size_t max_items = (size_t)(1u << e->log2P) + maxA / 128 + 2;
         RL_CUDA(e, e->d_chain_status.reserve(max_items));
@@ -737,15 +731,12 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
         for (int wi = 0; wi < rl_engine::kSets - 1; wi++) {
         WorkSet& w = e->wsx[wi];
         RL_CUDA(e, w.tile_cnt.reserve((size_t)(kMaxTiles + 1) * P1));
-        RL_CUDA(e, w.region_total.reserve(P1 + 1));
         RL_CUDA(e, w.part_base.reserve(P1 + 2));
         RL_CUDA(e, w.part_idx.reserve(maxA));
         RL_CUDA(e, w.part_row.reserve(maxA));
         RL_CUDA(e, w.reg_of.reserve(maxA));
         RL_CUDA(e, w.row_of.reserve(maxA));
-        RL_CUDA(e, w.part_acc.reserve(maxA * 3));
         RL_CUDA(e, w.items.reserve(max_items));
-        RL_CUDA(e, w.fallback.reserve(1u << e->log2P));
         RL_CUDA(e, w.chain_status.reserve(max_items));
         RL_CUDA(e, w.chain_wcnt.reserve(max_items));
         RL_CUDA(e, w.chain_w.reserve(max_items * 256));
@@ -790,13 +781,11 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_ns_limit_ids.release();
     e->d_group_ns.release();
     e->d_tile_cnt.release();
-    e->d_region_total.release();
     e->d_part_base.release();
     e->d_part_idx.release();
     e->d_reg_of.release();
     e->d_row_of.release();
     e->d_part_row.release();
-    e->d_part_acc.release();
     e->d_misc.release();
     e->d_acc.release();
     e->d_delta.release();
@@ -805,7 +794,6 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_fl_next.release();
     e->d_items.release();
     e->d_kstats.release();
-    e->d_fallback.release();
     e->d_chain_status.release();
     e->d_chain_wcnt.release();
     e->d_chain_w.release();

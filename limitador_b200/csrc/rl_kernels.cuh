@@ -1,17 +1,18 @@
 // rl_kernels.cuh — hand-written sm_100a kernels of the batched rate-limit engine.
 //
-// Pipeline for one batch:
-//   k_part<COUNT>  : per-tile histogram of accesses over the P table regions
-//   k_colscan      : per-region exclusive prefix over tiles + exclusive scan of region totals
-//   k_part<SCATTER>: STABLE scatter of access indices into per-region lists (stream order kept)
-//   k_main         : one CTA per region; groups the region's accesses by row key in shared
-//                    memory, and one walker thread per key replays that key's requests in
-//                    stream order against the row (fixed-window check / increment), so the
-//                    result equals one-at-a-time execution on the reference InMemoryStorage
-//                    (limitador/src/storage/in_memory.rs:72-156).
-// A region (contiguous slab of rows) is touched by exactly one CTA per launch, and a key by
-// exactly one thread, so counter values need no atomics at all; the only atomic on the table
-// is the 128-bit CAS that claims an empty row for a new key.
+// Pipeline for one batch, three launches:
+//   k_probe_count : every access finds (or claims) its table row — the one random HBM access of
+//                   the batch — and the per-tile histogram over the P table regions is taken on the
+//                   way; the LAST block to finish turns the histogram into stable offsets (column
+//                   scan over tiles), region bases and the work items of k_main
+//   k_part        : STABLE scatter of (access index, row index) pairs into per-region lists
+//   k_main        : one CTA per work item; gathers the 32-B records of its chunk, groups the accesses
+//                   by table row in shared memory and replays every row's requests in stream order
+//                   (fixed-window check / increment), so the result equals one-at-a-time execution
+//                   on the reference InMemoryStorage (limitador/src/storage/in_memory.rs:72-156).
+// A region (contiguous slab of rows) is touched by exactly one CTA at a time, and a row by exactly
+// one group, so counter values need no atomics at all; the only atomic on the table is the
+// 128-bit CAS that claims an empty row for a new key.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,9 +20,9 @@
 #include "../../include/rl_engine.h"
 #include "rl_core.h"
 
-#define RL_MAIN_THREADS 256  // accesses per chunk of k_main (one per thread)
 #define RL_PART_THREADS 256
 #define RL_PART_WARPS (RL_PART_THREADS / 32)
+#define RL_PROBE_THREADS 1024
 #define RL_IDENT_POSORIG 0x0654321006543210ull
 
 struct RlDev {
@@ -36,24 +37,23 @@ struct RlDev {
     const uint32_t* ns_limit_ids;
     uint32_t* err;    // sticky max of RL_DEV_*
     uint32_t* flags;  // bit0: batch has multi-row requests
-    unsigned long long tag_mask;  // ~0; tests narrow it to force in-CTA tag collisions
-    unsigned long long* kstats;   // nullptr = no accounting; [0] chunks, [1] replay rounds, [2] chained chunks, [3] ordered-fallback chunks
+    unsigned long long* kstats;   // nullptr = no accounting; [0] chunks, [1] replay rounds, [2] chained chunks, [3] ordered chunks
 };
 
 struct RlBatch {
-    uint32_t n_acc;
+    uint32_t n_acc;          // accesses of this batch (upper bound when n_dev != nullptr)
     uint32_t n_req;
+    const uint32_t* n_dev;   // nullable: the access count lives on the device (peer exchange: the inbox fill)
     // partition workspace
-    uint32_t* tile_cnt;      // [num_tiles][P+1]; after k_colscan: exclusive prefix over tiles
-    uint32_t* region_total;  // [P+1]
+    uint32_t* tile_cnt;      // [num_tiles][P+1]; after the probe's last block: exclusive prefix over tiles
     uint32_t* part_base;     // [P+2]
-    uint32_t* reg_of;        // [n_acc] region of access a (P = "no row"), written by k_probe_count
+    uint32_t* reg_of;        // [n_acc] partition of access a (P = "no row"), written by k_probe_count
     uint32_t* row_of;        // [n_acc] table row (index) of access a, probed / claimed by k_probe_count
-    uint32_t* part_idx;      // [n_acc]
-    uint32_t* part_row;      // [n_acc] table row (index) of the access, probed / claimed by k_part
-    ulonglong2* part_acc;    // [n_acc][3] the access itself, resolved, in partition order:
-                             //   {key_lo, hdr_hi} {req | cells<<32, posorig} {delta, now}
-    uint32_t* scan_ctr;      // last-block-done counter of k_colscan
+    uint32_t* part_idx;      // [n_acc] access index, in partition order (stream order kept inside a partition)
+    uint32_t* part_row;      // [n_acc] its table row
+    uint32_t* scan_ctr;      // blocks-done counter of k_probe_count
+    uint32_t* ticket;        // work-item ticket of k_main
+    uint32_t* exit_ctr;      // CTAs of k_main that found the ticket exhausted (the last one re-arms it)
     uint32_t nparts;         // partitions of this batch: table regions merged 2^part_shift at a time, so
     uint32_t part_shift;     //   that a small batch still fills its k_main chunks (nparts = P >> part_shift)
     uint32_t tile;           // accesses per tile (multiple of 256)
@@ -70,16 +70,15 @@ struct RlBatch {
     uint32_t* fl_next;
     int phase;          // RL_PHASE_*
     int load_counters;  // 0/1
-    // work items of k_main (built by k_colscan): x = region, y/z = [lo, hi) in part_idx,
-    // w = RL_NONE_U32 for a light region (its chunks run one after the other in one CTA) or the
-    // chunk's index inside a heavy region (one CTA per chunk, committed in order, see k_main)
+    // work items of k_main (built by the probe's last block): x = partition, y/z = [lo, hi) in part_idx,
+    // w = RL_NONE_U32 for a light partition (its chunks run one after the other in one CTA) or the
+    // chunk's index inside a heavy partition (one CTA per chunk, committed in order, see k_main)
     uint4* items;
     uint32_t* n_items;
-    uint32_t* region_fallback;  // [P] first chunk of a heavy region whose read set was written by an earlier chunk
-    uint32_t* chain_status;     // [items] 0 none, 1 write set published, 2 valid, 3 invalid, 4 committed
-    uint32_t* chain_wcnt;       // [items] size of the chunk's write set
-    uint32_t* chain_w;          // [items][chunk] rows the chunk writes
-    uint32_t heavy_len;         // regions longer than this are chained; 0xFFFFFFFF disables
+    uint32_t* chain_status;     // [items] 0 none, 1 read set published, 4 committed
+    uint32_t* chain_wcnt;       // [items] size of the chunk's published set
+    uint32_t* chain_w;          // [items][chunk] rows the chunk touches (bit 0: it writes the row)
+    uint32_t heavy_len;         // partitions longer than this are chained; 0xFFFFFFFF disables
     uint32_t chunk;             // accesses per chunk (= k_main block size)
     // undo log of the rows a coupled batch touches (RL_PHASE_SNAPSHOT / k_restore)
     uint8_t** log_row;     // [n_acc] row pointer logged at the partition position of a key's first access
@@ -159,7 +158,7 @@ __device__ uint8_t* rl_probe(const RlDev& D, uint64_t h, uint64_t key_lo, uint64
             }
             const ulonglong2 old = rl_cas128(target, expect, make_ulonglong2(key_lo, hdr_hi));
             if (old.x == expect.x && old.y == expect.y) return target;
-            // another walker of this CTA took the row first: rescan
+            // another prober took the row first: rescan
             if (++restarts > 4 * R) break;
             tomb = -1;
             i = 0;
@@ -205,20 +204,46 @@ __device__ __forceinline__ void rl_row_store(uint8_t* row, uint32_t dirty, const
 // Access sources.  RecordSrc: access == request, derived on the fly from the 32-B record
 // and the namespace table (every namespace is single-row).  AccSrc: materialised accesses
 // written by a resolve kernel (general CSR form, or records of multi-row namespaces).
+// k_main gathers its chunk straight from the source (one 32-B sector per access): `raw`
+// issues the loads, `decode` consumes them — the kernel puts its grouping barrier in between.
+struct RlRaw {
+    ulonglong2 w0, w1;
+};
+struct RlReq {       // what the replay needs of an access
+    uint32_t req;    // request index (outputs)
+    uint32_t cells;  // packed cell list (rl_core.h)
+    uint32_t group;  // row group: selects the RlCellDesc block
+    uint64_t posorig;
+    uint64_t delta, now;
+};
+
+// Segmented record source (peer exchange): the owner's inbox holds one fixed-size block per source
+// rank, block s filled with seg_prefix[s+1]-seg_prefix[s] records; access a of the batch is the
+// (a - seg_prefix[s])-th record of block s.  seg_prefix == nullptr: a plain array.
 struct RecordSrc {
     static constexpr bool kAccessIsRequest = true;
     static constexpr bool kCanBeMulti = false;  // every namespace maps to one row
     const rl_record* recs;
+    const uint32_t* seg_prefix;  // [nseg+1] exclusive prefix of the block fills (device), or nullptr
+    uint32_t nseg;
+    uint32_t seg_stride;         // records per block
+    __device__ __forceinline__ const rl_record* at(uint32_t a) const {
+        if (seg_prefix == nullptr) return recs + a;
+        uint32_t s = 0;
+        while (s + 1 < nseg && a >= __ldg(seg_prefix + s + 1)) s++;
+        return recs + (size_t)s * seg_stride + (a - __ldg(seg_prefix + s));
+    }
     // identity of access a: false => no row (namespace without limits)
     __device__ __forceinline__ bool ident(const RlDev& D, uint32_t a, uint64_t& key_lo, uint64_t& hdr_hi) const {
-        const ulonglong2 w0 = rl_ld_stream(&recs[a]);       // ns_id|hits, key_lo
+        const rl_record* r = at(a);
+        const ulonglong2 w0 = rl_ld_stream(r);       // ns_id|hits, key_lo
         const uint32_t ns_id = (uint32_t)w0.x;
         if (ns_id >= D.ns_cap) return false;
         const RlNsDev ns = D.ns[ns_id];
         if (ns.mode != 1) return false;
         if (ns.qualified_row) {
             const unsigned long long key_hi =
-                __ldcs(reinterpret_cast<const unsigned long long*>(&recs[a]) + 2) & RL_RECORD_KEY_HI_MASK;
+                __ldcs(reinterpret_cast<const unsigned long long*>(r) + 2) & RL_RECORD_KEY_HI_MASK;
             if (key_hi >> 32) {
                 rl_set_err(D, RL_DEV_KEY_RANGE);
                 return false;
@@ -231,19 +256,21 @@ struct RecordSrc {
         }
         return true;
     }
-    __device__ __forceinline__ void full(const RlDev& D, uint32_t a, RlAccess& acc, uint64_t& delta,
-                                         uint64_t& now) const {
-        const ulonglong2 w0 = rl_ld_stream(&recs[a]);
-        const ulonglong2 w1 = rl_ld_stream(reinterpret_cast<const ulonglong2*>(&recs[a]) + 1);
-        const uint32_t ns_id = (uint32_t)w0.x;
-        const RlNsDev ns = D.ns[ns_id];
-        acc.key_lo = ns.qualified_row ? w0.y : 0;
-        acc.hdr_hi = ((uint64_t)ns.group << 32) | (ns.qualified_row ? (w1.x & RL_RECORD_KEY_HI_MASK) : 0);
-        acc.req = a;
-        acc.cells = ns.cells;
-        acc.posorig = RL_IDENT_POSORIG;
-        delta = (uint64_t)(w0.x >> 32);
-        now = w1.y;
+    __device__ __forceinline__ RlRaw raw(uint32_t a) const {
+        const rl_record* r = at(a);
+        RlRaw w;
+        w.w0 = rl_ld_stream(r);
+        w.w1 = rl_ld_stream(reinterpret_cast<const ulonglong2*>(r) + 1);
+        return w;
+    }
+    __device__ __forceinline__ void decode(const RlDev& D, uint32_t a, const RlRaw& w, RlReq& q) const {
+        const RlNsDev ns = D.ns[(uint32_t)w.w0.x];
+        q.req = a;
+        q.cells = ns.cells;
+        q.group = ns.group;
+        q.posorig = RL_IDENT_POSORIG;
+        q.delta = (uint64_t)(w.w0.x >> 32);
+        q.now = w.w1.y;
     }
 };
 
@@ -259,52 +286,84 @@ struct AccSrc {
         hdr_hi = w0.y;
         return hdr_hi != 0;
     }
-    __device__ __forceinline__ void full(const RlDev&, uint32_t a, RlAccess& out, uint64_t& d,
-                                         uint64_t& t) const {
-        const ulonglong2 w0 = rl_ld_stream(&acc[a]);
-        const ulonglong2 w1 = rl_ld_stream(reinterpret_cast<const ulonglong2*>(&acc[a]) + 1);
-        out.key_lo = w0.x;
-        out.hdr_hi = w0.y;
-        out.req = (uint32_t)w1.x;
-        out.cells = (uint32_t)(w1.x >> 32);
-        out.posorig = w1.y;
-        d = delta[out.req];
-        t = now[out.req];
+    __device__ __forceinline__ RlRaw raw(uint32_t a) const {
+        RlRaw w;
+        w.w0 = rl_ld_stream(&acc[a]);
+        w.w1 = rl_ld_stream(reinterpret_cast<const ulonglong2*>(&acc[a]) + 1);
+        return w;
+    }
+    __device__ __forceinline__ void decode(const RlDev&, uint32_t, const RlRaw& w, RlReq& q) const {
+        q.req = (uint32_t)w.w1.x;
+        q.cells = (uint32_t)(w.w1.x >> 32);
+        q.group = (uint32_t)(w.w0.y >> 32);
+        q.posorig = w.w1.y;
+        q.delta = delta[q.req];
+        q.now = now[q.req];
     }
 };
 
 // ---------------------------------------------------------------------------------------
 // Stable partition of the accesses by table region.
-// Tile = B.tile consecutive accesses; warp w of the CTA owns the w-th contiguous slice, so
+// Tile = B.tile consecutive accesses; warp w of a k_part CTA owns the w-th contiguous slice, so
 // stream order == (tile, warp, step, lane) and a stable rank is
 //   region base + (accesses of earlier tiles) + (accesses of earlier warps) + rank in slice.
+//
 // Probe + count.  One pass over the batch with as many independent loads in flight as the SM
 // can hold: every access finds (or, for a new key, claims) its table row — the one random HBM
 // access of the batch — and the per-tile histogram over the table regions is taken on the way.
+// The last block to finish then does what used to be a kernel of its own: column scan of the
+// tile histogram (exclusive prefix over tiles), exclusive scan of the region totals, and the
+// work items of k_main — all of it out of shared memory, one global round trip per step.
+__device__ __forceinline__ uint32_t rl_block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    // exclusive prefix of v over the 1024 threads of the block; s_warp: 32 words of shared memory
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    uint32_t w = s_warp[lane];  // 32 warps: one per lane
+    uint32_t ws = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+        if ((int)lane >= o) ws += y;
+    }
+    total = __shfl_sync(0xffffffffu, ws, 31);
+    const uint32_t woff = __shfl_sync(0xffffffffu, ws - w, warp);
+    __syncthreads();  // s_warp may be reused by the caller
+    return woff + x - v;
+}
+
 template <int CELLS, class Src>
-__global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src src) {
-    extern __shared__ uint32_t rcnt[];  // [P+1]
+__global__ void __launch_bounds__(RL_PROBE_THREADS) k_probe_count(RlDev D, RlBatch B, Src src) {
+    extern __shared__ uint32_t rcnt[];  // [P+2]: per-tile counts; the last block reuses it for totals / bases
+    __shared__ uint32_t s_warp[32], s_warp2[32];
+    __shared__ uint32_t s_last;
     constexpr uint32_t RB = RlGeom<CELLS>::ROW_BYTES;
     constexpr int U = 4;
+    constexpr uint32_t NT = RL_PROBE_THREADS;
     const uint32_t P1 = B.nparts + 1;
     const uint32_t tid = threadIdx.x;
     const uint32_t tile = blockIdx.x;
-    const uint32_t t0 = tile * B.tile;
-    const uint32_t t1 = min(t0 + B.tile, B.n_acc);
-    for (uint32_t i = tid; i < P1; i += 1024) rcnt[i] = 0;
+    const uint32_t n = B.n_dev ? min(*B.n_dev, B.n_acc) : B.n_acc;
+    const uint32_t t0 = min(tile * B.tile, n);
+    const uint32_t t1 = min(t0 + B.tile, n);
+    for (uint32_t i = tid; i < P1 + 1; i += NT) rcnt[i] = 0;
     __syncthreads();
     const uint32_t R = 1u << D.log2R;
-#if RL_EXP_PAD_AGG
     uint32_t npad = 0;
-#endif
-    for (uint32_t base = t0 + tid; base < t1; base += 1024 * U) {
+    for (uint32_t base = t0 + tid; base < t1; base += NT * U) {
         uint64_t klo[U], hhi[U], h[U];
         bool ok[U];
         uint8_t* home[U];
         ulonglong2 hdr[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint32_t a = base + u * 1024;
+            const uint32_t a = base + u * NT;
             klo[u] = hhi[u] = 0;
             ok[u] = (a < t1) && src.ident(D, a, klo[u], hhi[u]);
         }
@@ -316,7 +375,7 @@ __global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src sr
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint32_t a = base + u * 1024;
+            const uint32_t a = base + u * NT;
             if (a >= t1) continue;
             uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
             if (ok[u]) {
@@ -328,39 +387,103 @@ __global__ void __launch_bounds__(1024) k_probe_count(RlDev D, RlBatch B, Src sr
             }
             B.reg_of[a] = r;
             B.row_of[a] = rowidx;
-#if RL_EXP_PAD_AGG
+            // accesses without limits (the padding of a fixed-size exchange block is thousands of them
+            // per tile) all count into one bucket: summed per warp below
             if (r != P1 - 1) atomicAdd(&rcnt[r], 1u);
             else npad++;
-#else
-            atomicAdd(&rcnt[r], 1u);
-#endif
         }
     }
-#if RL_EXP_PAD_AGG
-    {
-        // accesses without limits (the padding of a fixed-size exchange block is thousands of them per
-        // tile) all count into one bucket: sum them per warp first
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npad += __shfl_xor_sync(0xffffffffu, npad, o);
-        if ((tid & 31) == 0 && npad) atomicAdd(&rcnt[P1 - 1], npad);
-    }
-#endif
+    for (int o = 16; o > 0; o >>= 1) npad += __shfl_xor_sync(0xffffffffu, npad, o);
+    if ((tid & 31) == 0 && npad) atomicAdd(&rcnt[P1 - 1], npad);
     __syncthreads();
-    for (uint32_t r = tid; r < P1; r += 1024) B.tile_cnt[(size_t)tile * P1 + r] = rcnt[r];
+    for (uint32_t r = tid; r < P1; r += NT) B.tile_cnt[(size_t)tile * P1 + r] = rcnt[r];
+
+    // ---- last block: offsets, bases, work items ---------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(B.scan_ctr, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t nt = gridDim.x;
+    // column scan: thread r owns column r; 16 tiles' counts in flight at a time
+    for (uint32_t r = tid; r < P1; r += NT) {
+        uint32_t run = 0;
+        for (uint32_t tb = 0; tb < nt; tb += 16) {
+            uint32_t c[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                c[i] = (tb + i < nt) ? __ldcg(&B.tile_cnt[(size_t)(tb + i) * P1 + r]) : 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (tb + i < nt) B.tile_cnt[(size_t)(tb + i) * P1 + r] = run;
+                run += c[i];
+            }
+        }
+        rcnt[r] = run;  // column total
+    }
+    __syncthreads();
+    // exclusive scan of the totals -> part_base[0..P1] (kept in shared memory as well)
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < P1; base += NT) {
+        const uint32_t i = base + tid;
+        const uint32_t v = (i < P1) ? rcnt[i] : 0;
+        uint32_t total;
+        const uint32_t ex = rl_block_excl_scan_1024(v, s_warp, total);
+        if (i < P1) {
+            rcnt[i] = carry + ex;
+            B.part_base[i] = carry + ex;
+        }
+        carry += total;
+    }
+    if (tid == 0) {
+        rcnt[P1] = carry;
+        B.part_base[P1] = carry;
+    }
+    __syncthreads();
+    // work items for k_main: chunks of heavy partitions first (they chain in ticket order)
+    const uint32_t P = P1 - 1;
+    uint32_t hsum = 0, lsum = 0;
+    for (uint32_t q = tid; q < P; q += NT) {
+        const uint32_t len = rcnt[q + 1] - rcnt[q];
+        if (len > B.heavy_len) hsum += (len + B.chunk - 1) / B.chunk;
+        else if (len) lsum += 1;
+    }
+    uint32_t th, tl;
+    uint32_t hb = rl_block_excl_scan_1024(hsum, s_warp, th);
+    uint32_t lb = rl_block_excl_scan_1024(lsum, s_warp2, tl);
+    for (uint32_t q = tid; q < P; q += NT) {
+        const uint32_t lo = rcnt[q], hi = rcnt[q + 1];
+        const uint32_t len = hi - lo;
+        if (len > B.heavy_len) {
+            const uint32_t nc = (len + B.chunk - 1) / B.chunk;
+            for (uint32_t k = 0; k < nc; k++) {
+                B.chain_status[hb] = 0;
+                B.items[hb++] = make_uint4(q, lo + k * B.chunk, min(lo + (k + 1) * B.chunk, hi), k);
+            }
+        } else if (len) {
+            B.items[th + lb++] = make_uint4(q, lo, hi, RL_NONE_U32);
+        }
+    }
+    if (tid == 0) {
+        *B.n_items = th + tl;
+        *B.ticket = 0;
+        *B.scan_ctr = 0;  // re-arm for the next batch
+    }
 }
 
-// Stable scatter.  Tile = B.tile consecutive accesses; warp w of the CTA owns the w-th
-// contiguous slice, so stream order == (tile, warp, step, lane) and the stable rank of an
-// access is  region base + (accesses of earlier tiles) + (of earlier warps) + rank in slice.
-// Each access is written out resolved (part_acc) so that k_main reads its chunk coalesced.
+// Stable scatter of (access, row) pairs into partition order.
 template <class Src>
 __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Src src) {
     extern __shared__ uint32_t wcnt[];  // [RL_PART_WARPS][nparts+1]
     const uint32_t P1 = B.nparts + 1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
-    const uint32_t t0 = tile * B.tile;
-    const uint32_t t1 = min(t0 + B.tile, B.n_acc);
+    const uint32_t n = B.n_dev ? min(*B.n_dev, B.n_acc) : B.n_acc;
+    const uint32_t t0 = min(tile * B.tile, n);
+    const uint32_t t1 = min(t0 + B.tile, n);
+    if (t0 >= t1) return;
     const uint32_t slice = B.tile / RL_PART_WARPS;
     const uint32_t s0 = min(t0 + warp * slice, t1);
     const uint32_t s1 = min(s0 + slice, t1);
@@ -400,13 +523,9 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
         const uint32_t a = b + lane;
         const bool valid = a < s1;
         uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
-        RlAccess racc;
-        uint64_t rdelta = 0, rnow = 0;
-        racc.key_lo = 0; racc.hdr_hi = 0; racc.req = 0; racc.cells = 0; racc.posorig = 0;
         if (valid) {
             r = __ldcg(B.reg_of + a);
             rowidx = __ldcg(B.row_of + a);
-            if (r != P1 - 1) src.full(D, a, racc, rdelta, rnow);
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -419,15 +538,10 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
             }
             basepos = __shfl_sync(m, basepos, leader);
             const uint32_t mypos = basepos + __popc(m & ((1u << lane) - 1));
-            B.part_idx[mypos] = a;
-            B.part_row[mypos] = rowidx;
             if (r != P1 - 1) {
-                ulonglong2* pa = B.part_acc + (size_t)mypos * 3;
-                pa[0] = make_ulonglong2(racc.key_lo, racc.hdr_hi);
-                pa[1] = make_ulonglong2((unsigned long long)racc.req | ((unsigned long long)racc.cells << 32), racc.posorig);
-                pa[2] = make_ulonglong2(rdelta, rnow);
-            }
-            if (Src::kAccessIsRequest && r == P1 - 1 && B.out_limited) {
+                B.part_idx[mypos] = a;
+                B.part_row[mypos] = rowidx;
+            } else if (Src::kAccessIsRequest && B.out_limited) {
                 // request without any applicable limit: not limited (lib.rs:434-440)
                 B.out_limited[a] = 0;
                 if (B.out_first_limited) B.out_first_limited[a] = RL_NONE_U32;
@@ -437,166 +551,48 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
     }
 }
 
-// Column scan of tile_cnt: CTA c owns regions [32c, 32c+32); warp w a slice of the tiles.
-// The last CTA to finish turns region_total into part_base (exclusive scan, P+2 entries).
-__global__ void __launch_bounds__(256) k_colscan(RlDev D, RlBatch B) {
-    __shared__ uint32_t part[8][32];
-    __shared__ uint32_t s_last;
-    __shared__ uint32_t s_warp[8];
-    const uint32_t P1 = B.nparts + 1;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * 32 + lane;
-    const uint32_t nt = B.num_tiles;
-    const uint32_t per = (nt + 7) / 8;
-    const uint32_t a0 = min(warp * per, nt), a1 = min(a0 + per, nt);
-    // at most 32 tiles per warp (256 tiles / 8 warps): keep them in registers so that all the
-    // loads of a column slice are in flight together instead of one dependent load per tile
-    uint32_t cnt[32];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-        const uint32_t t = a0 + i;
-        cnt[i] = (r < P1 && t < a1) ? __ldcg(&B.tile_cnt[(size_t)t * P1 + r]) : 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i++) sum += cnt[i];
-    part[warp][lane] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (uint32_t w = 0; w < warp; w++) run += part[w][lane];
-    if (r < P1) {
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-            const uint32_t t = a0 + i;
-            if (t < a1) B.tile_cnt[(size_t)t * P1 + r] = run;
-            run += cnt[i];
-        }
-        if (warp == 7) B.region_total[r] = run;  // warp 7 ends with the full column sum
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(B.scan_ctr, 1) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // exclusive scan over region_total[0..P1) -> part_base[0..P1]
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < P1; base += 256) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = (i < P1) ? __ldcg(&B.region_total[i]) : 0;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((int)lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (uint32_t w = 0; w < warp; w++) woff += s_warp[w];
-        uint32_t total = 0;
-        for (uint32_t w = 0; w < 8; w++) total += s_warp[w];
-        if (i < P1) B.part_base[i] = carry + woff + x - v;
-        carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        B.part_base[P1] = carry;
-        *B.scan_ctr = 0;  // re-arm for the next batch
-    }
-    __syncthreads();
-    // ---- work items for k_main: chunks of heavy regions first (they chain in launch order) ----
-    const uint32_t P = P1 - 1;
-    uint32_t hsum = 0, lsum = 0;
-    for (uint32_t q = threadIdx.x; q < P; q += 256) {
-        const uint32_t len = B.part_base[q + 1] - B.part_base[q];
-        if (len > B.heavy_len) hsum += (len + B.chunk - 1) / B.chunk;
-        else if (len) lsum += 1;
-    }
-    __shared__ uint32_t s_hw[8], s_lw[8];
-    uint32_t hx = hsum, lx = lsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t hy = __shfl_up_sync(0xffffffffu, hx, o), ly = __shfl_up_sync(0xffffffffu, lx, o);
-        if ((int)lane >= o) {
-            hx += hy;
-            lx += ly;
-        }
-    }
-    if (lane == 31) {
-        s_hw[warp] = hx;
-        s_lw[warp] = lx;
-    }
-    __syncthreads();
-    uint32_t hb = hx - hsum, lb = lx - lsum, th = 0, tl = 0;
-    for (uint32_t w = 0; w < 8; w++) {
-        if (w < warp) {
-            hb += s_hw[w];
-            lb += s_lw[w];
-        }
-        th += s_hw[w];
-        tl += s_lw[w];
-    }
-    for (uint32_t q = threadIdx.x; q < P; q += 256) {
-        const uint32_t lo = B.part_base[q], hi = B.part_base[q + 1];
-        const uint32_t len = hi - lo;
-        if (len > B.heavy_len) {
-            const uint32_t nc = (len + B.chunk - 1) / B.chunk;
-            for (uint32_t k = 0; k < nc; k++) {
-                B.chain_status[hb] = 0;
-                B.items[hb++] = make_uint4(q, lo + k * B.chunk, min(lo + (k + 1) * B.chunk, hi), k);
-            }
-            B.region_fallback[q] = 0xFFFFFFFFu;
-        } else if (len) {
-            B.items[th + lb++] = make_uint4(q, lo, hi, RL_NONE_U32);
-        }
-    }
-    if (threadIdx.x == 0) *B.n_items = th + tl;
-}
-
 // ---------------------------------------------------------------------------------------
 // The main kernel.  MODE 0 = check_and_update, MODE 2 = update_counters.
 //
-// One CTA per table region; the region's accesses (already in stream order) are taken in
-// chunks of CH (one access per thread).  Per chunk:
-//   1. every thread loads its access (the next chunk's is prefetched), and the CTA groups
-//      the accesses by row key with a shared-memory hash table: 56-bit tag claimed by CAS,
-//      full key verified against the claimer's, a mismatch re-inserts under a salted tag.
-//      The claimer ("rep") of a key immediately probes / claims the table row — one probe
-//      per key, its HBM latency overlapping the grouping barriers;
-//   2. every access gets its stable ordinal inside its key group from one packed
-//      shared-memory counter per key (8 bits per warp, added warp-aggregated): ordinal order
-//      == thread order == stream order;
+// CTAs take work items from an atomic ticket (so every item a CTA may have to wait for is already
+// running: the chained commit below is live whatever order the hardware dispatches CTAs in).  A
+// partition's accesses (already in stream order) are taken in chunks of CH (one access per thread).
+// Per chunk:
+//   1. every thread fetches its (access index, table row) pair — prefetched one chunk ahead — and
+//      issues the gather of its 32-B record; while that is in flight the CTA groups the accesses by
+//      TABLE ROW with a shared-memory hash table (the probe already resolved key -> row, so the
+//      32-bit row index is the exact identity of the key: one CAS, no key comparison), and the
+//      claimer ("rep") of a row issues the load of the row state;
+//   2. every access gets its stable ordinal inside its row group from one packed shared-memory
+//      counter per row (8 bits per warp, added warp-aggregated): ordinal order == thread order ==
+//      stream order;
 //   3. the rep stages the row state in shared memory;
 //   4. the group is replayed by ALL its threads in lock-step run-length rounds (rl_core.h,
 //      hypotheses A and B; B in closed form for runs of equal deltas) — two barriers per
 //      round, one round for a saturated or an unconstrained hot key;
 //   5. the rep writes the dirty cells back.
-// Counter values never need atomics: a region belongs to one CTA, a key to one group.
+// Counter values never need atomics: a region belongs to one CTA at a time, a row to one group.
 template <int CELLS, int CH>
 struct RlMainSmem {
     static constexpr int GT = 2 * CH;
     static constexpr int NW = CH / 32;
     static constexpr int PW = (NW + 7) / 8;
-    unsigned long long g_tag[GT];
-    unsigned long long g_packed[GT * PW];  // per key: member count of every warp, 8 bits each
-    unsigned long long key_lo[CH];
-    unsigned long long key_hi[CH];
+    unsigned long long g_packed[GT * PW];  // per row: member count of every warp, 8 bits each
     unsigned long long d_arr[CH];
     unsigned long long s_val[CH * CELLS];  // row state of the group whose rep is thread `gid`
     unsigned long long s_exp[CH * CELLS];
-    uint32_t cells_arr[CH];
+    uint32_t g_row[GT];        // grouping table: row index claimed by CAS; also the chunk's read set
     uint32_t g_rep[GT];
+    uint32_t cells_arr[CH];
     uint32_t g_min[2][2][CH];  // [round parity][A|B][gid]
-    uint32_t g_flags[CH];      // by gid: bit0 = members differ in delta or cell list
+    uint32_t g_flags[CH];      // by gid: bit2 = replay again (chained chunk, state changed under it)
     uint32_t g_dirty[CH];
-    uint32_t rset[GT];         // chained chunks: rows this chunk read (its read set)
-    uint32_t rflag[GT];        // ... row is written by an earlier chunk
+    uint32_t rflag[GT];        // chained chunks: row of g_row[] is "ordered" (see below)
     uint32_t need_bits[64];    // earlier chunks (bit per chunk) whose commit I must wait for
     uint32_t scan_off[CH];     // dependency scan: offsets of the earlier chunks' sets, CH chunks at a time
     uint32_t scan_w[NW];
     uint32_t w_cnt;
-    uint32_t bcast;
+    uint32_t item;
 };
 
 // Per-thread view of the limits its access touches, in the access's own cell order.
@@ -636,18 +632,10 @@ __device__ __forceinline__ void rl_eval_ab(const unsigned long long* sv, const u
 }
 
 // With RL_FLAG_KERNEL_STATS (D.kstats != nullptr) k_main accounts its chunks, rounds and SM cycles per
-// phase (thread 0, one clock64 and one atomic per phase and chunk): rl_stats.phase_cycles, the numbers
-// DESIGN.md §10 quotes.  It costs ~7 % of the C2 step (600 chunks x 8 atomics on nine words), hence opt-in.
-// Experiments prepared for the next round, off in the product build; measure with
-// build.build_variant(name, ["RL_EXP_...=1"]) + RL_ENGINE_LIB before flipping a default.
-#ifndef RL_EXP_PAD_AGG
-#define RL_EXP_PAD_AGG 0  // k_probe_count: one shared-memory add per warp for the no-limit bucket (exchange padding)
-#endif
-#ifndef RL_EXP_ROW_PREFETCH
-#define RL_EXP_ROW_PREFETCH 0  // k_main: every thread fetches its row state before the grouping, not only the reps after it
-#endif
+// phase (thread 0, one clock64 and one atomic per phase and chunk): rl_stats.phase_cycles.  It costs a
+// few % of a 65536-request step, hence opt-in.
 #ifndef RL_MID_CTAS
-#define RL_MID_CTAS 6  // resident 128-thread k_main CTAs per SM asked of the compiler for 3..4-cell rows (registers = 512 / this)
+#define RL_MID_CTAS 5  // resident 128-thread k_main CTAs per SM asked of the compiler for 3..4-cell rows (registers = 512 / this)
 #endif
 #ifndef RL_WAIT_NS
 #define RL_WAIT_NS 100  // back-off of the chained-commit wait loops
@@ -733,24 +721,17 @@ __device__ __forceinline__ void rl_apply_update_smem(unsigned long long* sv, uns
     }
 }
 
-__device__ __forceinline__ void rl_load_part(const RlBatch& B, uint32_t p, RlAccess& acc, uint64_t& delta,
-                                             uint64_t& now, uint32_t& row) {
-    const ulonglong2* pa = B.part_acc + (size_t)p * 3;
-    const ulonglong2 a0 = __ldcs(pa), a1 = __ldcs(pa + 1), a2 = __ldcs(pa + 2);
-    row = __ldcs(B.part_row + p);
-    acc.key_lo = a0.x;
-    acc.hdr_hi = a0.y;
-    acc.req = (uint32_t)a1.x;
-    acc.cells = (uint32_t)(a1.x >> 32);
-    acc.posorig = a1.y;
-    delta = a2.x;
-    now = a2.y;
+template <int GT>
+__device__ __forceinline__ uint32_t rl_group_slot(uint32_t row, uint32_t weak) {
+    // weak (test aid, RL_FLAG_DEBUG_WEAK_TAGS): four home slots for the whole chunk, so the linear
+    // probing of the grouping table is exercised to its full length
+    return weak ? (row & 3u) : ((row * 2654435761u) >> 7) & (GT - 1);
 }
 
 // GEO = cells per row of the table layout (row bytes), CELLS = cells any row group actually
 // uses (<= GEO): loops, registers and shared memory are sized by the latter.
 template <int GEO, int CELLS, class Src, int MODE, int CH, bool LC>
-__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTAS : 4)) * 128 / CH) k_main(RlDev D, RlBatch B, Src src) {
+__global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTAS : 4)) * 128 / CH) k_main(RlDev D, RlBatch B, Src src, uint32_t weak) {
     using Smem = RlMainSmem<CELLS, CH>;
     constexpr int GT = Smem::GT;
     constexpr int PW = Smem::PW;
@@ -762,15 +743,27 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
     const bool write_out = (B.phase == RL_PHASE_COMMIT);
     const bool snapshot = Src::kCanBeMulti && (B.phase == RL_PHASE_SNAPSHOT);
 
-    // the work-item array is allocated for the launch's full grid: fetch my item together with
-    // the item count instead of after it
-    uint4 it0 = B.items[blockIdx.x];
     const uint32_t n_items = *B.n_items;
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        // ---- next work item: atomic ticket, broadcast through shared memory -----------------------
+        __syncthreads();  // the previous item is finished by every thread (sm.item is reused)
+        if (tid == 0) sm.item = atomicAdd(B.ticket, 1u);
+        for (uint32_t i = tid; i < GT; i += CH) sm.g_row[i] = 0xFFFFFFFFu;
+        for (uint32_t i = tid; i < GT * PW; i += CH) sm.g_packed[i] = 0ull;
+        __syncthreads();
+        const uint32_t item = sm.item;
+        if (item >= n_items) {
+            // the last CTA to leave re-arms the ticket for the next launch over this workspace
+            if (tid == 0 && atomicAdd(B.exit_ctr, 1u) == gridDim.x - 1) {
+                *B.exit_ctr = 0;
+                *B.ticket = 0;
+            }
+            break;
+        }
         long long tph = D.kstats != nullptr ? clock64() : 0;
-        const uint4 it = (item == blockIdx.x) ? it0 : B.items[item];
-        const uint32_t region = it.x, lo = it.y, hi = it.z;
-        // Heavy region: this CTA owns ONE chunk and the region's chunks run concurrently under
+        const uint4 it = B.items[item];
+        const uint32_t lo = it.y, hi = it.z;
+        // Heavy partition: this CTA owns ONE chunk and the partition's chunks run concurrently under
         // optimistic concurrency control, row by row.  A chunk replays its requests against the
         // rows as they are (no row is written) and publishes the rows it read, each tagged with
         // whether its replay changes it.  Requests of different keys never interact, so a row's
@@ -780,29 +773,61 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
         // is the one sequential execution shows it and nobody before it can be disturbed by its
         // writes (a saturated hot key is read by every chunk and written by none): it commits at
         // once.  Otherwise it waits for exactly the earlier chunks touching an ordered row,
-        // re-reads its rows and replays the keys whose state changed.
+        // re-reads its rows and replays the keys whose state changed.  Earlier chunks hold lower
+        // tickets, so they are running (or done) whenever a chunk waits for them.
         const bool chained = (it.w != RL_NONE_U32);
-        // prefetch of the first chunk
-        RlAccess nacc;
-        uint64_t ndelta = 0, nnow = 0;
-        uint32_t nrow = 0xFFFFFFFFu;
-        nacc.key_lo = 0; nacc.hdr_hi = 0; nacc.req = 0; nacc.cells = 0; nacc.posorig = 0;
-        if (lo + tid < hi) rl_load_part(B, lo + tid, nacc, ndelta, nnow, nrow);
+        // (access, row) pairs of the first chunk
+        uint32_t na = 0, nrow = 0xFFFFFFFFu;
+        if (lo + tid < hi) {
+            na = __ldcs(B.part_idx + lo + tid);
+            nrow = __ldcs(B.part_row + lo + tid);
+        }
 
         for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
-            for (uint32_t i = tid; i < GT; i += CH) sm.g_tag[i] = 0ull;
-            for (uint32_t i = tid; i < GT * PW; i += CH) sm.g_packed[i] = 0ull;
-
-            // ---- 1. my access (prefetched); issue the next chunk's loads -----------------------
+            // ---- 1. my access: gather the record, group by row while it is in flight --------------
             const uint32_t p = c0 + tid;
-            const bool valid = p < hi;
-            const RlAccess acc = nacc;
-            const uint64_t delta = ndelta, now = nnow;
-            const uint32_t myrow = nrow;
-            if (p + CH < hi) rl_load_part(B, p + CH, nacc, ndelta, nnow, nrow);
-            const uint64_t h = rl_row_hash(acc.key_lo, acc.hdr_hi);
-            const uint32_t group = (uint32_t)(acc.hdr_hi >> 32);
-            const RlCellDesc* gdesc = D.desc + (size_t)group * 8;
+            const uint32_t a = na, myrow = nrow;
+            const bool valid = (p < hi) && (myrow != 0xFFFFFFFFu);  // no row: the region is full (error flagged by the probe)
+            RlRaw rawrec;
+            rawrec.w0 = make_ulonglong2(0ull, 0ull);
+            rawrec.w1 = make_ulonglong2(0ull, 0ull);
+            if (valid) rawrec = src.raw(a);
+            if (p + CH < hi) {
+                na = __ldcs(B.part_idx + p + CH);
+                nrow = __ldcs(B.part_row + p + CH);
+            }
+            uint32_t slot = 0, gid = tid;
+            bool is_rep = false;
+            if (valid) {
+                uint32_t s = rl_group_slot<GT>(myrow, weak);
+                for (;;) {
+                    const uint32_t old = atomicCAS(&sm.g_row[s], 0xFFFFFFFFu, myrow);
+                    if (old == 0xFFFFFFFFu) {
+                        sm.g_rep[s] = tid;  // I claimed the slot: my row's group is mine to stage
+                        is_rep = true;
+                        break;
+                    }
+                    if (old == myrow) break;
+                    s = (s + 1) & (GT - 1);
+                }
+                slot = s;
+            }
+            uint8_t* row = nullptr;
+            RlRow<CELLS> st;
+            if (is_rep) {
+                // the row was located (or claimed) by the probe; its sectors are often still in L2
+                row = D.rows + (size_t)myrow * RlGeom<GEO>::ROW_BYTES;
+                rl_row_load<CELLS>(row, CELLS, st);
+            }
+            __syncthreads();
+            if (valid) gid = sm.g_rep[slot];
+
+            // ---- decode the record: limits of the cells I touch -----------------------------------
+            RlReq acc;
+            acc.req = 0; acc.cells = 0; acc.group = 0; acc.posorig = 0; acc.delta = 0; acc.now = 0;
+            if (valid) src.decode(D, a, rawrec, acc);
+            const uint64_t delta = acc.delta, now = acc.now;
+            const RlCellDesc* gdesc = D.desc + (size_t)acc.group * 8;
             const uint32_t ncell = rl_cells_n(acc.cells);
             const bool multi = Src::kCanBeMulti && (MODE == 0) && rl_cells_multi(acc.cells);  // coupled to other rows
             RlMyLimits L;
@@ -822,87 +847,30 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                 }
             }
             const RlCellDesc* desc = kGeneric ? mydesc : gdesc;
-            sm.key_lo[tid] = acc.key_lo;
-            sm.key_hi[tid] = acc.hdr_hi;
             sm.d_arr[tid] = delta;
             sm.cells_arr[tid] = acc.cells;
             sm.g_flags[tid] = 0;
             sm.g_dirty[tid] = 0;
             sm.g_min[0][0][tid] = sm.g_min[0][1][tid] = 0xFFFFFFFFu;
             sm.g_min[1][0][tid] = sm.g_min[1][1][tid] = 0xFFFFFFFFu;
-            __syncthreads();
-            RL_PHASE_TICK(0)  // item fetch + access load + init
+            RL_PHASE_TICK(0)  // item fetch + gather + grouping
 
-            // ---- group by key; the claimer of a key probes its row right away ------------------
-            uint32_t slot = 0, gid = tid;
-            uint8_t* row = nullptr;
-            bool is_rep = false;
-            RlRow<CELLS> st;
-#if RL_EXP_ROW_PREFETCH
-            // every thread fetches the state of its own row now (threads of one key hit the same sectors):
-            // the L2 round trip overlaps the grouping barriers; only the key's rep ends up using it.  The
-            // previous chunk of this CTA wrote its rows back before the barrier that ended it.
-            rl_row_load<CELLS>((valid && myrow != 0xFFFFFFFFu) ? D.rows + (size_t)myrow * RlGeom<GEO>::ROW_BYTES : nullptr,
-                               CELLS, st);
-#endif
-            {
-                bool pending = valid;
-                uint32_t salt = 0;
-                for (;;) {
-                    if (pending) {
-                        // 56 hash bits + the salt level in the top byte: keys that collided on one
-                        // level meet fresh tags on the next, so every level places >= 1 key
-                        unsigned long long tag = (salt ? rl_mix64(h + salt) : h) & D.tag_mask;
-                        tag = (tag & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)(salt & 0xFFu) << 56) | 1ull;
-                        uint32_t s = (uint32_t)(tag >> 24) & (GT - 1);
-                        for (;;) {
-                            const unsigned long long old = atomicCAS(&sm.g_tag[s], 0ull, tag);
-                            if (old == 0ull) {
-                                sm.g_rep[s] = tid;  // I claimed the slot: my key defines the group
-                                is_rep = true;
-                                break;
-                            }
-                            if (old == tag) break;
-                            s = (s + 1) & (GT - 1);
-                        }
-                        slot = s;
-                        if (is_rep && row == nullptr) {
-                            // the row was located (or claimed) by k_part; its sectors are in L2
-                            if (myrow != 0xFFFFFFFFu) row = D.rows + (size_t)myrow * RlGeom<GEO>::ROW_BYTES;
-#if !RL_EXP_ROW_PREFETCH
-                            rl_row_load<CELLS>(row, CELLS, st);
-#endif
-                        }
-                    }
-                    __syncthreads();
-                    if (pending) {
-                        gid = sm.g_rep[slot];
-                        pending = (sm.key_lo[gid] != acc.key_lo) || (sm.key_hi[gid] != acc.hdr_hi);
-                        salt++;
-                    }
-                    if (!__syncthreads_or(pending)) break;  // tag collision between different keys: re-insert salted
-                }
-            }
-
-            RL_PHASE_TICK(1)  // grouping (tag insert, verify)
-            // ---- 2. stable ordinal: one packed add per (warp, key), one barrier ------------------
+            // ---- 2. stable ordinal: one packed add per (warp, row), one barrier --------------------
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             unsigned peers = 0;
             if (valid) {
                 peers = __match_any_sync(vmask, slot);
                 if (lane == (uint32_t)(__ffs(peers) - 1))
                     atomicAdd(&sm.g_packed[slot * PW + (warp >> 3)], (unsigned long long)__popc(peers) << (8 * (warp & 7)));
-                if (sm.d_arr[gid] != delta || sm.cells_arr[gid] != acc.cells) atomicOr(&sm.g_flags[gid], 1u);
             }
-            // ---- 3. the rep stages the row state --------------------------------------------------
+            // ---- 3. the rep stages the row state -----------------------------------------------------
             if (is_rep) {
 #pragma unroll
                 for (int c = 0; c < CELLS; c++) {
                     sm.s_val[tid * CELLS + c] = st.value[c];
                     sm.s_exp[tid * CELLS + c] = st.expiry[c];
                 }
-                if (row == nullptr) atomicOr(&sm.g_flags[tid], 2u);  // table full: error already flagged
-                if (snapshot && row != nullptr) {
+                if (snapshot) {
                     B.log_row[p] = row;
 #pragma unroll
                     for (int c = 0; c < CELLS; c++)
@@ -920,12 +888,14 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                 }
                 ord += __popc(peers & ((1u << lane) - 1));
             }
-            const uint32_t gflags = valid ? sm.g_flags[gid] : 0;
-            const bool uniform = !(gflags & 1u);
+            // a run of allowed requests is closed-form only over members that carry the rep's delta and
+            // cell list: a member that differs is never part of a run (it ends the run before it and is
+            // applied alone), so the members of any run are mutually alike
+            const bool like_rep = valid && sm.d_arr[gid] == delta && sm.cells_arr[gid] == acc.cells;
             RL_PHASE_TICK(2)  // ordinals + row state staged
 
             // ---- 4. lock-step run-length replay -----------------------------------------------------
-            bool done = !valid || snapshot || (gflags & 2u);
+            bool done = !valid || snapshot;
             uint32_t pos = 0;
             const unsigned long long* sv = &sm.s_val[gid * CELLS];
             const unsigned long long* se = &sm.s_exp[gid * CELLS];
@@ -943,7 +913,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                         // update_counters never tests the limit: a run only needs live cells
                         rl_eval_ab<CELLS>(sv, se, L, acc.cells, acc.posorig, delta, dsum, now, lc, MODE == 0, aok, bok, fl);
                         if (MODE == 2) aok = false;
-                        bok = bok && uniform;
+                        bok = bok && like_rep;
                     }
                     if (lc) {
                         // remaining/ttl need the state this request sees: copy it before the barrier,
@@ -1084,24 +1054,16 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             RL_PHASE_TICK(3)  // replay rounds
             if (!chained || snapshot || attempt == 1) break;
             if (tid == 0) RL_KSTAT_ADD(2, 1);
-            const uint32_t base_item = item - it.w;  // first chunk of my region
-            // (b) publish my read set, each row tagged with "I write it" (under my speculation)
-            for (uint32_t i = tid; i < GT; i += CH) {
-                sm.rset[i] = 0xFFFFFFFFu;
-                sm.rflag[i] = 0;
-            }
+            const uint32_t base_item = item - it.w;  // first chunk of my partition
+            // (b) publish the rows I touched, each tagged with "I write it" (under my speculation);
+            //     the grouping table g_row IS the set of rows this chunk read
+            for (uint32_t i = tid; i < GT; i += CH) sm.rflag[i] = 0;
             for (uint32_t i = tid; i < 64; i += CH) sm.need_bits[i] = 0;
             if (tid == 0) sm.w_cnt = 0;
             __syncthreads();
-            if (is_rep && row != nullptr) {
-                uint32_t s2 = (myrow * 2654435761u) & (GT - 1);
-                for (;;) {
-                    const uint32_t old = atomicCAS(&sm.rset[s2], 0xFFFFFFFFu, myrow);
-                    if (old == 0xFFFFFFFFu || old == myrow) break;
-                    s2 = (s2 + 1) & (GT - 1);
-                }
+            if (is_rep) {
                 // a row I WRITE is ordered too: no earlier chunk may still be reading it when I commit
-                if (sm.g_dirty[tid]) sm.rflag[s2] = 1;
+                if (sm.g_dirty[tid]) sm.rflag[slot] = 1;
                 B.chain_w[(size_t)item * CH + atomicAdd(&sm.w_cnt, 1u)] = (myrow << 1) | (sm.g_dirty[tid] ? 1u : 0u);
                 __threadfence();  // my entry is visible device-wide before the status word says so
             }
@@ -1111,7 +1073,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                 __threadfence();
                 atomicExch(B.chain_status + item, 1u);
             }
-            // (c) wait until every earlier chunk of the region has published its set
+            // (c) wait until every earlier chunk of the partition has published its set
             for (;;) {
                 bool ok = true;
                 for (uint32_t j = tid; j < it.w; j += CH)
@@ -1129,7 +1091,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             //     dependent round trip per earlier chunk).
             bool any_dep = false;
             for (int pass = 0; pass < 2; pass++) {
-                bool flagged = is_rep && row != nullptr && sm.g_dirty[tid] != 0;
+                bool flagged = is_rep && sm.g_dirty[tid] != 0;
                 for (uint32_t blk = 0; blk < it.w; blk += CH) {
                     const uint32_t jn = min((uint32_t)CH, it.w - blk);  // chunks in this block
                     const uint32_t myc = (tid < jn) ? __ldcg(B.chain_wcnt + base_item + blk + tid) : 0;
@@ -1150,18 +1112,18 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                     __syncthreads();
                     for (uint32_t q = tid; q < total; q += CH) {
                         // chunk holding flattened entry q: last j with scan_off[j] <= q
-                        uint32_t lo = 0, hi = jn - 1;
-                        while (lo < hi) {
-                            const uint32_t mid = (lo + hi + 1) >> 1;
-                            if (sm.scan_off[mid] <= q) lo = mid;
-                            else hi = mid - 1;
+                        uint32_t blo = 0, bhi = jn - 1;
+                        while (blo < bhi) {
+                            const uint32_t mid = (blo + bhi + 1) >> 1;
+                            if (sm.scan_off[mid] <= q) blo = mid;
+                            else bhi = mid - 1;
                         }
-                        const uint32_t j = blk + lo;
-                        const uint32_t e = __ldcg(B.chain_w + (size_t)(base_item + j) * CH + (q - sm.scan_off[lo]));
+                        const uint32_t j = blk + blo;
+                        const uint32_t e = __ldcg(B.chain_w + (size_t)(base_item + j) * CH + (q - sm.scan_off[blo]));
                         const uint32_t w = e >> 1;
-                        uint32_t s2 = (w * 2654435761u) & (GT - 1);
+                        uint32_t s2 = rl_group_slot<GT>(w, weak);
                         for (;;) {
-                            const uint32_t xs = sm.rset[s2];
+                            const uint32_t xs = sm.g_row[s2];
                             if (xs == w) {
                                 if (pass == 0) {
                                     if (e & 1u) {
@@ -1200,7 +1162,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             }
             __threadfence();
             bool redo = false;
-            if (is_rep && row != nullptr) {
+            if (is_rep) {
                 RlRow<CELLS> cur;
                 rl_row_load<CELLS>(row, CELLS, cur);
                 bool same = true;
@@ -1222,14 +1184,14 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             }
             if (!__syncthreads_or(redo)) break;
             if (valid && (sm.g_flags[gid] & 4u)) {
-                done = (gflags & 2u) != 0;
+                done = false;
                 pos = 0;
             }
             }
 
             RL_PHASE_TICK(4)  // optimistic-commit protocol (chained chunks)
             // ---- 5. write the dirty cells back -------------------------------------------------------
-            if (is_rep && row != nullptr && !snapshot) {
+            if (is_rep && !snapshot) {
                 const uint32_t dirty = sm.g_dirty[tid];
 #pragma unroll
                 for (int c = 0; c < CELLS; c++)
@@ -1239,6 +1201,12 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             }
             __syncthreads();
             if (chained && !snapshot && tid == 0) atomicExch(B.chain_status + item, 4u);
+            // grouping tables of the next chunk of this item
+            if (c0 + CH < hi) {
+                for (uint32_t i = tid; i < GT; i += CH) sm.g_row[i] = 0xFFFFFFFFu;
+                for (uint32_t i = tid; i < GT * PW; i += CH) sm.g_packed[i] = 0ull;
+                __syncthreads();
+            }
             RL_PHASE_TICK(5)  // write-back
         }
     }
@@ -1679,3 +1647,4 @@ __global__ void k_unpermute_u8(uint32_t n, const uint8_t* __restrict__ in, const
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[src[i]] = in[i];
 }
+
