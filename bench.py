@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--exchange-lag", type=int, default=2,
                     help="N>1: verdicts return in the records of the step this many steps later (1..3)")
     ap.add_argument("--no-pipeline", action="store_true", help="disable the pipelining of successive steps")
+    ap.add_argument("--kstats", action="store_true", help="RL_FLAG_KERNEL_STATS: per-phase cycle accounting inside k_main (costs a few %)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads / legs reported under `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -261,7 +262,7 @@ def main():
     max_batch = batch if world == 1 else world * slot_cap
     # RL_FLAG_PIPELINE (2): the partition of step s+1 overlaps the replay of step s on the device
     eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank,
-                 flags=(0 if args.no_pipeline else 2))
+                 flags=(0 if args.no_pipeline else 2) | (4 if args.kstats else 0))
     eng.limits_set(limits)
     # a dedicated non-default stream: the engine launches on it and the CUDA events that time
     # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")

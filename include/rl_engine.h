@@ -228,6 +228,42 @@ int rl_record_lane_gather(rl_engine *e, uint64_t n, const rl_record *d_recs, con
 int rl_unpermute_u8(rl_engine *e, uint64_t n, const uint8_t *d_in, const uint32_t *d_src, uint8_t *d_out);
 uint32_t rl_owner_of(uint32_t ns_id, uint32_t world);
 
+/* ---- Namespace-sharded peer exchange ----------------------------------------------
+ * One process (and one engine) per GPU; the key space shards by rl_owner_of(ns_id, world) — every counter
+ * of a request belongs to its namespace (lib.rs:512), the property the reference relies on for Redis
+ * Cluster hash tags (storage/keys.rs:1-13).  Every rank owns an exchange slab in its HBM which the other
+ * ranks map (CUDA IPC; NVLink / NVSwitch peer access).  A step:
+ *   send    : bucket my slice of the global batch by owner (stable) and STORE the 32-B records straight
+ *             into the owners' inboxes over NVLink, then publish fill + step flag;
+ *   decide  : wait (on the device) for the blocks of all sources, run check_and_update over the inbox in
+ *             (source rank, source index) order — the canonical stream order of the sharded store — and
+ *             store the verdict bytes straight back into the sources' verdict inboxes;
+ *   collect : wait (on the device) for every owner's verdicts of the step sent `lag` steps ago and put them
+ *             back in request order into the out_limited buffer given with that step.
+ * No NCCL call, no padding and no host synchronisation on the data path; `lag`+1 steps are in flight.
+ * Every rank must issue the same sequence of calls.  cap = max records per rank and step; an owner can
+ * receive up to world*cap records in a step (rl_config.max_batch bounds it: more is an error, RL_FATAL at
+ * the next rl_sync).  All d_* pointers are device memory; everything is enqueued, nothing blocks the host. */
+typedef struct rl_shard rl_shard;
+int rl_shard_create(rl_engine *e, uint32_t rank, uint32_t world, uint32_t cap, uint32_t lag, rl_shard **out);
+void rl_shard_destroy(rl_shard *s);
+/* 64-byte CUDA IPC handle (cudaIpcGetMemHandle) of this rank's slab, to be all-gathered by the caller */
+int rl_shard_ipc_handle(rl_shard *s, void *out64);
+/* handles64: world x 64 bytes, rank-major; opens every peer's slab (cudaIpcOpenMemHandle) */
+int rl_shard_connect_ipc(rl_shard *s, const void *handles64);
+/* same-process peers (several engines in one process): slabs[r] = rl_shard_slab of rank r */
+int rl_shard_connect_ptrs(rl_shard *s, void *const *slabs);
+void *rl_shard_slab(rl_shard *s);
+uint64_t rl_shard_slab_bytes(rl_shard *s);
+int rl_shard_send(rl_shard *s, uint64_t n, const rl_record *d_recs, uint8_t *d_out_limited);
+int rl_shard_decide(rl_shard *s);
+/* *out_done (nullable) = the out_limited buffer whose delivery was enqueued by this call, or NULL */
+int rl_shard_collect(rl_shard *s, uint8_t **out_done);
+/* send + decide + collect: the one call of the one-process-per-GPU deployment */
+int rl_shard_step(rl_shard *s, uint64_t n, const rl_record *d_recs, uint8_t *d_out_limited, uint8_t **out_done);
+/* deliver every step still in flight (all ranks must have issued the same steps) */
+int rl_shard_flush(rl_shard *s);
+
 /* ---- Batching front (SURVEY §8b threading row) ---------------------------------------------
  * Thread-safe, blocking, one request per call: concurrent callers are coalesced by a dispatcher
  * thread into batches of at most max_batch requests (waiting at most max_delay_us for company)

@@ -31,6 +31,7 @@ enum : uint32_t {
     RL_DEV_KEY_RANGE = 3,          // key_hi >= 2^32
     RL_DEV_TOO_MANY_COUNTERS = 4,  // > RL_MAX_CTRS_PER_REQ counters in one request
     RL_DEV_GROUP_SPLIT = 5,        // one request touches > RL_MAX_CELLS cells of one row (cannot happen)
+    RL_DEV_EXCHANGE = 6,           // peer exchange: a rank's step flag did not arrive in time / a block fill is out of range
 };
 
 // Per-(row group, cell) limit parameters.  max_value lives here and never in the row,

@@ -16,7 +16,10 @@
 #include <utility>
 #include <vector>
 
+#include <functional>
+
 #include "rl_kernels.cuh"
+#include "rl_shard.cuh"
 
 #ifndef RL_SETS
 #define RL_SETS 3  // RL_FLAG_PIPELINE: calls in flight on the device (>= 3: one per pipeline stage)
@@ -27,7 +30,7 @@
 
 namespace {
 
-constexpr uint32_t kMaxTiles = 256;
+constexpr uint32_t kMaxTiles = RL_MAX_TILES;
 constexpr uint32_t kMaxRegions = 4096;
 
 struct HostLimit {
@@ -70,12 +73,12 @@ struct DevBuf {
 // A second copy of the per-batch workspace: with RL_FLAG_PIPELINE the partition kernels of
 // batch s+1 run (on their own stream) while k_main of batch s is still replaying.
 struct WorkSet {
-    DevBuf<uint32_t> tile_cnt, part_base, part_idx, part_row, reg_of, row_of, chain_status,
+    DevBuf<uint32_t> tile_loc, region_total, part_idx, part_row, row_of, chain_status,
         chain_wcnt, chain_w, small;  // small: [0] blocks-done counter of the probe, [1] item count, [2] ticket, [3] exit counter
     DevBuf<uint4> items;
     void release() {
-        tile_cnt.release(); part_base.release(); part_idx.release(); part_row.release();
-        reg_of.release(); row_of.release(); chain_status.release(); chain_wcnt.release();
+        tile_loc.release(); region_total.release(); part_idx.release(); part_row.release();
+        row_of.release(); chain_status.release(); chain_wcnt.release();
         chain_w.release(); small.release(); items.release();
     }
 };
@@ -107,7 +110,7 @@ struct rl_engine {
     uint32_t limits_cap = 0, ns_cap = 0;
 
     // workspace
-    DevBuf<uint32_t> d_tile_cnt, d_part_base, d_part_idx, d_part_row, d_reg_of, d_row_of, d_misc;  // misc: err, flags, scan_ctr, changed, ...
+    DevBuf<uint32_t> d_tile_loc, d_region_total, d_part_idx, d_part_row, d_row_of, d_misc;  // misc: err, flags, scan_ctr, changed, ...
     DevBuf<RlAccess> d_acc;
     DevBuf<uint64_t> d_delta, d_now;
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
@@ -323,6 +326,9 @@ int check_device_error(rl_engine* e) {
             return fail(e, RL_FATAL, "key_hi bits 32..55 must be zero (counter identity is a 96-bit digest)");
         case RL_DEV_TOO_MANY_COUNTERS:
             return fail(e, RL_FATAL, "a request has more than %d counters", RL_MAX_CTRS_PER_REQ);
+        case RL_DEV_EXCHANGE:
+            return fail(e, RL_FATAL, "peer exchange: a rank's step flag did not arrive within %.0f s (or a block fill was out of range)",
+                        (double)RL_XCHG_TIMEOUT_NS * 1e-9);
         default:
             return fail(e, RL_FATAL, "device error code %u", code);
     }
@@ -337,15 +343,14 @@ struct Outs {
     uint32_t stride = 0;
 };
 
-RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, int lc, int set = 0) {
+RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, int lc, int set = 0, uint32_t n_hint = 0) {
     RlBatch B;
     B.n_acc = n_acc;
     B.n_req = n_req;
     B.n_dev = nullptr;
-    B.tile_cnt = e->d_tile_cnt.p;
-    B.part_base = e->d_part_base.p;
+    B.tile_loc = e->d_tile_loc.p;
+    B.region_total = e->d_region_total.p;
     B.part_idx = e->d_part_idx.p;
-    B.reg_of = e->d_reg_of.p;
     B.row_of = e->d_row_of.p;
     B.part_row = e->d_part_row.p;
     B.scan_ctr = e->d_misc.p + MISC_SCANCTR;
@@ -355,6 +360,10 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     tile = std::max<uint32_t>(512, ((tile + 255) / 256) * 256);
     B.tile = tile;
     B.num_tiles = std::max<uint32_t>(1, ceil_div(n_acc, tile));
+    // n_hint (sharded steps): n_acc is only the upper bound of a device-side count; partitions are sized for
+    // the expected count, and the kernels derive the tile from the actual one (rl_tile_of)
+    const uint32_t n_size = n_hint ? std::min(n_hint, n_acc) : n_acc;
+    if (n_hint) B.num_tiles = std::min<uint32_t>(kMaxTiles, std::max<uint32_t>(1, ceil_div(n_acc, 256)));
     B.out_limited = o.limited;
     B.out_first_limited = o.first;
     B.out_remaining = o.rem;
@@ -374,22 +383,21 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     // a region is split into chained chunks only when it is far heavier than the average one
     // partition granularity: about one k_main chunk per partition, never finer than the table's regions
     {
-        uint32_t want = std::max<uint32_t>(64, ceil_div(n_acc, e->part_target));
+        uint32_t want = std::max<uint32_t>(64, ceil_div(n_size, e->part_target));
         uint32_t lp = 0;
         while ((1u << (lp + 1)) <= want) lp++;
         lp = std::min<uint32_t>(lp, e->log2P);
         B.part_shift = e->log2P - lp;
         B.nparts = 1u << lp;
     }
-    B.heavy_len = e->heavy_mult ? std::max<uint32_t>(2 * e->chunk, e->heavy_mult * ceil_div(n_acc, B.nparts)) : 0xFFFFFFFFu;
+    B.heavy_len = e->heavy_mult ? std::max<uint32_t>(2 * e->chunk, e->heavy_mult * ceil_div(n_size, B.nparts)) : 0xFFFFFFFFu;
     B.log_row = nullptr;
     B.log_state = nullptr;
     if (set >= 1) {
         WorkSet& w = e->wsx[set - 1];
-        B.tile_cnt = w.tile_cnt.p;
-        B.part_base = w.part_base.p;
+        B.tile_loc = w.tile_loc.p;
+        B.region_total = w.region_total.p;
         B.part_idx = w.part_idx.p;
-        B.reg_of = w.reg_of.p;
         B.row_of = w.row_of.p;
         B.part_row = w.part_row.p;
         B.scan_ctr = w.small.p + 0;
@@ -405,36 +413,30 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
 }
 
 template <int CELLS, class Src>
-int launch_partition_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st, int stage) {
+int launch_front_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
     const uint32_t P1 = B.nparts + 1;
-    const size_t smem = (size_t)RL_PART_WARPS * P1 * sizeof(uint32_t);
+    const size_t smem = ((size_t)RL_PART_WARPS * P1 + P1 + 1) * sizeof(uint32_t);
     static int smem_limit[64] = {};  // per instantiation and device: raised as engines with more regions appear
     const int dv = e->device & 63;
     if (smem > 48 * 1024 && (int)smem > smem_limit[dv]) {
-        const int max_smem = (int)((size_t)RL_PART_WARPS * ((1u << e->log2P) + 1) * sizeof(uint32_t));
-        RL_CUDA(e, cudaFuncSetAttribute(k_part<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        const uint32_t maxP1 = (1u << e->log2P) + 1;
+        const int max_smem = (int)(((size_t)RL_PART_WARPS * maxP1 + maxP1 + 1) * sizeof(uint32_t));
+        RL_CUDA(e, cudaFuncSetAttribute(k_front<CELLS, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         smem_limit[dv] = max_smem;
     }
-    if (stage & 1) {
-        k_probe_count<CELLS, Src><<<B.num_tiles, RL_PROBE_THREADS, (P1 + 1) * sizeof(uint32_t), st>>>(D, B, src);
-        RL_LAUNCH_CHECK(e);
-    }
-    if (stage & 2) {
-        k_part<Src><<<B.num_tiles, RL_PART_THREADS, smem, st>>>(D, B, src);
-        RL_LAUNCH_CHECK(e);
-    }
+    k_front<CELLS, Src><<<B.num_tiles, RL_PART_THREADS, smem, st>>>(D, B, src);
+    RL_LAUNCH_CHECK(e);
     return RL_OK;
 }
 
-// stage: 1 = probe + count, 2 = scan + scatter, 3 = both
+// probe + stable partition by table region (one launch)
 template <class Src>
-int launch_partition(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st = nullptr,
-                     int stage = 3) {
+int launch_front(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st = nullptr) {
     if (!st) st = e->stream;
     switch (e->cells) {
-        case 1: return launch_partition_cells<1, Src>(e, D, B, src, st, stage);
-        case 3: return launch_partition_cells<3, Src>(e, D, B, src, st, stage);
-        default: return launch_partition_cells<7, Src>(e, D, B, src, st, stage);
+        case 1: return launch_front_cells<1, Src>(e, D, B, src, st);
+        case 3: return launch_front_cells<3, Src>(e, D, B, src, st);
+        default: return launch_front_cells<7, Src>(e, D, B, src, st);
     }
 }
 
@@ -507,7 +509,7 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
     RlBatch B = make_batch(e, n_acc, n_req, o, lc);
     if (mode == 0) B.heavy_len = 0xFFFFFFFFu;  // may hold coupled requests: regions stay sequential
     AccSrc src{e->d_acc.p, d_delta, d_now};
-    int r = launch_partition(e, D, B, src);
+    int r = launch_front(e, D, B, src);
     if (r) return r;
     if (mode == 2) return launch_main<AccSrc, 2>(e, D, B, src);
     // does the batch contain coupled (multi-row) requests?
@@ -523,11 +525,12 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
         RL_CUDA(e, cudaMemsetAsync(B.fl_prev, 0xFF, n_req * sizeof(uint32_t), e->stream));
         RL_CUDA(e, cudaMemsetAsync(B.fl_next, 0xFF, n_req * sizeof(uint32_t), e->stream));
         // undo log: original state of every row the batch touches
-        RL_CUDA(e, e->d_log_row.reserve(n_acc));
-        RL_CUDA(e, e->d_log_state.reserve((size_t)n_acc * e->cells));
+        const uint32_t buf_len = B.num_tiles * B.tile;  // positions of part_idx/part_row in use
+        RL_CUDA(e, e->d_log_row.reserve(buf_len));
+        RL_CUDA(e, e->d_log_state.reserve((size_t)buf_len * e->cells));
         B.log_row = e->d_log_row.p;
         B.log_state = e->d_log_state.p;
-        RL_CUDA(e, cudaMemsetAsync(B.log_row, 0, (size_t)n_acc * sizeof(uint8_t*), e->stream));
+        RL_CUDA(e, cudaMemsetAsync(B.log_row, 0, (size_t)buf_len * sizeof(uint8_t*), e->stream));
         B.phase = RL_PHASE_SNAPSHOT;
         r = launch_main<AccSrc, 0>(e, D, B, src);
         if (r) return r;
@@ -540,9 +543,9 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
             r = launch_main<AccSrc, 0>(e, D, B, src);
             if (r) return r;
             switch (e->cells) {
-                case 1: k_restore<1><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, 1, B.log_row, B.log_state); break;
-                case 3: k_restore<3><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, 3, B.log_row, B.log_state); break;
-                default: k_restore<7><<<ceil_div(n_acc, 256), 256, 0, e->stream>>>(n_acc, e->max_cells_used <= 4 ? 4 : 7, B.log_row, B.log_state); break;
+                case 1: k_restore<1><<<ceil_div(buf_len, 256), 256, 0, e->stream>>>(buf_len, 1, B.log_row, B.log_state); break;
+                case 3: k_restore<3><<<ceil_div(buf_len, 256), 256, 0, e->stream>>>(buf_len, 3, B.log_row, B.log_state); break;
+                default: k_restore<7><<<ceil_div(buf_len, 256), 256, 0, e->stream>>>(buf_len, e->max_cells_used <= 4 ? 4 : 7, B.log_row, B.log_state); break;
             }
             RL_LAUNCH_CHECK(e);
             k_fl_step<<<ceil_div(n_req, 256), 256, 0, e->stream>>>(n_req, B.fl_prev, B.fl_next,
@@ -559,31 +562,48 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
     return launch_main<AccSrc, 0>(e, D, B, src);
 }
 
+// Hooks of the sharded step (rl_shard_*): the owner's inbox is a segmented record source whose size is
+// only known on the device; `pre_probe` runs on the probe stream right before the probe (it waits for
+// the peers' blocks), `post_main` on the replay stream right behind k_main (it returns the verdicts).
+struct PipeHooks {
+    RecordSrc src;
+    const uint32_t* n_dev = nullptr;
+    std::function<int(cudaStream_t, int)> pre_probe, post_main;  // (stream, workspace set)
+};
+
 int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int mode, int lc, const Outs& o,
-                        bool may_pipeline = false) {
+                        bool may_pipeline = false, const PipeHooks* hooks = nullptr, uint32_t n_hint = 0) {
     RlDev D = make_dev(e);
+    if (hooks && !(may_pipeline && e->pipeline && !e->any_multi_ns))
+        return fail(e, RL_FATAL, "sharded steps need RL_FLAG_PIPELINE and single-row namespaces");
     if (may_pipeline && e->pipeline && !e->any_multi_ns) {
-        // Three-stage software pipeline over successive calls: probe+count of batch s+2 (`sp`) and
-        // scan+scatter of batch s+1 (`sq`) overlap the replay of batch s (`sm`).  The probe only reads
-        // row headers and claims empty rows; the replay only touches the cells of rows found by ITS
-        // probe, and replays stay in call order on `sm`, so the table sees the batches in order.
+        // Two-stage software pipeline over successive calls: the front (probe + partition, `sp`) of
+        // batch s+1 (and s+2) overlaps the replay of batch s (`sm`).  The front only reads row headers
+        // and claims empty rows; the replay only touches the cells of rows found by ITS front, and
+        // replays stay in call order on `sm`, so the table sees the batches in order.
         const int k = (int)(e->pipe_seq % rl_engine::kSets);
-        RlBatch B = make_batch(e, n, n, o, lc, k);
-        RecordSrc src{d_recs};
-        RL_CUDA(e, cudaEventRecord(e->ev_in, e->stream));  // inputs: whatever the caller enqueued so far
-        RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_in, 0));
+        RlBatch B = make_batch(e, n, n, o, lc, k, n_hint);
+        RecordSrc src{d_recs, nullptr, 0, 0};
+        if (hooks) {
+            // the inbox is filled by the peers' kernels and handed over through step flags, not through
+            // anything on the caller's stream
+            src = hooks->src;
+            B.n_dev = hooks->n_dev;
+        } else {
+            RL_CUDA(e, cudaEventRecord(e->ev_in, e->stream));  // inputs: whatever the caller enqueued so far
+            RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_in, 0));
+        }
         if (e->pipe_seq >= (uint64_t)rl_engine::kSets)
             RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_main[k], 0));  // workspace set k is free again
-        int r = launch_partition(e, D, B, src, e->sp, 1);
+        int r = RL_OK;
+        if (hooks && hooks->pre_probe && (r = hooks->pre_probe(e->sp, k))) return r;
+        r = launch_front(e, D, B, src, e->sp);
         if (r) return r;
-        RL_CUDA(e, cudaEventRecord(e->ev_probe[k], e->sp));
-        RL_CUDA(e, cudaStreamWaitEvent(e->sq, e->ev_probe[k], 0));
-        r = launch_partition(e, D, B, src, e->sq, 2);
-        if (r) return r;
-        RL_CUDA(e, cudaEventRecord(e->ev_part[k], e->sq));
+        RL_CUDA(e, cudaEventRecord(e->ev_part[k], e->sp));
         RL_CUDA(e, cudaStreamWaitEvent(e->sm, e->ev_part[k], 0));
         r = mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src, e->sm) : launch_main<RecordSrc, 0>(e, D, B, src, e->sm);
         if (r) return r;
+        if (hooks && hooks->post_main && (r = hooks->post_main(e->sm, k))) return r;
         RL_CUDA(e, cudaEventRecord(e->ev_main[k], e->sm));
         e->pipe_seq++;
         e->pipe_pending = true;
@@ -595,8 +615,8 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
     }
     if (!e->any_multi_ns) {
         RlBatch B = make_batch(e, n, n, o, lc);
-        RecordSrc src{d_recs};
-        int r = launch_partition(e, D, B, src);
+        RecordSrc src{d_recs, nullptr, 0, 0};
+        int r = launch_front(e, D, B, src);
         if (r) return r;
         return mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src) : launch_main<RecordSrc, 0>(e, D, B, src);
     }
@@ -660,6 +680,11 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
     if (prop.major < 10) return fail(e, RL_FATAL, "device sm_%d%d is not sm_100a", prop.major, prop.minor);
     e->main_grid_cap = (uint32_t)prop.multiProcessorCount * 16u;
+    // The table is read one random 32-B sector (a row header, a cell) at a time: ask the L2 not to fetch the
+    // neighbouring sector from HBM along with it (the default granularity is 64 B).  A hint; per device.
+    if (const char* v = getenv("RL_L2_FETCH")) {
+        if (atoi(v) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v));
+    }
     RL_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     e->cells = cfg->cells_per_row;
@@ -693,18 +718,19 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
 
     const uint32_t P1 = (1u << e->log2P) + 1;
     const size_t maxA = e->max_counters;
-    RL_CUDA(e, e->d_tile_cnt.reserve((size_t)(kMaxTiles + 1) * P1));
-    RL_CUDA(e, e->d_part_base.reserve(P1 + 2));
-    RL_CUDA(e, e->d_part_idx.reserve(maxA));
-    RL_CUDA(e, e->d_reg_of.reserve(maxA));
+    const size_t bufA = maxA + maxA / 128 + 65536 + 1024;  // part_idx/part_row: every tile's slice is a whole tile
+    RL_CUDA(e, e->d_tile_loc.reserve((size_t)(kMaxTiles + 1) * (P1 + 1)));
+    RL_CUDA(e, e->d_region_total.reserve(P1 + 1));
+    RL_CUDA(e, cudaMemsetAsync(e->d_region_total.p, 0, (P1 + 1) * sizeof(uint32_t), e->stream));
+    RL_CUDA(e, e->d_part_idx.reserve(bufA));
     RL_CUDA(e, e->d_row_of.reserve(maxA));
-    RL_CUDA(e, e->d_part_row.reserve(maxA));
+    RL_CUDA(e, e->d_part_row.reserve(bufA));
     RL_CUDA(e, e->d_misc.reserve(MISC_N));
     RL_CUDA(e, cudaMemsetAsync(e->d_misc.p, 0, MISC_N * sizeof(uint32_t), e->stream));
     RL_CUDA(e, cudaMallocHost((void**)&e->h_misc, MISC_N * sizeof(uint32_t)));
     RL_CUDA(e, e->d_acc.reserve(maxA));
-    RL_CUDA(e, e->d_kstats.reserve(16));
-    RL_CUDA(e, cudaMemsetAsync(e->d_kstats.p, 0, 16 * sizeof(unsigned long long), e->stream));
+    RL_CUDA(e, e->d_kstats.reserve(32));
+    RL_CUDA(e, cudaMemsetAsync(e->d_kstats.p, 0, 32 * sizeof(unsigned long long), e->stream));
     RL_CUDA(e, e->d_items.reserve((size_t)(1u << e->log2P) + maxA / 128 + 2));
     {
         const size_t max_items = (size_t)(1u << e->log2P) + maxA / 128 + 2;
@@ -730,11 +756,11 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
         const size_t max_items = (size_t)(1u << e->log2P) + maxA / 128 + 2;
         for (int wi = 0; wi < rl_engine::kSets - 1; wi++) {
         WorkSet& w = e->wsx[wi];
-        RL_CUDA(e, w.tile_cnt.reserve((size_t)(kMaxTiles + 1) * P1));
-        RL_CUDA(e, w.part_base.reserve(P1 + 2));
-        RL_CUDA(e, w.part_idx.reserve(maxA));
-        RL_CUDA(e, w.part_row.reserve(maxA));
-        RL_CUDA(e, w.reg_of.reserve(maxA));
+        RL_CUDA(e, w.tile_loc.reserve((size_t)(kMaxTiles + 1) * (P1 + 1)));
+        RL_CUDA(e, w.region_total.reserve(P1 + 1));
+        RL_CUDA(e, cudaMemsetAsync(w.region_total.p, 0, (P1 + 1) * sizeof(uint32_t), e->stream));
+        RL_CUDA(e, w.part_idx.reserve(bufA));
+        RL_CUDA(e, w.part_row.reserve(bufA));
         RL_CUDA(e, w.row_of.reserve(maxA));
         RL_CUDA(e, w.items.reserve(max_items));
         RL_CUDA(e, w.chain_status.reserve(max_items));
@@ -780,10 +806,9 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_ns.release();
     e->d_ns_limit_ids.release();
     e->d_group_ns.release();
-    e->d_tile_cnt.release();
-    e->d_part_base.release();
+    e->d_tile_loc.release();
+    e->d_region_total.release();
     e->d_part_idx.release();
-    e->d_reg_of.release();
     e->d_row_of.release();
     e->d_part_row.release();
     e->d_misc.release();
@@ -889,7 +914,7 @@ int rl_get_stats(rl_engine* e, rl_stats* out) {
         int rf = pipe_fence(e);
         if (rf) return rf;
     }
-    unsigned long long ks[16];
+    unsigned long long ks[32];
     RL_CUDA(e, cudaMemcpyAsync(ks, e->d_kstats.p, sizeof ks, cudaMemcpyDeviceToHost, e->stream));
     RL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->stats.chunks = ks[0];
@@ -897,6 +922,7 @@ int rl_get_stats(rl_engine* e, rl_stats* out) {
     e->stats.chained_chunks = ks[2];
     e->stats.ordered_chunks = ks[3];
     for (int i = 0; i < 6; i++) e->stats.phase_cycles[i] = ks[8 + i];
+    e->stats.phase_cycles[1] = ks[16];  // slot 1 (unused by k_main): ns spent in the probe's last-block tail
     *out = e->stats;
     return RL_OK;
 }
@@ -1543,5 +1569,7 @@ int rl_unpermute_u8(rl_engine* e, uint64_t n, const uint8_t* d_in, const uint32_
     RL_LAUNCH_CHECK(e);
     return RL_OK;
 }
+
+#include "rl_shard_host.inc"
 
 }  // extern "C"

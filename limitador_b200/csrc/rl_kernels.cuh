@@ -1,15 +1,14 @@
 // rl_kernels.cuh — hand-written sm_100a kernels of the batched rate-limit engine.
 //
-// Pipeline for one batch, three launches:
-//   k_probe_count : every access finds (or claims) its table row — the one random HBM access of
-//                   the batch — and the per-tile histogram over the P table regions is taken on the
-//                   way; the LAST block to finish turns the histogram into stable offsets (column
-//                   scan over tiles), region bases and the work items of k_main
-//   k_part        : STABLE scatter of (access index, row index) pairs into per-region lists
-//   k_main        : one CTA per work item; gathers the 32-B records of its chunk, groups the accesses
-//                   by table row in shared memory and replays every row's requests in stream order
-//                   (fixed-window check / increment), so the result equals one-at-a-time execution
-//                   on the reference InMemoryStorage (limitador/src/storage/in_memory.rs:72-156).
+// Pipeline for one batch, two launches:
+//   k_front : every access finds (or claims) its table row — the one random HBM access of the batch —
+//             and every tile (CTA) lays its accesses out by table region inside its own slice of the
+//             partition arrays, stream order kept; the LAST block to finish builds the work items
+//   k_main  : one CTA per work item; merges the tiles' runs of its region, gathers the 32-B records of
+//             its chunk, groups the accesses by table row in shared memory and replays every row's
+//             requests in stream order (fixed-window check / increment), so the result equals
+//             one-at-a-time execution on the reference InMemoryStorage
+//             (limitador/src/storage/in_memory.rs:72-156).
 // A region (contiguous slab of rows) is touched by exactly one CTA at a time, and a row by exactly
 // one group, so counter values need no atomics at all; the only atomic on the table is the
 // 128-bit CAS that claims an empty row for a new key.
@@ -21,6 +20,7 @@
 #include "rl_core.h"
 
 #define RL_PART_THREADS 256
+#define RL_MAX_TILES 256  // tiles (CTAs of k_front) per batch
 #define RL_PART_WARPS (RL_PART_THREADS / 32)
 #define RL_PROBE_THREADS 1024
 #define RL_IDENT_POSORIG 0x0654321006543210ull
@@ -45,13 +45,12 @@ struct RlBatch {
     uint32_t n_req;
     const uint32_t* n_dev;   // nullable: the access count lives on the device (peer exchange: the inbox fill)
     // partition workspace
-    uint32_t* tile_cnt;      // [num_tiles][P+1]; after the probe's last block: exclusive prefix over tiles
-    uint32_t* part_base;     // [P+2]
-    uint32_t* reg_of;        // [n_acc] partition of access a (P = "no row"), written by k_probe_count
-    uint32_t* row_of;        // [n_acc] table row (index) of access a, probed / claimed by k_probe_count
-    uint32_t* part_idx;      // [n_acc] access index, in partition order (stream order kept inside a partition)
-    uint32_t* part_row;      // [n_acc] its table row
-    uint32_t* scan_ctr;      // blocks-done counter of k_probe_count
+    uint32_t* tile_loc;      // [num_tiles][P+2] offset of partition r's run inside tile t's slice of part_idx/part_row
+    uint32_t* region_total;  // [P+1] accumulated by the front's tiles; zero between batches
+    uint32_t* row_of;        // [n_acc] table row (index) of access a, probed / claimed in pass 1 of k_front
+    uint32_t* part_idx;      // [num_tiles * tile] access index; tile t's slice holds its accesses partition by partition
+    uint32_t* part_row;      // [num_tiles * tile] its table row
+    uint32_t* scan_ctr;      // blocks-done counter of k_front
     uint32_t* ticket;        // work-item ticket of k_main
     uint32_t* exit_ctr;      // CTAs of k_main that found the ticket exhausted (the last one re-arms it)
     uint32_t nparts;         // partitions of this batch: table regions merged 2^part_shift at a time, so
@@ -70,7 +69,7 @@ struct RlBatch {
     uint32_t* fl_next;
     int phase;          // RL_PHASE_*
     int load_counters;  // 0/1
-    // work items of k_main (built by the probe's last block): x = partition, y/z = [lo, hi) in part_idx,
+    // work items of k_main (built by the front's last block): x = partition, y/z = [lo, hi) in the partition's list,
     // w = RL_NONE_U32 for a light partition (its chunks run one after the other in one CTA) or the
     // chunk's index inside a heavy partition (one CTA per chunk, committed in order, see k_main)
     uint4* items;
@@ -303,19 +302,23 @@ struct AccSrc {
 };
 
 // ---------------------------------------------------------------------------------------
-// Stable partition of the accesses by table region.
-// Tile = B.tile consecutive accesses; warp w of a k_part CTA owns the w-th contiguous slice, so
-// stream order == (tile, warp, step, lane) and a stable rank is
-//   region base + (accesses of earlier tiles) + (accesses of earlier warps) + rank in slice.
+// The front kernel: probe + stable partition by table region, one launch.
 //
-// Probe + count.  One pass over the batch with as many independent loads in flight as the SM
-// can hold: every access finds (or, for a new key, claims) its table row — the one random HBM
-// access of the batch — and the per-tile histogram over the table regions is taken on the way.
-// The last block to finish then does what used to be a kernel of its own: column scan of the
-// tile histogram (exclusive prefix over tiles), exclusive scan of the region totals, and the
-// work items of k_main — all of it out of shared memory, one global round trip per step.
-__device__ __forceinline__ uint32_t rl_block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t& total) {
-    // exclusive prefix of v over the 1024 threads of the block; s_warp: 32 words of shared memory
+// Tile = a contiguous slice of the batch, one CTA; warp w of the CTA owns the w-th contiguous slice of
+// the tile, so stream order == (tile, warp, step, lane).
+//   pass 1  every access finds (or, for a new key, claims) its table row — the one random HBM access of
+//           the batch, U of them in flight per lane — and the warp counts its accesses per region;
+//   layout  the tile's accesses are laid out region by region inside the TILE'S OWN slice of
+//           part_idx/part_row (tile_loc[t][r] = offset of region r's run in tile t), so no CTA needs
+//           anything from another one: there is no cross-tile prefix and no second kernel.  A region's
+//           list is the concatenation over tiles of its runs; k_main merges them on read.
+//   pass 2  the same sweep hands out the positions (stable: earlier warps, then rank inside the warp);
+//   tail    region totals are accumulated by atomics; the LAST block to finish turns them into the work
+//           items of k_main (one global round trip, the rest out of shared memory).
+template <int NT>
+__device__ __forceinline__ uint32_t rl_block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    // exclusive prefix of v over the NT threads of the block; s_warp: NT/32 words of shared memory
+    constexpr int NW = NT / 32;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t x = v;
 #pragma unroll
@@ -325,47 +328,71 @@ __device__ __forceinline__ uint32_t rl_block_excl_scan_1024(uint32_t v, uint32_t
     }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    uint32_t w = s_warp[lane];  // 32 warps: one per lane
-    uint32_t ws = w;
+    uint32_t woff = 0, tot = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
-        if ((int)lane >= o) ws += y;
+    for (int w = 0; w < NW; w++) {
+        const uint32_t c = s_warp[w];
+        if ((uint32_t)w < warp) woff += c;
+        tot += c;
     }
-    total = __shfl_sync(0xffffffffu, ws, 31);
-    const uint32_t woff = __shfl_sync(0xffffffffu, ws - w, warp);
+    total = tot;
     __syncthreads();  // s_warp may be reused by the caller
     return woff + x - v;
 }
 
+__device__ __forceinline__ unsigned long long rl_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Tile size: fixed by the host for a host-side count; derived from the device-side count (sharded steps:
+// the inbox fill) so that every launched CTA gets its share whatever the fill is.
+__device__ __forceinline__ uint32_t rl_tile_of(const RlBatch& B, uint32_t n) {
+    if (B.n_dev == nullptr) return B.tile;
+    const uint32_t t = (n + B.num_tiles - 1) / B.num_tiles;
+    return max(256u, ((t + 255u) / 256u) * 256u);
+}
+__device__ __forceinline__ uint32_t rl_batch_n(const RlBatch& B) {
+    return B.n_dev ? min(*B.n_dev, B.n_acc) : B.n_acc;
+}
+
 template <int CELLS, class Src>
-__global__ void __launch_bounds__(RL_PROBE_THREADS) k_probe_count(RlDev D, RlBatch B, Src src) {
-    extern __shared__ uint32_t rcnt[];  // [P+2]: per-tile counts; the last block reuses it for totals / bases
-    __shared__ uint32_t s_warp[32], s_warp2[32];
+__global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, Src src) {
+    extern __shared__ uint32_t wcnt[];  // [RL_PART_WARPS][P+1] per-warp counts -> positions, then loc[P+2]
+    __shared__ uint32_t s_warp[RL_PART_WARPS], s_warp2[RL_PART_WARPS];
     __shared__ uint32_t s_last;
     constexpr uint32_t RB = RlGeom<CELLS>::ROW_BYTES;
     constexpr int U = 4;
-    constexpr uint32_t NT = RL_PROBE_THREADS;
+    constexpr uint32_t NT = RL_PART_THREADS;
     const uint32_t P1 = B.nparts + 1;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
-    const uint32_t n = B.n_dev ? min(*B.n_dev, B.n_acc) : B.n_acc;
-    const uint32_t t0 = min(tile * B.tile, n);
-    const uint32_t t1 = min(t0 + B.tile, n);
-    for (uint32_t i = tid; i < P1 + 1; i += NT) rcnt[i] = 0;
-    __syncthreads();
+    const uint32_t n = rl_batch_n(B);
+    const uint32_t tsz = rl_tile_of(B, n);
+    const uint32_t t0 = min(tile * tsz, n);
+    const uint32_t t1 = min(t0 + tsz, n);
+    const uint32_t slice = tsz / RL_PART_WARPS;
+    const uint32_t s0 = min(t0 + warp * slice, t1);
+    const uint32_t s1 = min(s0 + slice, t1);
+    uint32_t* mycnt = wcnt + warp * P1;
+    uint32_t* loc = wcnt + RL_PART_WARPS * P1;  // [P1 + 1]
     const uint32_t R = 1u << D.log2R;
-    uint32_t npad = 0;
-    for (uint32_t base = t0 + tid; base < t1; base += NT * U) {
+
+    for (uint32_t i = tid; i < RL_PART_WARPS * P1 + P1 + 1; i += NT) wcnt[i] = 0;
+    __syncthreads();
+
+    // ---- pass 1: probe, count ---------------------------------------------------------------------
+    for (uint32_t b = s0; b < s1; b += 32 * U) {
         uint64_t klo[U], hhi[U], h[U];
         bool ok[U];
         uint8_t* home[U];
         ulonglong2 hdr[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint32_t a = base + u * NT;
+            const uint32_t a = b + u * 32 + lane;
             klo[u] = hhi[u] = 0;
-            ok[u] = (a < t1) && src.ident(D, a, klo[u], hhi[u]);
+            ok[u] = (a < s1) && src.ident(D, a, klo[u], hhi[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -375,140 +402,55 @@ __global__ void __launch_bounds__(RL_PROBE_THREADS) k_probe_count(RlDev D, RlBat
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint32_t a = base + u * NT;
-            if (a >= t1) continue;
+            const uint32_t a = b + u * 32 + lane;
+            const bool valid = a < s1;
             uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
             if (ok[u]) {
-                r = (uint32_t)rl_region_of(D, h[u]) >> B.part_shift;
                 const uint8_t* row = (hdr[u].x == klo[u] && hdr[u].y == hhi[u])
                                          ? home[u]
                                          : rl_probe<CELLS>(D, h[u], klo[u], hhi[u], true);  // collision chain / insert
-                if (row) rowidx = (uint32_t)((size_t)(row - D.rows) / RB);
+                if (row) {
+                    rowidx = (uint32_t)((size_t)(row - D.rows) / RB);
+                    r = (rowidx >> D.log2R) >> B.part_shift;
+                }
             }
-            B.reg_of[a] = r;
-            B.row_of[a] = rowidx;
-            // accesses without limits (the padding of a fixed-size exchange block is thousands of them
-            // per tile) all count into one bucket: summed per warp below
-            if (r != P1 - 1) atomicAdd(&rcnt[r], 1u);
-            else npad++;
+            if (valid) B.row_of[a] = rowidx;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned m = __match_any_sync(vmask, r);
+                if (lane == (uint32_t)(__ffs(m) - 1)) mycnt[r] += __popc(m);
+            }
+            __syncwarp();
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) npad += __shfl_xor_sync(0xffffffffu, npad, o);
-    if ((tid & 31) == 0 && npad) atomicAdd(&rcnt[P1 - 1], npad);
     __syncthreads();
-    for (uint32_t r = tid; r < P1; r += NT) B.tile_cnt[(size_t)tile * P1 + r] = rcnt[r];
 
-    // ---- last block: offsets, bases, work items ---------------------------------------------
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(B.scan_ctr, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const uint32_t nt = gridDim.x;
-    // column scan: thread r owns column r; 16 tiles' counts in flight at a time
+    // ---- tile-local layout: region r's run starts at loc[r] inside this tile's slice ---------------
     for (uint32_t r = tid; r < P1; r += NT) {
-        uint32_t run = 0;
-        for (uint32_t tb = 0; tb < nt; tb += 16) {
-            uint32_t c[16];
+        uint32_t c = 0;
 #pragma unroll
-            for (int i = 0; i < 16; i++)
-                c[i] = (tb + i < nt) ? __ldcg(&B.tile_cnt[(size_t)(tb + i) * P1 + r]) : 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (tb + i < nt) B.tile_cnt[(size_t)(tb + i) * P1 + r] = run;
-                run += c[i];
+        for (int w = 0; w < RL_PART_WARPS; w++) c += wcnt[w * P1 + r];
+        loc[r] = c;
+    }
+    __syncthreads();
+    {
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < P1; base += NT) {
+            const uint32_t i = base + tid;
+            const uint32_t v = (i < P1) ? loc[i] : 0;
+            uint32_t total;
+            const uint32_t ex = rl_block_excl_scan<NT>(v, s_warp, total);
+            if (i < P1) {
+                loc[i] = carry + ex;
+                if (v && i != P1 - 1) atomicAdd(&B.region_total[i], v);
             }
+            carry += total;
         }
-        rcnt[r] = run;  // column total
+        if (tid == 0) loc[P1] = carry;
     }
     __syncthreads();
-    // exclusive scan of the totals -> part_base[0..P1] (kept in shared memory as well)
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < P1; base += NT) {
-        const uint32_t i = base + tid;
-        const uint32_t v = (i < P1) ? rcnt[i] : 0;
-        uint32_t total;
-        const uint32_t ex = rl_block_excl_scan_1024(v, s_warp, total);
-        if (i < P1) {
-            rcnt[i] = carry + ex;
-            B.part_base[i] = carry + ex;
-        }
-        carry += total;
-    }
-    if (tid == 0) {
-        rcnt[P1] = carry;
-        B.part_base[P1] = carry;
-    }
-    __syncthreads();
-    // work items for k_main: chunks of heavy partitions first (they chain in ticket order)
-    const uint32_t P = P1 - 1;
-    uint32_t hsum = 0, lsum = 0;
-    for (uint32_t q = tid; q < P; q += NT) {
-        const uint32_t len = rcnt[q + 1] - rcnt[q];
-        if (len > B.heavy_len) hsum += (len + B.chunk - 1) / B.chunk;
-        else if (len) lsum += 1;
-    }
-    uint32_t th, tl;
-    uint32_t hb = rl_block_excl_scan_1024(hsum, s_warp, th);
-    uint32_t lb = rl_block_excl_scan_1024(lsum, s_warp2, tl);
-    for (uint32_t q = tid; q < P; q += NT) {
-        const uint32_t lo = rcnt[q], hi = rcnt[q + 1];
-        const uint32_t len = hi - lo;
-        if (len > B.heavy_len) {
-            const uint32_t nc = (len + B.chunk - 1) / B.chunk;
-            for (uint32_t k = 0; k < nc; k++) {
-                B.chain_status[hb] = 0;
-                B.items[hb++] = make_uint4(q, lo + k * B.chunk, min(lo + (k + 1) * B.chunk, hi), k);
-            }
-        } else if (len) {
-            B.items[th + lb++] = make_uint4(q, lo, hi, RL_NONE_U32);
-        }
-    }
-    if (tid == 0) {
-        *B.n_items = th + tl;
-        *B.ticket = 0;
-        *B.scan_ctr = 0;  // re-arm for the next batch
-    }
-}
-
-// Stable scatter of (access, row) pairs into partition order.
-template <class Src>
-__global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Src src) {
-    extern __shared__ uint32_t wcnt[];  // [RL_PART_WARPS][nparts+1]
-    const uint32_t P1 = B.nparts + 1;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t n = B.n_dev ? min(*B.n_dev, B.n_acc) : B.n_acc;
-    const uint32_t t0 = min(tile * B.tile, n);
-    const uint32_t t1 = min(t0 + B.tile, n);
-    if (t0 >= t1) return;
-    const uint32_t slice = B.tile / RL_PART_WARPS;
-    const uint32_t s0 = min(t0 + warp * slice, t1);
-    const uint32_t s1 = min(s0 + slice, t1);
-    uint32_t* mycnt = wcnt + warp * P1;
-
-    for (uint32_t i = tid; i < RL_PART_WARPS * P1; i += RL_PART_THREADS) wcnt[i] = 0;
-    __syncthreads();
-
-    // pass 1: per-warp region counts
-    for (uint32_t b = s0; b < s1; b += 32) {
-        const uint32_t a = b + lane;
-        const bool valid = a < s1;
-        const uint32_t r = valid ? __ldcg(B.reg_of + a) : P1 - 1;
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned m = __match_any_sync(vmask, r);
-            if (lane == (uint32_t)(__ffs(m) - 1)) mycnt[r] += __popc(m);
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // bases: region base + earlier tiles + earlier warps of this tile
-    for (uint32_t r = tid; r < P1; r += RL_PART_THREADS) {
-        uint32_t run = B.part_base[r] + B.tile_cnt[(size_t)tile * P1 + r];
+    for (uint32_t r = tid; r < P1; r += NT) {
+        uint32_t run = loc[r];
 #pragma unroll
         for (int w = 0; w < RL_PART_WARPS; w++) {
             const uint32_t c = wcnt[w * P1 + r];
@@ -516,16 +458,18 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
             run += c;
         }
     }
+    for (uint32_t r = tid; r < P1 + 1; r += NT) B.tile_loc[(size_t)tile * (P1 + 1) + r] = loc[r];
     __syncthreads();
 
-    // pass 2: same sweep, now handing out positions
+    // ---- pass 2: same sweep, now handing out positions ----------------------------------------------
+    const size_t tbuf = (size_t)tile * tsz;
     for (uint32_t b = s0; b < s1; b += 32) {
         const uint32_t a = b + lane;
         const bool valid = a < s1;
         uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
         if (valid) {
-            r = __ldcg(B.reg_of + a);
             rowidx = __ldcg(B.row_of + a);
+            if (rowidx != 0xFFFFFFFFu) r = (rowidx >> D.log2R) >> B.part_shift;
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -539,8 +483,8 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
             basepos = __shfl_sync(m, basepos, leader);
             const uint32_t mypos = basepos + __popc(m & ((1u << lane) - 1));
             if (r != P1 - 1) {
-                B.part_idx[mypos] = a;
-                B.part_row[mypos] = rowidx;
+                B.part_idx[tbuf + mypos] = a;
+                B.part_row[tbuf + mypos] = rowidx;
             } else if (Src::kAccessIsRequest && B.out_limited) {
                 // request without any applicable limit: not limited (lib.rs:434-440)
                 B.out_limited[a] = 0;
@@ -548,6 +492,47 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_part(RlDev D, RlBatch B, Sr
             }
         }
         __syncwarp();
+    }
+
+    // ---- last block: work items ---------------------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(B.scan_ctr, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned long long tk0 = (D.kstats != nullptr && tid == 0) ? rl_globaltimer_ns() : 0ull;
+    // region lengths into shared memory (re-armed = zeroed for the next batch on the way); loc[] is free now
+    const uint32_t P = P1 - 1;
+    uint32_t hsum = 0, lsum = 0;
+    for (uint32_t q = tid; q < P; q += NT) {
+        const uint32_t len = __ldcg(&B.region_total[q]);
+        B.region_total[q] = 0;
+        loc[q] = len;
+        if (len > B.heavy_len) hsum += (len + B.chunk - 1) / B.chunk;
+        else if (len) lsum += 1;
+    }
+    uint32_t th, tl;
+    uint32_t hb = rl_block_excl_scan<NT>(hsum, s_warp, th);
+    uint32_t lb = rl_block_excl_scan<NT>(lsum, s_warp2, tl);
+    // chunks of heavy partitions first: they chain in ticket order
+    for (uint32_t q = tid; q < P; q += NT) {
+        const uint32_t len = loc[q];
+        if (len > B.heavy_len) {
+            const uint32_t nc = (len + B.chunk - 1) / B.chunk;
+            for (uint32_t k = 0; k < nc; k++) {
+                B.chain_status[hb] = 0;
+                B.items[hb++] = make_uint4(q, k * B.chunk, min((k + 1) * B.chunk, len), k);
+            }
+        } else if (len) {
+            B.items[th + lb++] = make_uint4(q, 0, len, RL_NONE_U32);
+        }
+    }
+    if (tid == 0) {
+        *B.n_items = th + tl;
+        *B.ticket = 0;
+        *B.scan_ctr = 0;  // re-arm for the next batch
+        if (D.kstats != nullptr) atomicAdd(D.kstats + 16, rl_globaltimer_ns() - tk0);  // ns spent in this tail
     }
 }
 
@@ -593,6 +578,8 @@ struct RlMainSmem {
     uint32_t scan_w[NW];
     uint32_t w_cnt;
     uint32_t item;
+    uint32_t t_pfx[RL_MAX_TILES + 1];  // my partition's list: exclusive prefix of its per-tile run lengths
+    uint32_t t_loc[RL_MAX_TILES];      // ... and where each tile's run starts in part_idx/part_row
 };
 
 // Per-thread view of the limits its access touches, in the access's own cell order.
@@ -744,6 +731,8 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
     const bool snapshot = Src::kCanBeMulti && (B.phase == RL_PHASE_SNAPSHOT);
 
     const uint32_t n_items = *B.n_items;
+    const uint32_t ntile = B.num_tiles;
+    const uint32_t tsz = rl_tile_of(B, rl_batch_n(B));
     for (;;) {
         // ---- next work item: atomic ticket, broadcast through shared memory -----------------------
         __syncthreads();  // the previous item is finished by every thread (sm.item is reused)
@@ -762,7 +751,53 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
         }
         long long tph = D.kstats != nullptr ? clock64() : 0;
         const uint4 it = B.items[item];
-        const uint32_t lo = it.y, hi = it.z;
+        const uint32_t lo = it.y, hi = it.z;  // [lo, hi) of the partition's list
+        // ---- the partition's list = its runs in the tiles' slices, tile after tile: merge on read --------
+        {
+            const uint32_t TL = B.nparts + 2;
+            constexpr uint32_t PER = (RL_MAX_TILES + CH - 1) / CH;  // consecutive tiles per thread
+            uint32_t c[PER], sum = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < PER; j++) {
+                const uint32_t t = tid * PER + j;
+                c[j] = 0;
+                if (t < ntile) {
+                    const uint32_t l0 = __ldcg(&B.tile_loc[(size_t)t * TL + it.x]);
+                    const uint32_t l1 = __ldcg(&B.tile_loc[(size_t)t * TL + it.x + 1]);
+                    c[j] = l1 - l0;
+                    sm.t_loc[t] = t * tsz + l0;
+                }
+                sum += c[j];
+            }
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if ((int)lane >= o) x += y;
+            }
+            if (lane == 31) sm.scan_w[warp] = x;
+            __syncthreads();
+            uint32_t run = x - sum;
+            for (uint32_t w = 0; w < warp; w++) run += sm.scan_w[w];
+#pragma unroll
+            for (uint32_t j = 0; j < PER; j++) {
+                const uint32_t t = tid * PER + j;
+                if (t < ntile) sm.t_pfx[t] = run;
+                run += c[j];
+            }
+            if (tid == CH - 1) sm.t_pfx[ntile] = run;  // threads past the last tile carry the total along
+            __syncthreads();
+        }
+        // position v of the list -> index into part_idx/part_row: the last tile whose prefix is <= v
+        auto list_at = [&](uint32_t v) -> uint32_t {
+            uint32_t a0 = 0, a1 = ntile - 1;
+            while (a0 < a1) {
+                const uint32_t mid = (a0 + a1 + 1) >> 1;
+                if (sm.t_pfx[mid] <= v) a0 = mid;
+                else a1 = mid - 1;
+            }
+            return sm.t_loc[a0] + (v - sm.t_pfx[a0]);
+        };
         // Heavy partition: this CTA owns ONE chunk and the partition's chunks run concurrently under
         // optimistic concurrency control, row by row.  A chunk replays its requests against the
         // rows as they are (no row is written) and publishes the rows it read, each tagged with
@@ -777,40 +812,53 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
         // tickets, so they are running (or done) whenever a chunk waits for them.
         const bool chained = (it.w != RL_NONE_U32);
         // (access, row) pairs of the first chunk
-        uint32_t na = 0, nrow = 0xFFFFFFFFu;
+        uint32_t na = 0, nrow = 0xFFFFFFFFu, npos = 0;
         if (lo + tid < hi) {
-            na = __ldcs(B.part_idx + lo + tid);
-            nrow = __ldcs(B.part_row + lo + tid);
+            npos = list_at(lo + tid);
+            na = __ldcs(B.part_idx + npos);
+            nrow = __ldcs(B.part_row + npos);
         }
 
         for (uint32_t c0 = lo; c0 < hi; c0 += CH) {
             // ---- 1. my access: gather the record, group by row while it is in flight --------------
             const uint32_t p = c0 + tid;
-            const uint32_t a = na, myrow = nrow;
+            const uint32_t a = na, myrow = nrow, mypos = npos;
             const bool valid = (p < hi) && (myrow != 0xFFFFFFFFu);  // no row: the region is full (error flagged by the probe)
             RlRaw rawrec;
             rawrec.w0 = make_ulonglong2(0ull, 0ull);
             rawrec.w1 = make_ulonglong2(0ull, 0ull);
             if (valid) rawrec = src.raw(a);
             if (p + CH < hi) {
-                na = __ldcs(B.part_idx + p + CH);
-                nrow = __ldcs(B.part_row + p + CH);
+                npos = list_at(p + CH);
+                na = __ldcs(B.part_idx + npos);
+                nrow = __ldcs(B.part_row + npos);
             }
             uint32_t slot = 0, gid = tid;
             bool is_rep = false;
+            // lanes of a warp that hit the same row insert once (a hot row would otherwise serialise 32
+            // same-address CAS per warp): `peers` = my row's lanes in this warp, kept for the ordinals and
+            // for the warp-aggregated minima of the replay rounds
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            unsigned peers = 0;
+            int leader = 0;
             if (valid) {
-                uint32_t s = rl_group_slot<GT>(myrow, weak);
-                for (;;) {
-                    const uint32_t old = atomicCAS(&sm.g_row[s], 0xFFFFFFFFu, myrow);
-                    if (old == 0xFFFFFFFFu) {
-                        sm.g_rep[s] = tid;  // I claimed the slot: my row's group is mine to stage
-                        is_rep = true;
-                        break;
+                peers = __match_any_sync(vmask, myrow);
+                leader = __ffs(peers) - 1;
+                uint32_t s = 0;
+                if ((int)lane == leader) {
+                    s = rl_group_slot<GT>(myrow, weak);
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&sm.g_row[s], 0xFFFFFFFFu, myrow);
+                        if (old == 0xFFFFFFFFu) {
+                            sm.g_rep[s] = tid;  // I claimed the slot: my row's group is mine to stage
+                            is_rep = true;
+                            break;
+                        }
+                        if (old == myrow) break;
+                        s = (s + 1) & (GT - 1);
                     }
-                    if (old == myrow) break;
-                    s = (s + 1) & (GT - 1);
                 }
-                slot = s;
+                slot = __shfl_sync(peers, s, leader);
             }
             uint8_t* row = nullptr;
             RlRow<CELLS> st;
@@ -856,13 +904,9 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             RL_PHASE_TICK(0)  // item fetch + gather + grouping
 
             // ---- 2. stable ordinal: one packed add per (warp, row), one barrier --------------------
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            unsigned peers = 0;
-            if (valid) {
-                peers = __match_any_sync(vmask, slot);
-                if (lane == (uint32_t)(__ffs(peers) - 1))
-                    atomicAdd(&sm.g_packed[slot * PW + (warp >> 3)], (unsigned long long)__popc(peers) << (8 * (warp & 7)));
-            }
+            if (valid && (int)lane == leader)
+                atomicAdd(&sm.g_packed[slot * PW + (warp >> 3)], (unsigned long long)__popc(peers) << (8 * (warp & 7)));
+            const bool solo = (peers & (peers - 1)) == 0;  // my row's only lane in this warp
             // ---- 3. the rep stages the row state -----------------------------------------------------
             if (is_rep) {
 #pragma unroll
@@ -871,10 +915,10 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                     sm.s_exp[tid * CELLS + c] = st.expiry[c];
                 }
                 if (snapshot) {
-                    B.log_row[p] = row;
+                    B.log_row[mypos] = row;
 #pragma unroll
                     for (int c = 0; c < CELLS; c++)
-                        B.log_state[(size_t)p * GEO + c] = make_ulonglong2(st.value[c], st.expiry[c]);
+                        B.log_state[(size_t)mypos * GEO + c] = make_ulonglong2(st.value[c], st.expiry[c]);
                 }
             }
             __syncthreads();
@@ -906,6 +950,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                 const uint32_t par = round & 1;
                 uint32_t fl = RL_NONE_U32;
                 RlRow<CELLS> loc;
+                uint32_t amin = 0xFFFFFFFFu, bmin = 0xFFFFFFFFu;  // my ordinal if hypothesis A / B fails for me
                 if (!done) {
                     bool aok = false, bok = false;
                     if (!multi) {
@@ -924,8 +969,19 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                             loc.expiry[c] = se[c];
                         }
                     }
-                    if (!aok) atomicMin(&sm.g_min[par][0][gid], ord);
-                    if (!bok) atomicMin(&sm.g_min[par][1][gid], ord);
+                    if (!aok) amin = ord;
+                    if (!bok) bmin = ord;
+                }
+                if (valid) {
+                    // one shared-memory atomic per (warp, row) instead of one per access
+                    if (!solo) {
+                        amin = __reduce_min_sync(peers, amin);
+                        bmin = __reduce_min_sync(peers, bmin);
+                    }
+                    if ((int)lane == leader) {
+                        if (amin != 0xFFFFFFFFu) atomicMin(&sm.g_min[par][0][gid], amin);
+                        if (bmin != 0xFFFFFFFFu) atomicMin(&sm.g_min[par][1][gid], bmin);
+                    }
                 }
                 __syncthreads();
                 if (!done) {

@@ -35,6 +35,9 @@ ABI_SYMBOLS = [
     "rl_sweep", "rl_dump_table", "rl_bucket_by_owner", "rl_unpermute_u8", "rl_owner_of",
     "rl_profile_begin", "rl_profile_end", "rl_bucket_by_owner_padded", "rl_gather_u8", "rl_record_lane_put", "rl_record_lane_gather", "rl_fence", "rl_fence_call",
     "rl_front_create", "rl_front_destroy", "rl_front_check_and_update", "rl_front_stats",
+    "rl_shard_create", "rl_shard_destroy", "rl_shard_ipc_handle", "rl_shard_connect_ipc", "rl_shard_connect_ptrs",
+    "rl_shard_slab", "rl_shard_slab_bytes", "rl_shard_send", "rl_shard_decide", "rl_shard_collect", "rl_shard_step",
+    "rl_shard_flush",
 ]
 
 
@@ -118,6 +121,21 @@ def load_library(path: str | None = None):
     L.rl_front_stats.argtypes = [vp, vp, vp]
     L.rl_owner_of.argtypes = [u32, u32]
     L.rl_owner_of.restype = u32
+    L.rl_shard_create.argtypes = [vp, u32, u32, u32, u32, C.POINTER(vp)]
+    L.rl_shard_destroy.argtypes = [vp]
+    L.rl_shard_destroy.restype = None
+    L.rl_shard_ipc_handle.argtypes = [vp, vp]
+    L.rl_shard_connect_ipc.argtypes = [vp, vp]
+    L.rl_shard_connect_ptrs.argtypes = [vp, vp]
+    L.rl_shard_slab.argtypes = [vp]
+    L.rl_shard_slab.restype = vp
+    L.rl_shard_slab_bytes.argtypes = [vp]
+    L.rl_shard_slab_bytes.restype = u64
+    L.rl_shard_send.argtypes = [vp, u64, vp, vp]
+    L.rl_shard_decide.argtypes = [vp]
+    L.rl_shard_collect.argtypes = [vp, C.POINTER(vp)]
+    L.rl_shard_step.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]
+    L.rl_shard_flush.argtypes = [vp]
     if path == _build.LIB_PATH:
         _lib = L
     return L
@@ -394,3 +412,68 @@ class Front:
         b, r = C.c_uint64(0), C.c_uint64(0)
         self._lib.rl_front_stats(self._h, C.addressof(b), C.addressof(r))
         return {"batches": b.value, "requests": r.value}
+
+
+class Shard:
+    """Namespace-sharded peer exchange of one rank (include/rl_engine.h: rl_shard_*): records travel to
+    their owner GPU and verdicts back by direct NVLink stores into IPC-mapped slabs, no NCCL on the data
+    path.  All pointers are device pointers (ints); every call only enqueues."""
+
+    def __init__(self, engine: "Engine", rank: int, world: int, cap: int, lag: int = 2):
+        self._lib = engine._lib
+        self._eng = engine
+        self._h = C.c_void_p()
+        engine._check(self._lib.rl_shard_create(engine._h, rank, world, cap, lag, C.byref(self._h)))
+        self.rank, self.world, self.cap, self.lag = rank, world, cap, lag
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rl_shard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def slab(self) -> int:
+        return int(self._lib.rl_shard_slab(self._h) or 0)
+
+    @property
+    def slab_bytes(self) -> int:
+        return int(self._lib.rl_shard_slab_bytes(self._h))
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._eng._check(self._lib.rl_shard_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def connect_ipc(self, handles: bytes):
+        assert len(handles) == 64 * self.world
+        self._eng._check(self._lib.rl_shard_connect_ipc(self._h, C.c_char_p(handles)))
+
+    def connect_ptrs(self, slabs):
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in slabs])
+        self._eng._check(self._lib.rl_shard_connect_ptrs(self._h, arr))
+
+    def send(self, n: int, recs_ptr: int, out_ptr: int):
+        self._eng._check(self._lib.rl_shard_send(self._h, n, C.c_void_p(recs_ptr), C.c_void_p(out_ptr)))
+
+    def decide(self):
+        self._eng._check(self._lib.rl_shard_decide(self._h))
+
+    def collect(self):
+        """Returns the device pointer of the out_limited buffer whose delivery was enqueued, or None."""
+        done = C.c_void_p()
+        self._eng._check(self._lib.rl_shard_collect(self._h, C.byref(done)))
+        return done.value
+
+    def step(self, n: int, recs_ptr: int, out_ptr: int):
+        done = C.c_void_p()
+        self._eng._check(self._lib.rl_shard_step(self._h, n, C.c_void_p(recs_ptr), C.c_void_p(out_ptr), C.byref(done)))
+        return done.value
+
+    def flush(self):
+        self._eng._check(self._lib.rl_shard_flush(self._h))

@@ -21,6 +21,11 @@ ncu)
 ncufull)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_main -s 8 -c 1 -o $out/${tag}_k_main_c2 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra > $out/${tag}_ncufull.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_main -s 4 -c 1 -o $out/${tag}_k_main_c3 python bench.py --workload C3 --steps 4 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra >> $out/${tag}_ncufull.log 2>&1;;
+kstats)
+  timeout 300 python bench.py --steps 200 --warmup 10 --kstats --no-cpu-baseline --no-extra > $out/${tag}_kstats_c2.json 2> $out/${tag}_kstats_c2.err; grep "engine stats" $out/${tag}_kstats_c2.err
+  timeout 300 python bench.py --steps 200 --warmup 10 --kstats --no-cpu-baseline --no-extra --no-pipeline > $out/${tag}_kstats_c2_np.json 2> $out/${tag}_kstats_c2_np.err; grep "engine stats" $out/${tag}_kstats_c2_np.err;;
+ncuprobe)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_probe_count -s 8 -c 1 -o $out/${tag}_k_probe_c2 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra > $out/${tag}_ncuprobe.log 2>&1;;
 san)
   timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fast_path or chained or hot_key or csr_general" > $out/${tag}_san_memcheck.log 2>&1; tail -5 $out/${tag}_san_memcheck.log
   timeout 1500 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fast_path or chained or hot_key" > $out/${tag}_san_racecheck.log 2>&1; tail -5 $out/${tag}_san_racecheck.log
