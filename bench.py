@@ -27,6 +27,11 @@ import numpy as np
 # (profiles/r01_e2e_queue_aliasing.txt).  More queues make that unlikely; a deployment sets the same
 # variable before CUDA is initialised.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# N>1: the peer exchange synchronises the GPUs with kernels that spin on flags.  With CUDA's lazy module loading
+# the first launch of ANY kernel in the process (ours are pre-loaded by rl_shard_create; torch's and NCCL's are
+# not) may wait for the context to go idle, i.e. for a spinning kernel whose peer waits for this very rank: load
+# everything up front.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -108,6 +113,66 @@ def counters_examined(lim: np.ndarray, first: np.ndarray, L: int):
     allowed = lim == 0
     k = (first[~allowed] % L).astype(np.int64) + 1  # C2: limit_id = ns*4 + k
     return int(allowed.sum()) * L + int(k.sum()), int(allowed.sum()) * L
+
+
+def table_digest(lid, lo, hi, val, exp):
+    """(count, blake2b hex) of a counter dump, order-independent: rows sorted lexicographically."""
+    import hashlib
+    n = len(lid)
+    if n == 0:
+        return 0, hashlib.blake2b(b"", digest_size=16).hexdigest()
+    order = np.lexsort((exp, val, hi, lo, lid))
+    rows = np.empty(n, dtype=[("lid", "<u8"), ("lo", "<u8"), ("hi", "<u8"), ("val", "<u8"), ("exp", "<u8")])
+    rows["lid"], rows["lo"], rows["hi"], rows["val"], rows["exp"] = lid[order], lo[order], hi[order], val[order], exp[order]
+    return n, hashlib.blake2b(rows.tobytes(), digest_size=16).hexdigest()
+
+
+def sharded_parity(dist, world, rank, dev, eng, limits, recs_steps, out_steps, owner_of):
+    """N>1 bit-exactness, driver-visible: every rank's first steps (records + verdicts) are gathered and
+    replayed on rank 0 through ONE global oracle in (step, source rank, source index) order — the canonical
+    stream order of the sharded store (in_memory.rs:72-156 applied request by request) — and every
+    rank's counter table is compared with the oracle's counters of the namespaces it owns (count + digest of
+    the sorted (limit, key, value, expiry) rows).  Returns the result dict on rank 0, None elsewhere."""
+    import torch
+    S, batch = recs_steps.shape[0], recs_steps.shape[1]
+    g_recs = torch.empty((world,) + tuple(recs_steps.shape), dtype=recs_steps.dtype, device=dev)
+    dist.all_gather_into_tensor(g_recs, recs_steps.contiguous())
+    g_out = torch.empty((world,) + tuple(out_steps.shape), dtype=out_steps.dtype, device=dev)
+    dist.all_gather_into_tensor(g_out, out_steps.contiguous())
+    mine = table_digest(*eng.dump_arrays(cap=1 << 24))
+    digests = [None] * world
+    dist.all_gather_object(digests, mine)
+    if rank != 0:
+        return None
+    from limitador_b200.engine import RECORD_DTYPE
+    from oracle import binding as ob
+    t0 = time.perf_counter()
+    o = ob.Oracle(1 << 22)
+    for d in limits:
+        o.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    h_recs = g_recs.cpu().numpy()
+    h_out = g_out.cpu().numpy()
+    mism = 0
+    for st in range(S):
+        for r in range(world):
+            want = o.batch_records(0, h_recs[r, st].view(RECORD_DTYPE).reshape(-1))[0]
+            mism += int((want != h_out[r, st]).sum())
+    lid, lo, hi, val, exp = o.dump_arrays()
+    ns_of = np.zeros(int(limits["limit_id"].max()) + 1, dtype=np.int64)
+    ns_of[limits["limit_id"]] = limits["ns_id"]
+    own_lut = np.array([owner_of(int(ns), world) for ns in range(int(limits["ns_id"].max()) + 1)], dtype=np.int64)
+    owner = own_lut[ns_of[lid]]
+    bad = []
+    for r in range(world):
+        sel = owner == r
+        want = table_digest(lid[sel], lo[sel], hi[sel], val[sel], exp[sel])
+        if tuple(want) != tuple(digests[r]):
+            bad.append({"rank": r, "oracle": list(want), "gpu": list(digests[r])})
+    res = {"steps": S, "decisions": int(S * world * batch), "order": "(step, source rank, source index)",
+           "gpu_verdict_mismatches": mism, "counters": int(len(lid)), "table_mismatch_ranks": bad,
+           "oracle_s": round(time.perf_counter() - t0, 2)}
+    print(f"[bench] sharded parity: {res}", file=sys.stderr)
+    return res
 
 
 def run_reference(args):
@@ -193,9 +258,15 @@ def main():
     ap.add_argument("--cpu-sample-batches", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange-lag", type=int, default=2,
-                    help="N>1: verdicts return in the records of the step this many steps later (1..3)")
+                    help="N>1: a step's verdicts are delivered this many steps later (steps in flight - 1)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: peer = in-library NVLink exchange (rl_shard_*: direct stores into IPC-mapped inboxes); "
+                         "nccl = one torch.distributed all-to-all of fixed-size blocks per step (round-1 path)")
+    ap.add_argument("--parity-steps", type=int, default=6,
+                    help="N>1: steps replayed through ONE global oracle on rank 0 (verdicts + tables), before the timed passes")
     ap.add_argument("--no-pipeline", action="store_true", help="disable the pipelining of successive steps")
     ap.add_argument("--kstats", action="store_true", help="RL_FLAG_KERNEL_STATS: per-phase cycle accounting inside k_main (costs a few %)")
+    ap.add_argument("--trace", default="", help="RL_FLAG_TRACE: write every rank's device-side event trace of pass A to <path>.rank<r>.json")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads / legs reported under `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -249,20 +320,22 @@ def main():
     out_lim_pool = torch.zeros((pool, batch), dtype=torch.uint8, device=dev)
     out_first_pool = torch.zeros((pool, batch), dtype=torch.int32, device=dev)
 
-    # exchange blocks: each rank sends `slot_cap` record slots to every owner.  Sized from the traffic itself,
-    # as a deployment would: the largest (rank -> owner) share seen in a sample of the stream, max over ranks,
-    # plus 20 % headroom (an overflow is detected and fails the run; 2x the mean share if nothing was sampled)
+    # N>1, peer exchange (default): every rank stores its records straight into the owners' inboxes over NVLink
+    # (rl_shard_*); an owner can receive up to world x batch records in a step, so the engine is sized for that.
+    # N>1, nccl exchange: each rank sends `slot_cap` record slots to every owner, sized from the traffic itself
+    # (largest (rank -> owner) share in a sample, max over ranks, plus 20 % headroom; an overflow fails the run).
+    use_peer = world > 1 and args.exchange == "peer"
     slot_cap = min(batch, ((2 * batch // world) + 255) // 256 * 256)
-    if world > 1:
+    if world > 1 and not use_peer:
         lut = torch.tensor([exchange.owner_of(ns, world) for ns in range(n_ns)], dtype=torch.int64, device=dev)
         seen = torch.tensor([exchange.observed_block_max(recs_pool[:min(pool, 64)], lut, world)], dtype=torch.int64, device=dev)
         dist.all_reduce(seen, op=dist.ReduceOp.MAX)
         slot_cap = exchange.slot_cap_for(int(seen.item()), batch)
         print(f"[bench] largest exchange block in the sample: {int(seen.item())} records -> slot_cap {slot_cap}", file=sys.stderr)
-    max_batch = batch if world == 1 else world * slot_cap
-    # RL_FLAG_PIPELINE (2): the partition of step s+1 overlaps the replay of step s on the device
-    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, device=local_rank,
-                 flags=(0 if args.no_pipeline else 2) | (4 if args.kstats else 0))
+    max_batch = batch if world == 1 else (world * batch if use_peer else world * slot_cap)
+    # RL_FLAG_PIPELINE (2): the front of step s+1 overlaps the replay of step s on the device
+    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, max_counters=max_batch, device=local_rank,
+                 flags=(0 if args.no_pipeline else 2) | (4 if args.kstats else 0) | (8 if args.trace else 0))
     eng.limits_set(limits)
     # a dedicated non-default stream: the engine launches on it and the CUDA events that time
     # the steps are recorded on it (the legacy default stream would be handle 0 == "engine's own")
@@ -289,8 +362,18 @@ def main():
     print(f"[bench] generated {total} batches of {batch} in {time.perf_counter() - t_gen:.1f}s", file=sys.stderr)
 
     ex = None
-    if world > 1:
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    shard = None
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    if use_peer:
+        from limitador_b200.engine import Shard
+        shard = Shard(eng, rank, world, batch, args.exchange_lag)
+        mine = torch.frombuffer(bytearray(shard.ipc_handle()), dtype=torch.uint8).to(dev)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine)
+        shard.connect_ipc(bytes(allh.cpu().numpy().tobytes()))
+        dist.barrier()
+        print(f"[bench] rank {rank}: peer exchange connected, slab {shard.slab_bytes >> 20} MiB", file=sys.stderr)
+    elif world > 1:
 
         class _EngineOps:
             """exchange.LanePipelinedExchange's device work: the engine's kernels on this rank's stream"""
@@ -321,20 +404,32 @@ def main():
 
         ex = exchange.LanePipelinedExchange(world, batch, slot_cap, dist, _EngineOps, dev, lag=args.exchange_lag)
 
+    out_by_ptr = {}
+
     def step_device(s: int):
         """One step with the batch resident in HBM."""
         if world == 1:
             eng.check_and_update_records_ptr(batch, recs[s].data_ptr(), out_lim[s].data_ptr(), MEM_DEVICE,
                                              out_first_ptr=out_first[s].data_ptr(), stride=cells)
             return None
-        # namespace-sharded (SURVEY §8e): bucket my slice by owner into fixed-size blocks, ONE NCCL
-        # all-to-all of the 32-B records over NVLink, decide on the owner.  The verdict bytes of step
-        # s-lag ride back in the lane byte of step s's records (exchange.LanePipelinedExchange), so there
-        # is no reverse collective and no host round trip; unused slots carry no-op records (a
-        # namespace without limits) that the engine ignores.  Returns the output completed by this step.
+        # namespace-sharded (SURVEY §8e).  peer: ONE library call — bucket by owner, store the records into
+        # the owners' inboxes over NVLink, decide my own inbox in (source rank, source index) order, store the
+        # verdicts back; the verdicts of step s-lag are delivered by this call.  nccl: fixed-size blocks, one
+        # all-to-all, verdicts ride back in the lane byte (exchange.LanePipelinedExchange).
+        # Returns the output tensor completed by this step (or None).
+        if shard is not None:
+            o = out_lim[s]
+            out_by_ptr[o.data_ptr()] = o
+            done = shard.step(batch, recs[s].data_ptr(), o.data_ptr())
+            return out_by_ptr.pop(done) if done else None
         return ex.step(recs[s], out_lim[s])
 
     def drain():
+        if shard is not None:
+            shard.flush()
+            left = list(out_by_ptr.values())
+            out_by_ptr.clear()
+            return left
         return ex.flush() if ex is not None else []
 
     def barrier():
@@ -367,8 +462,19 @@ def main():
 
     # ---- warm-up -------------------------------------------------------------------------
     t_w = time.perf_counter()
+    parity = None
+    S_par = 0
+    if world > 1 and pool == total:
+        S_par = max(1, min(args.parity_steps, W, (1 << 28) // (world * batch * 32)))
     for s in range(W):
         step_device(s)
+        if s == S_par - 1:
+            # the first steps of the stream, replayed through one global oracle (verdicts + tables)
+            drain()
+            eng.sync()
+            parity = sharded_parity(dist, world, rank, dev, eng, limits, recs[:S_par], out_lim[:S_par], exchange.owner_of)
+            if os.environ.get("RL_BENCH_PARITY_BARRIER"):
+                barrier()
     drain()
     eng.sync()
     print(f"[bench] warm-up {time.perf_counter() - t_w:.2f}s", file=sys.stderr)
@@ -378,9 +484,14 @@ def main():
 
     # ---- pass A: the headline device-resident throughput ----------------------------------
     launches0 = eng.stats()["kernel_launches"]
+    if args.trace:
+        eng.trace_dump()  # clear
     ms_a = timed(step_device, W, K)
     launches = eng.stats()["kernel_launches"] - launches0
     eng.sync()
+    if args.trace:
+        with open(f"{args.trace}.rank{rank}.json", "w") as f:
+            json.dump(eng.trace_dump(), f)
     value = world * batch * K / (ms_a * 1e-3)
 
     # ---- pass B: same K steps further down the stream, k_main bracketed by CUDA events ------
@@ -452,7 +563,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     os.sched_setaffinity(0, cpus_before)  # the CPU baseline below gets every host core again
-    if world > 1 and int(overflow.item()) != 0:
+    if world > 1 and not use_peer and int(overflow.item()) != 0:
         raise RuntimeError(f"an exchange block overflowed (more than {slot_cap} records for one owner): the sampled "
                            f"headroom was too small")
     print(f"[bench] engine stats {eng.stats()}", file=sys.stderr)
@@ -519,9 +630,12 @@ def main():
                                 f"delta=1, load_counters=false"),
                    "parallelism": ("single GPU, successive steps pipelined over 3 streams (probe | scan+scatter | replay)" if not args.no_pipeline else "single GPU")
                    if world == 1 else
-                   f"namespace-sharded x{world}, one NCCL all-to-all of fixed {slot_cap}-record blocks per peer and step "
-                   f"(block = 1.2 x the largest share sampled) "
-                   f"(verdicts return in the records' lane byte {args.exchange_lag} steps later)",
+                   (f"namespace-sharded x{world}, peer exchange: records stored straight into the owners' inboxes over NVLink "
+                    f"(CUDA-IPC slabs, flag-synchronised, no NCCL on the data path), verdicts stored back; "
+                    f"{args.exchange_lag + 1} steps in flight" if use_peer else
+                    f"namespace-sharded x{world}, one NCCL all-to-all of fixed {slot_cap}-record blocks per peer and step "
+                    f"(block = 1.2 x the largest share sampled) "
+                    f"(verdicts return in the records' lane byte {args.exchange_lag} steps later)"),
                    "l2": ("a distinct batch every step (never reused); table > L2" if pool == total else
                           f"{pool} distinct batches cycled (timestamps repeat); table > L2"),
                    "table_rows": cap, "row_bytes": 16 * (1 + cells)},
@@ -536,10 +650,23 @@ def main():
         line["roofline"] = roof
     if cpu:
         line["cpu_baseline"] = cpu
+    failed = False
+    if parity is not None:
+        # N>1: the live check against ONE global oracle (no CPU throughput is quoted from it: a single thread)
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"first {parity['steps']} steps of every rank ({parity['decisions']} decisions) replayed "
+                                          f"through one global oracle in {parity['order']} order; verdicts and per-owner tables compared",
+                                "gpu_verdict_mismatches": parity["gpu_verdict_mismatches"],
+                                "gpu_table_mismatch_ranks": parity["table_mismatch_ranks"], "counters_compared": parity["counters"]}
+        line["e2e"]["verdict_latency_steps"] = args.exchange_lag
+        failed = parity["gpu_verdict_mismatches"] != 0 or bool(parity["table_mismatch_ranks"])
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        print("[bench] FAILED: the sharded run differs from the global oracle", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

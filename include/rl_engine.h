@@ -46,6 +46,7 @@ enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1,
         * otherwise, or with load_counters outputs, it behaves like RL_MEM_HOST) */
        RL_MEM_HOST_ASYNC = 2 };
 #define RL_NONE 0xFFFFFFFFu
+#define RL_MAX_COUNTERS_PER_REQUEST 16 /* counters one request may name (general form); the matcher refuses more */
 /* test aid: narrow the in-kernel grouping tag so that distinct keys collide and the
  * collision path (salted re-insertion) is exercised */
 #define RL_FLAG_DEBUG_WEAK_TAGS 1u
@@ -56,6 +57,10 @@ enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1,
 /* rl_stats.chunks / replay_rounds / chained_chunks / ordered_chunks / phase_cycles are accounted by the
  * replay kernel (a few atomics per chunk, ~7 % of a 65536-request step); without the flag they stay 0. */
 #define RL_FLAG_KERNEL_STATS 4u
+/* Device-side event trace: the kernels of a step stamp the GPU's nanosecond timer at their start and end into a
+ * ring of 65536 events (rl_trace_dump), so the timeline of a pipelined / sharded step can be read without a
+ * profiler.  One atomic and one 16-B store per kernel and event. */
+#define RL_FLAG_TRACE 8u
 
 typedef struct rl_config {
     uint32_t struct_size;    /* sizeof(rl_config) */
@@ -137,6 +142,10 @@ int rl_fence_call(rl_engine *e, uint32_t age);
 /* Wait for all enqueued work; returns and clears any deferred device-side error. */
 int rl_sync(rl_engine *e);
 int rl_get_stats(rl_engine *e, rl_stats *out);
+/* RL_FLAG_TRACE: copy (and clear) the event ring.  out_ev[i] = event id | end << 8 (ids: 1 front, 2 replay,
+ * 3 exchange count, 4 exchange scatter, 5 inbox wait, 6 verdict return, 7 verdict wait, 8 verdict gather),
+ * out_seq[i] = call / exchange step number, out_ns[i] = GPU nanosecond timer.  Synchronises the device. */
+int rl_trace_dump(rl_engine *e, uint32_t cap, uint32_t *out_ev, uint32_t *out_seq, uint64_t *out_ns, uint32_t *out_count);
 
 /* CounterStorage::add_counter (storage/mod.rs:281, in_memory.rs:38-44) + Storage::update_limit
  * (storage/mod.rs:67-83): new ids are registered (unqualified ⇒ counter pre-created as
@@ -263,6 +272,9 @@ int rl_shard_collect(rl_shard *s, uint8_t **out_done);
 int rl_shard_step(rl_shard *s, uint64_t n, const rl_record *d_recs, uint8_t *d_out_limited, uint8_t **out_done);
 /* deliver every step still in flight (all ranks must have issued the same steps) */
 int rl_shard_flush(rl_shard *s);
+/* debugging aid: host copy of this rank's control words, out[(buf*world + peer)*4 + {0 fill, 1 record flag,
+ * 2 verdict flag}] for buf < lag+1, then the steps sent, decided, collected; out holds (lag+1)*world*4 + 3 words */
+int rl_shard_debug(rl_shard *s, uint32_t *out);
 
 /* ---- Batching front (SURVEY §8b threading row) ---------------------------------------------
  * Thread-safe, blocking, one request per call: concurrent callers are coalesced by a dispatcher

@@ -14,10 +14,15 @@
  *
  * Expressions accepted (anything else is refused at rl_matcher_add_limit with RL_FATAL, so that a deployment
  * can keep such limits on the reference's interpreter):
- *   operand   := IDENT ('.' IDENT)*                         a root binding, dots are part of the name
+ *   operand   := IDENT                                      a root binding (ASCII identifier, NO dots: `req.method`
+ *                                                           is CEL member access on the variable `req`, which the
+ *                                                           reference never binds — limit/cel.rs:314-322)
  *              | 'descriptors[' N '].' IDENT                the Envoy descriptor list (cel.rs:102-114)
  *              | 'descriptors[' N '][' QUOTED ']'
- *   condition := operand ('==' | '!=') QUOTED               QUOTED = '...' or "..."
+ *   condition := operand ('==' | '!=') QUOTED               QUOTED = '...' or "..." closed by the quote that opened
+ *                                                           it, without any backslash (CEL escape processing is not
+ *                                                           done here: such literals and keys are refused, not
+ *                                                           reinterpreted)
  *   variable  := operand
  *
  * Output = exactly the inputs of rl_check_and_update_batch (include/rl_engine.h): a CSR of rl_counter.
@@ -50,7 +55,10 @@ typedef struct rl_binding {
 
 int rl_matcher_create(rl_matcher **out);
 void rl_matcher_destroy(rl_matcher *m);
+/* The returned pointer is valid until the next failing call on this matcher (any thread): callers that share a
+ * matcher between threads use the _copy form. */
 const char *rl_matcher_last_error(rl_matcher *m);
+int rl_matcher_last_error_copy(rl_matcher *m, char *out, uint32_t cap);
 
 /* Limit::new + Storage::add_limit / update_limit (storage/mod.rs:60-83).  A limit with a known identity keeps
  * its limit_id and takes the new max_value / name.  *out_desc is what rl_limits_set needs. */
@@ -58,12 +66,22 @@ int rl_matcher_add_limit(rl_matcher *m, const char *ns, uint64_t max_value, uint
                          const char *const *conditions, uint32_t n_cond, const char *const *variables,
                          uint32_t n_var, const char *name /* nullable */, rl_limit_desc *out_desc);
 /* Storage::delete_limit (storage/mod.rs:93-117): the id is retired, never reused. */
+/* The same with the reference's two entry points told apart: keep_existing != 0 is Storage::add_limit — a
+ * HashSet::insert, i.e. a no-op that KEEPS the old max_value / name when an equal live limit exists
+ * (storage/mod.rs:60-65) — keep_existing == 0 is update_limit (:67-83).  *out_existed (nullable) = 1 if an equal
+ * live limit was already registered.  *out_desc always describes the limit as it now stands. */
+int rl_matcher_add_limit_ex(rl_matcher *m, const char *ns, uint64_t max_value, uint64_t seconds,
+                            const char *const *conditions, uint32_t n_cond, const char *const *variables,
+                            uint32_t n_var, const char *name /* nullable */, int keep_existing,
+                            rl_limit_desc *out_desc, int *out_existed /* nullable */);
 int rl_matcher_delete_limit(rl_matcher *m, uint32_t limit_id);
 /* RL_OK and *out_ns_id, or RL_FATAL if no limit was ever added for the namespace (no limits => allow,
  * lib.rs:434-440: the caller skips the engine). */
 int rl_matcher_namespace_id(rl_matcher *m, const char *ns, uint32_t *out_ns_id);
-/* Name of a limit (Authorization::Limited(name)), or NULL. */
+/* Name of a limit (Authorization::Limited(name)), or NULL.  The pointer is valid only while no
+ * rl_matcher_add_limit / _delete_limit runs; concurrent callers use the _copy form (*out_has_name nullable). */
 const char *rl_matcher_limit_name(rl_matcher *m, uint32_t limit_id);
+int rl_matcher_limit_name_copy(rl_matcher *m, uint32_t limit_id, char *out, uint32_t cap, int *out_has_name);
 
 /* counters_that_apply for one request: *out_n counters written to out_ctrs (RL_FATAL if more than cap). */
 int rl_matcher_counters(rl_matcher *m, uint32_t ns_id, const rl_binding *binds, uint32_t n_binds,

@@ -116,6 +116,9 @@ struct rl_engine {
     DevBuf<uint32_t> d_fl_prev, d_fl_next;
     DevBuf<uint4> d_items;
     DevBuf<unsigned long long> d_kstats;
+    DevBuf<uint4> d_trace;     // RL_FLAG_TRACE: event ring
+    DevBuf<uint32_t> d_misc2;  // [0] trace write position
+    uint32_t trace_seq = 0;
     DevBuf<uint32_t> d_chain_status, d_chain_wcnt, d_chain_w;
     DevBuf<uint8_t*> d_log_row;
     DevBuf<ulonglong2> d_log_state;
@@ -215,6 +218,9 @@ RlDev make_dev(rl_engine* e) {
     D.err = e->d_misc.p + MISC_ERR;
     D.flags = e->d_misc.p + MISC_FLAGS;
     D.kstats = e->kernel_stats ? e->d_kstats.p : nullptr;
+    D.trace = e->d_trace.p;
+    D.trace_pos = e->d_trace.p ? e->d_misc2.p : nullptr;
+    D.seq = e->trace_seq;
     return D;
 }
 
@@ -326,9 +332,13 @@ int check_device_error(rl_engine* e) {
             return fail(e, RL_FATAL, "key_hi bits 32..55 must be zero (counter identity is a 96-bit digest)");
         case RL_DEV_TOO_MANY_COUNTERS:
             return fail(e, RL_FATAL, "a request has more than %d counters", RL_MAX_CTRS_PER_REQ);
-        case RL_DEV_EXCHANGE:
-            return fail(e, RL_FATAL, "peer exchange: a rank's step flag did not arrive within %.0f s (or a block fill was out of range)",
-                        (double)RL_XCHG_TIMEOUT_NS * 1e-9);
+        case RL_DEV_EXCHANGE: {
+            const uint32_t d = e->h_misc[7];
+            RL_CUDA(e, cudaMemsetAsync(e->d_misc.p + 7, 0, sizeof(uint32_t), e->stream));
+            const char* what = (d >> 28) == 1 ? "records of source rank" : (d >> 28) == 2 ? "verdicts of owner rank" : "inbox larger than max_batch, rank";
+            return fail(e, RL_FATAL, "peer exchange failed at step %u: %s %u did not arrive within %.0f s (or a block fill was out of range)",
+                        d & 0xFFFFFu, what, (d >> 20) & 0xFFu, (double)RL_XCHG_TIMEOUT_NS * 1e-9);
+        }
         default:
             return fail(e, RL_FATAL, "device error code %u", code);
     }
@@ -651,6 +661,39 @@ int ensure_ready(rl_engine* e, uint64_t n, bool fence = true) {
     return upload_tables(e);
 }
 
+// Force the (lazy) loading of the kernels a record-form check_and_update launches for this engine's geometry.
+template <int GEO, int CELLS>
+int preload_main(rl_engine* e) {
+    cudaFuncAttributes fa;
+    if (e->chunk == 128) {
+        RL_CUDA(e, cudaFuncGetAttributes(&fa, k_main<GEO, CELLS, RecordSrc, 0, 128, false>));
+        RL_CUDA(e, cudaFuncSetAttribute(k_main<GEO, CELLS, RecordSrc, 0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(RlMainSmem<CELLS, 128>)));
+    } else {
+        RL_CUDA(e, cudaFuncGetAttributes(&fa, k_main<GEO, CELLS, RecordSrc, 0, 256, false>));
+        RL_CUDA(e, cudaFuncSetAttribute(k_main<GEO, CELLS, RecordSrc, 0, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(RlMainSmem<CELLS, 256>)));
+    }
+    return RL_OK;
+}
+int preload_record_kernels(rl_engine* e) {
+    cudaFuncAttributes fa;
+    int r = upload_tables(e);  // max_cells_used selects the k_main instantiation
+    if (r) return r;
+    switch (e->cells) {
+        case 1:
+            RL_CUDA(e, cudaFuncGetAttributes(&fa, k_front<1, RecordSrc>));
+            return preload_main<1, 1>(e);
+        case 3:
+            RL_CUDA(e, cudaFuncGetAttributes(&fa, k_front<3, RecordSrc>));
+            return preload_main<3, 3>(e);
+        default:
+            RL_CUDA(e, cudaFuncGetAttributes(&fa, k_front<7, RecordSrc>));
+            if ((r = preload_main<7, 4>(e))) return r;
+            return preload_main<7, 7>(e);
+    }
+}
+
 }  // namespace
 
 // =======================================================================================
@@ -741,6 +784,12 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
     e->kernel_stats = (cfg->flags & RL_FLAG_KERNEL_STATS) != 0;
+    RL_CUDA(e, e->d_misc2.reserve(4));
+    RL_CUDA(e, cudaMemsetAsync(e->d_misc2.p, 0, 4 * sizeof(uint32_t), e->stream));
+    if (cfg->flags & RL_FLAG_TRACE) {
+        RL_CUDA(e, e->d_trace.reserve(RL_TRACE_CAP));
+        RL_CUDA(e, cudaMemsetAsync(e->d_trace.p, 0, RL_TRACE_CAP * sizeof(uint4), e->stream));
+    }
     if (cfg->flags & 2u) {  // RL_FLAG_PIPELINE
         e->pipeline = true;
         RL_CUDA(e, cudaStreamCreateWithFlags(&e->sp, cudaStreamNonBlocking));
@@ -819,6 +868,8 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_fl_next.release();
     e->d_items.release();
     e->d_kstats.release();
+    e->d_trace.release();
+    e->d_misc2.release();
     e->d_chain_status.release();
     e->d_chain_wcnt.release();
     e->d_chain_w.release();
@@ -904,6 +955,28 @@ int rl_profile_end(rl_engine* e, double* out_main_ms, uint64_t* out_main_launche
     if (out_main_ms) *out_main_ms = ms;
     if (out_main_launches) *out_main_launches = e->prof_events.size();
     e->prof_events.clear();
+    return RL_OK;
+}
+
+int rl_trace_dump(rl_engine* e, uint32_t cap, uint32_t* out_ev, uint32_t* out_seq, uint64_t* out_ns, uint32_t* out_count) {
+    if (!e || !out_count) return RL_FATAL;
+    *out_count = 0;
+    if (!e->d_trace.p) return RL_OK;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    RL_CUDA(e, cudaDeviceSynchronize());
+    uint32_t pos = 0;
+    RL_CUDA(e, cudaMemcpy(&pos, e->d_misc2.p, sizeof pos, cudaMemcpyDeviceToHost));
+    const uint32_t n = std::min<uint32_t>(pos, RL_TRACE_CAP);
+    std::vector<uint4> ev(n);
+    if (n) RL_CUDA(e, cudaMemcpy(ev.data(), e->d_trace.p, (size_t)n * sizeof(uint4), cudaMemcpyDeviceToHost));
+    const uint32_t m = std::min(n, cap);
+    for (uint32_t i = 0; i < m; i++) {
+        out_ev[i] = ev[i].x;
+        out_seq[i] = ev[i].y;
+        out_ns[i] = ((uint64_t)ev[i].w << 32) | ev[i].z;
+    }
+    *out_count = m;
+    RL_CUDA(e, cudaMemset(e->d_misc2.p, 0, sizeof(uint32_t)));
     return RL_OK;
 }
 
@@ -1225,6 +1298,7 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
         return fail(e, RL_FATAL, "out_stride %u < limits per namespace %u", out_stride, e->max_ns_limits);
     e->stats.batches++;
     e->stats.requests += n;
+    e->trace_seq = (uint32_t)e->stats.batches;
     if (mem == RL_MEM_DEVICE) {
         Outs o;
         o.limited = out_limited;

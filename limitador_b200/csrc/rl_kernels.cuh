@@ -38,7 +38,24 @@ struct RlDev {
     uint32_t* err;    // sticky max of RL_DEV_*
     uint32_t* flags;  // bit0: batch has multi-row requests
     unsigned long long* kstats;   // nullptr = no accounting; [0] chunks, [1] replay rounds, [2] chained chunks, [3] ordered chunks
+    uint4* trace;                 // nullptr = no tracing (RL_FLAG_TRACE): ring of {event id, call seq, globaltimer lo, hi}
+    uint32_t* trace_pos;
+    uint32_t seq;                 // call sequence number stamped into the events of this launch
 };
+
+// Device-side event trace (RL_FLAG_TRACE, rl_trace_dump): kernels stamp the GPU's nanosecond timer at their
+// first block's start and at their last block's end, so that the timeline of a pipelined step — which
+// spans several streams and, for sharded steps, several GPUs — can be read without a profiler.
+#define RL_TRACE_CAP 65536u
+enum { RL_EV_FRONT = 1, RL_EV_MAIN = 2, RL_EV_XCOUNT = 3, RL_EV_XSCATTER = 4, RL_EV_XWAIT = 5, RL_EV_XRETURN = 6,
+       RL_EV_XWAITV = 7, RL_EV_XGATHER = 8 };
+__device__ __forceinline__ void rl_trace(uint4* trace, uint32_t* pos, uint32_t ev, uint32_t end, uint32_t seq) {
+    if (trace == nullptr) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const uint32_t i = atomicAdd(pos, 1u) & (RL_TRACE_CAP - 1);
+    trace[i] = make_uint4(ev | (end << 8), seq, (uint32_t)t, (uint32_t)(t >> 32));
+}
 
 struct RlBatch {
     uint32_t n_acc;          // accesses of this batch (upper bound when n_dev != nullptr)
@@ -380,6 +397,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
     const uint32_t R = 1u << D.log2R;
 
     for (uint32_t i = tid; i < RL_PART_WARPS * P1 + P1 + 1; i += NT) wcnt[i] = 0;
+    if (tile == 0 && tid == 0) rl_trace(D.trace, D.trace_pos, RL_EV_FRONT, 0, D.seq);
     __syncthreads();
 
     // ---- pass 1: probe, count ---------------------------------------------------------------------
@@ -533,6 +551,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
         *B.ticket = 0;
         *B.scan_ctr = 0;  // re-arm for the next batch
         if (D.kstats != nullptr) atomicAdd(D.kstats + 16, rl_globaltimer_ns() - tk0);  // ns spent in this tail
+        rl_trace(D.trace, D.trace_pos, RL_EV_FRONT, 1, D.seq);
     }
 }
 
@@ -730,6 +749,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
     const bool write_out = (B.phase == RL_PHASE_COMMIT);
     const bool snapshot = Src::kCanBeMulti && (B.phase == RL_PHASE_SNAPSHOT);
 
+    if (blockIdx.x == 0 && tid == 0) rl_trace(D.trace, D.trace_pos, RL_EV_MAIN, 0, D.seq);
     const uint32_t n_items = *B.n_items;
     const uint32_t ntile = B.num_tiles;
     const uint32_t tsz = rl_tile_of(B, rl_batch_n(B));
@@ -746,6 +766,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             if (tid == 0 && atomicAdd(B.exit_ctr, 1u) == gridDim.x - 1) {
                 *B.exit_ctr = 0;
                 *B.ticket = 0;
+                rl_trace(D.trace, D.trace_pos, RL_EV_MAIN, 1, D.seq);
             }
             break;
         }

@@ -191,7 +191,7 @@ struct MLimit {
 
 // ---- the accepted expression grammar (see rl_match.h) -----------------------------------------
 inline bool is_ident_start(unsigned char c) { return c == '_' || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'); }
-inline bool is_word(unsigned char c) { return is_ident_start(c) || (c >= '0' && c <= '9') || c >= 0x80; }
+inline bool is_word(unsigned char c) { return is_ident_start(c) || (c >= '0' && c <= '9'); }  // CEL identifiers are ASCII
 inline void skip_ws(const char*& p) {
     while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r' || *p == '\f' || *p == '\v') p++;
 }
@@ -217,11 +217,14 @@ bool parse_operand(const char*& p, uint32_t& desc, std::string& key) {
             key.assign(s, q);
         } else if (*q == '[') {
             q++;
-            if (*q != '\'' && *q != '"') return false;
+            const char kq = *q;
+            if (kq != '\'' && kq != '"') return false;
             q++;
             const char* s = q;
-            while (*q && *q != '\'' && *q != '"') q++;
-            if (!*q || q == s) return false;
+            // the closing quote must be the opening one (CEL rejects descriptors[0]['k"] at parse time) and the
+            // key must not need CEL's escape processing, which this subset does not do: refuse instead
+            while (*q && *q != kq && *q != '\\') q++;
+            if (*q != kq || q == s) return false;
             key.assign(s, q);
             q++;
             if (*q != ']') return false;
@@ -235,7 +238,11 @@ bool parse_operand(const char*& p, uint32_t& desc, std::string& key) {
     }
     if (!is_ident_start((unsigned char)*p)) return false;
     const char* s = p;
-    while (is_word((unsigned char)*p) || *p == '.') p++;
+    while (is_word((unsigned char)*p)) p++;
+    // `req.method` is member access on the variable `req` in CEL, not a root binding named "req.method"
+    // (the reference would never apply such a limit: Predicate::test fails on the unbound `req`,
+    // limit/cel.rs:314-322); dotted keys are only reachable as descriptors[0]['req.method'].  Refused.
+    if (*p == '.') return false;
     key.assign(s, p);
     desc = RL_BIND_ROOT;
     return true;
@@ -254,8 +261,9 @@ bool parse_condition(const char* src, uint32_t& desc, std::string& key, bool& ne
     if (quote != '\'' && quote != '"') return false;
     p++;
     const char* s = p;
-    while (*p && *p != quote) p++;
-    if (!*p) return false;
+    // a literal that needs CEL's escape processing ("a\nb") would compare differently here: refused
+    while (*p && *p != quote && *p != '\\') p++;
+    if (*p != quote) return false;
     lit.assign(s, p);
     p++;
     skip_ws(p);
@@ -361,7 +369,9 @@ int match_one(const rl_matcher* m, uint32_t ns_id, const rl_binding* binds, uint
                 break;
             }
         if (!ok) continue;
-        if (n_out >= cap) return RL_FATAL;
+        // the engine takes at most RL_MAX_COUNTERS_PER_REQUEST counters per request: refuse here, before
+        // anything is enqueued, instead of letting the device resolve fail the batch half-applied
+        if (n_out >= cap || n_out >= RL_MAX_COUNTERS_PER_REQUEST) return RL_FATAL;
         rl_counter& c = out[n_out++];
         c.limit_id = lid;
         c._pad = 0;
@@ -404,10 +414,24 @@ void rl_matcher_destroy(rl_matcher* m) { delete m; }
 
 const char* rl_matcher_last_error(rl_matcher* m) { return m ? m->last_error.c_str() : "null matcher"; }
 
+int rl_matcher_last_error_copy(rl_matcher* m, char* out, uint32_t cap) {
+    if (!m || !out || !cap) return RL_FATAL;
+    std::lock_guard<std::mutex> g(m->err_mu);
+    snprintf(out, cap, "%s", m->last_error.c_str());
+    return RL_OK;
+}
+
 int rl_matcher_add_limit(rl_matcher* m, const char* ns, uint64_t max_value, uint64_t seconds,
                          const char* const* conditions, uint32_t n_cond, const char* const* variables, uint32_t n_var,
                          const char* name, rl_limit_desc* out_desc) {
+    return rl_matcher_add_limit_ex(m, ns, max_value, seconds, conditions, n_cond, variables, n_var, name, 0, out_desc, nullptr);
+}
+
+int rl_matcher_add_limit_ex(rl_matcher* m, const char* ns, uint64_t max_value, uint64_t seconds,
+                            const char* const* conditions, uint32_t n_cond, const char* const* variables, uint32_t n_var,
+                            const char* name, int keep_existing, rl_limit_desc* out_desc, int* out_existed) {
     if (!m || !ns || !out_desc || (n_cond && !conditions) || (n_var && !variables)) return RL_FATAL;
+    if (out_existed) *out_existed = 0;
     std::unique_lock<std::shared_mutex> lock(m->mu);
     MLimit L;
     L.ns = ns;
@@ -446,9 +470,14 @@ int rl_matcher_add_limit(rl_matcher* m, const char* ns, uint64_t max_value, uint
         // update_limit (storage/mod.rs:67-83): same identity, new max_value / name; a deleted one comes back
         lid = it->second;
         MLimit& E = m->limits[lid];
-        E.max_value = max_value;
-        E.name = L.name;
-        E.has_name = L.has_name;
+        if (out_existed) *out_existed = E.deleted ? 0 : 1;
+        // Storage::add_limit is a HashSet::insert: on an equal (live) element it is a no-op and the OLD
+        // max_value / name stay (storage/mod.rs:60-65); only update_limit swaps them (:67-83)
+        if (!(keep_existing && !E.deleted)) {
+            E.max_value = max_value;
+            E.name = L.name;
+            E.has_name = L.has_name;
+        }
         if (E.deleted) {  // deleted and added again: it is the namespace's newest limit
             auto& order = m->ns_limits[E.ns_id];
             order.erase(std::remove(order.begin(), order.end(), lid), order.end());
@@ -509,6 +538,20 @@ const char* rl_matcher_limit_name(rl_matcher* m, uint32_t limit_id) {
     return m->limits[limit_id].name.c_str();
 }
 
+int rl_matcher_limit_name_copy(rl_matcher* m, uint32_t limit_id, char* out, uint32_t cap, int* out_has_name) {
+    if (!m || !out || !cap) return RL_FATAL;
+    std::shared_lock<std::shared_mutex> lock(m->mu);
+    out[0] = 0;
+    if (out_has_name) *out_has_name = 0;
+    if (limit_id >= m->limits.size()) return mfail(m, "unknown limit_id %u", limit_id);
+    const MLimit& L = m->limits[limit_id];
+    if (!L.has_name) return RL_OK;
+    if (L.name.size() + 1 > cap) return mfail(m, "limit name needs %zu bytes", L.name.size() + 1);
+    memcpy(out, L.name.c_str(), L.name.size() + 1);
+    if (out_has_name) *out_has_name = 1;
+    return RL_OK;
+}
+
 int rl_matcher_counters(rl_matcher* m, uint32_t ns_id, const rl_binding* binds, uint32_t n_binds, rl_counter* out_ctrs,
                         uint32_t cap, uint32_t* out_n) {
     if (!m || !out_n || (n_binds && !binds) || (cap && !out_ctrs)) return RL_FATAL;
@@ -516,7 +559,7 @@ int rl_matcher_counters(rl_matcher* m, uint32_t ns_id, const rl_binding* binds, 
     uint64_t n = 0;
     const int r = match_one(m, ns_id, binds, n_binds, out_ctrs, cap, n, tls_scratch);
     *out_n = (uint32_t)n;
-    if (r) return mfail(m, "more than %u counters apply to one request", cap);
+    if (r) return mfail(m, "more than %u counters apply to one request (engine limit %d)", cap, RL_MAX_COUNTERS_PER_REQUEST);
     return RL_OK;
 }
 
@@ -532,8 +575,8 @@ int rl_matcher_counters_batch(rl_matcher* m, uint64_t n, const uint32_t* ns_id, 
         const int r = match_one(m, ns_id[i], binds + bind_off[i], bind_off[i + 1] - bind_off[i], out_ctrs + total,
                                 cap - total, k, s);
         if (r || total + k > 0xFFFFFFFFull) {
-            return mfail(m, "counter capacity %llu exhausted at request %llu", (unsigned long long)cap,
-                         (unsigned long long)i);
+            return mfail(m, "counter capacity %llu exhausted, or more than %d counters apply, at request %llu",
+                         (unsigned long long)cap, RL_MAX_COUNTERS_PER_REQUEST, (unsigned long long)i);
         }
         total += k;
         out_ctr_off[i + 1] = (uint32_t)total;

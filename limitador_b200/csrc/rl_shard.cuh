@@ -25,6 +25,8 @@ struct RlXCtl {  // one per (buffer, peer rank) in every slab
 };
 
 struct RlXchg {
+    uint4* trace;                      // RL_FLAG_TRACE (see rl_kernels.cuh), else nullptr
+    uint32_t* trace_pos;
     uint8_t* base[RL_XCHG_MAX_WORLD];  // slab of every rank, as mapped in this process
     unsigned long long off_recs, off_vin, off_ctl;
     uint32_t world, rank, cap, depth;
@@ -67,7 +69,8 @@ __device__ __forceinline__ bool rl_wait_flag(const uint32_t* p, uint32_t want) {
 // per-owner totals.  tile_cnt: [tiles][32], totals: [32].
 __global__ void __launch_bounds__(RL_PART_THREADS) k_xcount(const rl_record* __restrict__ recs, uint32_t n,
                                                            uint32_t world, uint32_t tile, uint32_t* tile_cnt,
-                                                           uint32_t* totals, uint32_t* ctr) {
+                                                           uint32_t* totals, uint32_t* ctr, uint4* trace,
+                                                           uint32_t* trace_pos, uint32_t step) {
     __shared__ uint32_t wcnt[RL_PART_WARPS][32];
     __shared__ uint32_t s_last;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_xcount(const rl_record* __r
     const uint32_t slice = tile / RL_PART_WARPS;
     const uint32_t s0 = min(t0 + warp * slice, t1), s1 = min(s0 + slice, t1);
     wcnt[warp][lane] = 0;
+    if (blockIdx.x == 0 && tid == 0) rl_trace(trace, trace_pos, RL_EV_XCOUNT, 0, step);
     __syncthreads();
     for (uint32_t b = s0; b < s1; b += 32) {
         const uint32_t a = b + lane;
@@ -109,7 +113,10 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_xcount(const rl_record* __r
         }
         totals[tid] = run;
     }
-    if (tid == 0) *ctr = 0;
+    if (tid == 0) {
+        *ctr = 0;
+        rl_trace(trace, trace_pos, RL_EV_XCOUNT, 1, step);
+    }
 }
 
 // Stable scatter of my records into the owners' inboxes (peer stores over NVLink); the last block
@@ -189,7 +196,10 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_xscatter(RlXchg X, const rl
         c->cnt = totals[tid];
         rl_st_release_sys(&c->rflag, step + 1);
     }
-    if (tid == 0) *ctr = 0;
+    if (tid == 0) {
+        *ctr = 0;
+        rl_trace(X.trace, X.trace_pos, RL_EV_XSCATTER, 1, step);
+    }
 }
 
 // Owner side: wait for the step's blocks of every source, publish the fills as an exclusive prefix
@@ -199,6 +209,7 @@ __global__ void __launch_bounds__(32) k_xwait(RlXchg X, uint32_t buf, uint32_t s
     const uint32_t lane = threadIdx.x;
     uint32_t cnt = 0;
     bool ok = true;
+    if (lane == 0) rl_trace(X.trace, X.trace_pos, RL_EV_XWAIT, 0, step);
     if (lane < X.world) {
         const RlXCtl* c = X.ctl(X.rank, buf, lane);
         ok = rl_wait_flag(&c->rflag, step + 1);
@@ -208,7 +219,10 @@ __global__ void __launch_bounds__(32) k_xwait(RlXchg X, uint32_t buf, uint32_t s
             ok = false;
         }
     }
-    if (!ok) atomicMax(err, (uint32_t)RL_DEV_EXCHANGE);
+    if (!ok) {
+        atomicMax(err, (uint32_t)RL_DEV_EXCHANGE);
+        atomicCAS(err + 7, 0u, (1u << 28) | (lane << 20) | (step & 0xFFFFFu));  // detail: k_xwait, source rank, step
+    }
     uint32_t x = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -217,7 +231,10 @@ __global__ void __launch_bounds__(32) k_xwait(RlXchg X, uint32_t buf, uint32_t s
     }
     const uint32_t total = __shfl_sync(0xffffffffu, x, X.world - 1);
     if (total > n_max) {  // more records than the engine was sized for (rl_config.max_batch): refuse the step
-        if (lane == 0) atomicMax(err, (uint32_t)RL_DEV_EXCHANGE);
+        if (lane == 0) {
+            atomicMax(err, (uint32_t)RL_DEV_EXCHANGE);
+            atomicCAS(err + 7, 0u, (3u << 28) | (step & 0xFFFFFu));  // detail: inbox larger than max_batch
+        }
         x = 0;
         cnt = 0;
     }
@@ -225,6 +242,7 @@ __global__ void __launch_bounds__(32) k_xwait(RlXchg X, uint32_t buf, uint32_t s
     if (lane == X.world - 1) {
         seg_prefix[X.world] = x;
         *n_dev = x;
+        rl_trace(X.trace, X.trace_pos, RL_EV_XWAIT, 1, step);
     }
 }
 
@@ -250,23 +268,30 @@ __global__ void __launch_bounds__(256) k_xreturn(RlXchg X, const uint8_t* __rest
     if (!s_last) return;
     __threadfence_system();
     if (tid < X.world) rl_st_release_sys(&X.ctl(tid, buf, X.rank)->vflag, step + 1);
-    if (tid == 0) *ctr = 0;
+    if (tid == 0) {
+        *ctr = 0;
+        rl_trace(X.trace, X.trace_pos, RL_EV_XRETURN, 1, step);
+    }
 }
 
-// Source side: wait for every owner's verdicts of the step, then put them back in request order.
-__global__ void __launch_bounds__(256) k_xcollect(RlXchg X, uint32_t n, const uint32_t* __restrict__ dest, uint32_t buf,
-                                                 uint32_t step, uint8_t* out, uint32_t* err) {
-    __shared__ uint32_t s_ok;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_ok = 1;
-    __syncthreads();
-    if (tid < X.world && !rl_wait_flag(&X.ctl(X.rank, buf, tid)->vflag, step + 1)) s_ok = 0;
-    __syncthreads();
-    if (!s_ok) {
-        if (tid == 0) atomicMax(err, (uint32_t)RL_DEV_EXCHANGE);
-        return;
+// Source side: wait for every owner's verdicts of the step ...
+// Only single-warp kernels ever spin.  A spinning CTA pins its SM: the SM cannot change its shared-memory
+// carveout while a CTA is resident, so a grid of spinners spread over all SMs keeps k_front / k_main (which
+// need a larger carveout) from being scheduled at all — the very kernels whose results the spinners wait for.
+__global__ void __launch_bounds__(32) k_xwaitv(RlXchg X, uint32_t buf, uint32_t step, uint32_t* err) {
+    const uint32_t lane = threadIdx.x;
+    if (lane == 0) rl_trace(X.trace, X.trace_pos, RL_EV_XWAITV, 0, step);
+    if (lane < X.world && !rl_wait_flag(&X.ctl(X.rank, buf, lane)->vflag, step + 1)) {
+        atomicMax(err, (uint32_t)RL_DEV_EXCHANGE);
+        atomicCAS(err + 7, 0u, (2u << 28) | (lane << 20) | (step & 0xFFFFFu));  // detail: verdicts, owner rank, step
     }
-    for (uint32_t i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
+    __syncwarp();
+    if (lane == 0) rl_trace(X.trace, X.trace_pos, RL_EV_XWAITV, 1, step);
+}
+// ... then put them back in request order.
+__global__ void __launch_bounds__(256) k_xgather(RlXchg X, uint32_t n, const uint32_t* __restrict__ dest, uint32_t buf,
+                                                uint8_t* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t d = dest[i];
         out[i] = __ldcg(X.vin(X.rank, buf, d >> 27) + (d & 0x07FFFFFFu));
     }

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "rl_front_create", "rl_front_destroy", "rl_front_check_and_update", "rl_front_stats",
     "rl_shard_create", "rl_shard_destroy", "rl_shard_ipc_handle", "rl_shard_connect_ipc", "rl_shard_connect_ptrs",
     "rl_shard_slab", "rl_shard_slab_bytes", "rl_shard_send", "rl_shard_decide", "rl_shard_collect", "rl_shard_step",
-    "rl_shard_flush",
+    "rl_shard_flush", "rl_shard_debug", "rl_trace_dump",
 ]
 
 
@@ -136,6 +136,8 @@ def load_library(path: str | None = None):
     L.rl_shard_collect.argtypes = [vp, C.POINTER(vp)]
     L.rl_shard_step.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]
     L.rl_shard_flush.argtypes = [vp]
+    L.rl_shard_debug.argtypes = [vp, vp]
+    L.rl_trace_dump.argtypes = [vp, u32, vp, vp, vp, vp]
     if path == _build.LIB_PATH:
         _lib = L
     return L
@@ -206,6 +208,16 @@ class Engine:
         d = {f[0]: getattr(s, f[0]) for f in RlStats._fields_ if not f[0].startswith("_")}
         d["phase_cycles"] = list(d["phase_cycles"])
         return d
+
+    def trace_dump(self, cap: int = 65536):
+        """RL_FLAG_TRACE: list of (event name, is_end, seq, gpu_ns), in ring order; clears the ring."""
+        names = {1: "front", 2: "main", 3: "xcount", 4: "xscatter", 5: "xwait", 6: "xreturn", 7: "xwaitv", 8: "xgather"}
+        ev = np.zeros(cap, dtype=np.uint32)
+        seq = np.zeros(cap, dtype=np.uint32)
+        ns = np.zeros(cap, dtype=np.uint64)
+        cnt = C.c_uint32(0)
+        self._check(self._lib.rl_trace_dump(self._h, cap, _p(ev), _p(seq), _p(ns), C.byref(cnt)))
+        return [(names.get(int(ev[i]) & 0xFF, "?"), int(ev[i]) >> 8, int(seq[i]), int(ns[i])) for i in range(cnt.value)]
 
     def fence_call(self, age: int):
         """Order only the pipelined call issued `age` calls ago (0 = last, 1 = the one before)."""
@@ -477,3 +489,11 @@ class Shard:
 
     def flush(self):
         self._eng._check(self._lib.rl_shard_flush(self._h))
+
+    def debug(self):
+        """{'ctl': [buf][peer] -> (fill, record flag, verdict flag), 'sent', 'decided', 'collected'} of this rank."""
+        depth = self.lag + 1
+        out = np.zeros(depth * self.world * 4 + 3, dtype=np.uint32)
+        self._lib.rl_shard_debug(self._h, _p(out))
+        ctl = out[:-3].reshape(depth, self.world, 4)[:, :, :3].tolist()
+        return {"ctl": ctl, "sent": int(out[-3]), "decided": int(out[-2]), "collected": int(out[-1])}

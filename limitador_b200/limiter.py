@@ -26,9 +26,14 @@ import numpy as np
 
 from . import engine as _eng
 
-_OPERAND = r"(?:descriptors\[(\d+)\](?:\.([A-Za-z_][\w]*)|\[['\"]([^'\"]+)['\"]\])|([A-Za-z_][\w.]*))"
-_PRED = re.compile(r"^\s*" + _OPERAND + r"\s*(==|!=)\s*(?:'([^']*)'|\"([^\"]*)\")\s*$")
-_VAR = re.compile(r"^\s*" + _OPERAND + r"\s*$")
+# The table-driven subset (rl_match.cpp mirrors these rules): ASCII identifiers; a ROOT operand has no dots
+# (`req.method` is CEL member access on the unbound variable `req`: the reference never applies such a limit,
+# limit/cel.rs:314-322); bracket keys close with the quote they opened with; no backslash in keys or literals
+# (CEL escape processing is not done here, so such expressions are refused instead of reinterpreted).
+_OPERAND = (r"(?:descriptors\[(\d+)\](?:\.([A-Za-z_][A-Za-z0-9_]*)|\[(?:'([^'\\]+)'|\"([^\"\\]+)\")\])"
+            r"|([A-Za-z_][A-Za-z0-9_]*))")
+_PRED = re.compile(r"^\s*" + _OPERAND + r"\s*(==|!=)\s*(?:'([^'\\]*)'|\"([^\"\\]*)\")\s*$", re.ASCII)
+_VAR = re.compile(r"^\s*" + _OPERAND + r"\s*$", re.ASCII)
 
 
 class Context(dict):
@@ -39,7 +44,8 @@ class Context(dict):
         self.descriptors = descriptors or []
 
     def _lookup(self, m_groups) -> Optional[str]:
-        idx, attr, key, ident = m_groups
+        idx, attr, key1, key2, ident = m_groups
+        key = key1 if key1 is not None else key2
         if ident is not None:
             return self.get(ident)
         i = int(idx)
@@ -90,9 +96,9 @@ class Limit:
         for c in self.conditions:
             m = _PRED.match(c)
             g = m.groups()
-            val = _operand_value(ctx, g[0:4])
-            lit = g[5] if g[5] is not None else g[6]
-            ok = (val == lit) if g[4] == "==" else (val is not None and val != lit)
+            val = _operand_value(ctx, g[0:5])
+            lit = g[6] if g[6] is not None else g[7]
+            ok = (val == lit) if g[5] == "==" else (val is not None and val != lit)
             if not ok:
                 return False
         return self.resolve_variables(ctx) is not None

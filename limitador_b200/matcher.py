@@ -20,6 +20,7 @@ MATCH_SYMBOLS = (
     "rl_matcher_create", "rl_matcher_destroy", "rl_matcher_last_error", "rl_matcher_add_limit",
     "rl_matcher_delete_limit", "rl_matcher_namespace_id", "rl_matcher_limit_name", "rl_matcher_counters",
     "rl_matcher_counters_batch", "rl_counter_key", "rl_matcher_response_headers",
+    "rl_matcher_add_limit_ex", "rl_matcher_limit_name_copy", "rl_matcher_last_error_copy",
 )
 
 
@@ -43,6 +44,10 @@ def _lib():
     L.rl_matcher_last_error.restype = C.c_char_p
     L.rl_matcher_add_limit.argtypes = [vp, C.c_char_p, u64, u64, C.POINTER(C.c_char_p), u32, C.POINTER(C.c_char_p), u32,
                                        C.c_char_p, vp]
+    L.rl_matcher_add_limit_ex.argtypes = [vp, C.c_char_p, u64, u64, C.POINTER(C.c_char_p), u32, C.POINTER(C.c_char_p), u32,
+                                          C.c_char_p, C.c_int, vp, C.POINTER(C.c_int)]
+    L.rl_matcher_limit_name_copy.argtypes = [vp, u32, C.c_char_p, u32, C.POINTER(C.c_int)]
+    L.rl_matcher_last_error_copy.argtypes = [vp, C.c_char_p, u32]
     L.rl_matcher_delete_limit.argtypes = [vp, u32]
     L.rl_matcher_namespace_id.argtypes = [vp, C.c_char_p, C.POINTER(u32)]
     L.rl_matcher_limit_name.argtypes = [vp, u32]
@@ -111,6 +116,18 @@ class Matcher:
                                                    desc.ctypes.data))
         return desc[0]
 
+    def add_limit_keep(self, namespace: str, max_value: int, seconds: int, conditions: Iterable[str] = (),
+                       variables: Iterable[str] = (), name: Optional[str] = None):
+        """Storage::add_limit (storage/mod.rs:60-65): an equal live limit keeps its max_value and name.
+        -> (LIMIT_DESC_DTYPE row as the limit now stands, existed)."""
+        conds, vars_ = list(conditions), list(variables)
+        desc = np.zeros(1, dtype=_eng.LIMIT_DESC_DTYPE)
+        existed = C.c_int(0)
+        self._check(self._lib.rl_matcher_add_limit_ex(self._h, namespace.encode(), max_value, seconds, _strs(conds), len(conds),
+                                                      _strs(vars_), len(vars_), None if name is None else name.encode(), 1,
+                                                      desc.ctypes.data, C.byref(existed)))
+        return desc[0], bool(existed.value)
+
     def delete_limit(self, limit_id: int):
         self._check(self._lib.rl_matcher_delete_limit(self._h, limit_id))
 
@@ -119,8 +136,10 @@ class Matcher:
         return out.value if self._lib.rl_matcher_namespace_id(self._h, namespace.encode(), C.byref(out)) == 0 else None
 
     def limit_name(self, limit_id: int) -> Optional[str]:
-        s = self._lib.rl_matcher_limit_name(self._h, limit_id)
-        return None if s is None else s.decode()
+        buf = C.create_string_buffer(1024)
+        has = C.c_int(0)
+        self._check(self._lib.rl_matcher_limit_name_copy(self._h, limit_id, buf, 1024, C.byref(has)))
+        return buf.value.decode() if has.value else None
 
     def counters(self, ns_id: int, root: Optional[Dict[str, str]] = None,
                  descriptors: Optional[List[Dict[str, str]]] = None, cap: int = 64) -> np.ndarray:

@@ -89,7 +89,7 @@ def random_limit(rng, namespaces, keys, values):
             return f"descriptors[{int(rng.integers(0, 2))}].{k}"
         if style == 2:
             return f"descriptors[{int(rng.integers(0, 2))}]['{k}']"
-        return f"req.{k}"
+        return f"descriptors[{int(rng.integers(0, 2))}]['req.{k}']"  # a dotted key is only reachable through the bracket form
     conds = []
     for _ in range(int(rng.integers(0, 4))):
         op = "==" if rng.random() < 0.7 else "!="
@@ -107,10 +107,12 @@ def random_context(rng, keys, values):
         if rng.random() < 0.5:
             root[k] = str(rng.choice(values))
         if rng.random() < 0.3:
-            root[f"req.{k}"] = str(rng.choice(values))
+            root[f"req.{k}"] = str(rng.choice(values))  # never matched: root operands have no dots
     descriptors = []
     for _ in range(int(rng.integers(0, 3))):
-        descriptors.append({k: str(rng.choice(values)) for k in keys if rng.random() < 0.5})
+        d = {k: str(rng.choice(values)) for k in keys if rng.random() < 0.5}
+        d.update({f"req.{k}": str(rng.choice(values)) for k in keys if rng.random() < 0.3})
+        descriptors.append(d)
     return root, descriptors
 
 
@@ -171,6 +173,62 @@ def test_limits_sharing_a_variable_set_share_the_counter_key_and_the_varset_id()
     assert (int(got["key_lo"][0]), int(got["key_hi"][0])) == MT.counter_key({"descriptors[0].user": "bob"})
     got = m.counters(int(a["ns_id"]), None, [{"user": "bob", "method": "PUT"}])
     assert got["limit_id"].tolist() == [0, 2]
+
+
+def test_cel_shapes_with_other_semantics_in_the_reference_are_refused():
+    """expressions the table-driven subset would silently give a different meaning than CEL.
+    * a dotted ROOT operand: CEL parses `req.method` as member access on the variable `req`; with the binding
+      {"req.method": "GET"} the reference's Predicate::test fails on the unbound `req` (limit/cel.rs:314-322) and
+      the limit never applies — so it must not be matched against a root key "req.method" here;
+    * escapes: `x == "a\\nb"` compares against a<LF>b in CEL, not against backslash-n;
+    * `descriptors[0]['k"]` is a CEL parse error;  * identifiers are ASCII."""
+    m = MT.Matcher()
+    for conds, vars_ in ((["req.method == 'GET'"], []), ([], ["req.method"]), (["x == 'a\\nb'"], []), (['x == "a\\"b"'], []),
+                         (["descriptors[0]['k\"] == 'v'"], []), ([], ["descriptors[0][\"k']"]), ([], ["descriptors[0]['a\\nb']"]),
+                         (["n\u00e9 == 'v'"], []), ([], ["descriptors[0].k\u00e9"])):
+        with pytest.raises(MT.MatcherError):
+            m.add_limit("ns", 5, 60, conds, vars_)
+        with pytest.raises(ValueError):
+            LM.Limit("ns", 5, 60, conds, vars_)
+    assert m.namespace_id("ns") is None
+    # the bracket form is how a dotted key IS reached, and non-ASCII bytes are fine inside literals and bracket keys
+    d = m.add_limit("ns", 5, 60, ["descriptors[0]['req.method'] == 'G\u00c9T'"], ["descriptors[0]['cl\u00e9']"])
+    got = m.counters(int(d["ns_id"]), None, [{"req.method": "G\u00c9T", "cl\u00e9": "7"}])
+    assert got["limit_id"].tolist() == [int(d["limit_id"])]
+    lim = LM.Limit("ns", 5, 60, ["descriptors[0]['req.method'] == 'G\u00c9T'"], ["descriptors[0]['cl\u00e9']"])
+    assert lim.applies(LM.Context({}, [{"req.method": "G\u00c9T", "cl\u00e9": "7"}]))
+    assert not lim.applies(LM.Context({"req.method": "G\u00c9T"}, [{"cl\u00e9": "7"}]))
+
+
+def test_add_limit_keeps_an_equal_live_limit_update_limit_replaces_it():
+    """ADVICE r1 / storage/mod.rs:60-83: Storage::add_limit is HashSet::insert (no-op on an equal element: old
+    max_value and name stay); update_limit swaps them.  The C API tells the two apart (rl_matcher_add_limit_ex)."""
+    m = MT.Matcher()
+    d0 = m.add_limit("ns", 5, 60, ["a == 'x'"], ["u"], name="first")
+    d1, existed = m.add_limit_keep("ns", 9, 60, ["a == 'x'"], ["u"], name="second")
+    assert existed and int(d1["limit_id"]) == int(d0["limit_id"]) and int(d1["max_value"]) == 5
+    assert m.limit_name(int(d0["limit_id"])) == "first"
+    d2 = m.add_limit("ns", 9, 60, ["a == 'x'"], ["u"], name="second")  # update_limit
+    assert int(d2["max_value"]) == 9 and m.limit_name(int(d0["limit_id"])) == "second"
+    d3, existed = m.add_limit_keep("ns", 1, 61, ["a == 'x'"], ["u"])
+    assert not existed and int(d3["limit_id"]) != int(d0["limit_id"]) and m.limit_name(int(d3["limit_id"])) is None
+    m.delete_limit(int(d0["limit_id"]))
+    d4, existed = m.add_limit_keep("ns", 3, 60, ["a == 'x'"], ["u"], name="again")  # deleted: a fresh insert
+    assert not existed and int(d4["max_value"]) == 3 and m.limit_name(int(d0["limit_id"])) == "again"
+
+
+def test_more_counters_than_the_engine_takes_per_request_is_refused_by_the_matcher():
+    """RL_MAX_COUNTERS_PER_REQUEST = 16 is an engine limit; 17 applicable limits are refused by the
+    matcher before anything is enqueued (the device-side resolve would fail the whole batch half-applied)."""
+    m = MT.Matcher()
+    for i in range(17):
+        d = m.add_limit("big", 5, 60 + i, [], [])
+    with pytest.raises(MT.MatcherError):
+        m.counters(int(d["ns_id"]), {}, None, cap=64)
+    m2 = MT.Matcher()
+    for i in range(16):
+        d = m2.add_limit("ok", 5, 60 + i, [], [])
+    assert len(m2.counters(int(d["ns_id"]), {}, None, cap=64)) == 16
 
 
 def test_too_many_counters_is_an_error_not_a_truncation():
@@ -318,9 +376,12 @@ def test_parser_accepts_exactly_what_the_python_mirror_accepts():
     m = MT.Matcher()
     n_acc_c = n_acc_v = 0
     operands = ["a", "b_1", "req.path", "descriptors[0].k", "descriptors[12]['k.v']", 'descriptors[1]["x"]', "descriptors[0]",
-                "descriptors[0].9", "descriptors[x].k", "descriptors[0]['']", "9z", "_u", "é", "descriptors", "a.b.c", "a b"]
+                "descriptors[0].9", "descriptors[x].k", "descriptors[0]['']", "9z", "_u", "é", "descriptors", "a.b.c", "a b",
+                "descriptors[0]['k\"]", "descriptors[0][\"k']", "descriptors[0]['a\\nb']", "aé", "descriptors[0].ké",
+                'descriptors[0]["it\'s"]', "req.method"]
     ops = ["==", "!=", " == ", "\t!= ", "=", "!==", "<", ""]
-    lits = ["'lit'", '"lit"', "''", "'x y'", "'unterminated", "bare", "'a'b'", '"q\'q"', "'tail' x", ""]
+    lits = ["'lit'", '"lit"', "''", "'x y'", "'unterminated", "bare", "'a'b'", '"q\'q"', "'tail' x", "",
+            "'a\\nb'", '"a\\"b"', "'\\'", '"tab\there"', "'é'"]
     for i in range(4000):
         if rng.random() < 0.6:  # near-valid: operand op literal with optional padding
             pad = [" ", "", "  ", "\t"]
