@@ -175,6 +175,148 @@ def sharded_parity(dist, world, rank, dev, eng, limits, recs_steps, out_steps, o
     return res
 
 
+def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
+    """A short pass of another BASELINE.json config, reported under `extra` in the one JSON line:
+    C3 (configs[2], single GPU), C4 / C5 (configs[3], configs[4]: namespace-sharded over all ranks).
+    Same call path as the headline (C-ABI record calls; peer exchange at N>1), device-resident batches,
+    CUDA-event timing, max over ranks; a parity leg against the oracle first (verdicts + tables)."""
+    import torch
+    from limitador_b200 import Engine, exchange, streams
+    from limitador_b200.engine import MEM_DEVICE, RECORD_DTYPE, Shard
+    t_all = time.perf_counter()
+    hot = name == "C5"
+    if name == "C3":
+        batch = args.extra_batch or (1 << 20)
+        limits = streams.c3_uniform_1limit(batch=1, n_keys=16).limits
+        cells, cap, L = 1, 1 << 25, 1
+        K, Wx = 30, 4
+        gen = lambda n: streams.c3_device_stream(n, batch, dev, n_keys=16_000_000)
+        desc = f"C3: 1 limit (100/60s), 16000000 keys uniform, batch={batch}, delta=1, reference fixed-window semantics"
+    else:
+        batch = args.extra_batch or (1 << 20)
+        n_keys, n_ns = 16_000_000 * world, 10_000
+        limits = streams.c4_namespace_sharded(batch=1, n_keys=n_keys, n_ns=n_ns, hot=hot).limits
+        cells, cap, L = 7, 1 << 25, None
+        K, Wx = 20, 3
+        gen = lambda n: streams.c4_device_stream(n, batch, dev, n_keys=n_keys, n_ns=n_ns, hot=hot, seed=streams.SEED + 1000 * rank)
+        desc = (f"{name}: {n_ns} namespaces x 1-4 limits, {n_keys} keys, "
+                + ("Zipf(0.7) keys with 50% of the traffic on 100 fixed keys (max 2^32: they keep incrementing)" if hot else
+                   "namespace popularity Zipf(1.0), keys uniform inside a namespace")
+                + f", batch={batch}/GPU, delta=1")
+    S_par = 2 if world > 1 else 3
+    total = S_par + Wx + 2 * K
+    recs = gen(total)
+    out = torch.zeros((total, batch), dtype=torch.uint8, device=dev)
+    max_batch = batch if world == 1 else min(world, 4) * batch  # an owner may receive up to 4 source batches in a step
+    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, max_counters=max_batch, device=local_rank, flags=2)
+    eng.limits_set(limits)
+    torch.cuda.synchronize()
+    eng.set_stream(stream.cuda_stream)
+    shard = None
+    if world > 1:
+        shard = Shard(eng, rank, world, batch, args.exchange_lag)
+        mine = torch.frombuffer(bytearray(shard.ipc_handle()), dtype=torch.uint8).to(dev)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine)
+        shard.connect_ipc(bytes(allh.cpu().numpy().tobytes()))
+        dist.barrier()
+
+    def step(s):
+        if shard is not None:
+            shard.step(batch, recs[s].data_ptr(), out[s].data_ptr())
+        else:
+            eng.check_and_update_records_ptr(batch, recs[s].data_ptr(), out[s].data_ptr(), MEM_DEVICE, stride=cells)
+
+    def finish():
+        if shard is not None:
+            shard.flush()
+        eng.fence()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity leg -------------------------------------------------------------------------------------
+    for s in range(S_par):
+        step(s)
+    finish()
+    eng.sync()
+    if world > 1:
+        par = sharded_parity(dist, world, rank, dev, eng, limits, recs[:S_par], out[:S_par], exchange.owner_of)
+    else:
+        from oracle import binding as ob
+        o = ob.Oracle(1 << 22)
+        for d in limits:
+            o.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+        h = recs[:S_par].cpu().numpy()
+        mism = 0
+        for st in range(S_par):
+            mism += int((o.batch_records(0, h[st].view(RECORD_DTYPE).reshape(-1))[0] != out[st].cpu().numpy()).sum())
+        want, got = table_digest(*o.dump_arrays()), table_digest(*eng.dump_arrays(cap=1 << 24))
+        par = {"steps": S_par, "decisions": S_par * batch, "gpu_verdict_mismatches": mism, "counters": want[0],
+               "table_mismatch_ranks": [] if tuple(want) == tuple(got) else [{"rank": 0, "oracle": list(want), "gpu": list(got)}]}
+    # per-owner load of one step (SURVEY §8e "Skew"): records every owner receives, max / mean
+    imbalance = None
+    if world > 1:
+        n_ns_all = int(limits["ns_id"].max()) + 1
+        lut = torch.tensor([exchange.owner_of(ns, world) for ns in range(n_ns_all)], dtype=torch.int64, device=dev)
+        load = torch.bincount(lut[recs[S_par, :, 0] & 0xFFFFFFFF], minlength=world).to(torch.float64)
+        dist.all_reduce(load)
+        imbalance = {"owner_load_max_over_mean": float(load.max() / load.mean()), "owner_load": [int(x) for x in load.tolist()]}
+    # ---- warm-up, timed pass, (N=1) k_main pass ------------------------------------------------------------
+    for s in range(S_par, S_par + Wx):
+        step(s)
+    finish()
+    eng.sync()
+
+    def timed(first, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(first, first + n):
+            step(s)
+        finish()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ms_a = timed(S_par + Wx, K)
+    eng.sync()
+    res = {"config": desc, "value": world * batch * K / (ms_a * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wx,
+           "ms_per_step": ms_a / K, "parity": par, "table_rows": cap, "row_bytes": 16 * (1 + cells)}
+    if imbalance:
+        res["imbalance"] = imbalance
+    if world == 1 and L is not None:
+        eng.profile_begin()
+        ms_b = timed(S_par + Wx + K, K)
+        main_ms, main_launches = eng.profile_end()
+        lim_b = out[S_par + Wx + K:S_par + Wx + 2 * K].cpu().numpy().reshape(-1)
+        allowed = int((lim_b == 0).sum())
+        alg = streams.algorithmic_bytes(len(lim_b), len(lim_b) * L, allowed * L)  # L = 1: every decision examines its one counter
+        peak, peak_src = peaks()
+        k_ach = alg / max(main_launches, 1) / (main_ms / max(main_launches, 1) * 1e-3) / 1e9
+        s_ach = alg / K / (ms_a / K * 1e-3) / 1e9
+        res["roofline"] = {"bound": "hbm", "kernel": f"k_main<{cells},{cells},RecordSrc,0,128,false>", "achieved": k_ach, "peak": peak,
+                           "unit": "GB/s", "frac": k_ach / peak, "peak_source": peak_src, "alg_bytes_per_launch": alg / max(main_launches, 1),
+                           "avg_launch_ms": main_ms / max(main_launches, 1), "kernel_share_of_step": main_ms / ms_b,
+                           "whole_step_achieved": s_ach, "whole_step_frac": s_ach / peak, "allowed_frac": allowed / len(lim_b)}
+    res["hot_rows"] = eng.stats().get("hot_rows")
+    res["wall_s"] = round(time.perf_counter() - t_all, 1)
+    if shard is not None:
+        shard.close()
+    eng.close()
+    del recs, out
+    torch.cuda.empty_cache()
+    barrier()
+    return res if rank == 0 else None
+
+
 def run_reference(args):
     """CPU arm: the oracle port of InMemoryStorage::check_and_update on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -267,6 +409,7 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="disable the pipelining of successive steps")
     ap.add_argument("--kstats", action="store_true", help="RL_FLAG_KERNEL_STATS: per-phase cycle accounting inside k_main (costs a few %)")
     ap.add_argument("--trace", default="", help="RL_FLAG_TRACE: write every rank's device-side event trace of pass A to <path>.rank<r>.json")
+    ap.add_argument("--extra-batch", type=int, default=0, help="requests per GPU and step of the `extra` workloads (default 1048576)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads / legs reported under `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -566,9 +709,28 @@ def main():
     if world > 1 and not use_peer and int(overflow.item()) != 0:
         raise RuntimeError(f"an exchange block overflowed (more than {slot_cap} records for one owner): the sampled "
                            f"headroom was too small")
-    print(f"[bench] engine stats {eng.stats()}", file=sys.stderr)
+    eng_stats = eng.stats()
+    print(f"[bench] engine stats {eng_stats}", file=sys.stderr)
     print(f"[bench] host enqueue us/step per pass: {[round(x, 1) for x in host_enqueue_us]}", file=sys.stderr)
     print(f"[bench] passes: A {ms_a:.1f} ms, B {ms_b:.1f} ms, e2e {ms_e:.1f} ms (wall {wall_e:.1f})", file=sys.stderr)
+
+    # ---- the other BASELINE.json configs, short passes reported under `extra` (all ranks take part) --------
+    extra = {}
+    if not args.no_extra and args.workload == "C2":
+        if shard is not None:
+            shard.close()
+        eng.close()
+        torch.cuda.empty_cache()
+        for xn in (["C3"] if world == 1 else ["C4", "C5"]):
+            try:
+                r = run_extra(xn, world, rank, local_rank, dev, dist, args, stream)
+            except Exception as ex:  # an extra must not take the headline down with it; say what happened
+                import traceback
+                traceback.print_exc()
+                r = {"error": f"{type(ex).__name__}: {ex}"}
+            if rank == 0:
+                extra[xn] = r
+                print(f"[bench] extra {xn}: {r}", file=sys.stderr)
 
     if rank != 0:
         if world > 1:
@@ -650,7 +812,11 @@ def main():
         line["roofline"] = roof
     if cpu:
         line["cpu_baseline"] = cpu
-    failed = False
+    if extra:
+        line["extra"] = extra
+    line["hot_rows"] = eng_stats.get("hot_rows")
+    failed = any(isinstance(x, dict) and x.get("parity") and (x["parity"]["gpu_verdict_mismatches"] != 0 or x["parity"]["table_mismatch_ranks"])
+                 for x in extra.values())
     if parity is not None:
         # N>1: the live check against ONE global oracle (no CPU throughput is quoted from it: a single thread)
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
@@ -659,7 +825,7 @@ def main():
                                 "gpu_verdict_mismatches": parity["gpu_verdict_mismatches"],
                                 "gpu_table_mismatch_ranks": parity["table_mismatch_ranks"], "counters_compared": parity["counters"]}
         line["e2e"]["verdict_latency_steps"] = args.exchange_lag
-        failed = parity["gpu_verdict_mismatches"] != 0 or bool(parity["table_mismatch_ranks"])
+        failed = failed or parity["gpu_verdict_mismatches"] != 0 or bool(parity["table_mismatch_ranks"])
     emit(line)
     if world > 1:
         dist.barrier()

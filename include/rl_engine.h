@@ -46,6 +46,9 @@ enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1,
         * otherwise, or with load_counters outputs, it behaves like RL_MEM_HOST) */
        RL_MEM_HOST_ASYNC = 2 };
 #define RL_NONE 0xFFFFFFFFu
+/* out_limited[i] of a request that could NOT be evaluated (malformed key, full table region, exchange block
+ * overflow): the call (or the next rl_sync) also reports the error; the byte is never a silent 0 = allowed */
+#define RL_VERDICT_ERROR 0xFFu
 #define RL_MAX_COUNTERS_PER_REQUEST 16 /* counters one request may name (general form); the matcher refuses more */
 /* test aid: narrow the in-kernel grouping tag so that distinct keys collide and the
  * collision path (salted re-insertion) is exercised */
@@ -123,6 +126,8 @@ typedef struct rl_stats {
     uint64_t chained_chunks; /* chunks of heavy regions (optimistic concurrency control) */
     uint64_t ordered_chunks; /* ... of which had to commit in order */
     uint64_t phase_cycles[6]; /* k_main SM cycles summed over chunks: load, group, stage, replay, commit protocol, write-back */
+    uint32_t hot_rows;        /* table rows that currently have a partition of their own (k_hot), of 256 slots */
+    uint32_t _pad2;
 } rl_stats;
 
 int rl_engine_create(const rl_config *cfg, rl_engine **out);

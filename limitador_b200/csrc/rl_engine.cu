@@ -117,6 +117,8 @@ struct rl_engine {
     DevBuf<uint4> d_items;
     DevBuf<unsigned long long> d_kstats;
     DevBuf<uint4> d_trace;     // RL_FLAG_TRACE: event ring
+    DevBuf<uint32_t> d_hot;    // [RL_HOT_SLOTS] hot rows + [RL_HOT_CAND] candidates + [1] candidate count
+    bool hot_rows = true;      // RL_HOT=0 disables the hot-row partitions
     DevBuf<uint32_t> d_misc2;  // [0] trace write position
     uint32_t trace_seq = 0;
     DevBuf<uint32_t> d_chain_status, d_chain_wcnt, d_chain_w;
@@ -218,6 +220,9 @@ RlDev make_dev(rl_engine* e) {
     D.err = e->d_misc.p + MISC_ERR;
     D.flags = e->d_misc.p + MISC_FLAGS;
     D.kstats = e->kernel_stats ? e->d_kstats.p : nullptr;
+    D.hot_rows = e->d_hot.p;
+    D.hot_cand = e->d_hot.p + RL_HOT_SLOTS;
+    D.hot_cand_n = e->d_hot.p + RL_HOT_SLOTS + RL_HOT_CAND;
     D.trace = e->d_trace.p;
     D.trace_pos = e->d_trace.p ? e->d_misc2.p : nullptr;
     D.seq = e->trace_seq;
@@ -344,6 +349,19 @@ int check_device_error(rl_engine* e) {
     }
 }
 
+// A resolve kernel (request -> accesses) found a request the engine cannot take (unknown limit, more than
+// RL_MAX_COUNTERS_PER_REQUEST counters, key out of range): refuse the WHOLE call before anything touches the
+// table, so that the caller can fix the batch and retry without double counting.
+int check_resolve_error(rl_engine* e) {
+    RL_CUDA(e, cudaMemcpyAsync(e->h_misc, e->d_misc.p, MISC_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    RL_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->h_misc[MISC_ERR] == RL_DEV_OK) return RL_OK;
+    int r = check_device_error(e);
+    if (r == RL_OK) r = RL_FATAL;
+    e->last_error += " — the call was refused before the table was touched";
+    return r;
+}
+
 struct Outs {
     uint8_t* limited = nullptr;
     uint32_t* first = nullptr;
@@ -353,8 +371,10 @@ struct Outs {
     uint32_t stride = 0;
 };
 
-RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, int lc, int set = 0, uint32_t n_hint = 0) {
+RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, int lc, int set = 0, uint32_t n_hint = 0,
+                   bool hot_ok = true) {
     RlBatch B;
+    B.nhot = (hot_ok && e->hot_rows) ? RL_HOT_SLOTS : 0;
     B.n_acc = n_acc;
     B.n_req = n_req;
     B.n_dev = nullptr;
@@ -424,12 +444,13 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
 
 template <int CELLS, class Src>
 int launch_front_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
-    const uint32_t P1 = B.nparts + 1;
+    const uint32_t P1 = B.nparts + B.nhot + 1;
     const size_t smem = ((size_t)RL_PART_WARPS * P1 + P1 + 1) * sizeof(uint32_t);
     static int smem_limit[64] = {};  // per instantiation and device: raised as engines with more regions appear
     const int dv = e->device & 63;
-    if (smem > 48 * 1024 && (int)smem > smem_limit[dv]) {
-        const uint32_t maxP1 = (1u << e->log2P) + 1;
+    // (k_front also has ~8 KB of static shared memory: opt in well before the 48 KB default is reached)
+    if (smem > 32 * 1024 && (int)smem > smem_limit[dv]) {
+        const uint32_t maxP1 = (1u << e->log2P) + RL_HOT_SLOTS + 1;
         const int max_smem = (int)(((size_t)RL_PART_WARPS * maxP1 + maxP1 + 1) * sizeof(uint32_t));
         RL_CUDA(e, cudaFuncSetAttribute(k_front<CELLS, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         smem_limit[dv] = max_smem;
@@ -469,6 +490,11 @@ int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& sr
 
 template <int GEO, int CELLS, class Src, int MODE, bool LC>
 int launch_main_cells(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& src, cudaStream_t st) {
+    if (B.nhot && B.phase == RL_PHASE_COMMIT) {
+        // the hot rows' partitions: one CTA per hot slot (most exit at once), ahead of the cold partitions
+        k_hot<GEO, CELLS, Src, MODE, LC><<<B.nhot, RL_HOT_THREADS, 0, st>>>(D, B, src);
+        RL_LAUNCH_CHECK(e);
+    }
     return e->chunk == 128 ? launch_main_ch<GEO, CELLS, Src, MODE, LC, 128>(e, D, B, src, st)
                            : launch_main_ch<GEO, CELLS, Src, MODE, LC, 256>(e, D, B, src, st);
 }
@@ -516,8 +542,10 @@ int pipe_fence(rl_engine* e) {
 int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_t* d_delta, const uint64_t* d_now,
                      int mode, int lc, const Outs& o) {
     RlDev D = make_dev(e);
-    RlBatch B = make_batch(e, n_acc, n_req, o, lc);
-    if (mode == 0) B.heavy_len = 0xFFFFFFFFu;  // may hold coupled requests: regions stay sequential
+    // check_and_update in the general form may hold coupled (multi-row) requests, replayed in phases: partitions
+    // stay sequential and no row gets a partition of its own
+    RlBatch B = make_batch(e, n_acc, n_req, o, lc, 0, 0, mode != 0);
+    if (mode == 0) B.heavy_len = 0xFFFFFFFFu;
     AccSrc src{e->d_acc.p, d_delta, d_now};
     int r = launch_front(e, D, B, src);
     if (r) return r;
@@ -640,6 +668,10 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
     RlResolveOut O{e->d_acc.p, e->d_delta.p, e->d_now.p, o.limited, o.first};
     k_resolve_records<<<ceil_div(n, 128), 128, 0, e->stream>>>(D, n, d_recs, stride, O, mode == 0);
     RL_LAUNCH_CHECK(e);
+    {
+        int r = check_resolve_error(e);
+        if (r) return r;
+    }
     return run_acc_pipeline(e, (uint32_t)n_acc, n, e->d_delta.p, e->d_now.p, mode, lc, o);
 }
 
@@ -665,6 +697,7 @@ int ensure_ready(rl_engine* e, uint64_t n, bool fence = true) {
 template <int GEO, int CELLS>
 int preload_main(rl_engine* e) {
     cudaFuncAttributes fa;
+    RL_CUDA(e, cudaFuncGetAttributes(&fa, k_hot<GEO, CELLS, RecordSrc, 0, false>));
     if (e->chunk == 128) {
         RL_CUDA(e, cudaFuncGetAttributes(&fa, k_main<GEO, CELLS, RecordSrc, 0, 128, false>));
         RL_CUDA(e, cudaFuncSetAttribute(k_main<GEO, CELLS, RecordSrc, 0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -759,7 +792,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, cudaMalloc((void**)&e->d_rows, bytes));
     RL_CUDA(e, cudaMemsetAsync(e->d_rows, 0, bytes, e->stream));
 
-    const uint32_t P1 = (1u << e->log2P) + 1;
+    const uint32_t P1 = (1u << e->log2P) + RL_HOT_SLOTS + 1;  // cold partitions + hot slots + the no-row bucket
     const size_t maxA = e->max_counters;
     const size_t bufA = maxA + maxA / 128 + 65536 + 1024;  // part_idx/part_row: every tile's slice is a whole tile
     RL_CUDA(e, e->d_tile_loc.reserve((size_t)(kMaxTiles + 1) * (P1 + 1)));
@@ -784,6 +817,10 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
     e->kernel_stats = (cfg->flags & RL_FLAG_KERNEL_STATS) != 0;
+    if (const char* v = getenv("RL_HOT")) e->hot_rows = atoi(v) != 0;
+    RL_CUDA(e, e->d_hot.reserve(RL_HOT_SLOTS + RL_HOT_CAND + 4));
+    RL_CUDA(e, cudaMemsetAsync(e->d_hot.p, 0xFF, (RL_HOT_SLOTS + RL_HOT_CAND) * sizeof(uint32_t), e->stream));
+    RL_CUDA(e, cudaMemsetAsync(e->d_hot.p + RL_HOT_SLOTS + RL_HOT_CAND, 0, 4 * sizeof(uint32_t), e->stream));
     RL_CUDA(e, e->d_misc2.reserve(4));
     RL_CUDA(e, cudaMemsetAsync(e->d_misc2.p, 0, 4 * sizeof(uint32_t), e->stream));
     if (cfg->flags & RL_FLAG_TRACE) {
@@ -869,6 +906,7 @@ void rl_engine_destroy(rl_engine* e) {
     e->d_items.release();
     e->d_kstats.release();
     e->d_trace.release();
+    e->d_hot.release();
     e->d_misc2.release();
     e->d_chain_status.release();
     e->d_chain_wcnt.release();
@@ -995,7 +1033,14 @@ int rl_get_stats(rl_engine* e, rl_stats* out) {
     e->stats.chained_chunks = ks[2];
     e->stats.ordered_chunks = ks[3];
     for (int i = 0; i < 6; i++) e->stats.phase_cycles[i] = ks[8 + i];
-    e->stats.phase_cycles[1] = ks[16];  // slot 1 (unused by k_main): ns spent in the probe's last-block tail
+    e->stats.phase_cycles[1] = ks[16];  // slot 1 (unused by k_main): ns spent in the front's last-block tail
+    {
+        uint32_t hot[RL_HOT_SLOTS];
+        RL_CUDA(e, cudaMemcpyAsync(hot, e->d_hot.p, sizeof hot, cudaMemcpyDeviceToHost, e->stream));
+        RL_CUDA(e, cudaStreamSynchronize(e->stream));
+        e->stats.hot_rows = 0;
+        for (uint32_t h : hot) e->stats.hot_rows += (h != 0xFFFFFFFFu);
+    }
     *out = e->stats;
     return RL_OK;
 }
@@ -1428,6 +1473,7 @@ int rl_check_and_update_batch(rl_engine* e, uint64_t n, const uint32_t* ctr_off,
     RlResolveOut O{e->d_acc.p, nullptr, nullptr, o.limited, o.first};
     k_resolve_csr<<<ceil_div(n, 128), 128, 0, e->stream>>>(D, (uint32_t)n, c.off, c.ctrs, O, 1);
     RL_LAUNCH_CHECK(e);
+    if ((r = check_resolve_error(e))) return r;
     if (c.total) {
         if ((r = run_acc_pipeline(e, (uint32_t)c.total, (uint32_t)n, c.delta, c.now, 0, load_counters ? 1 : 0, o))) return r;
     }
@@ -1459,6 +1505,7 @@ int rl_update_batch(rl_engine* e, uint64_t n, const uint32_t* ctr_off, const rl_
     RlResolveOut O{e->d_acc.p, nullptr, nullptr, nullptr, nullptr};
     k_resolve_csr<<<ceil_div(n, 128), 128, 0, e->stream>>>(D, (uint32_t)n, c.off, c.ctrs, O, 0);
     RL_LAUNCH_CHECK(e);
+    if ((r = check_resolve_error(e))) return r;
     if ((r = run_acc_pipeline(e, (uint32_t)c.total, (uint32_t)n, c.delta, c.now, 2, 0, o))) return r;
     if (mem == RL_MEM_HOST) return check_device_error(e);
     return RL_OK;

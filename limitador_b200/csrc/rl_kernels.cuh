@@ -21,9 +21,22 @@
 
 #define RL_PART_THREADS 256
 #define RL_MAX_TILES 256  // tiles (CTAs of k_front) per batch
+// Hot rows: a row that draws a large share of a batch gets a partition of its own and is
+// replayed by one CTA of k_hot over its whole request list, instead of being chopped into chained chunks.
+#define RL_HOT_SLOTS 256   // rows that can be hot at a time (= threads of k_front's last block)
+#define RL_HOT_CAND 128    // candidates k_main can report per batch
+#define RL_HOT_THREADS 512
+#ifndef RL_HOT_MIN
+#define RL_HOT_MIN 32      // a row with this many requests in one k_main chunk becomes a candidate
+#endif
+#ifndef RL_HOT_KEEP
+#define RL_HOT_KEEP 24     // a hot row with fewer requests than this in a batch is dropped again
+#endif
 #define RL_PART_WARPS (RL_PART_THREADS / 32)
 #define RL_PROBE_THREADS 1024
 #define RL_IDENT_POSORIG 0x0654321006543210ull
+#define RL_ROW_NONE 0xFFFFFFFFu   // row_of: the access has no row (namespace without limits)
+#define RL_ROW_ERROR 0xFFFFFFFEu  // row_of: the access could not be evaluated (error flagged)
 
 struct RlDev {
     uint8_t* rows;
@@ -38,6 +51,9 @@ struct RlDev {
     uint32_t* err;    // sticky max of RL_DEV_*
     uint32_t* flags;  // bit0: batch has multi-row requests
     unsigned long long* kstats;   // nullptr = no accounting; [0] chunks, [1] replay rounds, [2] chained chunks, [3] ordered chunks
+    uint32_t* hot_rows;           // [RL_HOT_SLOTS] table row index of hot slot h, or 0xFFFFFFFF; rewritten by k_front's tail
+    uint32_t* hot_cand;           // [RL_HOT_CAND] rows k_main saw dominate a chunk
+    uint32_t* hot_cand_n;
     uint4* trace;                 // nullptr = no tracing (RL_FLAG_TRACE): ring of {event id, call seq, globaltimer lo, hi}
     uint32_t* trace_pos;
     uint32_t seq;                 // call sequence number stamped into the events of this launch
@@ -48,7 +64,7 @@ struct RlDev {
 // spans several streams and, for sharded steps, several GPUs — can be read without a profiler.
 #define RL_TRACE_CAP 65536u
 enum { RL_EV_FRONT = 1, RL_EV_MAIN = 2, RL_EV_XCOUNT = 3, RL_EV_XSCATTER = 4, RL_EV_XWAIT = 5, RL_EV_XRETURN = 6,
-       RL_EV_XWAITV = 7, RL_EV_XGATHER = 8 };
+       RL_EV_XWAITV = 7, RL_EV_XGATHER = 8, RL_EV_HOT = 9 };
 __device__ __forceinline__ void rl_trace(uint4* trace, uint32_t* pos, uint32_t ev, uint32_t end, uint32_t seq) {
     if (trace == nullptr) return;
     unsigned long long t;
@@ -70,6 +86,7 @@ struct RlBatch {
     uint32_t* scan_ctr;      // blocks-done counter of k_front
     uint32_t* ticket;        // work-item ticket of k_main
     uint32_t* exit_ctr;      // CTAs of k_main that found the ticket exhausted (the last one re-arms it)
+    uint32_t nhot;           // 0, or RL_HOT_SLOTS: partitions nparts .. nparts+nhot-1 hold one hot row each
     uint32_t nparts;         // partitions of this batch: table regions merged 2^part_shift at a time, so
     uint32_t part_shift;     //   that a small batch still fills its k_main chunks (nparts = P >> part_shift)
     uint32_t tile;           // accesses per tile (multiple of 256)
@@ -249,20 +266,21 @@ struct RecordSrc {
         while (s + 1 < nseg && a >= __ldg(seg_prefix + s + 1)) s++;
         return recs + (size_t)s * seg_stride + (a - __ldg(seg_prefix + s));
     }
-    // identity of access a: false => no row (namespace without limits)
-    __device__ __forceinline__ bool ident(const RlDev& D, uint32_t a, uint64_t& key_lo, uint64_t& hdr_hi) const {
+    // identity of access a: 1 = a row; 0 = no row (namespace without limits: allowed, lib.rs:434-440);
+    // -1 = malformed request (error flagged; its verdict byte becomes RL_VERDICT_ERROR, never a silent allow)
+    __device__ __forceinline__ int ident(const RlDev& D, uint32_t a, uint64_t& key_lo, uint64_t& hdr_hi) const {
         const rl_record* r = at(a);
         const ulonglong2 w0 = rl_ld_stream(r);       // ns_id|hits, key_lo
         const uint32_t ns_id = (uint32_t)w0.x;
-        if (ns_id >= D.ns_cap) return false;
+        if (ns_id >= D.ns_cap) return 0;
         const RlNsDev ns = D.ns[ns_id];
-        if (ns.mode != 1) return false;
+        if (ns.mode != 1) return 0;
         if (ns.qualified_row) {
             const unsigned long long key_hi =
                 __ldcs(reinterpret_cast<const unsigned long long*>(r) + 2) & RL_RECORD_KEY_HI_MASK;
             if (key_hi >> 32) {
                 rl_set_err(D, RL_DEV_KEY_RANGE);
-                return false;
+                return -1;
             }
             key_lo = w0.y;
             hdr_hi = ((uint64_t)ns.group << 32) | key_hi;
@@ -270,7 +288,7 @@ struct RecordSrc {
             key_lo = 0;
             hdr_hi = (uint64_t)ns.group << 32;
         }
-        return true;
+        return 1;
     }
     __device__ __forceinline__ RlRaw raw(uint32_t a) const {
         const rl_record* r = at(a);
@@ -296,11 +314,11 @@ struct AccSrc {
     const RlAccess* acc;
     const uint64_t* delta;  // per request
     const uint64_t* now;    // per request
-    __device__ __forceinline__ bool ident(const RlDev&, uint32_t a, uint64_t& key_lo, uint64_t& hdr_hi) const {
+    __device__ __forceinline__ int ident(const RlDev&, uint32_t a, uint64_t& key_lo, uint64_t& hdr_hi) const {
         const ulonglong2 w0 = rl_ld_stream(&acc[a]);
         key_lo = w0.x;
         hdr_hi = w0.y;
-        return hdr_hi != 0;
+        return hdr_hi != 0 ? 1 : 0;
     }
     __device__ __forceinline__ RlRaw raw(uint32_t a) const {
         RlRaw w;
@@ -382,7 +400,10 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
     constexpr uint32_t RB = RlGeom<CELLS>::ROW_BYTES;
     constexpr int U = 4;
     constexpr uint32_t NT = RL_PART_THREADS;
-    const uint32_t P1 = B.nparts + 1;
+    static_assert(RL_HOT_SLOTS == RL_PART_THREADS, "the tail handles one hot slot per thread");
+    __shared__ uint32_t hs_key[2 * RL_HOT_SLOTS], hs_val[2 * RL_HOT_SLOTS];  // row -> hot slot
+    const uint32_t nhot = B.nhot;
+    const uint32_t P1 = B.nparts + nhot + 1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
     const uint32_t n = rl_batch_n(B);
@@ -398,19 +419,56 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
 
     for (uint32_t i = tid; i < RL_PART_WARPS * P1 + P1 + 1; i += NT) wcnt[i] = 0;
     if (tile == 0 && tid == 0) rl_trace(D.trace, D.trace_pos, RL_EV_FRONT, 0, D.seq);
+    if (nhot) {
+        // the hot-row table of this batch (fixed while the batch is partitioned: every access of a row takes
+        // the same route whichever CTA sees it).  A row listed twice resolves to its LOWEST slot everywhere.
+        for (uint32_t i = tid; i < 2 * RL_HOT_SLOTS; i += NT) {
+            hs_key[i] = 0xFFFFFFFFu;
+            hs_val[i] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        const uint32_t hr = __ldcg(D.hot_rows + tid);
+        if (hr != 0xFFFFFFFFu) {
+            uint32_t s2 = (hr * 2654435761u) >> 23;  // 9 bits
+            for (;;) {
+                const uint32_t old = atomicCAS(&hs_key[s2], 0xFFFFFFFFu, hr);
+                if (old == 0xFFFFFFFFu || old == hr) {
+                    atomicMin(&hs_val[s2], tid);
+                    break;
+                }
+                s2 = (s2 + 1) & (2 * RL_HOT_SLOTS - 1);
+            }
+        }
+    }
     __syncthreads();
+    auto hot_of = [&](uint32_t rowidx) -> uint32_t {
+        if (!nhot) return 0xFFFFFFFFu;
+        uint32_t s2 = (rowidx * 2654435761u) >> 23;
+        for (;;) {
+            const uint32_t k = hs_key[s2];
+            if (k == rowidx) return hs_val[s2];
+            if (k == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+            s2 = (s2 + 1) & (2 * RL_HOT_SLOTS - 1);
+        }
+    };
+    auto part_of = [&](uint32_t rowidx) -> uint32_t {
+        const uint32_t h = hot_of(rowidx);
+        return h != 0xFFFFFFFFu ? B.nparts + h : (rowidx >> D.log2R) >> B.part_shift;
+    };
 
     // ---- pass 1: probe, count ---------------------------------------------------------------------
     for (uint32_t b = s0; b < s1; b += 32 * U) {
         uint64_t klo[U], hhi[U], h[U];
-        bool ok[U];
+        bool ok[U], bad[U];
         uint8_t* home[U];
         ulonglong2 hdr[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t a = b + u * 32 + lane;
             klo[u] = hhi[u] = 0;
-            ok[u] = (a < s1) && src.ident(D, a, klo[u], hhi[u]);
+            const int id = (a < s1) ? src.ident(D, a, klo[u], hhi[u]) : 0;
+            ok[u] = id > 0;
+            bad[u] = id < 0;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -422,14 +480,16 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
         for (int u = 0; u < U; u++) {
             const uint32_t a = b + u * 32 + lane;
             const bool valid = a < s1;
-            uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
+            uint32_t r = P1 - 1, rowidx = bad[u] ? RL_ROW_ERROR : RL_ROW_NONE;
             if (ok[u]) {
                 const uint8_t* row = (hdr[u].x == klo[u] && hdr[u].y == hhi[u])
                                          ? home[u]
                                          : rl_probe<CELLS>(D, h[u], klo[u], hhi[u], true);  // collision chain / insert
                 if (row) {
                     rowidx = (uint32_t)((size_t)(row - D.rows) / RB);
-                    r = (rowidx >> D.log2R) >> B.part_shift;
+                    r = part_of(rowidx);
+                } else {
+                    rowidx = RL_ROW_ERROR;  // the region is full (error flagged): not evaluated
                 }
             }
             if (valid) B.row_of[a] = rowidx;
@@ -487,7 +547,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
         uint32_t r = P1 - 1, rowidx = 0xFFFFFFFFu;
         if (valid) {
             rowidx = __ldcg(B.row_of + a);
-            if (rowidx != 0xFFFFFFFFu) r = (rowidx >> D.log2R) >> B.part_shift;
+            if (rowidx < RL_ROW_ERROR) r = part_of(rowidx);
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -504,8 +564,9 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
                 B.part_idx[tbuf + mypos] = a;
                 B.part_row[tbuf + mypos] = rowidx;
             } else if (Src::kAccessIsRequest && B.out_limited) {
-                // request without any applicable limit: not limited (lib.rs:434-440)
-                B.out_limited[a] = 0;
+                // request without any applicable limit: not limited (lib.rs:434-440); a request that could
+                // not be evaluated (malformed key, full table region) says so instead of reading as allowed
+                B.out_limited[a] = (rowidx == RL_ROW_ERROR) ? (uint8_t)RL_VERDICT_ERROR : (uint8_t)0;
                 if (B.out_first_limited) B.out_first_limited[a] = RL_NONE_U32;
             }
         }
@@ -521,7 +582,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
     __threadfence();
     const unsigned long long tk0 = (D.kstats != nullptr && tid == 0) ? rl_globaltimer_ns() : 0ull;
     // region lengths into shared memory (re-armed = zeroed for the next batch on the way); loc[] is free now
-    const uint32_t P = P1 - 1;
+    const uint32_t P = B.nparts;  // cold partitions: work items of k_main (hot ones belong to k_hot)
     uint32_t hsum = 0, lsum = 0;
     for (uint32_t q = tid; q < P; q += NT) {
         const uint32_t len = __ldcg(&B.region_total[q]);
@@ -545,6 +606,48 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
         } else if (len) {
             B.items[th + lb++] = make_uint4(q, 0, len, RL_NONE_U32);
         }
+    }
+    if (nhot) {
+        // ---- the hot-row table of the NEXT batch: drop the rows that cooled down, admit the candidates ----
+        __shared__ uint32_t s_free[RL_HOT_SLOTS], s_ck[2 * RL_HOT_CAND], s_keep[RL_HOT_SLOTS], s_used;
+        const uint32_t h = tid;
+        const uint32_t hrow = __ldcg(D.hot_rows + h);
+        const uint32_t hlen = __ldcg(&B.region_total[B.nparts + h]);
+        B.region_total[B.nparts + h] = 0;
+        const bool keep = (hrow != 0xFFFFFFFFu) && hlen >= RL_HOT_KEEP;
+        if (!keep && hrow != 0xFFFFFFFFu) D.hot_rows[h] = 0xFFFFFFFFu;
+        s_keep[h] = keep ? 1u : 0u;
+        for (uint32_t i = tid; i < 2 * RL_HOT_CAND; i += NT) s_ck[i] = 0xFFFFFFFFu;
+        if (tid == 0) s_used = 0;
+        uint32_t nfree;
+        const uint32_t fpos = rl_block_excl_scan<NT>(keep ? 0u : 1u, s_warp, nfree);  // barriers inside
+        if (!keep) s_free[fpos] = h;
+        __syncthreads();
+        const uint32_t ncand = min(__ldcg(D.hot_cand_n), (uint32_t)RL_HOT_CAND);
+        if (tid < ncand) {
+            const uint32_t c = __ldcg(D.hot_cand + tid);
+            const uint32_t hh = (c != 0xFFFFFFFFu) ? hot_of(c) : 0u;
+            const bool already = (c == 0xFFFFFFFFu) || (hh != 0xFFFFFFFFu && s_keep[hh]);
+            if (!already) {
+                uint32_t s2 = (c * 2654435761u) >> 24;  // 8 bits
+                bool first = false;
+                for (;;) {  // reported by several chunks: one of them admits it
+                    const uint32_t old = atomicCAS(&s_ck[s2], 0xFFFFFFFFu, c);
+                    if (old == 0xFFFFFFFFu) {
+                        first = true;
+                        break;
+                    }
+                    if (old == c) break;
+                    s2 = (s2 + 1) & (2 * RL_HOT_CAND - 1);
+                }
+                if (first) {
+                    const uint32_t k = atomicAdd(&s_used, 1u);
+                    if (k < nfree) D.hot_rows[s_free[k]] = c;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) *D.hot_cand_n = 0;
     }
     if (tid == 0) {
         *B.n_items = th + tl;
@@ -727,6 +830,187 @@ __device__ __forceinline__ void rl_apply_update_smem(unsigned long long* sv, uns
     }
 }
 
+// The lock-step run-length replay of ONE row group by all its member threads, shared by k_main
+// (many groups per chunk) and k_hot (one hot row per CTA).  Every thread of the CTA calls it — the rounds
+// are separated by CTA barriers — with the view of ITS group:
+//   gsv/gse  staged row state of the group (CELLS values / expiries, shared memory)
+//   gmin     the group's minima words: gmin[(parity * 2 + {0 A, 1 B}) * gstride], armed to 0xFFFFFFFF
+//   gdirty   the group's dirty-cell mask
+//   ord/cnt  my stream-order ordinal inside the group and the group's size
+//   peers    the lanes of my warp that belong to my group (leader = lowest of them; solo = I am alone)
+// Returns the number of rounds the CTA ran.
+template <int CELLS, int MODE, bool LC>
+__device__ __forceinline__ uint32_t rl_replay_rounds(const RlBatch& B, bool write_out, unsigned long long* gsv,
+                                                     unsigned long long* gse, uint32_t* gmin, uint32_t gstride,
+                                                     uint32_t* gdirty, const RlReq& acc, const RlMyLimits& L,
+                                                     const RlCellDesc* desc, const RlCellDesc* gdesc, bool multi,
+                                                     bool like_rep, bool valid, unsigned peers, bool solo, int leader,
+                                                     uint32_t lane, uint32_t ord, uint32_t cnt, bool& done, uint32_t& pos) {
+    constexpr bool lc = LC;
+    const uint64_t delta = acc.delta, now = acc.now;
+    const uint32_t ncell = rl_cells_n(acc.cells);
+    uint32_t nrounds = 0;
+    for (uint32_t round = 0;; round++) {
+        nrounds++;
+        const uint32_t par = round & 1;
+        uint32_t fl = RL_NONE_U32;
+        RlRow<CELLS> loc;
+        uint32_t amin = 0xFFFFFFFFu, bmin = 0xFFFFFFFFu;  // my ordinal if hypothesis A / B fails for me
+        if (!done) {
+            bool aok = false, bok = false;
+            if (!multi) {
+                const uint64_t dsum = (uint64_t)(ord - pos + 1) * delta;
+                // update_counters never tests the limit: a run only needs live cells
+                rl_eval_ab<CELLS>(gsv, gse, L, acc.cells, acc.posorig, delta, dsum, now, lc, MODE == 0, aok, bok, fl);
+                if (MODE == 2) aok = false;
+                bok = bok && like_rep;
+            }
+            if (lc) {
+                // remaining/ttl need the state this request sees: copy it before the barrier,
+                // the run's last member republishes S right after it
+#pragma unroll
+                for (int c = 0; c < CELLS; c++) {
+                    loc.value[c] = gsv[c];
+                    loc.expiry[c] = gse[c];
+                }
+            }
+            if (!aok) amin = ord;
+            if (!bok) bmin = ord;
+        }
+        if (valid) {
+            // one shared-memory atomic per (warp, row) instead of one per access
+            if (!solo) {
+                amin = __reduce_min_sync(peers, amin);
+                bmin = __reduce_min_sync(peers, bmin);
+            }
+            if ((int)lane == leader) {
+                if (amin != 0xFFFFFFFFu) atomicMin(&gmin[(par * 2 + 0) * gstride], amin);
+                if (bmin != 0xFFFFFFFFu) atomicMin(&gmin[(par * 2 + 1) * gstride], bmin);
+            }
+        }
+        __syncthreads();
+        if (!done) {
+            const uint32_t mA = min(gmin[(par * 2 + 0) * gstride], cnt);
+            const uint32_t mB = min(gmin[(par * 2 + 1) * gstride], cnt);
+            uint32_t newpos;
+            bool mine = false, store = false, fast_store = false;
+            uint32_t dirty = 0;
+            uint64_t* rem = nullptr;
+            uint64_t* ttl = nullptr;
+            if (MODE == 0 && lc && write_out) {
+                const size_t ob = B.out_off ? (size_t)B.out_off[acc.req] : (size_t)acc.req * B.out_stride;
+                if (B.out_remaining) rem = B.out_remaining + ob;
+                if (B.out_ttl) ttl = B.out_ttl + ob;
+            }
+            if (mA > pos) {  // run of denied requests: state untouched, fl from the evaluation
+                newpos = mA;
+                if (ord < mA) {
+                    mine = true;
+                    if (lc && write_out) {  // remaining / ttl of every counter
+                        fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, true, rem, ttl);
+                        dirty = 0;
+                    }
+                }
+            } else if (mB > pos) {  // run of allowed requests with equal deltas: values accumulate
+                newpos = mB;
+                if (ord < mB) {
+                    mine = true;
+                    fl = RL_NONE_U32;
+                    store = (ord == mB - 1);
+                    if (MODE == 0 && lc && write_out) {
+                        rl_advance_run<CELLS>(loc, acc.cells, (uint64_t)(ord - pos) * delta);
+                        fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                        fast_store = false;
+                    } else if (store) {
+                        // the run's last member is the sole writer of S (nobody reads it until
+                        // the next barrier): add the run's deltas in place
+                        const uint64_t add = (uint64_t)(mB - pos) * delta;
+#pragma unroll
+                        for (int k = 0; k < CELLS; k++)
+                            if ((uint32_t)k < ncell) {
+                                const uint32_t c = rl_cells_at(acc.cells, k);
+                                gsv[c] += add;
+                                dirty |= 1u << c;
+                            }
+                        fast_store = true;
+                    }
+                }
+            } else {  // the request at `pos` is applied alone, sequential rule
+                newpos = pos + 1;
+                if (ord == pos) {
+                    mine = true;
+                    store = true;
+                    if (!lc && !multi) {
+                        fast_store = true;  // operate on the staged state in place
+                        if (MODE == 2)
+                            rl_apply_update_smem<CELLS>(gsv, gse, gdesc, acc.cells,
+                                                        delta, now, dirty);
+                        else
+                            fl = rl_apply_check_smem<CELLS>(gsv, gse, L, gdesc,
+                                                            acc.cells, acc.posorig, delta, now, dirty);
+                    } else {
+                        if (!lc) {
+#pragma unroll
+                            for (int c = 0; c < CELLS; c++) {
+                                loc.value[c] = gsv[c];
+                                loc.expiry[c] = gse[c];
+                            }
+                        }
+                        if (MODE == 2) {
+                            rl_walk_update<CELLS>(loc, dirty, desc, acc.cells, delta, now);
+                        } else if (!multi) {
+                            fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
+                        } else {
+                            const uint32_t fl_in = B.fl_prev[acc.req];
+                            const uint32_t local = rl_walk_check_multi<CELLS>(loc, dirty, desc, acc.cells, acc.posorig,
+                                                                             delta, now, lc, fl_in, rem, ttl);
+                            if (!write_out && local != RL_NONE_U32) atomicMin(&B.fl_next[acc.req], local);
+                            fl = fl_in;
+                        }
+                    }
+                }
+            }
+            if (mine) {
+                done = true;
+                if (MODE == 0 && write_out) {
+                    B.out_limited[acc.req] = (fl != RL_NONE_U32);
+                    if (B.out_first_limited) {
+                        if (fl == RL_NONE_U32) {
+                            B.out_first_limited[acc.req] = RL_NONE_U32;
+                        } else {
+                            // the access holding position fl names the limit
+#pragma unroll
+                            for (int k = 0; k < CELLS; k++)
+                                if ((uint32_t)k < ncell && rl_pos_at(acc.posorig, k) == fl)
+                                    B.out_first_limited[acc.req] = desc[rl_cells_at(acc.cells, k)].limit_id;
+                        }
+                    }
+                }
+            }
+            // the barrier between evaluation and this point ordered every read of S
+            // before the publication of the new state
+            if (store && dirty) {
+                if (!fast_store) {
+#pragma unroll
+                    for (int c = 0; c < CELLS; c++)
+                        if (dirty & (1u << c)) {
+                            gsv[c] = loc.value[c];
+                            gse[c] = loc.expiry[c];
+                        }
+                }
+                atomicOr(&*gdirty, dirty);
+            }
+            if (mine && ord == newpos - 1) {  // last finalised member re-arms the group
+                gmin[((par ^ 1) * 2 + 0) * gstride] = 0xFFFFFFFFu;
+                gmin[((par ^ 1) * 2 + 1) * gstride] = 0xFFFFFFFFu;
+            }
+            pos = newpos;
+        }
+        if (!__syncthreads_or(!done)) break;
+    }
+    return nrounds;
+}
+
 template <int GT>
 __device__ __forceinline__ uint32_t rl_group_slot(uint32_t row, uint32_t weak) {
     // weak (test aid, RL_FLAG_DEBUG_WEAK_TAGS): four home slots for the whole chunk, so the linear
@@ -775,7 +1059,7 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
         const uint32_t lo = it.y, hi = it.z;  // [lo, hi) of the partition's list
         // ---- the partition's list = its runs in the tiles' slices, tile after tile: merge on read --------
         {
-            const uint32_t TL = B.nparts + 2;
+            const uint32_t TL = B.nparts + B.nhot + 2;
             constexpr uint32_t PER = (RL_MAX_TILES + CH - 1) / CH;  // consecutive tiles per thread
             uint32_t c[PER], sum = 0;
 #pragma unroll
@@ -953,6 +1237,11 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
                 }
                 ord += __popc(peers & ((1u << lane) - 1));
             }
+            // a row that dominates this chunk is a candidate for a partition of its own in the coming batches
+            if (is_rep && B.nhot && cnt >= RL_HOT_MIN) {
+                const uint32_t k = atomicAdd(D.hot_cand_n, 1u);
+                if (k < RL_HOT_CAND) D.hot_cand[k] = myrow;
+            }
             // a run of allowed requests is closed-form only over members that carry the rep's delta and
             // cell list: a member that differs is never part of a run (it ends the run before it and is
             // applied alone), so the members of any run are mutually alike
@@ -962,168 +1251,10 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             // ---- 4. lock-step run-length replay -----------------------------------------------------
             bool done = !valid || snapshot;
             uint32_t pos = 0;
-            const unsigned long long* sv = &sm.s_val[gid * CELLS];
-            const unsigned long long* se = &sm.s_exp[gid * CELLS];
             for (int attempt = 0;; attempt++) {
-            uint32_t nrounds = 0;
-            for (uint32_t round = 0;; round++) {
-                nrounds++;
-                const uint32_t par = round & 1;
-                uint32_t fl = RL_NONE_U32;
-                RlRow<CELLS> loc;
-                uint32_t amin = 0xFFFFFFFFu, bmin = 0xFFFFFFFFu;  // my ordinal if hypothesis A / B fails for me
-                if (!done) {
-                    bool aok = false, bok = false;
-                    if (!multi) {
-                        const uint64_t dsum = (uint64_t)(ord - pos + 1) * delta;
-                        // update_counters never tests the limit: a run only needs live cells
-                        rl_eval_ab<CELLS>(sv, se, L, acc.cells, acc.posorig, delta, dsum, now, lc, MODE == 0, aok, bok, fl);
-                        if (MODE == 2) aok = false;
-                        bok = bok && like_rep;
-                    }
-                    if (lc) {
-                        // remaining/ttl need the state this request sees: copy it before the barrier,
-                        // the run's last member republishes S right after it
-#pragma unroll
-                        for (int c = 0; c < CELLS; c++) {
-                            loc.value[c] = sv[c];
-                            loc.expiry[c] = se[c];
-                        }
-                    }
-                    if (!aok) amin = ord;
-                    if (!bok) bmin = ord;
-                }
-                if (valid) {
-                    // one shared-memory atomic per (warp, row) instead of one per access
-                    if (!solo) {
-                        amin = __reduce_min_sync(peers, amin);
-                        bmin = __reduce_min_sync(peers, bmin);
-                    }
-                    if ((int)lane == leader) {
-                        if (amin != 0xFFFFFFFFu) atomicMin(&sm.g_min[par][0][gid], amin);
-                        if (bmin != 0xFFFFFFFFu) atomicMin(&sm.g_min[par][1][gid], bmin);
-                    }
-                }
-                __syncthreads();
-                if (!done) {
-                    const uint32_t mA = min(sm.g_min[par][0][gid], cnt);
-                    const uint32_t mB = min(sm.g_min[par][1][gid], cnt);
-                    uint32_t newpos;
-                    bool mine = false, store = false, fast_store = false;
-                    uint32_t dirty = 0;
-                    uint64_t* rem = nullptr;
-                    uint64_t* ttl = nullptr;
-                    if (MODE == 0 && lc && write_out) {
-                        const size_t ob = B.out_off ? (size_t)B.out_off[acc.req] : (size_t)acc.req * B.out_stride;
-                        if (B.out_remaining) rem = B.out_remaining + ob;
-                        if (B.out_ttl) ttl = B.out_ttl + ob;
-                    }
-                    if (mA > pos) {  // run of denied requests: state untouched, fl from the evaluation
-                        newpos = mA;
-                        if (ord < mA) {
-                            mine = true;
-                            if (lc && write_out) {  // remaining / ttl of every counter
-                                fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, true, rem, ttl);
-                                dirty = 0;
-                            }
-                        }
-                    } else if (mB > pos) {  // run of allowed requests with equal deltas: values accumulate
-                        newpos = mB;
-                        if (ord < mB) {
-                            mine = true;
-                            fl = RL_NONE_U32;
-                            store = (ord == mB - 1);
-                            if (MODE == 0 && lc && write_out) {
-                                rl_advance_run<CELLS>(loc, acc.cells, (uint64_t)(ord - pos) * delta);
-                                fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
-                                fast_store = false;
-                            } else if (store) {
-                                // the run's last member is the sole writer of S (nobody reads it until
-                                // the next barrier): add the run's deltas in place
-                                const uint64_t add = (uint64_t)(mB - pos) * delta;
-#pragma unroll
-                                for (int k = 0; k < CELLS; k++)
-                                    if ((uint32_t)k < ncell) {
-                                        const uint32_t c = rl_cells_at(acc.cells, k);
-                                        sm.s_val[gid * CELLS + c] += add;
-                                        dirty |= 1u << c;
-                                    }
-                                fast_store = true;
-                            }
-                        }
-                    } else {  // the request at `pos` is applied alone, sequential rule
-                        newpos = pos + 1;
-                        if (ord == pos) {
-                            mine = true;
-                            store = true;
-                            if (!lc && !multi) {
-                                fast_store = true;  // operate on the staged state in place
-                                if (MODE == 2)
-                                    rl_apply_update_smem<CELLS>(&sm.s_val[gid * CELLS], &sm.s_exp[gid * CELLS], gdesc, acc.cells,
-                                                                delta, now, dirty);
-                                else
-                                    fl = rl_apply_check_smem<CELLS>(&sm.s_val[gid * CELLS], &sm.s_exp[gid * CELLS], L, gdesc,
-                                                                    acc.cells, acc.posorig, delta, now, dirty);
-                            } else {
-                                if (!lc) {
-#pragma unroll
-                                    for (int c = 0; c < CELLS; c++) {
-                                        loc.value[c] = sv[c];
-                                        loc.expiry[c] = se[c];
-                                    }
-                                }
-                                if (MODE == 2) {
-                                    rl_walk_update<CELLS>(loc, dirty, desc, acc.cells, delta, now);
-                                } else if (!multi) {
-                                    fl = rl_walk_check_single<CELLS>(loc, dirty, desc, acc.cells, acc.posorig, delta, now, lc, rem, ttl);
-                                } else {
-                                    const uint32_t fl_in = B.fl_prev[acc.req];
-                                    const uint32_t local = rl_walk_check_multi<CELLS>(loc, dirty, desc, acc.cells, acc.posorig,
-                                                                                     delta, now, lc, fl_in, rem, ttl);
-                                    if (!write_out && local != RL_NONE_U32) atomicMin(&B.fl_next[acc.req], local);
-                                    fl = fl_in;
-                                }
-                            }
-                        }
-                    }
-                    if (mine) {
-                        done = true;
-                        if (MODE == 0 && write_out) {
-                            B.out_limited[acc.req] = (fl != RL_NONE_U32);
-                            if (B.out_first_limited) {
-                                if (fl == RL_NONE_U32) {
-                                    B.out_first_limited[acc.req] = RL_NONE_U32;
-                                } else {
-                                    // the access holding position fl names the limit
-#pragma unroll
-                                    for (int k = 0; k < CELLS; k++)
-                                        if ((uint32_t)k < ncell && rl_pos_at(acc.posorig, k) == fl)
-                                            B.out_first_limited[acc.req] = desc[rl_cells_at(acc.cells, k)].limit_id;
-                                }
-                            }
-                        }
-                    }
-                    // the barrier between evaluation and this point ordered every read of S
-                    // before the publication of the new state
-                    if (store && dirty) {
-                        if (!fast_store) {
-#pragma unroll
-                            for (int c = 0; c < CELLS; c++)
-                                if (dirty & (1u << c)) {
-                                    sm.s_val[gid * CELLS + c] = loc.value[c];
-                                    sm.s_exp[gid * CELLS + c] = loc.expiry[c];
-                                }
-                        }
-                        atomicOr(&sm.g_dirty[gid], dirty);
-                    }
-                    if (mine && ord == newpos - 1) {  // last finalised member re-arms the group
-                        sm.g_min[par ^ 1][0][gid] = 0xFFFFFFFFu;
-                        sm.g_min[par ^ 1][1][gid] = 0xFFFFFFFFu;
-                    }
-                    pos = newpos;
-                }
-                if (!__syncthreads_or(!done)) break;
-            }
+            const uint32_t nrounds = rl_replay_rounds<CELLS, MODE, LC>(
+                B, write_out, &sm.s_val[gid * CELLS], &sm.s_exp[gid * CELLS], &sm.g_min[0][0][gid], CH, &sm.g_dirty[gid], acc, L,
+                desc, gdesc, multi, like_rep, valid, peers, solo, leader, lane, ord, cnt, done, pos);
             if (tid == 0) {
                 RL_KSTAT_ADD(0, 1);
                 RL_KSTAT_ADD(1, nrounds);
@@ -1287,6 +1418,125 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             RL_PHASE_TICK(5)  // write-back
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Hot rows.  CTA h replays the whole request list of hot slot h (partition nparts + h: ONE table row) in
+// stream order, RL_HOT_THREADS requests per block of the list, with the same run-length rounds as k_main
+// (rl_replay_rounds) — but there is nothing to group and nothing to chain: the row state stays in shared
+// memory from the first request of the batch to the last, a saturated row (all denied) or a row far from its
+// limit (all allowed, values accumulate in closed form) costs one round per block, and the next block's
+// records are in flight while the current one is replayed.  This is what replaces "warp-aggregated atomics"
+// for the hot-key case (BASELINE.json configs[4]): atomics would hand out allow/deny by arrival order.
+template <int GEO, int CELLS, class Src, int MODE, bool LC>
+__global__ void __launch_bounds__(RL_HOT_THREADS) k_hot(RlDev D, RlBatch B, Src src) {
+    constexpr int CH = RL_HOT_THREADS;
+    __shared__ uint32_t t_pfx[RL_MAX_TILES + 1], t_loc[RL_MAX_TILES], scan_w[CH / 32];
+    __shared__ unsigned long long s_val[CELLS], s_exp[CELLS], s_d0;
+    __shared__ uint32_t s_min[4], s_dirty, s_cells0;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t q = B.nparts + blockIdx.x;
+    const uint32_t ntile = B.num_tiles;
+    const uint32_t tsz = rl_tile_of(B, rl_batch_n(B));
+    const uint32_t TL = B.nparts + B.nhot + 2;
+    static_assert(RL_MAX_TILES <= RL_HOT_THREADS, "one tile per thread in the list merge");
+    {
+        uint32_t c = 0;
+        if (tid < ntile) {
+            const uint32_t l0 = __ldcg(&B.tile_loc[(size_t)tid * TL + q]);
+            const uint32_t l1 = __ldcg(&B.tile_loc[(size_t)tid * TL + q + 1]);
+            c = l1 - l0;
+            t_loc[tid] = tid * tsz + l0;
+        }
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        if (lane == 31) scan_w[warp] = x;
+        __syncthreads();
+        uint32_t run = x - c;
+        for (uint32_t w = 0; w < warp; w++) run += scan_w[w];
+        if (tid < ntile) t_pfx[tid] = run;
+        if (tid == CH - 1) t_pfx[ntile] = run + c;
+        __syncthreads();
+    }
+    const uint32_t total = t_pfx[ntile];
+    if (total == 0) return;
+    if (tid == 0) rl_trace(D.trace, D.trace_pos, RL_EV_HOT, 0, total);  // per hot row: list length, start .. end
+    auto list_at = [&](uint32_t v) -> uint32_t {
+        uint32_t a0 = 0, a1 = ntile - 1;
+        while (a0 < a1) {
+            const uint32_t mid = (a0 + a1 + 1) >> 1;
+            if (t_pfx[mid] <= v) a0 = mid;
+            else a1 = mid - 1;
+        }
+        return t_loc[a0] + (v - t_pfx[a0]);
+    };
+    const uint32_t rowidx = __ldcg(B.part_row + list_at(0));
+    uint8_t* row = D.rows + (size_t)rowidx * RlGeom<GEO>::ROW_BYTES;
+    if (tid < CELLS) {
+        const ulonglong2 v = rl_ld_cg(row + 16 + 16 * tid);
+        s_val[tid] = v.x;
+        s_exp[tid] = v.y;
+    }
+    if (tid == 0) s_dirty = 0;
+    // software pipeline over the list: access index two blocks ahead, record one block ahead
+    uint32_t a_cur = 0, a_nxt = 0;
+    RlRaw raw_cur;
+    raw_cur.w0 = make_ulonglong2(0ull, 0ull);
+    raw_cur.w1 = raw_cur.w0;
+    if (tid < total) a_cur = __ldcs(B.part_idx + list_at(tid));
+    if (tid + CH < total) a_nxt = __ldcs(B.part_idx + list_at(tid + CH));
+    if (tid < total) raw_cur = src.raw(a_cur);
+    for (uint32_t b = 0; b < total; b += CH) {
+        const uint32_t v = b + tid;
+        const bool valid = v < total;
+        const uint32_t a = a_cur;
+        const RlRaw rawrec = raw_cur;
+        a_cur = a_nxt;
+        if (v + CH < total) raw_cur = src.raw(a_cur);                                   // next block's record
+        if (v + 2 * CH < total) a_nxt = __ldcs(B.part_idx + list_at(v + 2 * CH));       // the one after: its index
+        RlReq acc;
+        acc.req = 0; acc.cells = 0; acc.group = 0; acc.posorig = 0; acc.delta = 0; acc.now = 0;
+        if (valid) src.decode(D, a, rawrec, acc);
+        const RlCellDesc* gdesc = D.desc + (size_t)acc.group * 8;
+        const uint32_t ncell = rl_cells_n(acc.cells);
+        RlMyLimits L;
+        L.qmask = 0;
+        constexpr bool kGeneric = LC || Src::kCanBeMulti;
+        RlCellDesc mydesc[kGeneric ? CELLS : 1];
+#pragma unroll
+        for (int k = 0; k < CELLS; k++) {
+            L.mx[k] = 0;
+            if (valid && (uint32_t)k < ncell) {
+                const uint32_t c = rl_cells_at(acc.cells, k);
+                const RlCellDesc d = gdesc[c];
+                if (kGeneric) mydesc[kGeneric ? c : 0] = d;
+                L.mx[k] = d.max_value;
+                L.qmask |= (d.qualified ? 1u : 0u) << k;
+            }
+        }
+        const RlCellDesc* desc = kGeneric ? mydesc : gdesc;
+        if (tid == 0) {  // the block's first request stands in for k_main's "rep"
+            s_d0 = acc.delta;
+            s_cells0 = acc.cells;
+            s_min[0] = s_min[1] = s_min[2] = s_min[3] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        const bool like_rep = valid && s_d0 == acc.delta && s_cells0 == acc.cells;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const int leader = vmask ? (__ffs(vmask) - 1) : 0;
+        const bool solo = (vmask & (vmask - 1)) == 0;
+        bool done = !valid;
+        uint32_t pos = 0;
+        rl_replay_rounds<CELLS, MODE, LC>(B, true, s_val, s_exp, s_min, 1, &s_dirty, acc, L, desc, gdesc, false, like_rep, valid,
+                                          vmask, solo, leader, lane, tid, min((uint32_t)CH, total - b), done, pos);
+    }
+    __syncthreads();
+    if (tid < CELLS && ((s_dirty >> tid) & 1u)) rl_st_cg(row + 16 + 16 * tid, s_val[tid], s_exp[tid]);
+    if (tid == 0) rl_trace(D.trace, D.trace_pos, RL_EV_HOT, 1, total);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1703,7 +1953,7 @@ __global__ void k_bucket_scan(uint32_t num_tiles, uint32_t world, uint32_t* tile
 __global__ void k_gather_u8(uint32_t n, const uint8_t* __restrict__ in, const uint32_t* __restrict__ pos,
                             uint8_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (pos[i] != 0xFFFFFFFFu) ? in[pos[i]] : 0;
+    if (i < n) out[i] = (pos[i] != 0xFFFFFFFFu) ? in[pos[i]] : (uint8_t)RL_VERDICT_ERROR;  // block overflow: not decided
 }
 
 // The lane byte of rl_record (top byte of key_hi) is opaque to the engine: the pipelined exchange
@@ -1716,7 +1966,7 @@ __global__ void k_lane_put(uint32_t n_slots, rl_record* recs, const uint8_t* __r
 __global__ void k_lane_gather(uint32_t n, const rl_record* __restrict__ recs, const uint32_t* __restrict__ pos,
                               uint8_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (pos[i] != 0xFFFFFFFFu) ? reinterpret_cast<const uint8_t*>(recs + pos[i])[RL_RECORD_LANE_BYTE] : 0;
+    if (i < n) out[i] = (pos[i] != 0xFFFFFFFFu) ? reinterpret_cast<const uint8_t*>(recs + pos[i])[RL_RECORD_LANE_BYTE] : (uint8_t)RL_VERDICT_ERROR;
 }
 
 __global__ void k_unpermute_u8(uint32_t n, const uint8_t* __restrict__ in, const uint32_t* __restrict__ src,

@@ -56,6 +56,7 @@ class RlStats(C.Structure):
         ("fixed_point_rounds", C.c_uint32), ("_pad", C.c_uint32),
         ("chunks", C.c_uint64), ("replay_rounds", C.c_uint64), ("chained_chunks", C.c_uint64),
         ("ordered_chunks", C.c_uint64), ("phase_cycles", C.c_uint64 * 6),
+        ("hot_rows", C.c_uint32), ("_pad2", C.c_uint32),
     ]
 
 
@@ -211,7 +212,7 @@ class Engine:
 
     def trace_dump(self, cap: int = 65536):
         """RL_FLAG_TRACE: list of (event name, is_end, seq, gpu_ns), in ring order; clears the ring."""
-        names = {1: "front", 2: "main", 3: "xcount", 4: "xscatter", 5: "xwait", 6: "xreturn", 7: "xwaitv", 8: "xgather"}
+        names = {1: "front", 2: "main", 3: "xcount", 4: "xscatter", 5: "xwait", 6: "xreturn", 7: "xwaitv", 8: "xgather", 9: "hot"}
         ev = np.zeros(cap, dtype=np.uint32)
         seq = np.zeros(cap, dtype=np.uint32)
         ns = np.zeros(cap, dtype=np.uint64)

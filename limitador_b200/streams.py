@@ -249,3 +249,38 @@ def c3_device_stream(n_batches: int, batch: int, device, n_keys: int = 16_000_00
         o[:, 2] = 0
         o[:, 3] = T0_US + i // 1000 + 1_000_000 * (i // batch // 64)
     return out
+
+
+def c4_device_stream(n_batches: int, batch: int, device, n_keys: int = 128_000_000, n_ns: int = 10_000, hot: bool = False,
+                     first_batch: int = 0, seed: int = SEED, chunk_batches: int = 4):
+    """C4 / C5 records on `device`: namespace popularity Zipf(1.0) over n_ns namespaces, keys uniform inside a
+    namespace (C4) or Zipf(0.7) with 50 % of the traffic forced onto 100 fixed keys (C5, hot=True) — the same
+    distributions as c4_namespace_sharded (torch's RNG, seeded), limits from c4_namespace_sharded(...).limits."""
+    import torch
+
+    ns_cdf = torch.from_numpy(_zipf_cdf(n_ns, 1.0)).to(device)
+    keys_per_ns = max(1, n_keys // n_ns)
+    key_cdf = torch.from_numpy(_zipf_cdf(min(keys_per_ns, 1 << 20), 0.7)).to(device) if hot else None
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 1_000_003 + first_batch + (29 if hot else 17))
+    out = torch.empty((n_batches, batch, 4), dtype=torch.int64, device=device)
+    for b0 in range(0, n_batches, chunk_batches):
+        nb = min(chunk_batches, n_batches - b0)
+        m = nb * batch
+        ns = torch.searchsorted(ns_cdf, torch.rand(m, dtype=torch.float64, device=device, generator=g)).clamp_(max=n_ns - 1)
+        if hot:
+            k = torch.searchsorted(key_cdf, torch.rand(m, dtype=torch.float64, device=device, generator=g)).clamp_(max=key_cdf.numel() - 1)
+            hot_sel = torch.rand(m, device=device, generator=g) < 0.5
+            hot_idx = torch.randint(0, 100, (m,), dtype=torch.int64, device=device, generator=g)
+            ns = torch.where(hot_sel, hot_idx * 97 % n_ns, ns)
+            k = torch.where(hot_sel, torch.zeros_like(k), k)
+        else:
+            k = torch.randint(0, keys_per_ns, (m,), dtype=torch.int64, device=device, generator=g)
+        gb = torch.arange(first_batch + b0, first_batch + b0 + nb, device=device, dtype=torch.int64)
+        i = gb.repeat_interleave(batch) * batch + torch.arange(batch, device=device, dtype=torch.int64).repeat(nb)
+        o = out[b0:b0 + nb].view(m, 4)
+        o[:, 0] = ns | (1 << 32)
+        o[:, 1] = _mix_torch(ns * keys_per_ns + k + 1)
+        o[:, 2] = 0
+        o[:, 3] = T0_US + i // 1000 + 1_000_000 * (i // batch // 64)
+    return out

@@ -75,6 +75,9 @@ def lib():
         L.lo_mt_run.restype = C.c_double
         L.lo_mt_run.argtypes = [vp, u64, vp, vp]
         L.lo_mt_destroy.argtypes = [vp]
+        L.lo_mt_destroy.restype = None
+        L.lo_mt_pinned.argtypes = [vp]
+        L.lo_mt_pinned.restype = u32
         L.lo_bench_records_mt.restype = C.c_double
         L.lo_bench_records_mt.argtypes = [vp, u32, u64, vp, u32, u64, vp]
         _lib = L
@@ -259,6 +262,11 @@ class OracleMT:
         out = np.zeros(len(recs), dtype=np.uint8)
         t = lib().lo_mt_run(self._h, len(recs), _p(recs), _p(out))
         return float(t), out
+
+    @property
+    def pinned(self) -> int:
+        """worker threads pinned to a CPU of their own"""
+        return int(lib().lo_mt_pinned(self._h))
 
     def close(self):
         if self._h:

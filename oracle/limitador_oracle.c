@@ -1,3 +1,6 @@
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 /*
  * limitador_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT THE PRODUCT).
  * See limitador_oracle.h for the scope and the parity pin.  Every function cites the
@@ -8,6 +11,7 @@
 #include "limitador_oracle.h"
 
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -569,41 +573,56 @@ uint64_t lo_size(lo_oracle *o) {
 /* T persistent oracles; every namespace is owned by one of them (all counters
  * of a request belong to its namespace), chosen once by longest-processing-time-first on
  * the first run's per-namespace request counts so the threads are balanced under Zipf. */
+struct lo_mt;
+typedef struct {
+    struct lo_mt *m;
+    uint32_t t;
+    lo_oracle *o;
+    const lo_record *recs;
+    const uint32_t *idx;
+    uint64_t n;
+    uint8_t *out_limited;
+} mt_arg;
+
+/* The workers are PERSISTENT and PINNED (one per CPU of the process's affinity mask, round robin): a run
+ * only hands them their index lists between two barriers, so the timed region holds no thread creation, no
+ * join and no migration — the baseline does not swing with the scheduler's mood. */
 struct lo_mt {
     uint32_t threads;
     lo_oracle **o;
     uint32_t *ns_owner; /* [ns_cap] */
     uint32_t ns_cap;
     int assigned;
+    pthread_t *tids;
+    mt_arg *args;
+    pthread_barrier_t start, end;
+    volatile int stop;
+    uint32_t pinned; /* workers whose pthread_setaffinity_np succeeded */
 };
-
-typedef struct {
-    lo_oracle *o;
-    const lo_record *recs;
-    const uint32_t *idx;
-    uint64_t n;
-    uint8_t *out_limited;
-    pthread_barrier_t *start;
-} mt_arg;
 
 static void *mt_worker(void *p) {
     mt_arg *a = (mt_arg *)p;
-    pthread_barrier_wait(a->start);
+    struct lo_mt *m = a->m;
     enum { MAXC = 64 };
     lo_counter c[MAXC];
-    lo_oracle *o = a->o;
-    for (uint64_t j = 0; j < a->n; j++) {
-        uint32_t i = a->idx[j];
-        const lo_record *r = &a->recs[i];
-        uint32_t m = (r->ns_id < o->ns_cap) ? o->ns_count[r->ns_id] : 0;
-        for (uint32_t k = 0; k < m; k++) {
-            c[k].limit_id = o->ns_limits[r->ns_id][k];
-            int q = o->limits[c[k].limit_id].qualified;
-            c[k].key_lo = q ? r->key_lo : 0;
-            c[k].key_hi = q ? (r->key_hi & LO_RECORD_KEY_HI_MASK) : 0; /* top byte: opaque lane */
+    for (;;) {
+        pthread_barrier_wait(&m->start);
+        if (m->stop) break;
+        lo_oracle *o = a->o;
+        for (uint64_t j = 0; j < a->n; j++) {
+            uint32_t i = a->idx[j];
+            const lo_record *r = &a->recs[i];
+            uint32_t k_n = (r->ns_id < o->ns_cap) ? o->ns_count[r->ns_id] : 0;
+            for (uint32_t k = 0; k < k_n; k++) {
+                c[k].limit_id = o->ns_limits[r->ns_id][k];
+                int q = o->limits[c[k].limit_id].qualified;
+                c[k].key_lo = q ? r->key_lo : 0;
+                c[k].key_hi = q ? (r->key_hi & LO_RECORD_KEY_HI_MASK) : 0; /* top byte: opaque lane */
+            }
+            int res = k_n ? lo_check_and_update(o, c, k_n, r->hits_addend, 0, r->now_us, NULL, NULL, NULL) : 0;
+            a->out_limited[i] = (uint8_t)(res > 0);
         }
-        int res = m ? lo_check_and_update(o, c, m, r->hits_addend, 0, r->now_us, NULL, NULL, NULL) : 0;
-        a->out_limited[i] = (uint8_t)(res > 0);
+        pthread_barrier_wait(&m->end);
     }
     return NULL;
 }
@@ -628,12 +647,44 @@ lo_mt *lo_mt_create(const lo_limit_desc *limits, uint32_t n_limits, uint32_t thr
                          (int)limits[k].qualified);
         m->o[t] = o;
     }
+    /* persistent workers, pinned round robin over the CPUs this process may run on */
+    cpu_set_t allowed;
+    int cpus[CPU_SETSIZE], ncpu = 0;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+    m->tids = (pthread_t *)calloc(threads, sizeof(pthread_t));
+    m->args = (mt_arg *)calloc(threads, sizeof(mt_arg));
+    pthread_barrier_init(&m->start, NULL, threads + 1);
+    pthread_barrier_init(&m->end, NULL, threads + 1);
+    for (uint32_t t = 0; t < threads; t++) {
+        m->args[t].m = m;
+        m->args[t].t = t;
+        m->args[t].o = m->o[t];
+        pthread_create(&m->tids[t], NULL, mt_worker, &m->args[t]);
+        if (ncpu > 0) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[t % (uint32_t)ncpu], &one);
+            if (pthread_setaffinity_np(m->tids[t], sizeof one, &one) == 0) m->pinned++;
+        }
+    }
     return m;
 }
 
+uint32_t lo_mt_pinned(lo_mt *m) { return m ? m->pinned : 0; }
+
 void lo_mt_destroy(lo_mt *m) {
     if (!m) return;
+    m->stop = 1;
+    pthread_barrier_wait(&m->start);
+    for (uint32_t t = 0; t < m->threads; t++) pthread_join(m->tids[t], NULL);
+    pthread_barrier_destroy(&m->start);
+    pthread_barrier_destroy(&m->end);
     for (uint32_t t = 0; t < m->threads; t++) lo_destroy(m->o[t]);
+    free(m->tids);
+    free(m->args);
     free(m->o);
     free(m->ns_owner);
     free(m);
@@ -667,8 +718,6 @@ double lo_mt_run(lo_mt *m, uint64_t n, const lo_record *recs, uint8_t *out_limit
         free(done);
         m->assigned = 1;
     }
-    mt_arg *args = (mt_arg *)calloc(T, sizeof(mt_arg));
-    pthread_t *tids = (pthread_t *)calloc(T, sizeof(pthread_t));
     uint64_t *cnt = (uint64_t *)calloc(T, sizeof(uint64_t));
     uint32_t **idx = (uint32_t **)calloc(T, sizeof(uint32_t *));
 #define OWNER(i) (recs[i].ns_id < m->ns_cap ? m->ns_owner[recs[i].ns_id] : 0)
@@ -682,28 +731,20 @@ double lo_mt_run(lo_mt *m, uint64_t n, const lo_record *recs, uint8_t *out_limit
         idx[t][cnt[t]++] = (uint32_t)i;
     }
 #undef OWNER
-    pthread_barrier_t start;
-    pthread_barrier_init(&start, NULL, T + 1);
     for (uint32_t t = 0; t < T; t++) {
-        args[t].o = m->o[t];
-        args[t].recs = recs;
-        args[t].idx = idx[t];
-        args[t].n = cnt[t];
-        args[t].out_limited = out_limited;
-        args[t].start = &start;
-        pthread_create(&tids[t], NULL, mt_worker, &args[t]);
+        m->args[t].recs = recs;
+        m->args[t].idx = idx[t];
+        m->args[t].n = cnt[t];
+        m->args[t].out_limited = out_limited;
     }
     struct timespec t0, t1;
-    pthread_barrier_wait(&start);
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (uint32_t t = 0; t < T; t++) pthread_join(tids[t], NULL);
+    pthread_barrier_wait(&m->start); /* the workers are parked on this barrier */
+    pthread_barrier_wait(&m->end);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     for (uint32_t t = 0; t < T; t++) free(idx[t]);
-    pthread_barrier_destroy(&start);
     free(idx);
     free(cnt);
-    free(tids);
-    free(args);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 

@@ -137,6 +137,8 @@ typedef struct lo_mt lo_mt;
 lo_mt *lo_mt_create(const lo_limit_desc *limits, uint32_t n_limits, uint32_t threads, uint64_t capacity_hint);
 double lo_mt_run(lo_mt *m, uint64_t n, const lo_record *recs, uint8_t *out_limited);
 void lo_mt_destroy(lo_mt *m);
+/* workers pinned to a CPU of their own (pthread_setaffinity_np succeeded) */
+uint32_t lo_mt_pinned(lo_mt *m);
 double lo_bench_records_mt(const lo_limit_desc *limits, uint32_t n_limits, uint64_t n,
                            const lo_record *recs, uint32_t threads, uint64_t capacity_hint,
                            uint8_t *out_limited);

@@ -46,7 +46,7 @@ def test_struct_layouts_match_header():
     assert engine.COUNTER_DTYPE.itemsize == 24
     assert engine.LIMIT_DESC_DTYPE.itemsize == 32
     assert ctypes.sizeof(engine.RlConfig) == 40
-    assert ctypes.sizeof(engine.RlStats) == 128
+    assert ctypes.sizeof(engine.RlStats) == 136
 
 
 def test_owner_of_is_pure_host_function():

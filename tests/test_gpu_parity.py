@@ -250,6 +250,52 @@ def test_errors_are_loud():
         e2.check_and_update_records(np.zeros((1 << 16) + 1, dtype=RECORD_DTYPE))
 
 
+def test_unevaluated_requests_never_read_as_allowed():
+    """a request the engine cannot evaluate gets RL_VERDICT_ERROR (0xFF), not 0 = allowed, and a
+    general-form call with an unresolvable request is refused BEFORE the table is touched (a retry of the
+    corrected batch must not double count the other requests)."""
+    import torch
+    descs = np.array([(0, 0, 1, 1, 3, 60 * S), (1, 1, 1, 1, 3, 60 * S)], dtype=LIMIT_DESC_DTYPE)
+    e = engine_with_limits(descs, 1, flags=2)
+    o = H.oracle_with_limits(descs)
+    recs = np.zeros(64, dtype=RECORD_DTYPE)
+    recs["ns_id"] = np.arange(64) % 2
+    recs["hits_addend"] = 1
+    recs["key_lo"] = 1 + np.arange(64) % 5
+    recs["now_us"] = H.T0
+    bad = recs.copy()
+    bad["key_hi"][[3, 17]] = np.uint64(1 << 40)  # bits 32..55 set: malformed
+    d = torch.from_numpy(bad.view(np.int64).reshape(-1, 4).copy()).cuda()
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    e.check_and_update_records_ptr(64, d.data_ptr(), out.data_ptr(), 1, stride=1)
+    with pytest.raises(EngineError):
+        e.sync()
+    got = out.cpu().numpy()
+    assert got[3] == 0xFF and got[17] == 0xFF
+    good = np.ones(64, dtype=bool)
+    good[[3, 17]] = False
+    want = o.batch_records(0, recs[good])[0]
+    assert np.array_equal(got[good], want)  # the well-formed requests were decided as if the bad ones were absent
+    assert_tables_equal(e, o, descs)
+    # general form: unknown limit in request 2 of 3 -> the whole call is refused, nothing is counted
+    e2 = engine_with_limits(descs, 1)
+    off = np.array([0, 1, 2, 3], dtype=np.uint32)
+    ctrs = np.array([(0, 0, 7, 0), (9, 0, 7, 0), (1, 0, 7, 0)], dtype=COUNTER_DTYPE)
+    with pytest.raises(EngineError) as ei:
+        e2.check_and_update_batch(off, ctrs, [1, 1, 1], [H.T0] * 3)
+    assert "before the table was touched" in str(ei.value)
+    assert e2.dump() == []
+    ctrs["limit_id"][1] = 0
+    lim = e2.check_and_update_batch(off, ctrs, [1, 1, 1], [H.T0] * 3)[0]
+    assert lim.tolist() == [0, 0, 0] and len(e2.dump()) == 2
+    # 17 counters in one request (the engine takes 16)
+    many = np.zeros(17, dtype=COUNTER_DTYPE)
+    many["key_lo"] = 1
+    with pytest.raises(EngineError):
+        e2.check_and_update_batch(np.array([0, 17], dtype=np.uint32), many, [1], [H.T0])
+    assert len(e2.dump()) == 2
+
+
 @pytest.mark.parametrize("name,kw,nb", [
     ("C1", dict(batch=65536), 3),
     ("C2", dict(batch=65536, n_rows=100_000), 4),
@@ -512,14 +558,62 @@ def test_batching_front_concurrent_callers_linearise():
     assert_tables_equal(e, o, descs)
 
 
+@pytest.mark.parametrize("load_counters", [False, True])
+def test_hot_rows_get_partitions_of_their_own(load_counters):
+    """a row that dominates its k_main chunks is admitted to the hot-row table and from the next batch on
+    its whole request list is replayed by one CTA of k_hot (no chained chunks); rows that cool down are dropped.
+    Verdicts, named limits, remaining/ttl and the table equal the oracle's throughout — with windows rolling over
+    (a 1-s limit), values accumulating (max 2^40), saturated rows (max 3) and mixed deltas on the hot rows."""
+    descs = np.array([(0, 0, 1, 1, 3, 1 * S), (1, 0, 1, 1, 1 << 40, 3600 * S), (2, 1, 1, 1, 50, 2 * S),
+                      (3, 2, 0, 0, 1 << 40, 60 * S), (4, 3, 1, 1, 5, 60 * S)], dtype=LIMIT_DESC_DTYPE)
+    e = engine_with_limits(descs, 3, capacity=1 << 12, regions=4)
+    o = H.oracle_with_limits(descs)
+    rng = np.random.default_rng(9)
+    n = 20000
+    t = H.T0
+    for b in range(9):
+        recs = np.zeros(n, dtype=RECORD_DTYPE)
+        hot = rng.random(n) < (0.0 if b == 6 else 0.8)  # batch 6: the hot keys vanish, the table drains
+        recs["ns_id"] = np.where(hot, rng.integers(0, 3, n), rng.integers(0, 4, n))
+        recs["key_lo"] = np.where(hot, 1 + rng.integers(0, 2, n), 10 + rng.integers(0, 3000, n))
+        recs["hits_addend"] = np.where(rng.random(n) < 0.9, 1, rng.integers(1, 4, n))
+        recs["now_us"] = t + np.sort(rng.integers(0, 1_500_000, n)).astype(np.uint64)
+        t += 1_600_000
+        got = e.check_and_update_records(recs, load_counters, stride=3)
+        want = o.batch_records(0, recs, load_counters, 3)
+        assert got[0].tolist() == want[0].tolist(), f"batch {b}"
+        assert got[1].tolist() == want[1].tolist()
+        if load_counters:
+            assert got[2].tolist() == want[2].tolist() and got[3].tolist() == want[3].tolist()
+        assert_tables_equal(e, o, descs)
+        hot_now = e.stats()["hot_rows"]
+        if b in (2, 3, 4, 5):
+            assert hot_now >= 4, f"batch {b}: {hot_now} hot rows"  # (ns 0..2) x (key 1..2), unqualified ns 2 -> one row
+        if b == 8:
+            assert hot_now >= 4
+    # update_counters through the hot path as well
+    for b in range(3):
+        recs = np.zeros(n, dtype=RECORD_DTYPE)
+        recs["ns_id"] = rng.integers(0, 3, n)
+        recs["key_lo"] = 1 + rng.integers(0, 2, n)
+        recs["hits_addend"] = 1
+        recs["now_us"] = t + np.sort(rng.integers(0, 1_500_000, n)).astype(np.uint64)
+        t += 1_600_000
+        e.update_records(recs)
+        o.batch_records(2, recs)
+        assert_tables_equal(e, o, descs)
+
+
+@pytest.mark.parametrize("hot", [0, 1])
 @pytest.mark.parametrize("chunk,mult", [(128, 1), (256, 1), (128, 2)])
-def test_chained_commit_stress(monkeypatch, chunk, mult):
+def test_chained_commit_stress(monkeypatch, chunk, mult, hot):
     """Optimistic-commit protocol under stress: RL_HEAVY_MULT=1 chains every partition above the
     average, and a tiny key space makes the chunks of a partition share written rows in every
     direction (earlier writer -> later reader AND later writer -> earlier reader, the case a
     round-1 bug missed).  Records and CSR forms, both load_counters values."""
     monkeypatch.setenv("RL_CHUNK", str(chunk))
     monkeypatch.setenv("RL_HEAVY_MULT", str(mult))
+    monkeypatch.setenv("RL_HOT", str(hot))  # 0: every heavy partition stays on the chained path
     for cells in (1, 3):
         descs = single_row_limits(cells, seed=20 + cells)
         e = engine_with_limits(descs, cells, regions=4, flags=4)  # RL_FLAG_KERNEL_STATS: chunk accounting on
@@ -534,7 +628,7 @@ def test_chained_commit_stress(monkeypatch, chunk, mult):
             if lc:
                 assert got[2].tolist() == want[2].tolist() and got[3].tolist() == want[3].tolist()
             assert_tables_equal(e, o, descs)
-        if mult == 1:  # every partition above the average is chained
+        if mult == 1 and not hot:  # every partition above the average is chained
             assert e.stats()["chained_chunks"] > 0 and e.stats()["ordered_chunks"] > 0
     # update_counters through the same chained path
     descs = single_row_limits(3, seed=31)
