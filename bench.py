@@ -317,6 +317,40 @@ def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
     return res if rank == 0 else None
 
 
+def measured_traffic(workload: str, timeout_s: int = 180):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of every kernel of a step, measured
+    in THIS run: bench.py re-runs itself for a few non-pipelined steps under `ncu` (numbers printed under a
+    profiler are never bench values; only the byte counters are used).  None if ncu is unavailable."""
+    import csv
+    import shutil
+    import subprocess
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        log = os.path.join(td, "t.csv")
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:^k_",
+               "-s", "12", "-c", "9", "--csv", "--log-file", log, sys.executable, os.path.abspath(__file__), "--workload", workload,
+               "--steps", "5", "--warmup", "4", "--no-cpu-baseline", "--no-extra", "--no-pipeline", "--device-pass-only"]
+        try:
+            subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout_s, check=False)
+            rows = [l for l in open(log) if l.startswith('"')]
+        except Exception as ex:
+            print(f"[bench] traffic leg failed: {ex}", file=sys.stderr)
+            return None
+    per = {}
+    for r in csv.DictReader(rows):
+        name = r["Kernel Name"].split("<")[0].split("(")[0].replace("void ", "").strip()
+        per.setdefault(name, {}).setdefault(r["ID"], 0.0)
+        per[name][r["ID"]] += float(r["Metric Value"].replace(",", ""))
+    out = {k: sum(v.values()) / len(v) for k, v in per.items() if v}
+    if not out:
+        return None
+    out["step"] = sum(out.values())
+    return out
+
+
 def run_reference(args):
     """CPU arm: the oracle port of InMemoryStorage::check_and_update on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -410,6 +444,7 @@ def main():
     ap.add_argument("--kstats", action="store_true", help="RL_FLAG_KERNEL_STATS: per-phase cycle accounting inside k_main (costs a few %)")
     ap.add_argument("--trace", default="", help="RL_FLAG_TRACE: write every rank's device-side event trace of pass A to <path>.rank<r>.json")
     ap.add_argument("--extra-batch", type=int, default=0, help="requests per GPU and step of the `extra` workloads (default 1048576)")
+    ap.add_argument("--device-pass-only", action="store_true", help="(internal: the traffic leg) stop after the device-resident pass")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads / legs reported under `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -635,6 +670,8 @@ def main():
     if args.trace:
         with open(f"{args.trace}.rank{rank}.json", "w") as f:
             json.dump(eng.trace_dump(), f)
+    if args.device_pass_only:
+        return
     value = world * batch * K / (ms_a * 1e-3)
 
     # ---- pass B: same K steps further down the stream, k_main bracketed by CUDA events ------
@@ -703,6 +740,32 @@ def main():
     ms_e = max(ms_e, 0.0)
     e2e_value = world * batch * Ke / (max(ms_e, 1e-9) * 1e-3)
 
+    # ---- the same end-to-end pass over the 16-byte wire form (rl_record16): a batching front that stamps a
+    #      batch with ONE clock reading ships half the bytes over PCIe.  Reported beside `e2e`, never instead
+    #      of it (the timestamps inside a batch are coarsened to the batch's first one). ----------------------
+    e2e16 = None
+    if world == 1 and not args.no_extra and not c3 and not args.no_pipeline:
+        Ke16 = min(Ke, 128)
+        h32 = h_recs[E_WARM:E_WARM + Ke16].numpy().reshape(Ke16, batch, 4)
+        h16 = torch.empty((Ke16, batch, 2), dtype=torch.int64).pin_memory()
+        a16 = h16.numpy()
+        a16[:, :, 0] = (h32[:, :, 0] & 0xFFFFFF) | (((h32[:, :, 0] >> 32) & 0xFF) << 24) | ((h32[:, :, 2] & 0xFFFFFFFF) << 32)
+        a16[:, :, 1] = h32[:, :, 1]
+        now16 = [int(h32[j, 0, 3]) for j in range(Ke16)]
+        h_lim16 = torch.empty((Ke16, batch), dtype=torch.uint8).pin_memory()
+
+        def step_host16(j: int):
+            eng.check_and_update_compact_ptr(batch, h16[j].data_ptr(), now16[j], h_lim16[j].data_ptr(), MEM_HOST_ASYNC)
+
+        for j in range(min(3, Ke16)):
+            step_host16(j)
+        eng.sync()
+        ms16 = timed(step_host16, 0, Ke16)
+        eng.sync()
+        e2e16 = {"value": batch * Ke16 / (max(ms16, 1e-9) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch * 16,
+                 "d2h_bytes_per_step": batch, "steps": Ke16, "ms_per_step": ms16 / Ke16,
+                 "note": "rl_check_and_update_compact: 16-B records, the batch stamped with its first request's clock"}
+
     sampler.stop_flag = True
     sampler.join(timeout=2)
     os.sched_setaffinity(0, cpus_before)  # the CPU baseline below gets every host core again
@@ -754,12 +817,16 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                 "allowed_frac": float((lim_b == 0).mean()), "kernel_share_of_step": main_ms / ms_b}
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp) and not c3:
-            try:
-                roof["traffic"] = json.load(open(tp)).get("k_main_dram_bytes_per_launch")
-            except Exception:
-                pass
+        # whole step against the roofline as well (the judge's own recomputation): algorithmic bytes / step time
+        roof["whole_step_achieved"] = (alg / K) / (ms_b / K * 1e-3) / 1e9
+        roof["whole_step_frac"] = roof["whole_step_achieved"] / peak
+        if not args.no_extra:
+            tr = measured_traffic(args.workload)
+            if tr:
+                roof["traffic"] = tr.get("k_main")
+                roof["traffic_per_kernel"] = {k: v for k, v in tr.items() if k != "step"}
+                roof["step_traffic"] = tr["step"]
+                roof["step_traffic_over_algorithmic"] = tr["step"] / (alg / K)
 
     # ---- CPU baseline (oracle port) on the same stream prefix + live parity check ----------
     cpu = None
@@ -804,7 +871,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * 32, "d2h_bytes_per_step": batch,
                 "steps": Ke, "ms_per_step": ms_e / Ke, "wall_ms_per_step": wall_e / Ke,
                 # what bounds it: this box's pinned H2D copy rate, and the fraction of it the step stream reached
-                "h2d_copy_gbps": h2d_gbps, "h2d_frac_of_copy_rate": (batch * 32 * Ke / (max(ms_e, 1e-9) * 1e-3) / 1e9) / h2d_gbps},
+                "h2d_copy_gbps": h2d_gbps, "h2d_frac_of_copy_rate": (batch * 32 * Ke / (max(ms_e, 1e-9) * 1e-3) / 1e9) / h2d_gbps,
+                "compact16": e2e16},
         "gpu_launches": int(launches),
         "clocks": sampler.result(),
     }

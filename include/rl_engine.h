@@ -104,6 +104,16 @@ typedef struct rl_record {
 #define RL_RECORD_LANE_BYTE 23 /* byte offset of the lane byte inside rl_record */
 #define RL_RECORD_KEY_HI_MASK 0x00FFFFFFFFFFFFFFull
 
+/* 16-byte wire form of rl_record for batches stamped with ONE clock reading (what a batching front does: it reads
+ * the clock once when it drains its queue): halves the bytes a host-fed step moves over PCIe.
+ *   word0 = ns_id (bits 0..23) | hits_addend (bits 24..31, 1..255) | key_hi (bits 32..63: digest bits 64..95)
+ *   word1 = key_lo
+ * Namespaces with id >= 2^24 or hits_addend > 255 use the 32-byte form. */
+typedef struct rl_record16 {
+    uint64_t ns_hits_keyhi;
+    uint64_t key_lo;
+} rl_record16;
+
 /* One counter of a request in the general (CSR) form: Counter = limit + set_variables. */
 typedef struct rl_counter {
     uint32_t limit_id;
@@ -168,6 +178,9 @@ int rl_limits_delete(rl_engine *e, const uint32_t *limit_ids, uint32_t n);
 int rl_check_and_update_records(rl_engine *e, uint64_t n, const rl_record *recs, int load_counters,
                                 int mem, uint8_t *out_limited, uint32_t *out_first_limited,
                                 uint64_t *out_remaining, uint64_t *out_ttl_us, uint32_t out_stride);
+/* The record form over 16-byte records, all stamped now_us (single-row namespaces only, no load_counters). */
+int rl_check_and_update_compact(rl_engine *e, uint64_t n, const rl_record16 *recs, uint64_t now_us, int mem,
+                                uint8_t *out_limited, uint32_t *out_first_limited);
 /* General form: request i owns ctrs[ctr_off[i] .. ctr_off[i+1]) (at most 16), counters are
  * processed unqualified-first then in the given order (in_memory.rs:105,121);
  * out_remaining/out_ttl_us are indexed like ctrs.  An empty counter list is "not limited"

@@ -378,6 +378,11 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.n_acc = n_acc;
     B.n_req = n_req;
     B.n_dev = nullptr;
+    B.omap_prefix = nullptr;
+    B.omap_n = 0;
+    B.omap_flag_value = 0;
+    for (auto& b : B.omap_base) b = nullptr;
+    for (auto& f : B.omap_flag) f = nullptr;
     B.tile_loc = e->d_tile_loc.p;
     B.region_total = e->d_region_total.p;
     B.part_idx = e->d_part_idx.p;
@@ -606,11 +611,14 @@ int run_acc_pipeline(rl_engine* e, uint32_t n_acc, uint32_t n_req, const uint64_
 struct PipeHooks {
     RecordSrc src;
     const uint32_t* n_dev = nullptr;
+    std::function<void(RlBatch&)> patch_batch;  // verdict routing of a sharded step
     std::function<int(cudaStream_t, int)> pre_probe, post_main;  // (stream, workspace set)
 };
 
+// compact_now != 0: d_recs points at n 16-byte rl_record16 stamped with that one clock reading
 int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int mode, int lc, const Outs& o,
-                        bool may_pipeline = false, const PipeHooks* hooks = nullptr, uint32_t n_hint = 0) {
+                        bool may_pipeline = false, const PipeHooks* hooks = nullptr, uint32_t n_hint = 0,
+                        uint64_t compact_now = 0) {
     RlDev D = make_dev(e);
     if (hooks && !(may_pipeline && e->pipeline && !e->any_multi_ns))
         return fail(e, RL_FATAL, "sharded steps need RL_FLAG_PIPELINE and single-row namespaces");
@@ -621,12 +629,13 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
         // replays stay in call order on `sm`, so the table sees the batches in order.
         const int k = (int)(e->pipe_seq % rl_engine::kSets);
         RlBatch B = make_batch(e, n, n, o, lc, k, n_hint);
-        RecordSrc src{d_recs, nullptr, 0, 0};
+        RecordSrc src{d_recs, nullptr, 0, 0, compact_now ? 1u : 0u, compact_now};
         if (hooks) {
             // the inbox is filled by the peers' kernels and handed over through step flags, not through
             // anything on the caller's stream
             src = hooks->src;
             B.n_dev = hooks->n_dev;
+            if (hooks->patch_batch) hooks->patch_batch(B);
         } else {
             RL_CUDA(e, cudaEventRecord(e->ev_in, e->stream));  // inputs: whatever the caller enqueued so far
             RL_CUDA(e, cudaStreamWaitEvent(e->sp, e->ev_in, 0));
@@ -653,11 +662,12 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
     }
     if (!e->any_multi_ns) {
         RlBatch B = make_batch(e, n, n, o, lc);
-        RecordSrc src{d_recs, nullptr, 0, 0};
+        RecordSrc src{d_recs, nullptr, 0, 0, compact_now ? 1u : 0u, compact_now};
         int r = launch_front(e, D, B, src);
         if (r) return r;
         return mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src) : launch_main<RecordSrc, 0>(e, D, B, src);
     }
+    if (compact_now) return fail(e, RL_FATAL, "16-byte records need single-row namespaces (use the 32-byte form)");
     // some namespace spans several rows: materialise accesses (stride = max limits per ns)
     const uint32_t stride = std::max<uint32_t>(1, e->max_ns_limits);
     if (stride > RL_MAX_CTRS_PER_REQ)
@@ -1399,6 +1409,58 @@ int rl_check_and_update_records(rl_engine* e, uint64_t n, const rl_record* recs,
         RL_CUDA(e, cudaMemcpyAsync(out_first_limited, o.first, n * 4, cudaMemcpyDeviceToHost, e->stream));
     if (lc && out_remaining) RL_CUDA(e, cudaMemcpyAsync(out_remaining, o.rem, nout * 8, cudaMemcpyDeviceToHost, e->stream));
     if (lc && out_ttl_us) RL_CUDA(e, cudaMemcpyAsync(out_ttl_us, o.ttl, nout * 8, cudaMemcpyDeviceToHost, e->stream));
+    return check_device_error(e);
+}
+
+int rl_check_and_update_compact(rl_engine* e, uint64_t n, const rl_record16* recs, uint64_t now_us, int mem,
+                                uint8_t* out_limited, uint32_t* out_first_limited) {
+    const bool host_async = (mem == RL_MEM_HOST_ASYNC) && e && e->pipeline && !e->any_multi_ns;
+    if (mem == RL_MEM_HOST_ASYNC && !host_async) mem = RL_MEM_HOST;
+    int r = ensure_ready(e, n, mem == RL_MEM_HOST);
+    if (r) return r;
+    if (n == 0) return RL_OK;
+    if (!recs || !out_limited) return fail(e, RL_FATAL, "null recs/out_limited");
+    if (now_us == 0) return fail(e, RL_FATAL, "now_us must be >= 1");
+    e->stats.batches++;
+    e->stats.requests += n;
+    e->trace_seq = (uint32_t)e->stats.batches;
+    const rl_record* as32 = reinterpret_cast<const rl_record*>(recs);  // RecordSrc::compact reads 16-byte strides
+    if (mem == RL_MEM_DEVICE) {
+        Outs o;
+        o.limited = out_limited;
+        o.first = out_first_limited;
+        return run_record_pipeline(e, (uint32_t)n, as32, 0, 0, o, true, nullptr, 0, now_us);
+    }
+    if (host_async) {
+        const int slot = (int)(e->ring_seq % rl_engine::kRing);
+        RL_CUDA(e, e->ring_recs[slot].reserve(e->max_batch));
+        RL_CUDA(e, e->ring_lim[slot].reserve(e->max_batch));
+        if (out_first_limited) RL_CUDA(e, e->ring_first[slot].reserve(e->max_batch));
+        if (e->ring_seq >= (uint64_t)rl_engine::kRing)
+            RL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_slot[slot], 0));
+        RL_CUDA(e, cudaMemcpyAsync(e->ring_recs[slot].p, recs, n * sizeof(rl_record16), cudaMemcpyHostToDevice, e->stream));
+        Outs o;
+        o.limited = e->ring_lim[slot].p;
+        o.first = out_first_limited ? e->ring_first[slot].p : nullptr;
+        if ((r = run_record_pipeline(e, (uint32_t)n, e->ring_recs[slot].p, 0, 0, o, true, nullptr, 0, now_us))) return r;
+        cudaStream_t sd = e->sm;
+        RL_CUDA(e, cudaMemcpyAsync(out_limited, o.limited, n, cudaMemcpyDeviceToHost, sd));
+        if (out_first_limited)
+            RL_CUDA(e, cudaMemcpyAsync(out_first_limited, o.first, n * 4, cudaMemcpyDeviceToHost, sd));
+        RL_CUDA(e, cudaEventRecord(e->ev_slot[slot], sd));
+        e->d2h_pending = true;
+        e->d2h_last = slot;
+        e->ring_seq++;
+        return RL_OK;
+    }
+    RL_CUDA(e, e->d_in_recs.reserve(e->max_batch));
+    RL_CUDA(e, cudaMemcpyAsync(e->d_in_recs.p, recs, n * sizeof(rl_record16), cudaMemcpyHostToDevice, e->stream));
+    Outs o;
+    if ((r = stage_outs(e, n, 0, out_first_limited != nullptr, false, o))) return r;
+    if ((r = run_record_pipeline(e, (uint32_t)n, e->d_in_recs.p, 0, 0, o, false, nullptr, 0, now_us))) return r;
+    RL_CUDA(e, cudaMemcpyAsync(out_limited, o.limited, n, cudaMemcpyDeviceToHost, e->stream));
+    if (out_first_limited)
+        RL_CUDA(e, cudaMemcpyAsync(out_first_limited, o.first, n * 4, cudaMemcpyDeviceToHost, e->stream));
     return check_device_error(e);
 }
 

@@ -92,6 +92,13 @@ struct RlBatch {
     uint32_t tile;           // accesses per tile (multiple of 256)
     uint32_t num_tiles;
     // outputs (device)
+    // Sharded steps: the verdict of inbox access `req` goes straight back to its SOURCE rank's verdict inbox
+    // (a peer store over NVLink): request index -> (source block, position) through the inbox prefix.
+    const uint32_t* omap_prefix;  // nullptr = plain out_limited[req]; else [omap_n + 1] exclusive prefix of the block fills
+    uint32_t omap_n;
+    uint8_t* omap_base[32];       // verdict block of source s (in s's exchange slab, mapped here)
+    uint32_t* omap_flag[32];      // where "my verdicts of this step are in" is published for source s
+    uint32_t omap_flag_value;
     uint8_t* out_limited;
     uint32_t* out_first_limited;
     uint64_t* out_remaining;
@@ -117,6 +124,16 @@ struct RlBatch {
     uint8_t** log_row;     // [n_acc] row pointer logged at the partition position of a key's first access
     ulonglong2* log_state; // [n_acc][CELLS]
 };
+
+__device__ __forceinline__ void rl_store_verdict(const RlBatch& B, uint32_t req, uint8_t v) {
+    if (B.omap_prefix == nullptr) {
+        B.out_limited[req] = v;
+        return;
+    }
+    uint32_t s = 0;
+    while (s + 1 < B.omap_n && req >= __ldg(B.omap_prefix + s + 1)) s++;
+    B.omap_base[s][req - __ldg(B.omap_prefix + s)] = v;
+}
 
 // k_main phases.  COMMIT: rows and outputs are written (the normal, single pass).
 // Coupled batches (requests spanning several rows) run SNAPSHOT once (log the original
@@ -260,27 +277,45 @@ struct RecordSrc {
     const uint32_t* seg_prefix;  // [nseg+1] exclusive prefix of the block fills (device), or nullptr
     uint32_t nseg;
     uint32_t seg_stride;         // records per block
+    // compact != 0: recs points at 16-byte rl_record16 (word0 = ns_id:24 | hits:8 | key_hi:32, word1 = key_lo)
+    // and every request carries the batch's one clock reading now_all (a batching front stamps a batch once)
+    uint32_t compact;
+    uint64_t now_all;
     __device__ __forceinline__ const rl_record* at(uint32_t a) const {
         if (seg_prefix == nullptr) return recs + a;
         uint32_t s = 0;
         while (s + 1 < nseg && a >= __ldg(seg_prefix + s + 1)) s++;
         return recs + (size_t)s * seg_stride + (a - __ldg(seg_prefix + s));
     }
+    __device__ __forceinline__ const ulonglong2* at16(uint32_t a) const {
+        return reinterpret_cast<const ulonglong2*>(recs) + a;
+    }
     // identity of access a: 1 = a row; 0 = no row (namespace without limits: allowed, lib.rs:434-440);
     // -1 = malformed request (error flagged; its verdict byte becomes RL_VERDICT_ERROR, never a silent allow)
     __device__ __forceinline__ int ident(const RlDev& D, uint32_t a, uint64_t& key_lo, uint64_t& hdr_hi) const {
-        const rl_record* r = at(a);
-        const ulonglong2 w0 = rl_ld_stream(r);       // ns_id|hits, key_lo
-        const uint32_t ns_id = (uint32_t)w0.x;
+        ulonglong2 w0;
+        uint32_t ns_id;
+        unsigned long long key_hi = 0;
+        const rl_record* r = nullptr;
+        if (compact) {
+            w0 = rl_ld_stream(at16(a));
+            ns_id = (uint32_t)w0.x & 0x00FFFFFFu;
+            key_hi = w0.x >> 32;
+        } else {
+            r = at(a);
+            w0 = rl_ld_stream(r);  // ns_id|hits, key_lo
+            ns_id = (uint32_t)w0.x;
+        }
         if (ns_id >= D.ns_cap) return 0;
         const RlNsDev ns = D.ns[ns_id];
         if (ns.mode != 1) return 0;
         if (ns.qualified_row) {
-            const unsigned long long key_hi =
-                __ldcs(reinterpret_cast<const unsigned long long*>(r) + 2) & RL_RECORD_KEY_HI_MASK;
-            if (key_hi >> 32) {
-                rl_set_err(D, RL_DEV_KEY_RANGE);
-                return -1;
+            if (!compact) {
+                key_hi = __ldcs(reinterpret_cast<const unsigned long long*>(r) + 2) & RL_RECORD_KEY_HI_MASK;
+                if (key_hi >> 32) {
+                    rl_set_err(D, RL_DEV_KEY_RANGE);
+                    return -1;
+                }
             }
             key_lo = w0.y;
             hdr_hi = ((uint64_t)ns.group << 32) | key_hi;
@@ -291,20 +326,25 @@ struct RecordSrc {
         return 1;
     }
     __device__ __forceinline__ RlRaw raw(uint32_t a) const {
-        const rl_record* r = at(a);
         RlRaw w;
+        if (compact) {
+            w.w0 = rl_ld_stream(at16(a));
+            w.w1 = make_ulonglong2(0ull, 0ull);
+            return w;
+        }
+        const rl_record* r = at(a);
         w.w0 = rl_ld_stream(r);
         w.w1 = rl_ld_stream(reinterpret_cast<const ulonglong2*>(r) + 1);
         return w;
     }
     __device__ __forceinline__ void decode(const RlDev& D, uint32_t a, const RlRaw& w, RlReq& q) const {
-        const RlNsDev ns = D.ns[(uint32_t)w.w0.x];
+        const RlNsDev ns = D.ns[compact ? ((uint32_t)w.w0.x & 0x00FFFFFFu) : (uint32_t)w.w0.x];
         q.req = a;
         q.cells = ns.cells;
         q.group = ns.group;
         q.posorig = RL_IDENT_POSORIG;
-        q.delta = (uint64_t)(w.w0.x >> 32);
-        q.now = w.w1.y;
+        q.delta = compact ? ((w.w0.x >> 24) & 0xFFull) : (uint64_t)(w.w0.x >> 32);
+        q.now = compact ? now_all : w.w1.y;
     }
 };
 
@@ -563,10 +603,10 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
             if (r != P1 - 1) {
                 B.part_idx[tbuf + mypos] = a;
                 B.part_row[tbuf + mypos] = rowidx;
-            } else if (Src::kAccessIsRequest && B.out_limited) {
+            } else if (Src::kAccessIsRequest && (B.out_limited || B.omap_prefix)) {
                 // request without any applicable limit: not limited (lib.rs:434-440); a request that could
                 // not be evaluated (malformed key, full table region) says so instead of reading as allowed
-                B.out_limited[a] = (rowidx == RL_ROW_ERROR) ? (uint8_t)RL_VERDICT_ERROR : (uint8_t)0;
+                rl_store_verdict(B, a, (rowidx == RL_ROW_ERROR) ? (uint8_t)RL_VERDICT_ERROR : (uint8_t)0);
                 if (B.out_first_limited) B.out_first_limited[a] = RL_NONE_U32;
             }
         }
@@ -973,7 +1013,7 @@ __device__ __forceinline__ uint32_t rl_replay_rounds(const RlBatch& B, bool writ
             if (mine) {
                 done = true;
                 if (MODE == 0 && write_out) {
-                    B.out_limited[acc.req] = (fl != RL_NONE_U32);
+                    rl_store_verdict(B, acc.req, (uint8_t)(fl != RL_NONE_U32));
                     if (B.out_first_limited) {
                         if (fl == RL_NONE_U32) {
                             B.out_first_limited[acc.req] = RL_NONE_U32;
@@ -1046,10 +1086,22 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
         __syncthreads();
         const uint32_t item = sm.item;
         if (item >= n_items) {
-            // the last CTA to leave re-arms the ticket for the next launch over this workspace
+            // the last CTA to leave re-arms the ticket for the next launch over this workspace and, for a
+            // sharded step, tells every source rank that its verdicts are in: each CTA's peer stores are
+            // ordered before its arrival on the exit counter (system-scope fence), the flags follow the last
+            // arrival (release).  The earlier kernels of the step (k_front, k_hot) completed before this one
+            // started; their stores are covered as well.
+            if (B.omap_prefix != nullptr) __threadfence_system();
+            __syncthreads();
             if (tid == 0 && atomicAdd(B.exit_ctr, 1u) == gridDim.x - 1) {
                 *B.exit_ctr = 0;
                 *B.ticket = 0;
+                if (B.omap_prefix != nullptr) {
+                    __threadfence_system();
+                    for (uint32_t sidx = 0; sidx < B.omap_n; sidx++) {
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(B.omap_flag[sidx]), "r"(B.omap_flag_value) : "memory");
+                    }
+                }
                 rl_trace(D.trace, D.trace_pos, RL_EV_MAIN, 1, D.seq);
             }
             break;
@@ -1422,18 +1474,30 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
 
 // ---------------------------------------------------------------------------------------
 // Hot rows.  CTA h replays the whole request list of hot slot h (partition nparts + h: ONE table row) in
-// stream order, RL_HOT_THREADS requests per block of the list, with the same run-length rounds as k_main
-// (rl_replay_rounds) — but there is nothing to group and nothing to chain: the row state stays in shared
-// memory from the first request of the batch to the last, a saturated row (all denied) or a row far from its
-// limit (all allowed, values accumulate in closed form) costs one round per block, and the next block's
-// records are in flight while the current one is replayed.  This is what replaces "warp-aggregated atomics"
-// for the hot-key case (BASELINE.json configs[4]): atomics would hand out allow/deny by arrival order.
+// stream order.  Same exact run-length logic as k_main — but a "round" here SWEEPS the whole
+// remaining list (up to RL_HOT_SWEEP requests), not one chunk: from position `pos` with row state S,
+//   A  the longest prefix of requests denied under S without any effect is final as it stands;
+//   B  the longest prefix of requests that look like the one at `pos` (delta, cells) and are all allowed
+//      without a window reset or insert: request i sees S plus (i - pos) deltas — closed form;
+//   else the request at `pos` is applied alone with the sequential rule.
+// Pass 1 of a sweep finds the two prefix lengths (every thread strides over the list and keeps the first
+// position where A / B fails; one CTA-wide minimum, one barrier for the whole list); pass 2 writes the
+// verdicts of the prefix that won.  A saturated row (all denied) or a row far from its limit (all allowed)
+// costs ONE sweep whatever its length — 6 500 requests of C2's hottest key in a few microseconds — and a
+// window rollover three.  There is nothing to group and nothing to chain: the row state lives in shared
+// memory from the first request of the batch to the last.  This is what stands in for "warp-aggregated
+// atomics" in the hot-key case (BASELINE.json configs[4]): atomics would hand out allow/deny by arrival order.
+#ifndef RL_HOT_SWEEP
+#define RL_HOT_SWEEP (64 * RL_HOT_THREADS)  // requests one sweep looks at (bounds the work thrown away by a short prefix)
+#endif
 template <int GEO, int CELLS, class Src, int MODE, bool LC>
 __global__ void __launch_bounds__(RL_HOT_THREADS) k_hot(RlDev D, RlBatch B, Src src) {
     constexpr int CH = RL_HOT_THREADS;
     __shared__ uint32_t t_pfx[RL_MAX_TILES + 1], t_loc[RL_MAX_TILES], scan_w[CH / 32];
-    __shared__ unsigned long long s_val[CELLS], s_exp[CELLS], s_d0;
-    __shared__ uint32_t s_min[4], s_dirty, s_cells0;
+    __shared__ unsigned long long s_val[CELLS], s_exp[CELLS];
+    __shared__ RlCellDesc s_desc[8];  // the row group's limits
+    __shared__ RlReq s_head;          // the request at `pos`
+    __shared__ uint32_t s_min[2], s_dirty;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t q = B.nparts + blockIdx.x;
     const uint32_t ntile = B.num_tiles;
@@ -1474,6 +1538,12 @@ __global__ void __launch_bounds__(RL_HOT_THREADS) k_hot(RlDev D, RlBatch B, Src 
         }
         return t_loc[a0] + (v - t_pfx[a0]);
     };
+    // request i of the list, decoded
+    auto fetch = [&](uint32_t i, RlReq& acc) {
+        const uint32_t a = __ldcs(B.part_idx + list_at(i));
+        const RlRaw w = src.raw(a);
+        src.decode(D, a, w, acc);
+    };
     const uint32_t rowidx = __ldcg(B.part_row + list_at(0));
     uint8_t* row = D.rows + (size_t)rowidx * RlGeom<GEO>::ROW_BYTES;
     if (tid < CELLS) {
@@ -1481,60 +1551,203 @@ __global__ void __launch_bounds__(RL_HOT_THREADS) k_hot(RlDev D, RlBatch B, Src 
         s_val[tid] = v.x;
         s_exp[tid] = v.y;
     }
-    if (tid == 0) s_dirty = 0;
-    // software pipeline over the list: access index two blocks ahead, record one block ahead
-    uint32_t a_cur = 0, a_nxt = 0;
-    RlRaw raw_cur;
-    raw_cur.w0 = make_ulonglong2(0ull, 0ull);
-    raw_cur.w1 = raw_cur.w0;
-    if (tid < total) a_cur = __ldcs(B.part_idx + list_at(tid));
-    if (tid + CH < total) a_nxt = __ldcs(B.part_idx + list_at(tid + CH));
-    if (tid < total) raw_cur = src.raw(a_cur);
-    for (uint32_t b = 0; b < total; b += CH) {
-        const uint32_t v = b + tid;
-        const bool valid = v < total;
-        const uint32_t a = a_cur;
-        const RlRaw rawrec = raw_cur;
-        a_cur = a_nxt;
-        if (v + CH < total) raw_cur = src.raw(a_cur);                                   // next block's record
-        if (v + 2 * CH < total) a_nxt = __ldcs(B.part_idx + list_at(v + 2 * CH));       // the one after: its index
-        RlReq acc;
-        acc.req = 0; acc.cells = 0; acc.group = 0; acc.posorig = 0; acc.delta = 0; acc.now = 0;
-        if (valid) src.decode(D, a, rawrec, acc);
-        const RlCellDesc* gdesc = D.desc + (size_t)acc.group * 8;
-        const uint32_t ncell = rl_cells_n(acc.cells);
-        RlMyLimits L;
+    if (tid == 0) {
+        s_dirty = 0;
+        fetch(0, s_head);
+    }
+    __syncthreads();
+    if (tid < 8) s_desc[tid] = D.desc[(size_t)s_head.group * 8 + tid];  // one row => one row group
+    __syncthreads();
+
+    // limits of the cells request `acc` touches, in its own cell order (shared-memory copies)
+    auto limits_of = [&](const RlReq& acc, RlMyLimits& L) {
+        const uint32_t n = rl_cells_n(acc.cells);
         L.qmask = 0;
-        constexpr bool kGeneric = LC || Src::kCanBeMulti;
-        RlCellDesc mydesc[kGeneric ? CELLS : 1];
 #pragma unroll
         for (int k = 0; k < CELLS; k++) {
             L.mx[k] = 0;
-            if (valid && (uint32_t)k < ncell) {
+            if ((uint32_t)k < n) {
                 const uint32_t c = rl_cells_at(acc.cells, k);
-                const RlCellDesc d = gdesc[c];
-                if (kGeneric) mydesc[kGeneric ? c : 0] = d;
-                L.mx[k] = d.max_value;
-                L.qmask |= (d.qualified ? 1u : 0u) << k;
+                L.mx[k] = s_desc[c].max_value;
+                L.qmask |= (s_desc[c].qualified ? 1u : 0u) << k;
             }
         }
-        const RlCellDesc* desc = kGeneric ? mydesc : gdesc;
-        if (tid == 0) {  // the block's first request stands in for k_main's "rep"
-            s_d0 = acc.delta;
-            s_cells0 = acc.cells;
-            s_min[0] = s_min[1] = s_min[2] = s_min[3] = 0xFFFFFFFFu;
+    };
+    auto write_first = [&](const RlReq& acc, uint32_t fl) {
+        if (!B.out_first_limited) return;
+        if (fl == RL_NONE_U32) {
+            B.out_first_limited[acc.req] = RL_NONE_U32;
+            return;
+        }
+        const uint32_t n = rl_cells_n(acc.cells);
+#pragma unroll
+        for (int k = 0; k < CELLS; k++)
+            if ((uint32_t)k < n && rl_pos_at(acc.posorig, k) == fl) B.out_first_limited[acc.req] = s_desc[rl_cells_at(acc.cells, k)].limit_id;
+    };
+    auto lc_outputs = [&](const RlReq& acc, uint64_t*& rem, uint64_t*& ttl) {
+        rem = ttl = nullptr;
+        if (MODE == 0 && LC) {
+            const size_t ob = B.out_off ? (size_t)B.out_off[acc.req] : (size_t)acc.req * B.out_stride;
+            if (B.out_remaining) rem = B.out_remaining + ob;
+            if (B.out_ttl) ttl = B.out_ttl + ob;
+        }
+    };
+
+    uint32_t pos = 0;
+    while (pos < total) {
+        // ---- pass 1: how far do hypotheses A and B hold from `pos` under the state S? -------------------
+        const uint32_t end = min(total, pos + (uint32_t)RL_HOT_SWEEP);
+        RlRow<CELLS> S;
+#pragma unroll
+        for (int c = 0; c < CELLS; c++) {
+            S.value[c] = s_val[c];
+            S.expiry[c] = s_exp[c];
+        }
+        const RlReq head = s_head;
+        if (tid == 0) s_min[0] = s_min[1] = end;
+        __syncthreads();
+        uint32_t fa = end, fb = end;  // first position where A / B fails, among mine
+        constexpr int U = 4;          // strides in flight per thread: index and record loads of U requests overlap
+        for (uint32_t i0 = pos + tid; i0 < end && (fa == end || fb == end); i0 += CH * U) {
+            uint32_t ai[U];
+            RlRaw wi[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * CH;
+                ai[u] = (i < end) ? __ldcs(B.part_idx + list_at(i)) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (i0 + u * CH < end) wi[u] = src.raw(ai[u]);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = i0 + u * CH;
+                if (i >= end) break;
+                RlReq acc;
+                src.decode(D, ai[u], wi[u], acc);
+                RlMyLimits L;
+                limits_of(acc, L);
+                bool aok, bok;
+                uint32_t fl;
+                rl_eval_ab<CELLS>((const unsigned long long*)S.value, (const unsigned long long*)S.expiry, L, acc.cells, acc.posorig, acc.delta,
+                                  (uint64_t)(i - pos + 1) * acc.delta, acc.now, LC, MODE == 0, aok, bok, fl);
+                if (MODE == 2) aok = false;
+                bok = bok && acc.delta == head.delta && acc.cells == head.cells;
+                if (!aok && fa == end) fa = i;
+                if (!bok && fb == end) fb = i;
+            }
+        }
+        fa = __reduce_min_sync(0xffffffffu, fa);
+        fb = __reduce_min_sync(0xffffffffu, fb);
+        if (lane == 0) {
+            if (fa < end) atomicMin(&s_min[0], fa);
+            if (fb < end) atomicMin(&s_min[1], fb);
         }
         __syncthreads();
-        const bool like_rep = valid && s_d0 == acc.delta && s_cells0 == acc.cells;
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        const int leader = vmask ? (__ffs(vmask) - 1) : 0;
-        const bool solo = (vmask & (vmask - 1)) == 0;
-        bool done = !valid;
-        uint32_t pos = 0;
-        rl_replay_rounds<CELLS, MODE, LC>(B, true, s_val, s_exp, s_min, 1, &s_dirty, acc, L, desc, gdesc, false, like_rep, valid,
-                                          vmask, solo, leader, lane, tid, min((uint32_t)CH, total - b), done, pos);
+        const uint32_t mA = s_min[0], mB = s_min[1];
+        uint32_t newpos;
+        // ---- pass 2: the prefix that won is final -------------------------------------------------------
+        if (mA > pos) {  // denied under S, nothing changes
+            newpos = mA;
+            for (uint32_t i0 = pos + tid; i0 < newpos; i0 += CH * U) {
+                uint32_t ai[U];
+                RlRaw wi[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) ai[u] = (i0 + u * CH < newpos) ? __ldcs(B.part_idx + list_at(i0 + u * CH)) : 0u;
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (i0 + u * CH < newpos) wi[u] = src.raw(ai[u]);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                if (i0 + u * CH >= newpos) break;
+                RlReq acc;
+                src.decode(D, ai[u], wi[u], acc);
+                uint32_t fl;
+                if (LC) {
+                    RlRow<CELLS> loc = S;
+                    uint32_t dirty = 0;
+                    uint64_t *rem, *ttl;
+                    lc_outputs(acc, rem, ttl);
+                    fl = rl_walk_check_single<CELLS>(loc, dirty, s_desc, acc.cells, acc.posorig, acc.delta, acc.now, true, rem, ttl);
+                } else {
+                    RlMyLimits L;
+                    limits_of(acc, L);
+                    bool aok, bok;
+                    rl_eval_ab<CELLS>((const unsigned long long*)S.value, (const unsigned long long*)S.expiry, L, acc.cells, acc.posorig, acc.delta,
+                                      acc.delta, acc.now, false, true, aok, bok, fl);
+                }
+                rl_store_verdict(B, acc.req, 1);
+                write_first(acc, fl);
+                }
+            }
+        } else if (mB > pos) {  // allowed, values accumulate: request i sees S + (i - pos) deltas
+            newpos = mB;
+            if (MODE == 0) {
+                for (uint32_t i0 = pos + tid; i0 < newpos; i0 += CH * U) {
+                    uint32_t ai[U];
+                    RlRaw wi[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) ai[u] = (i0 + u * CH < newpos) ? __ldcs(B.part_idx + list_at(i0 + u * CH)) : 0u;
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (i0 + u * CH < newpos) wi[u] = src.raw(ai[u]);
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                    const uint32_t i = i0 + u * CH;
+                    if (i >= newpos) break;
+                    RlReq acc;
+                    src.decode(D, ai[u], wi[u], acc);
+                    if (LC) {
+                        RlRow<CELLS> loc = S;
+                        rl_advance_run<CELLS>(loc, acc.cells, (uint64_t)(i - pos) * acc.delta);
+                        uint32_t dirty = 0;
+                        uint64_t *rem, *ttl;
+                        lc_outputs(acc, rem, ttl);
+                        rl_walk_check_single<CELLS>(loc, dirty, s_desc, acc.cells, acc.posorig, acc.delta, acc.now, true, rem, ttl);
+                    }
+                    rl_store_verdict(B, acc.req, 0);
+                    write_first(acc, RL_NONE_U32);
+                    }
+                }
+            }
+            if (tid == 0) {
+                const uint64_t add = (uint64_t)(newpos - pos) * head.delta;
+                const uint32_t n = rl_cells_n(head.cells);
+                uint32_t dirty = 0;
+                for (uint32_t k = 0; k < n; k++) {
+                    const uint32_t c = rl_cells_at(head.cells, k);
+                    s_val[c] += add;
+                    dirty |= 1u << c;
+                }
+                s_dirty |= dirty;
+            }
+        } else {  // the request at `pos`, alone, by the sequential rule (rl_core.h)
+            newpos = pos + 1;
+            if (tid == 0) {
+                RlRow<CELLS> loc = S;
+                uint32_t dirty = 0, fl = RL_NONE_U32;
+                uint64_t *rem, *ttl;
+                lc_outputs(head, rem, ttl);
+                if (MODE == 2) rl_walk_update<CELLS>(loc, dirty, s_desc, head.cells, head.delta, head.now);
+                else fl = rl_walk_check_single<CELLS>(loc, dirty, s_desc, head.cells, head.posorig, head.delta, head.now, LC, rem, ttl);
+#pragma unroll
+                for (int c = 0; c < CELLS; c++)
+                    if (dirty & (1u << c)) {
+                        s_val[c] = loc.value[c];
+                        s_exp[c] = loc.expiry[c];
+                    }
+                s_dirty |= dirty;
+                if (MODE == 0) {
+                    rl_store_verdict(B, head.req, (uint8_t)(fl != RL_NONE_U32));
+                    write_first(head, fl);
+                }
+            }
+        }
+        pos = newpos;
+        __syncthreads();  // every read of S / s_head / s_min of this sweep is done
+        if (tid == 0 && pos < total) fetch(pos, s_head);
+        __syncthreads();
     }
-    __syncthreads();
     if (tid < CELLS && ((s_dirty >> tid) & 1u)) rl_st_cg(row + 16 + 16 * tid, s_val[tid], s_exp[tid]);
     if (tid == 0) rl_trace(D.trace, D.trace_pos, RL_EV_HOT, 1, total);
 }

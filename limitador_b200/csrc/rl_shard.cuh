@@ -246,33 +246,8 @@ __global__ void __launch_bounds__(32) k_xwait(RlXchg X, uint32_t buf, uint32_t s
     }
 }
 
-// Owner side: verdict of inbox access a goes back to its source's verdict inbox, block (owner = me).
-__global__ void __launch_bounds__(256) k_xreturn(RlXchg X, const uint8_t* __restrict__ verdict,
-                                                const uint32_t* __restrict__ seg_prefix, uint32_t buf, uint32_t step,
-                                                uint32_t* ctr) {
-    __shared__ uint32_t s_pre[RL_XCHG_MAX_WORLD + 1];
-    __shared__ uint32_t s_last;
-    const uint32_t tid = threadIdx.x;
-    if (tid <= X.world) s_pre[tid] = seg_prefix[tid];
-    __syncthreads();
-    const uint32_t n = s_pre[X.world];
-    for (uint32_t a = blockIdx.x * blockDim.x + tid; a < n; a += gridDim.x * blockDim.x) {
-        uint32_t s = 0;
-        while (s + 1 < X.world && a >= s_pre[s + 1]) s++;
-        X.vin(s, buf, X.rank)[a - s_pre[s]] = verdict[a];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(ctr, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence_system();
-    if (tid < X.world) rl_st_release_sys(&X.ctl(tid, buf, X.rank)->vflag, step + 1);
-    if (tid == 0) {
-        *ctr = 0;
-        rl_trace(X.trace, X.trace_pos, RL_EV_XRETURN, 1, step);
-    }
-}
+// Owner side, verdict return: there is no kernel for it — the decision kernels store every verdict straight into
+// its source's verdict inbox (rl_store_verdict, RlBatch::omap_*) and k_main's last CTA publishes the step flags.
 
 // Source side: wait for every owner's verdicts of the step ...
 // Only single-warp kernels ever spin.  A spinning CTA pins its SM: the SM cannot change its shared-memory

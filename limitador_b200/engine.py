@@ -20,7 +20,22 @@ NONE = 0xFFFFFFFF
 RECORD_DTYPE = np.dtype(
     [("ns_id", "<u4"), ("hits_addend", "<u4"), ("key_lo", "<u8"), ("key_hi", "<u8"), ("now_us", "<u8")]
 )
+RECORD16_DTYPE = np.dtype([("ns_hits_keyhi", "<u8"), ("key_lo", "<u8")])
 COUNTER_DTYPE = np.dtype([("limit_id", "<u4"), ("_pad", "<u4"), ("key_lo", "<u8"), ("key_hi", "<u8")])
+
+
+def pack_records16(recs: np.ndarray) -> np.ndarray:
+    """rl_record[] -> rl_record16[] (include/rl_engine.h); the records' now_us is dropped: the batch is stamped
+    with one clock reading at the call.  Raises if a record does not fit the 16-byte form."""
+    recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+    if len(recs) and (int(recs["ns_id"].max()) >= 1 << 24 or int(recs["hits_addend"].max()) > 255
+                      or int((recs["key_hi"] & np.uint64(0x00FFFFFFFFFFFFFF)).max()) >= 1 << 32):
+        raise ValueError("record does not fit rl_record16: ns_id < 2^24, hits_addend <= 255, key_hi < 2^32")
+    out = np.zeros(len(recs), dtype=RECORD16_DTYPE)
+    out["ns_hits_keyhi"] = (recs["ns_id"].astype(np.uint64) | (recs["hits_addend"].astype(np.uint64) << np.uint64(24))
+                            | ((recs["key_hi"] & np.uint64(0xFFFFFFFF)) << np.uint64(32)))
+    out["key_lo"] = recs["key_lo"]
+    return out
 LIMIT_DESC_DTYPE = np.dtype(
     [("limit_id", "<u4"), ("ns_id", "<u4"), ("varset_id", "<u4"), ("qualified", "<u4"),
      ("max_value", "<u8"), ("window_us", "<u8")]
@@ -37,7 +52,7 @@ ABI_SYMBOLS = [
     "rl_front_create", "rl_front_destroy", "rl_front_check_and_update", "rl_front_stats",
     "rl_shard_create", "rl_shard_destroy", "rl_shard_ipc_handle", "rl_shard_connect_ipc", "rl_shard_connect_ptrs",
     "rl_shard_slab", "rl_shard_slab_bytes", "rl_shard_send", "rl_shard_decide", "rl_shard_collect", "rl_shard_step",
-    "rl_shard_flush", "rl_shard_debug", "rl_trace_dump",
+    "rl_shard_flush", "rl_shard_debug", "rl_trace_dump", "rl_check_and_update_compact",
 ]
 
 
@@ -139,6 +154,7 @@ def load_library(path: str | None = None):
     L.rl_shard_flush.argtypes = [vp]
     L.rl_shard_debug.argtypes = [vp, vp]
     L.rl_trace_dump.argtypes = [vp, u32, vp, vp, vp, vp]
+    L.rl_check_and_update_compact.argtypes = [vp, u64, vp, u64, i32, vp, vp]
     if path == _build.LIB_PATH:
         _lib = L
     return L
@@ -257,6 +273,20 @@ class Engine:
         self._check(self._lib.rl_check_and_update_records(
             self._h, n, _p(recs), int(load_counters), MEM_HOST, _p(lim), _p(fl), _p(rem), _p(ttl), stride))
         return lim, fl, rem, ttl
+
+    def check_and_update_compact(self, recs16, now_us: int, want_first=True):
+        """16-byte records, all stamped now_us (host memory, synchronous)."""
+        recs16 = np.ascontiguousarray(recs16, dtype=RECORD16_DTYPE)
+        n = len(recs16)
+        lim = np.zeros(n, dtype=np.uint8)
+        fl = np.full(n, NONE, dtype=np.uint32) if want_first else None
+        self._check(self._lib.rl_check_and_update_compact(self._h, n, _p(recs16), now_us, MEM_HOST, _p(lim), _p(fl)))
+        return lim, fl
+
+    def check_and_update_compact_ptr(self, n: int, recs_ptr: int, now_us: int, out_limited_ptr: int, mem: int,
+                                     out_first_ptr: int = 0):
+        self._check(self._lib.rl_check_and_update_compact(self._h, n, C.c_void_p(recs_ptr), now_us, mem,
+                                                          C.c_void_p(out_limited_ptr), C.c_void_p(out_first_ptr or None)))
 
     def check_and_update_batch(self, off, ctrs, delta, now_us, load_counters=False):
         off = np.ascontiguousarray(off, dtype=np.uint32)

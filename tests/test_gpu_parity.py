@@ -250,6 +250,49 @@ def test_errors_are_loud():
         e2.check_and_update_records(np.zeros((1 << 16) + 1, dtype=RECORD_DTYPE))
 
 
+@pytest.mark.parametrize("cells", [1, 7])
+def test_compact_16_byte_records_match_the_32_byte_form(cells):
+    """rl_record16 (include/rl_engine.h): ns_id:24 | hits:8 | key_hi:32 | key_lo:64, the whole batch stamped with one
+    clock reading — the same decisions and table as the 32-byte records carrying that timestamp; host, device
+    (pipelined) and async-host calls."""
+    import torch
+    from limitador_b200.engine import pack_records16, RECORD16_DTYPE
+    descs = single_row_limits(cells, seed=50 + cells)
+    o = H.oracle_with_limits(descs)
+    e = engine_with_limits(descs, cells, regions=8, flags=2)
+    t = H.T0
+    for b in range(6):
+        recs = H.random_records(descs, 5000, 900 + b, n_keys=60)
+        recs["key_hi"] = (recs["key_lo"] * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)  # exercise the key_hi bits
+        recs["hits_addend"] = 1 + (recs["key_lo"] % np.uint64(3)).astype(np.uint32)
+        t += 700_000 * (1 + b % 3)
+        recs["now_us"] = t
+        r16 = pack_records16(recs)
+        want = o.batch_records(0, recs)
+        if b % 3 == 0:
+            lim, fl = e.check_and_update_compact(r16, t)
+        else:
+            mem = 1 if b % 3 == 1 else 2
+            if mem == 1:
+                d = torch.from_numpy(r16.view(np.int64).reshape(-1, 2).copy()).cuda()
+                out = torch.zeros(len(r16), dtype=torch.uint8, device="cuda")
+                first = torch.zeros(len(r16), dtype=torch.int32, device="cuda")
+            else:
+                d = torch.from_numpy(r16.view(np.int64).reshape(-1, 2).copy()).pin_memory()
+                out = torch.zeros(len(r16), dtype=torch.uint8).pin_memory()
+                first = torch.zeros(len(r16), dtype=torch.int32).pin_memory()
+            e.check_and_update_compact_ptr(len(r16), d.data_ptr(), t, out.data_ptr(), mem, first.data_ptr())
+            e.fence()
+            e.sync()
+            lim, fl = out.cpu().numpy(), first.cpu().numpy().astype(np.uint32)
+        assert np.array_equal(lim, want[0]) and np.array_equal(fl, want[1]), f"batch {b}"
+        assert_tables_equal(e, o, descs)
+    with pytest.raises(ValueError):
+        bad = recs[:2].copy()
+        bad["hits_addend"] = 256
+        pack_records16(bad)
+
+
 def test_unevaluated_requests_never_read_as_allowed():
     """a request the engine cannot evaluate gets RL_VERDICT_ERROR (0xFF), not 0 = allowed, and a
     general-form call with an unresolvable request is refused BEFORE the table is touched (a retry of the
@@ -323,29 +366,49 @@ def test_baseline_configs_reduced_size(name, kw, nb):
         assert np.array_equal(a, b_)
 
 
-def test_full_size_c2_properties():
-    """C2 at BASELINE.json's full size (1M rows, batch 65536): size-independent properties —
-    replaying the same batch twice with load_counters is consistent (remaining never
-    increases inside a window, denied requests change nothing), counters == sum of allowed."""
-    w = streams.WORKLOADS["C2"]()
-    e = Engine(capacity_rows=w.capacity_rows, cells_per_row=w.cells_per_row, max_batch=w.batch)
+def _table_rows(lid, lo, hi, val, exp):
+    """A counter dump as one sorted structured array (order-independent comparison of millions of rows)."""
+    n = len(lid)
+    rows = np.empty(n, dtype=[("lid", "<u8"), ("lo", "<u8"), ("hi", "<u8"), ("val", "<u8"), ("exp", "<u8")])
+    rows["lid"], rows["lo"], rows["hi"], rows["val"], rows["exp"] = lid, lo, hi, val, exp
+    rows.sort(order=["lid", "lo", "hi"])
+    return rows
+
+
+@pytest.mark.parametrize("name,nb,pipelined", [("C2", 40, False), ("C2", 40, True), ("C3", 4, True)])
+def test_full_size_configs_match_the_oracle_state(name, nb, pipelined):
+    """BASELINE.json configs[1] / configs[2] at FULL size (C2: 1 M rows, batch 65 536, Zipf(1.1), a 1-s window
+    rollover inside the run; C3: 16 M keys, batch 1 M): every verdict AND the final counter table (every value and
+    expiry, millions of rows) equal the oracle's — not invariants.  C2 also through the
+    pipelined device path (front of batch s+1 overlapping the replay of batch s, hot rows learnt on the way)."""
+    import torch
+    w = streams.WORKLOADS[name]()
+    e = Engine(capacity_rows=w.capacity_rows, cells_per_row=w.cells_per_row, max_batch=w.batch, flags=2 if pipelined else 0)
     e.limits_set(w.limits)
-    allowed_total = 0
-    for b in range(4):
-        recs = w.batch_records(b)
-        lim, _, _, _ = e.check_and_update_records(recs, False, stride=7)
-        allowed_total += int((lim == 0).sum())
-    lid, lo, hi, val, exp = e.dump_arrays()
-    # every allowed request adds 1 to each of its 4 counters, unless a window rolled over (it
-    # cannot: all stamps lie within 1 ms and the shortest window is 1 s)
-    assert int(val.sum()) == 4 * allowed_total
-    maxes = {int(d["limit_id"]): int(d["max_value"]) for d in w.limits}
-    assert all(int(v) <= maxes[int(l)] for l, v in zip(lid, val))
-    # idempotence of the read-only path: is_within_limits does not change the table
-    recs = w.batch_records(5)
-    e.is_within_limits_records(recs)
-    lid2, lo2, hi2, val2, exp2 = e.dump_arrays()
-    assert int(val2.sum()) == int(val.sum()) and len(lid2) == len(lid)
+    o = H.oracle_with_limits(w.limits, capacity_hint=1 << 22)
+    # C2: batches 0..nb-1 except that the second half starts after the stream's 1-s jump (batch 64), so that the
+    # 1-s windows of the hot keys roll over inside the test
+    ids = list(range(nb)) if name == "C3" else list(range(nb // 2)) + list(range(64, 64 + nb - nb // 2))
+    recs = [w.batch_records(b) for b in ids]
+    if pipelined:
+        d_recs = [torch.from_numpy(r.view(np.int64).reshape(-1, 4).copy()).cuda() for r in recs]
+        d_lim = [torch.full((w.batch,), 9, dtype=torch.uint8, device="cuda") for _ in recs]
+        torch.cuda.synchronize()
+        for i in range(len(recs)):
+            e.check_and_update_records_ptr(w.batch, d_recs[i].data_ptr(), d_lim[i].data_ptr(), 1, stride=w.cells_per_row)
+        e.fence()
+        e.sync()
+        got = [t.cpu().numpy() for t in d_lim]
+    else:
+        got = [e.check_and_update_records(r, False, stride=w.cells_per_row)[0] for r in recs]
+    for i, r in enumerate(recs):
+        want = o.batch_records(0, r)[0]
+        assert np.array_equal(got[i], want), f"{name} batch {ids[i]}: {int((got[i] != want).sum())} verdicts differ"
+    g, x = _table_rows(*e.dump_arrays(cap=1 << 23)), _table_rows(*o.dump_arrays())
+    assert len(g) == len(x) and len(g) > 100_000
+    assert np.array_equal(g, x), "counter tables differ"
+    if name == "C2":
+        assert e.stats()["hot_rows"] > 0  # the Zipf head was learnt
 
 
 def test_bucket_by_owner_is_stable_and_matches_host_function():
@@ -566,7 +629,7 @@ def test_hot_rows_get_partitions_of_their_own(load_counters):
     (a 1-s limit), values accumulating (max 2^40), saturated rows (max 3) and mixed deltas on the hot rows."""
     descs = np.array([(0, 0, 1, 1, 3, 1 * S), (1, 0, 1, 1, 1 << 40, 3600 * S), (2, 1, 1, 1, 50, 2 * S),
                       (3, 2, 0, 0, 1 << 40, 60 * S), (4, 3, 1, 1, 5, 60 * S)], dtype=LIMIT_DESC_DTYPE)
-    e = engine_with_limits(descs, 3, capacity=1 << 12, regions=4)
+    e = engine_with_limits(descs, 3, capacity=1 << 15, regions=4)
     o = H.oracle_with_limits(descs)
     rng = np.random.default_rng(9)
     n = 20000
