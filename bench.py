@@ -720,6 +720,8 @@ def main():
             recs[s].copy_(h_recs[j], non_blocking=True)
             done = step_device(s)
             if done is not None:
+                if shard is not None:
+                    shard.fence()  # the delivery ran on the shard's own stream
                 e2e_deliver(done)
 
     def e2e_deliver(t):

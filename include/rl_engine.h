@@ -267,7 +267,8 @@ uint32_t rl_owner_of(uint32_t ns_id, uint32_t world);
  *             store the verdict bytes straight back into the sources' verdict inboxes;
  *   collect : wait (on the device) for every owner's verdicts of the step sent `lag` steps ago and put them
  *             back in request order into the out_limited buffer given with that step.
- * No NCCL call, no padding and no host synchronisation on the data path; `lag`+1 steps are in flight.
+ * No NCCL call, no padding and no host synchronisation on the data path; `lag`+1 steps are in flight (`lag`+2
+ * buffers, so that a send never waits for an earlier step's delivery).
  * Every rank must issue the same sequence of calls.  cap = max records per rank and step; an owner can
  * receive up to world*cap records in a step (rl_config.max_batch bounds it: more is an error, RL_FATAL at
  * the next rl_sync).  All d_* pointers are device memory; everything is enqueued, nothing blocks the host. */
@@ -284,14 +285,18 @@ void *rl_shard_slab(rl_shard *s);
 uint64_t rl_shard_slab_bytes(rl_shard *s);
 int rl_shard_send(rl_shard *s, uint64_t n, const rl_record *d_recs, uint8_t *d_out_limited);
 int rl_shard_decide(rl_shard *s);
-/* *out_done (nullable) = the out_limited buffer whose delivery was enqueued by this call, or NULL */
+/* *out_done (nullable) = the out_limited buffer whose delivery was enqueued by this call, or NULL.  Deliveries run on
+ * a stream of the shard's own (the caller's stream, which carries the sends, never parks on a verdict wait):
+ * rl_shard_fence orders the caller's stream after every delivery enqueued so far (it does not block the host);
+ * rl_shard_flush does it too. */
 int rl_shard_collect(rl_shard *s, uint8_t **out_done);
+int rl_shard_fence(rl_shard *s);
 /* send + decide + collect: the one call of the one-process-per-GPU deployment */
 int rl_shard_step(rl_shard *s, uint64_t n, const rl_record *d_recs, uint8_t *d_out_limited, uint8_t **out_done);
 /* deliver every step still in flight (all ranks must have issued the same steps) */
 int rl_shard_flush(rl_shard *s);
 /* debugging aid: host copy of this rank's control words, out[(buf*world + peer)*4 + {0 fill, 1 record flag,
- * 2 verdict flag}] for buf < lag+1, then the steps sent, decided, collected; out holds (lag+1)*world*4 + 3 words */
+ * 2 verdict flag}] for buf < lag+2, then the steps sent, decided, collected; out holds (lag+2)*world*4 + 3 words */
 int rl_shard_debug(rl_shard *s, uint32_t *out);
 
 /* ---- Batching front (SURVEY §8b threading row) ---------------------------------------------

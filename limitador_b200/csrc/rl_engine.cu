@@ -118,7 +118,7 @@ struct rl_engine {
     DevBuf<unsigned long long> d_kstats;
     DevBuf<uint4> d_trace;     // RL_FLAG_TRACE: event ring
     DevBuf<uint32_t> d_hot;    // [RL_HOT_SLOTS] hot rows + [RL_HOT_CAND] candidates + [1] candidate count
-    bool hot_rows = true;      // RL_HOT=0 disables the hot-row partitions
+    bool hot_rows = false;     // RL_HOT=1 enables the hot-row partitions (k_hot); see DESIGN.md §3.4 for why it is opt-in
     DevBuf<uint32_t> d_misc2;  // [0] trace write position
     uint32_t trace_seq = 0;
     DevBuf<uint32_t> d_chain_status, d_chain_wcnt, d_chain_w;
@@ -147,7 +147,7 @@ struct rl_engine {
     WorkSet wsx[kSets - 1];                // sets 1.. (set 0 = the engine's own members)
     cudaStream_t sq = nullptr;       // scan + scatter stream
     cudaStream_t sp = nullptr, sm = nullptr;  // partition / replay streams
-    cudaEvent_t ev_in = nullptr, ev_probe[kSets] = {}, ev_part[kSets] = {}, ev_main[kSets] = {};
+    cudaEvent_t ev_in = nullptr, ev_probe[kSets] = {}, ev_part[kSets] = {}, ev_main[kSets] = {};  // ev_probe: replay done, before a post_main hook
     uint64_t pipe_seq = 0;
     bool pipe_pending = false;
     // RL_MEM_HOST_ASYNC: ring of device staging slots; copies overlap the kernels of other calls
@@ -200,6 +200,7 @@ int pipe_fence(rl_engine* e);
     } while (0)
 
 uint32_t ceil_div(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
 uint32_t log2_ceil(uint64_t x) {
     uint32_t l = 0;
     while ((1ull << l) < x) l++;
@@ -380,9 +381,7 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     B.n_dev = nullptr;
     B.omap_prefix = nullptr;
     B.omap_n = 0;
-    B.omap_flag_value = 0;
-    for (auto& b : B.omap_base) b = nullptr;
-    for (auto& f : B.omap_flag) f = nullptr;
+    B.omap_stride = 0;
     B.tile_loc = e->d_tile_loc.p;
     B.region_total = e->d_region_total.p;
     B.part_idx = e->d_part_idx.p;
@@ -481,14 +480,20 @@ int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& sr
     using Smem = RlMainSmem<CELLS, CH>;
     auto kern = k_main<GEO, CELLS, Src, MODE, CH, LC>;
     static bool attr_set[64] = {};  // per instantiation and device (function attributes are per device)
+    static uint32_t resident[64] = {};
     const int dv = e->device & 63;
     if (!attr_set[dv]) {
         RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        int per_sm = 0;
+        RL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CH, sizeof(Smem)));
+        resident[dv] = (uint32_t)std::max(per_sm, 1) * (e->main_grid_cap / 16);  // CTAs that fit at once (one wave)
         attr_set[dv] = true;
     }
     // upper bound of the work-item count: one per partition + one per chunk of a heavy partition; CTAs take
     // items from a ticket, so a smaller grid only means that some CTAs take several
-    const uint32_t grid = std::min<uint32_t>(B.nparts + ceil_div(B.n_acc, CH), e->main_grid_cap);
+    // ... and no more CTAs than fit at once: the surplus would only queue behind the wave, take a ticket and leave,
+    // while holding back the CTAs of the next call's front
+    const uint32_t grid = std::min<uint32_t>(B.nparts + ceil_div(B.n_acc, CH), std::min(e->main_grid_cap, resident[dv]));
     kern<<<grid, CH, sizeof(Smem), st>>>(D, B, src, e->weak_slots);
     return RL_OK;
 }
@@ -650,8 +655,16 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
         RL_CUDA(e, cudaStreamWaitEvent(e->sm, e->ev_part[k], 0));
         r = mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src, e->sm) : launch_main<RecordSrc, 0>(e, D, B, src, e->sm);
         if (r) return r;
-        if (hooks && hooks->post_main && (r = hooks->post_main(e->sm, k))) return r;
-        RL_CUDA(e, cudaEventRecord(e->ev_main[k], e->sm));
+        if (hooks && hooks->post_main) {
+            // the hook (a sharded step's verdict return) runs on its own stream: the replay of the next call does
+            // not wait for it, only the reuse of this workspace set does
+            RL_CUDA(e, cudaEventRecord(e->ev_probe[k], e->sm));
+            RL_CUDA(e, cudaStreamWaitEvent(e->sq, e->ev_probe[k], 0));
+            if ((r = hooks->post_main(e->sq, k))) return r;
+            RL_CUDA(e, cudaEventRecord(e->ev_main[k], e->sq));
+        } else {
+            RL_CUDA(e, cudaEventRecord(e->ev_main[k], e->sm));
+        }
         e->pipe_seq++;
         e->pipe_pending = true;
         return RL_OK;

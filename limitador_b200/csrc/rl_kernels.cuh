@@ -96,9 +96,7 @@ struct RlBatch {
     // (a peer store over NVLink): request index -> (source block, position) through the inbox prefix.
     const uint32_t* omap_prefix;  // nullptr = plain out_limited[req]; else [omap_n + 1] exclusive prefix of the block fills
     uint32_t omap_n;
-    uint8_t* omap_base[32];       // verdict block of source s (in s's exchange slab, mapped here)
-    uint32_t* omap_flag[32];      // where "my verdicts of this step are in" is published for source s
-    uint32_t omap_flag_value;
+    uint32_t omap_stride;         // out_limited is then a mirror of the sources' verdict blocks: [omap_n][omap_stride]
     uint8_t* out_limited;
     uint32_t* out_first_limited;
     uint64_t* out_remaining;
@@ -132,7 +130,7 @@ __device__ __forceinline__ void rl_store_verdict(const RlBatch& B, uint32_t req,
     }
     uint32_t s = 0;
     while (s + 1 < B.omap_n && req >= __ldg(B.omap_prefix + s + 1)) s++;
-    B.omap_base[s][req - __ldg(B.omap_prefix + s)] = v;
+    B.out_limited[(size_t)s * B.omap_stride + (req - __ldg(B.omap_prefix + s))] = v;
 }
 
 // k_main phases.  COMMIT: rows and outputs are written (the normal, single pass).
@@ -603,7 +601,7 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_front(RlDev D, RlBatch B, S
             if (r != P1 - 1) {
                 B.part_idx[tbuf + mypos] = a;
                 B.part_row[tbuf + mypos] = rowidx;
-            } else if (Src::kAccessIsRequest && (B.out_limited || B.omap_prefix)) {
+            } else if (Src::kAccessIsRequest && B.out_limited) {
                 // request without any applicable limit: not limited (lib.rs:434-440); a request that could
                 // not be evaluated (malformed key, full table region) says so instead of reading as allowed
                 rl_store_verdict(B, a, (rowidx == RL_ROW_ERROR) ? (uint8_t)RL_VERDICT_ERROR : (uint8_t)0);
@@ -1086,22 +1084,10 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
         __syncthreads();
         const uint32_t item = sm.item;
         if (item >= n_items) {
-            // the last CTA to leave re-arms the ticket for the next launch over this workspace and, for a
-            // sharded step, tells every source rank that its verdicts are in: each CTA's peer stores are
-            // ordered before its arrival on the exit counter (system-scope fence), the flags follow the last
-            // arrival (release).  The earlier kernels of the step (k_front, k_hot) completed before this one
-            // started; their stores are covered as well.
-            if (B.omap_prefix != nullptr) __threadfence_system();
-            __syncthreads();
+            // the last CTA to leave re-arms the ticket for the next launch over this workspace
             if (tid == 0 && atomicAdd(B.exit_ctr, 1u) == gridDim.x - 1) {
                 *B.exit_ctr = 0;
                 *B.ticket = 0;
-                if (B.omap_prefix != nullptr) {
-                    __threadfence_system();
-                    for (uint32_t sidx = 0; sidx < B.omap_n; sidx++) {
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(B.omap_flag[sidx]), "r"(B.omap_flag_value) : "memory");
-                    }
-                }
                 rl_trace(D.trace, D.trace_pos, RL_EV_MAIN, 1, D.seq);
             }
             break;

@@ -103,15 +103,35 @@ __global__ void __launch_bounds__(RL_PART_THREADS) k_xcount(const rl_record* __r
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid < 32) {
-        uint32_t run = 0;
-#pragma unroll 8
-        for (uint32_t t = 0; t < gridDim.x; t++) {
-            const uint32_t c = __ldcg(&tile_cnt[t * 32 + tid]);
-            tile_cnt[t * 32 + tid] = run;
-            run += c;
+    // exclusive prefix over tiles, per owner (lane = owner): warp w takes the w-th slice of the tiles, its
+    // loads are independent (16 in flight), the slices are stitched through shared memory
+    {
+        const uint32_t nt = gridDim.x;
+        const uint32_t per = (nt + RL_PART_WARPS - 1) / RL_PART_WARPS;
+        const uint32_t a0 = min(warp * per, nt), a1 = min(a0 + per, nt);
+        uint32_t sum = 0;
+        for (uint32_t tb = a0; tb < a1; tb += 16) {
+            uint32_t c[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) c[i] = (tb + i < a1) ? __ldcg(&tile_cnt[(tb + i) * 32 + lane]) : 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) sum += c[i];
         }
-        totals[tid] = run;
+        wcnt[warp][lane] = sum;
+        __syncthreads();
+        uint32_t run = 0;
+        for (uint32_t w = 0; w < warp; w++) run += wcnt[w][lane];
+        for (uint32_t tb = a0; tb < a1; tb += 16) {
+            uint32_t c[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) c[i] = (tb + i < a1) ? __ldcg(&tile_cnt[(tb + i) * 32 + lane]) : 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (tb + i < a1) tile_cnt[(tb + i) * 32 + lane] = run;
+                run += c[i];
+            }
+        }
+        if (warp == RL_PART_WARPS - 1) totals[lane] = run;
     }
     if (tid == 0) {
         *ctr = 0;
@@ -246,8 +266,33 @@ __global__ void __launch_bounds__(32) k_xwait(RlXchg X, uint32_t buf, uint32_t s
     }
 }
 
-// Owner side, verdict return: there is no kernel for it — the decision kernels store every verdict straight into
-// its source's verdict inbox (rl_store_verdict, RlBatch::omap_*) and k_main's last CTA publishes the step flags.
+// Owner side, verdict return.  The decision kernels write every verdict into a LOCAL mirror of the sources' verdict
+// blocks (rl_store_verdict: request index -> (source, position) through the inbox prefix; a byte store to peer memory
+// is a transaction of its own over NVLink — 32 k of them per step cost k_main 17 us).  This kernel ships block s to
+// source s with 16-byte stores — CTA (s, j) the j-th slice of block s — and the last block publishes the step flags.
+#define RL_XRET_SLICES 8
+__global__ void __launch_bounds__(256) k_xreturn(RlXchg X, const uint8_t* __restrict__ vmirror, const uint32_t* __restrict__ seg_prefix,
+                                                uint32_t buf, uint32_t step, uint32_t* ctr) {
+    __shared__ uint32_t s_last;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t s = blockIdx.x / RL_XRET_SLICES, j = blockIdx.x % RL_XRET_SLICES;
+    const uint32_t n = seg_prefix[s + 1] - seg_prefix[s];
+    const uint32_t nvec = (n + 15) / 16;  // whole 16-byte words of the block (blocks are 16-byte aligned, cap % 16 == 0)
+    const uint4* src = reinterpret_cast<const uint4*>(vmirror + (size_t)s * X.cap);
+    uint4* dst = reinterpret_cast<uint4*>(X.vin(s, buf, X.rank));
+    for (uint32_t i = j * blockDim.x + tid; i < nvec; i += RL_XRET_SLICES * blockDim.x) dst[i] = __ldcg(src + i);
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ctr, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (tid < X.world) rl_st_release_sys(&X.ctl(tid, buf, X.rank)->vflag, step + 1);
+    if (tid == 0) {
+        *ctr = 0;
+        rl_trace(X.trace, X.trace_pos, RL_EV_XRETURN, 1, step);
+    }
+}
 
 // Source side: wait for every owner's verdicts of the step ...
 // Only single-warp kernels ever spin.  A spinning CTA pins its SM: the SM cannot change its shared-memory

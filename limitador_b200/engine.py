@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "rl_front_create", "rl_front_destroy", "rl_front_check_and_update", "rl_front_stats",
     "rl_shard_create", "rl_shard_destroy", "rl_shard_ipc_handle", "rl_shard_connect_ipc", "rl_shard_connect_ptrs",
     "rl_shard_slab", "rl_shard_slab_bytes", "rl_shard_send", "rl_shard_decide", "rl_shard_collect", "rl_shard_step",
-    "rl_shard_flush", "rl_shard_debug", "rl_trace_dump", "rl_check_and_update_compact",
+    "rl_shard_flush", "rl_shard_debug", "rl_trace_dump", "rl_check_and_update_compact", "rl_shard_fence",
 ]
 
 
@@ -152,6 +152,7 @@ def load_library(path: str | None = None):
     L.rl_shard_collect.argtypes = [vp, C.POINTER(vp)]
     L.rl_shard_step.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]
     L.rl_shard_flush.argtypes = [vp]
+    L.rl_shard_fence.argtypes = [vp]
     L.rl_shard_debug.argtypes = [vp, vp]
     L.rl_trace_dump.argtypes = [vp, u32, vp, vp, vp, vp]
     L.rl_check_and_update_compact.argtypes = [vp, u64, vp, u64, i32, vp, vp]
@@ -521,9 +522,13 @@ class Shard:
     def flush(self):
         self._eng._check(self._lib.rl_shard_flush(self._h))
 
+    def fence(self):
+        """Order the engine's stream after every verdict delivery enqueued so far (no host blocking)."""
+        self._eng._check(self._lib.rl_shard_fence(self._h))
+
     def debug(self):
         """{'ctl': [buf][peer] -> (fill, record flag, verdict flag), 'sent', 'decided', 'collected'} of this rank."""
-        depth = self.lag + 1
+        depth = self.lag + 2
         out = np.zeros(depth * self.world * 4 + 3, dtype=np.uint32)
         self._lib.rl_shard_debug(self._h, _p(out))
         ctl = out[:-3].reshape(depth, self.world, 4)[:, :, :3].tolist()
