@@ -171,7 +171,7 @@ def sharded_parity(dist, world, rank, dev, eng, limits, recs_steps, out_steps, o
     res = {"steps": S, "decisions": int(S * world * batch), "order": "(step, source rank, source index)",
            "gpu_verdict_mismatches": mism, "counters": int(len(lid)), "table_mismatch_ranks": bad,
            "oracle_s": round(time.perf_counter() - t0, 2)}
-    print(f"[bench] sharded parity: {res}", file=sys.stderr)
+    log(f"sharded parity: {res}")
     return res
 
 
@@ -184,6 +184,7 @@ def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
     from limitador_b200 import Engine, exchange, streams
     from limitador_b200.engine import MEM_DEVICE, RECORD_DTYPE, Shard
     t_all = time.perf_counter()
+    log(f"extra {name}: start")
     hot = name == "C5"
     if name == "C3":
         batch = args.extra_batch or (1 << 20)
@@ -203,12 +204,14 @@ def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
                 + ("Zipf(0.7) keys with 50% of the traffic on 100 fixed keys (max 2^32: they keep incrementing)" if hot else
                    "namespace popularity Zipf(1.0), keys uniform inside a namespace")
                 + f", batch={batch}/GPU, delta=1")
-    S_par = 2 if world > 1 else 3
+    S_par = 1 if world > 1 else 3
     total = S_par + Wx + 2 * K
     recs = gen(total)
     out = torch.zeros((total, batch), dtype=torch.uint8, device=dev)
     max_batch = batch if world == 1 else min(world, 4) * batch  # an owner may receive up to 4 source batches in a step
-    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, max_counters=max_batch, device=local_rank, flags=2)
+    # C5 is the hot-key regime: rows that dominate their chunks get partitions of their own (RL_FLAG_HOT_ROWS = 16)
+    eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, max_counters=max_batch, device=local_rank,
+                 flags=2 | (16 if hot else 0))
     eng.limits_set(limits)
     torch.cuda.synchronize()
     eng.set_stream(stream.cuda_stream)
@@ -237,6 +240,7 @@ def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log(f"extra {name}: engine, stream and exchange ready")
     # ---- parity leg -------------------------------------------------------------------------------------
     for s in range(S_par):
         step(s)
@@ -307,13 +311,14 @@ def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
                            "avg_launch_ms": main_ms / max(main_launches, 1), "kernel_share_of_step": main_ms / ms_b,
                            "whole_step_achieved": s_ach, "whole_step_frac": s_ach / peak, "allowed_frac": allowed / len(lim_b)}
     res["hot_rows"] = eng.stats().get("hot_rows")
-    res["wall_s"] = round(time.perf_counter() - t_all, 1)
+    log(f"extra {name}: timed passes done")
     if shard is not None:
         shard.close()
     eng.close()
     del recs, out
     torch.cuda.empty_cache()
     barrier()
+    res["wall_s"] = round(time.perf_counter() - t_all, 1)
     return res if rank == 0 else None
 
 
@@ -337,7 +342,7 @@ def measured_traffic(workload: str, timeout_s: int = 180):
             subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout_s, check=False)
             rows = [l for l in open(log) if l.startswith('"')]
         except Exception as ex:
-            print(f"[bench] traffic leg failed: {ex}", file=sys.stderr)
+            log(f"traffic leg failed: {ex}")
             return None
     per = {}
     for r in csv.DictReader(rows):
@@ -404,6 +409,12 @@ def run_reference(args):
 
 
 _REAL_STDOUT = None
+_T0 = time.perf_counter()
+
+
+def log(msg: str):
+    """progress line on stderr, stamped with the seconds since start (where does a run spend its wall time?)"""
+    print(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def emit(line: dict):
@@ -509,7 +520,7 @@ def main():
         seen = torch.tensor([exchange.observed_block_max(recs_pool[:min(pool, 64)], lut, world)], dtype=torch.int64, device=dev)
         dist.all_reduce(seen, op=dist.ReduceOp.MAX)
         slot_cap = exchange.slot_cap_for(int(seen.item()), batch)
-        print(f"[bench] largest exchange block in the sample: {int(seen.item())} records -> slot_cap {slot_cap}", file=sys.stderr)
+        log(f"largest exchange block in the sample: {int(seen.item())} records -> slot_cap {slot_cap}")
     max_batch = batch if world == 1 else (world * batch if use_peer else world * slot_cap)
     # RL_FLAG_PIPELINE (2): the front of step s+1 overlaps the replay of step s on the device
     eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, max_counters=max_batch, device=local_rank,
@@ -537,7 +548,7 @@ def main():
 
     recs, out_lim, out_first = _Cyc(recs_pool), _Cyc(out_lim_pool), _Cyc(out_first_pool)
     torch.cuda.synchronize()
-    print(f"[bench] generated {total} batches of {batch} in {time.perf_counter() - t_gen:.1f}s", file=sys.stderr)
+    log(f"generated {total} batches of {batch} in {time.perf_counter() - t_gen:.1f}s")
 
     ex = None
     shard = None
@@ -550,7 +561,7 @@ def main():
         dist.all_gather_into_tensor(allh, mine)
         shard.connect_ipc(bytes(allh.cpu().numpy().tobytes()))
         dist.barrier()
-        print(f"[bench] rank {rank}: peer exchange connected, slab {shard.slab_bytes >> 20} MiB", file=sys.stderr)
+        log(f"rank {rank}: peer exchange connected, slab {shard.slab_bytes >> 20} MiB")
     elif world > 1:
 
         class _EngineOps:
@@ -655,7 +666,7 @@ def main():
                 barrier()
     drain()
     eng.sync()
-    print(f"[bench] warm-up {time.perf_counter() - t_w:.2f}s", file=sys.stderr)
+    log(f"warm-up {time.perf_counter() - t_w:.2f}s")
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -687,7 +698,7 @@ def main():
     try:
         sampler.nv.nvmlDeviceSetCpuAffinity(sampler.h)
     except Exception as ex:  # restricted cpuset, no NVML: measure as placed
-        print(f"[bench] GPU-local CPU affinity not applied: {ex}", file=sys.stderr)
+        log(f"GPU-local CPU affinity not applied: {ex}")
     Kh = E_WARM + Ke
     h_recs = torch.empty((Kh, batch, 4), dtype=torch.int64).pin_memory()
     h_recs.copy_(recs[W + 2 * K:W + 2 * K + Kh])
@@ -775,17 +786,19 @@ def main():
         raise RuntimeError(f"an exchange block overflowed (more than {slot_cap} records for one owner): the sampled "
                            f"headroom was too small")
     eng_stats = eng.stats()
-    print(f"[bench] engine stats {eng_stats}", file=sys.stderr)
-    print(f"[bench] host enqueue us/step per pass: {[round(x, 1) for x in host_enqueue_us]}", file=sys.stderr)
-    print(f"[bench] passes: A {ms_a:.1f} ms, B {ms_b:.1f} ms, e2e {ms_e:.1f} ms (wall {wall_e:.1f})", file=sys.stderr)
+    log(f"engine stats {eng_stats}")
+    log(f"host enqueue us/step per pass: {[round(x, 1) for x in host_enqueue_us]}")
+    log(f"passes: A {ms_a:.1f} ms, B {ms_b:.1f} ms, e2e {ms_e:.1f} ms (wall {wall_e:.1f})")
 
     # ---- the other BASELINE.json configs, short passes reported under `extra` (all ranks take part) --------
     extra = {}
     if not args.no_extra and args.workload == "C2":
+        log("closing the C2 engine")
         if shard is not None:
             shard.close()
         eng.close()
         torch.cuda.empty_cache()
+        log("closed")
         for xn in (["C3"] if world == 1 else ["C4", "C5"]):
             try:
                 r = run_extra(xn, world, rank, local_rank, dev, dist, args, stream)
@@ -795,7 +808,7 @@ def main():
                 r = {"error": f"{type(ex).__name__}: {ex}"}
             if rank == 0:
                 extra[xn] = r
-                print(f"[bench] extra {xn}: {r}", file=sys.stderr)
+                log(f"extra {xn}: {r}")
 
     if rank != 0:
         if world > 1:
@@ -843,7 +856,7 @@ def main():
         mt = ob.OracleMT(ldesc, cores, 2 * (16_000_000 if c3 else n_rows))
         t_cpu, v_cpu = mt.run(sample)
         mt.close()
-        print(f"[bench] cpu baseline {t_cpu:.2f}s", file=sys.stderr)
+        log(f"cpu baseline {t_cpu:.2f}s")
         v_gpu = out_lim[:S].cpu().numpy().reshape(-1)
         mism = int((v_cpu != v_gpu).sum()) if pool == total else None  # cycled pool: outputs were overwritten
         cpu = {"value": len(sample) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
@@ -901,7 +914,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if failed:
-        print("[bench] FAILED: the sharded run differs from the global oracle", file=sys.stderr)
+        log("FAILED: the sharded run differs from the global oracle")
         sys.exit(3)
 
 

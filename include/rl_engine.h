@@ -64,6 +64,10 @@ enum { RL_MEM_HOST = 0, RL_MEM_DEVICE = 1,
  * ring of 65536 events (rl_trace_dump), so the timeline of a pipelined / sharded step can be read without a
  * profiler.  One atomic and one 16-B store per kernel and event. */
 #define RL_FLAG_TRACE 8u
+/* Hot rows: a table row that dominates its replay chunks gets a partition of its own and is replayed
+ * by one CTA of k_hot over its whole request list — the hot-key regime of BASELINE.json configs[4].  Opt-in (also
+ * RL_HOT=1 in the environment): for Zipf(1.1) traffic at batch 65536 the chained chunks of k_main are as fast. */
+#define RL_FLAG_HOT_ROWS 16u
 
 typedef struct rl_config {
     uint32_t struct_size;    /* sizeof(rl_config) */

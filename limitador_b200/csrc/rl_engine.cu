@@ -840,6 +840,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
     RL_CUDA(e, e->d_delta.reserve(e->max_batch));
     RL_CUDA(e, e->d_now.reserve(e->max_batch));
     e->kernel_stats = (cfg->flags & RL_FLAG_KERNEL_STATS) != 0;
+    e->hot_rows = (cfg->flags & RL_FLAG_HOT_ROWS) != 0;
     if (const char* v = getenv("RL_HOT")) e->hot_rows = atoi(v) != 0;
     RL_CUDA(e, e->d_hot.reserve(RL_HOT_SLOTS + RL_HOT_CAND + 4));
     RL_CUDA(e, cudaMemsetAsync(e->d_hot.p, 0xFF, (RL_HOT_SLOTS + RL_HOT_CAND) * sizeof(uint32_t), e->stream));

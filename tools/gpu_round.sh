@@ -11,16 +11,16 @@ case $w in
 tests)
   timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log; tail -3 $out/${tag}_pytest.log;;
 bench)
-  timeout 600 python bench.py --steps 400 --warmup 10 > $out/${tag}_bench_c2.json 2> $out/${tag}_bench_c2.err; echo "bench rc=$?"; tail -c 600 $out/${tag}_bench_c2.json;;
+  timeout 600 python bench.py --steps 1000 --warmup 20 > $out/${tag}_bench_c2.json 2> $out/${tag}_bench_c2.err; echo "bench rc=$?"; grep -h "passes\|host enq" $out/${tag}_bench_c2.err; python tools/bench_summary.py $out/${tag}_bench_c2.json;;
 c3)
   timeout 600 python bench.py --workload C3 --steps 60 --warmup 5 > $out/${tag}_bench_c3.json 2> $out/${tag}_bench_c3.err; echo "c3 rc=$?"; tail -c 600 $out/${tag}_bench_c3.json;;
 ncu)
-  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:^k_ -s 30 -c 12 --csv --log-file $out/${tag}_launches_c2.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra > $out/${tag}_ncu_c2.log 2>&1
-  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:^k_ -s 15 -c 9 --csv --log-file $out/${tag}_launches_c3.csv python bench.py --workload C3 --steps 4 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra > $out/${tag}_ncu_c3.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:^k_ -s 8 -c 8 --csv --log-file $out/${tag}_launches_c2.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra --device-pass-only > $out/${tag}_ncu_c2.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:^k_ -s 8 -c 6 --csv --log-file $out/${tag}_launches_c3.csv python bench.py --workload C3 --steps 4 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra --device-pass-only > $out/${tag}_ncu_c3.log 2>&1
   python tools/ncu_summary.py $out/${tag}_launches_c2.csv $out/${tag}_launches_c3.csv;;
 ncufull)
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_main -s 8 -c 1 -o $out/${tag}_k_main_c2 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra > $out/${tag}_ncufull.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_main -s 4 -c 1 -o $out/${tag}_k_main_c3 python bench.py --workload C3 --steps 4 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra >> $out/${tag}_ncufull.log 2>&1;;
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_main -s 8 -c 1 -o $out/${tag}_k_main_c2 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra --device-pass-only > $out/${tag}_ncufull.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_front -s 8 -c 1 -o $out/${tag}_k_front_c2 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-pipeline --no-extra --device-pass-only >> $out/${tag}_ncufull.log 2>&1;;
 kstats)
   timeout 300 python bench.py --steps 200 --warmup 10 --kstats --no-cpu-baseline --no-extra > $out/${tag}_kstats_c2.json 2> $out/${tag}_kstats_c2.err; grep "engine stats" $out/${tag}_kstats_c2.err
   timeout 300 python bench.py --steps 200 --warmup 10 --kstats --no-cpu-baseline --no-extra --no-pipeline > $out/${tag}_kstats_c2_np.json 2> $out/${tag}_kstats_c2_np.err; grep "engine stats" $out/${tag}_kstats_c2_np.err;;
