@@ -397,7 +397,7 @@ RlBatch make_batch(rl_engine* e, uint32_t n_acc, uint32_t n_req, const Outs& o, 
     // n_hint (sharded steps): n_acc is only the upper bound of a device-side count; partitions are sized for
     // the expected count, and the kernels derive the tile from the actual one (rl_tile_of)
     const uint32_t n_size = n_hint ? std::min(n_hint, n_acc) : n_acc;
-    if (n_hint) B.num_tiles = std::min<uint32_t>(kMaxTiles, std::max<uint32_t>(1, ceil_div(n_acc, 256)));
+    if (n_hint) B.num_tiles = std::min<uint32_t>(256, std::max<uint32_t>(1, ceil_div(n_acc, 256)));
     B.out_limited = o.limited;
     B.out_first_limited = o.first;
     B.out_remaining = o.rem;
@@ -483,7 +483,8 @@ int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& sr
     static uint32_t resident[64] = {};
     const int dv = e->device & 63;
     if (!attr_set[dv]) {
-        RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        RL_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)rl_main_smem_bytes<CELLS, CH>(RL_MAX_TILES)));
         int per_sm = 0;
         RL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CH, sizeof(Smem)));
         resident[dv] = (uint32_t)std::max(per_sm, 1) * (e->main_grid_cap / 16);  // CTAs that fit at once (one wave)
@@ -495,7 +496,7 @@ int launch_main_ch(rl_engine* e, const RlDev& D, const RlBatch& B, const Src& sr
     // two chunk latencies — 29.5 instead of 23 us on C2)
     (void)resident;
     const uint32_t grid = std::min<uint32_t>(B.nparts + ceil_div(B.n_acc, CH), e->main_grid_cap);
-    kern<<<grid, CH, sizeof(Smem), st>>>(D, B, src, e->weak_slots);
+    kern<<<grid, CH, rl_main_smem_bytes<CELLS, CH>(B.num_tiles), st>>>(D, B, src, e->weak_slots);
     return RL_OK;
 }
 
@@ -725,11 +726,11 @@ int preload_main(rl_engine* e) {
     if (e->chunk == 128) {
         RL_CUDA(e, cudaFuncGetAttributes(&fa, k_main<GEO, CELLS, RecordSrc, 0, 128, false>));
         RL_CUDA(e, cudaFuncSetAttribute(k_main<GEO, CELLS, RecordSrc, 0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(RlMainSmem<CELLS, 128>)));
+                                        (int)rl_main_smem_bytes<CELLS, 128>(RL_MAX_TILES)));
     } else {
         RL_CUDA(e, cudaFuncGetAttributes(&fa, k_main<GEO, CELLS, RecordSrc, 0, 256, false>));
         RL_CUDA(e, cudaFuncSetAttribute(k_main<GEO, CELLS, RecordSrc, 0, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(RlMainSmem<CELLS, 256>)));
+                                        (int)rl_main_smem_bytes<CELLS, 256>(RL_MAX_TILES)));
     }
     return RL_OK;
 }
@@ -818,7 +819,7 @@ int rl_engine_create(const rl_config* cfg, rl_engine** out) {
 
     const uint32_t P1 = (1u << e->log2P) + RL_HOT_SLOTS + 1;  // cold partitions + hot slots + the no-row bucket
     const size_t maxA = e->max_counters;
-    const size_t bufA = maxA + maxA / 128 + 65536 + 1024;  // part_idx/part_row: every tile's slice is a whole tile
+    const size_t bufA = maxA + maxA / 128 + 256 * 1024 + 1024;  // part_idx/part_row: every tile's slice is a whole tile
     RL_CUDA(e, e->d_tile_loc.reserve((size_t)(kMaxTiles + 1) * (P1 + 1)));
     RL_CUDA(e, e->d_region_total.reserve(P1 + 1));
     RL_CUDA(e, cudaMemsetAsync(e->d_region_total.p, 0, (P1 + 1) * sizeof(uint32_t), e->stream));

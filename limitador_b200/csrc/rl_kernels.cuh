@@ -20,7 +20,7 @@
 #include "rl_core.h"
 
 #define RL_PART_THREADS 256
-#define RL_MAX_TILES 256  // tiles (CTAs of k_front) per batch
+#define RL_MAX_TILES 1024  // tiles (CTAs of k_front) per batch: a 1 M-request batch gives every warp one 4-deep probe iteration
 // Hot rows: a row that draws a large share of a batch gets a partition of its own and is
 // replayed by one CTA of k_hot over its whole request list, instead of being chopped into chained chunks.
 #define RL_HOT_SLOTS 256   // rows that can be hot at a time (= threads of k_front's last block)
@@ -738,9 +738,14 @@ struct RlMainSmem {
     uint32_t scan_w[NW];
     uint32_t w_cnt;
     uint32_t item;
-    uint32_t t_pfx[RL_MAX_TILES + 1];  // my partition's list: exclusive prefix of its per-tile run lengths
-    uint32_t t_loc[RL_MAX_TILES];      // ... and where each tile's run starts in part_idx/part_row
+    // followed in dynamic shared memory by t_pfx[num_tiles + 1] (my partition's list: exclusive prefix of its per-tile
+    // run lengths) and t_loc[num_tiles] (where each tile's run starts in part_idx/part_row): sized by the batch's
+    // tile count, not by RL_MAX_TILES — shared memory a 128-tile batch does not need would come out of k_main's L1
 };
+template <int CELLS, int CH>
+__host__ __device__ constexpr size_t rl_main_smem_bytes(uint32_t num_tiles) {
+    return sizeof(RlMainSmem<CELLS, CH>) + (2 * (size_t)num_tiles + 1) * sizeof(uint32_t);
+}
 
 // Per-thread view of the limits its access touches, in the access's own cell order.
 struct RlMyLimits {
@@ -1065,6 +1070,8 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
     constexpr int PW = Smem::PW;
     extern __shared__ __align__(16) unsigned char rl_smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(rl_smem_raw);
+    uint32_t* const sm_t_pfx = reinterpret_cast<uint32_t*>(rl_smem_raw + sizeof(Smem));
+    uint32_t* const sm_t_loc = sm_t_pfx + B.num_tiles + 1;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool lc = LC;  // load_counters: compile-time, so the default kernel carries none of it
@@ -1098,37 +1105,34 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
         // ---- the partition's list = its runs in the tiles' slices, tile after tile: merge on read --------
         {
             const uint32_t TL = B.nparts + B.nhot + 2;
-            constexpr uint32_t PER = (RL_MAX_TILES + CH - 1) / CH;  // consecutive tiles per thread
-            uint32_t c[PER], sum = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < PER; j++) {
-                const uint32_t t = tid * PER + j;
-                c[j] = 0;
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < ntile; base += CH) {  // CH tiles at a time: one pass for batches up to CH tiles
+                const uint32_t t = base + tid;
+                uint32_t c = 0;
                 if (t < ntile) {
                     const uint32_t l0 = __ldcg(&B.tile_loc[(size_t)t * TL + it.x]);
                     const uint32_t l1 = __ldcg(&B.tile_loc[(size_t)t * TL + it.x + 1]);
-                    c[j] = l1 - l0;
-                    sm.t_loc[t] = t * tsz + l0;
+                    c = l1 - l0;
+                    sm_t_loc[t] = t * tsz + l0;
                 }
-                sum += c[j];
-            }
-            uint32_t x = sum;
+                uint32_t x = c;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                if ((int)lane >= o) x += y;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                    if ((int)lane >= o) x += y;
+                }
+                if (lane == 31) sm.scan_w[warp] = x;
+                __syncthreads();
+                uint32_t woff = 0, tot = 0;
+                for (uint32_t w = 0; w < (uint32_t)Smem::NW; w++) {
+                    if (w < warp) woff += sm.scan_w[w];
+                    tot += sm.scan_w[w];
+                }
+                if (t < ntile) sm_t_pfx[t] = carry + woff + x - c;
+                carry += tot;
+                __syncthreads();
             }
-            if (lane == 31) sm.scan_w[warp] = x;
-            __syncthreads();
-            uint32_t run = x - sum;
-            for (uint32_t w = 0; w < warp; w++) run += sm.scan_w[w];
-#pragma unroll
-            for (uint32_t j = 0; j < PER; j++) {
-                const uint32_t t = tid * PER + j;
-                if (t < ntile) sm.t_pfx[t] = run;
-                run += c[j];
-            }
-            if (tid == CH - 1) sm.t_pfx[ntile] = run;  // threads past the last tile carry the total along
+            if (tid == 0) sm_t_pfx[ntile] = carry;
             __syncthreads();
         }
         // position v of the list -> index into part_idx/part_row: the last tile whose prefix is <= v
@@ -1136,10 +1140,10 @@ __global__ void __launch_bounds__(CH, (CELLS <= 2 ? 8 : (CELLS <= 4 ? RL_MID_CTA
             uint32_t a0 = 0, a1 = ntile - 1;
             while (a0 < a1) {
                 const uint32_t mid = (a0 + a1 + 1) >> 1;
-                if (sm.t_pfx[mid] <= v) a0 = mid;
+                if (sm_t_pfx[mid] <= v) a0 = mid;
                 else a1 = mid - 1;
             }
-            return sm.t_loc[a0] + (v - sm.t_pfx[a0]);
+            return sm_t_loc[a0] + (v - sm_t_pfx[a0]);
         };
         // Heavy partition: this CTA owns ONE chunk and the partition's chunks run concurrently under
         // optimistic concurrency control, row by row.  A chunk replays its requests against the
@@ -1489,27 +1493,35 @@ __global__ void __launch_bounds__(RL_HOT_THREADS) k_hot(RlDev D, RlBatch B, Src 
     const uint32_t ntile = B.num_tiles;
     const uint32_t tsz = rl_tile_of(B, rl_batch_n(B));
     const uint32_t TL = B.nparts + B.nhot + 2;
-    static_assert(RL_MAX_TILES <= RL_HOT_THREADS, "one tile per thread in the list merge");
     {
-        uint32_t c = 0;
-        if (tid < ntile) {
-            const uint32_t l0 = __ldcg(&B.tile_loc[(size_t)tid * TL + q]);
-            const uint32_t l1 = __ldcg(&B.tile_loc[(size_t)tid * TL + q + 1]);
-            c = l1 - l0;
-            t_loc[tid] = tid * tsz + l0;
-        }
-        uint32_t x = c;
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < ntile; base += CH) {
+            const uint32_t t = base + tid;
+            uint32_t c = 0;
+            if (t < ntile) {
+                const uint32_t l0 = __ldcg(&B.tile_loc[(size_t)t * TL + q]);
+                const uint32_t l1 = __ldcg(&B.tile_loc[(size_t)t * TL + q + 1]);
+                c = l1 - l0;
+                t_loc[t] = t * tsz + l0;
+            }
+            uint32_t x = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((int)lane >= o) x += y;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if ((int)lane >= o) x += y;
+            }
+            if (lane == 31) scan_w[warp] = x;
+            __syncthreads();
+            uint32_t woff = 0, tot = 0;
+            for (uint32_t w = 0; w < CH / 32; w++) {
+                if (w < warp) woff += scan_w[w];
+                tot += scan_w[w];
+            }
+            if (t < ntile) t_pfx[t] = carry + woff + x - c;
+            carry += tot;
+            __syncthreads();
         }
-        if (lane == 31) scan_w[warp] = x;
-        __syncthreads();
-        uint32_t run = x - c;
-        for (uint32_t w = 0; w < warp; w++) run += scan_w[w];
-        if (tid < ntile) t_pfx[tid] = run;
-        if (tid == CH - 1) t_pfx[ntile] = run + c;
+        if (tid == 0) t_pfx[ntile] = carry;
         __syncthreads();
     }
     const uint32_t total = t_pfx[ntile];
