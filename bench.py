@@ -381,6 +381,7 @@ def run_reference(args):
     span = int(pool["now_us"].max() - pool["now_us"].min()) + 1_000_000
     times = []
     mt = ob.OracleMT(ldesc, cores, 2 * n_rows)
+    pinned = mt.pinned
     for s in range(n_steps):
         chunk = pool[s % pool_steps]
         if s >= pool_steps and s % pool_steps == 0:
@@ -392,7 +393,27 @@ def run_reference(args):
     n_dec = args.steps * per_step * batch
     value = n_dec / sum(times)
     sample = (f"{per_step} batches of {batch} per step ({pool_steps} distinct steps, re-used with the clock "
-              f"advanced), table kept warm across steps, {cores} threads, namespaces assigned to threads by load")
+              f"advanced), table kept warm across steps, {cores} persistent threads ({pinned} pinned one per CPU of the "
+              f"affinity mask, nproc {cores}), namespaces assigned to threads by load")
+    # The reference's own bench scenario, single thread (limitador/benches/bench.rs:72-77,553-568: 1 namespace,
+    # 1 limit max = u64::MAX / 10 s, ONE key, every request allowed) = C1b of SURVEY §8(d), and C1a as BASELINE.json
+    # words configs[0] (1 limit 10 / 60 s, 1 000 uniform keys, one 60-s rollover: deny-dominated).
+    c1 = {}
+    for name, mx, win, nkeys, step_us in (("C1b", (1 << 64) - 1, 10, 1, 0), ("C1a", 10, 60, 1000, 10)):
+        o = ob.Oracle(1 << 12)
+        o.limit_set(0, 0, mx, win * 1_000_000, True)
+        n1 = 2_000_000
+        r = np.zeros(n1, dtype=ob.RECORD_DTYPE)
+        r["hits_addend"] = 1
+        r["key_lo"] = 1 if nkeys == 1 else np.random.default_rng(42).integers(1, nkeys + 1, n1, dtype=np.uint64)
+        r["now_us"] = np.uint64(1_700_000_000_000_000) + np.arange(n1, dtype=np.uint64) * np.uint64(step_us)
+        w_ = ob.Oracle(1 << 12)  # warm the code path on a throw-away store
+        w_.limit_set(0, 0, mx, win * 1_000_000, True)
+        w_.batch_records(0, r[:100_000])
+        t0 = time.perf_counter()
+        lim = o.batch_records(0, r)[0]
+        dt = time.perf_counter() - t0
+        c1[name] = {"value": n1 / dt, "unit": UNIT, "cores": 1, "decisions": n1, "allowed_frac": float((lim == 0).mean())}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
@@ -401,9 +422,11 @@ def run_reference(args):
         "config": {"workload": f"C2: {n_ns} namespaces x 4 limits, {n_rows} keys Zipf(1.1), batch={args.batch}/GPU, "
                                f"delta=1, load_counters=false",
                    "parallelism": f"{cores} host threads, namespaces assigned to threads by load"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "threads_pinned": pinned, "nproc": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "extra": c1,
     }
     emit(line)
 
@@ -854,6 +877,7 @@ def main():
             ldesc[f] = limits[f]
         cores = min(os.cpu_count() or 1, len(set(limits['ns_id'].tolist())))  # one owner thread per namespace
         mt = ob.OracleMT(ldesc, cores, 2 * (16_000_000 if c3 else n_rows))
+        pinned = mt.pinned
         t_cpu, v_cpu = mt.run(sample)
         mt.close()
         log(f"cpu baseline {t_cpu:.2f}s")
@@ -861,8 +885,8 @@ def main():
         mism = int((v_cpu != v_gpu).sum()) if pool == total else None  # cycled pool: outputs were overwritten
         cpu = {"value": len(sample) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {S} batches of the same stream ({len(sample)} decisions) from an empty "
-                         f"pre-faulted table, {cores} threads, namespaces assigned to threads by load",
-               "gpu_verdict_mismatches": mism}
+                         f"pre-faulted table, {cores} persistent threads ({pinned} pinned), namespaces assigned to threads by load",
+               "threads_pinned": pinned, "nproc": os.cpu_count(), "gpu_verdict_mismatches": mism}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
