@@ -115,16 +115,28 @@ def counters_examined(lim: np.ndarray, first: np.ndarray, L: int):
     return int(allowed.sum()) * L + int(k.sum()), int(allowed.sum()) * L
 
 
+def _mix64(x):
+    """splitmix64 finaliser on a uint64 array (wrapping arithmetic)."""
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
 def table_digest(lid, lo, hi, val, exp):
-    """(count, blake2b hex) of a counter dump, order-independent: rows sorted lexicographically."""
-    import hashlib
+    """(count, sum, xor) over a 64-bit hash of every (limit, key, value, expiry) row of a counter dump: order-independent
+    and linear in the table size (tables of tens of millions of rows are compared at N = 8; sorting them would take
+    longer than the bench).  A difference in any field of any row changes the hash of that row."""
     n = len(lid)
     if n == 0:
-        return 0, hashlib.blake2b(b"", digest_size=16).hexdigest()
-    order = np.lexsort((exp, val, hi, lo, lid))
-    rows = np.empty(n, dtype=[("lid", "<u8"), ("lo", "<u8"), ("hi", "<u8"), ("val", "<u8"), ("exp", "<u8")])
-    rows["lid"], rows["lo"], rows["hi"], rows["val"], rows["exp"] = lid[order], lo[order], hi[order], val[order], exp[order]
-    return n, hashlib.blake2b(rows.tobytes(), digest_size=16).hexdigest()
+        return 0, "0" * 16, "0" * 16
+    with np.errstate(over="ignore"):
+        h = _mix64(np.asarray(exp, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+        h = _mix64(np.asarray(val, dtype=np.uint64) ^ h)
+        h = _mix64(np.asarray(hi, dtype=np.uint64) ^ h)
+        h = _mix64(np.asarray(lo, dtype=np.uint64) ^ h)
+        h = _mix64(np.asarray(lid, dtype=np.uint64) ^ h)
+        total = int(h.sum(dtype=np.uint64))
+    return n, f"{total:016x}", f"{int(np.bitwise_xor.reduce(h)):016x}"
 
 
 def sharded_parity(dist, world, rank, dev, eng, limits, recs_steps, out_steps, owner_of):
@@ -143,6 +155,7 @@ def sharded_parity(dist, world, rank, dev, eng, limits, recs_steps, out_steps, o
     digests = [None] * world
     dist.all_gather_object(digests, mine)
     if rank != 0:
+        dist.barrier()  # wait for rank 0's replay: a rank that went on would spin on rank 0's step flags and time out
         return None
     from limitador_b200.engine import RECORD_DTYPE
     from oracle import binding as ob
@@ -172,6 +185,7 @@ def sharded_parity(dist, world, rank, dev, eng, limits, recs_steps, out_steps, o
            "gpu_verdict_mismatches": mism, "counters": int(len(lid)), "table_mismatch_ranks": bad,
            "oracle_s": round(time.perf_counter() - t0, 2)}
     log(f"sharded parity: {res}")
+    dist.barrier()  # the other ranks wait here: nobody goes on stepping (and spinning on this rank's flags) meanwhile
     return res
 
 
@@ -685,8 +699,6 @@ def main():
             drain()
             eng.sync()
             parity = sharded_parity(dist, world, rank, dev, eng, limits, recs[:S_par], out_lim[:S_par], exchange.owner_of)
-            if os.environ.get("RL_BENCH_PARITY_BARRIER"):
-                barrier()
     drain()
     eng.sync()
     log(f"warm-up {time.perf_counter() - t_w:.2f}s")
