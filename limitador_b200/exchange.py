@@ -63,7 +63,10 @@ class LanePipelinedExchange:
     """Sharded steps with ONE all-to-all each (include/rl_engine.h: rl_record_lane_put/_gather).
 
     Blocks are fixed-size (`slot_cap` record slots per peer, unused slots are no-op records), so no
-    counts travel and nothing synchronises with the host.  The verdict byte of the record that sat in
+    counts travel and nothing synchronises with the host.  A record that does not fit its owner's block is NOT
+    decided: its verdict byte comes back as RL_VERDICT_ERROR (0xFF, include/rl_engine.h) — never as 0 = allowed —
+    and the bucket kernel raises the overflow flag the caller passed (bench.py fails the run on it).  The peer
+    exchange of the engine (`rl_shard_*`, engine.Shard) has no such limit and is what bench.py runs by default.  The verdict byte of the record that sat in
     slot (p, k) of step s-lag rides back in the lane byte of slot (p, k) of step s: the reverse
     all-to-all of the two-collective scheme disappears, and the decisions of the last lag-1 steps
     overlap the exchange of step s (a step's period is bounded by (decision latency + exchange) / lag,
