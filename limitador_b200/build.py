@@ -29,28 +29,59 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: limitador_b200 needs the CUDA toolkit to build librl_engine.so")
 
 
+# translation units and what (besides themselves) they are rebuilt for
+_PUBLIC = ("rl_engine.h", "rl_match.h", "rl_rls.h", "rl_crdt.h")
+_UNITS = {
+    "rl_engine.cu": "csrc",   # the kernels' headers live beside it: any change under csrc/ rebuilds it
+    "rl_maint.cu": "csrc",
+    "rl_crdt.cu": "csrc",
+    "rl_front.cu": "public",
+    "rl_match.cpp": "public",
+    "rl_rls.cpp": "public",
+}
+OBJ_DIR = os.path.join(_PKG, "_obj")
+
+
 def sources():
-    return [os.path.join(CSRC, f) for f in ("rl_engine.cu", "rl_front.cu", "rl_match.cpp")]
+    return [os.path.join(CSRC, f) for f in _UNITS if os.path.exists(os.path.join(CSRC, f))]
 
 
-def _deps():
-    out = [os.path.join(_ROOT, "include", "rl_engine.h")]
-    for f in os.listdir(CSRC):
-        out.append(os.path.join(CSRC, f))
+def _deps(unit: str = None):
+    out = [os.path.join(_ROOT, "include", h) for h in _PUBLIC if os.path.exists(os.path.join(_ROOT, "include", h))]
+    if unit is None or _UNITS[unit] == "csrc":
+        for f in os.listdir(CSRC):
+            if f.endswith((".h", ".cuh", ".inc")) or (unit is None and f in _UNITS):
+                out.append(os.path.join(CSRC, f))
+    if unit is not None:
+        out.append(os.path.join(CSRC, unit))
     return out
 
 
+def _compile_flags(defines=()):
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    return [*flags, *[f"-D{d}" for d in defines], "-I", os.path.join(_ROOT, "include")]
+
+
 def build_engine(force: bool = False, verbose: bool = False) -> str:
-    """Compile librl_engine.so if missing or stale; returns its path."""
-    if not force and os.path.exists(LIB_PATH):
-        t = os.path.getmtime(LIB_PATH)
-        if all(os.path.getmtime(d) <= t for d in _deps()):
-            return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, *sources()]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    """Compile librl_engine.so if missing or stale; returns its path.  Every translation unit is compiled to an object
+    of its own (limitador_b200/_obj/), so that a change to the host-only fronts does not recompile the kernels."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs, relink = [], force or not os.path.exists(LIB_PATH)
+    for src in sources():
+        unit = os.path.basename(src)
+        obj = os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
+        objs.append(obj)
+        stale = force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in _deps(unit))
+        if stale:
+            cmd = [_nvcc(), *_compile_flags(), "-c", "-o", obj, src]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
+            relink = True
+    if relink or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
+        subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+                               "-o", LIB_PATH, *objs])
     return LIB_PATH
 
 

@@ -32,6 +32,12 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(mnames) == 14 and sorted(matcher.MATCH_SYMBOLS) == mnames
     for n in mnames:
         assert hasattr(lib, n), f"{n} declared in include/rl_match.h but not exported"
+    # the RLS wire surface
+    from limitador_b200 import rls
+    rnames = declared_functions("rl_rls.h")
+    assert sorted(rls.RLS_SYMBOLS) == rnames
+    for n in rnames:
+        assert hasattr(lib, n), f"{n} declared in include/rl_rls.h but not exported"
 
 
 def test_binary_targets_sm_100a_only():
