@@ -223,6 +223,43 @@ int rl_clear(rl_engine *e);
  * qualified counter with expiry <= now_us and free rows left empty.  Mirrored in the
  * oracle as lo_invalidate_expired.  *out_invalidated (nullable) = counters dropped. */
 int rl_sweep(rl_engine *e, uint64_t now_us, uint64_t *out_invalidated);
+/* Tombstone reclamation (no reference function: moka evicts, in_memory.rs:205-212).  rl_sweep turns emptied rows into
+ * tombstones, which keep lengthening the probe chains of their region.  rl_compact rebuilds, in place, every region whose
+ * tombstones reach min_tombstone_pct percent of its rows (0 = any region with a tombstone): the region's rows go to a
+ * scratch slab (one table-sized device allocation for the call), the region is cleared and the rows that still hold a
+ * counter are inserted again by the hot path's own probing rule.  Rows whose cells are all (0, 0) hold nothing and are
+ * dropped as well.  Observable state is unchanged: rl_dump_table before == after.  Serialise with the request path. */
+typedef struct rl_compact_stats {
+    uint64_t regions;          /* table regions */
+    uint64_t regions_rebuilt;
+    uint64_t rows_live;        /* rows holding a key before the call, whole table */
+    uint64_t rows_tombstoned;  /* tombstones before the call, whole table */
+    uint64_t rows_moved;       /* rows inserted again in the rebuilt regions */
+    uint64_t rows_reclaimed;   /* slots freed in the rebuilt regions: tombstones + rows without any counter */
+} rl_compact_stats;
+int rl_compact(rl_engine *e, uint32_t min_tombstone_pct, rl_compact_stats *out /* nullable */);
+
+/* ---- Per-namespace metrics on the device ----------------------------------------------------------
+ * The reference increments authorized_calls / authorized_hits / limited_calls once per request on the host, after the
+ * decision (limitador-server/src/prometheus_metrics.rs:93-125, called at envoy_rls/server.rs:183-195).  Here they are ONE
+ * segmented reduction per decided batch, keyed by the records' ns_id (and, for limited_calls by limit name, by the limit
+ * named in out_first_limited), accumulated in device memory until read.
+ *   rl_ns_metrics_enable    : from now on every rl_check_and_update_records / _compact call adds its batch, with one
+ *                             kernel enqueued right behind the replay (same stream; nothing blocks).  Sharded steps
+ *                             decide other ranks' requests: there the SOURCE rank accumulates what it collected with
+ *                             rl_ns_metrics_accumulate.
+ *   rl_ns_metrics_accumulate: add an already decided batch: n records of record_bytes (32 = rl_record, 16 = rl_record16),
+ *                             their verdict bytes (RL_VERDICT_ERROR entries are not counted) and, nullable, the limit ids
+ *                             named.  mem = RL_MEM_HOST or RL_MEM_DEVICE for all three arrays.
+ *   rl_ns_metrics_read      : copy out (and optionally reset) the counts of namespaces [0, ns_cap) and limits
+ *                             [0, limits_cap); *out_dropped = requests not counted (error verdicts).  Nullable outputs. */
+int rl_ns_metrics_enable(rl_engine *e, int on);
+int rl_ns_metrics_accumulate(rl_engine *e, uint64_t n, const void *recs, uint32_t record_bytes, const uint8_t *limited,
+                             const uint32_t *first_limited, int mem);
+int rl_ns_metrics_read(rl_engine *e, uint32_t ns_cap, uint64_t *out_authorized_calls, uint64_t *out_authorized_hits,
+                       uint64_t *out_limited_calls, uint32_t limits_cap, uint64_t *out_limited_by_limit,
+                       uint64_t *out_dropped, int reset);
+
 /* Parity aid: every present counter (limit_id, key, value, expiry_us), unordered. */
 int rl_dump_table(rl_engine *e, uint64_t cap, uint32_t *out_limit_id, uint64_t *out_key_lo,
                   uint64_t *out_key_hi, uint64_t *out_value, uint64_t *out_expiry_us,

@@ -20,6 +20,7 @@
 
 #include "rl_kernels.cuh"
 #include "rl_shard.cuh"
+#include "rl_internal.h"
 
 #ifndef RL_SETS
 #define RL_SETS 3  // RL_FLAG_PIPELINE: calls in flight on the device (>= 3: one per pipeline stage)
@@ -166,6 +167,11 @@ struct rl_engine {
     uint32_t heavy_mult = 2;           // regions > heavy_mult x average are chained (0 = never; RL_HEAVY_MULT)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    // rl_maint.cu: its per-engine state, and the per-namespace metrics hook (nullptr = off) called behind the replay
+    // of a record call, on the stream that carries it
+    void* ext = nullptr;
+    void (*ext_free)(void*) = nullptr;
+    rl_ns_hook_fn ns_hook = nullptr;
 };
 
 namespace {
@@ -657,6 +663,10 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
         RL_CUDA(e, cudaStreamWaitEvent(e->sm, e->ev_part[k], 0));
         r = mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src, e->sm) : launch_main<RecordSrc, 0>(e, D, B, src, e->sm);
         if (r) return r;
+        // per-namespace metrics (rl_ns_metrics_enable): one reduction kernel right behind the replay, same stream
+        if (e->ns_hook && !hooks && mode == 0 && o.limited &&
+            (r = e->ns_hook(e, e->sm, n, d_recs, compact_now ? 16 : 32, o.limited, o.first)))
+            return r;
         if (hooks && hooks->post_main) {
             // the hook (a sharded step's verdict return) runs on its own stream: the replay of the next call does
             // not wait for it, only the reuse of this workspace set does
@@ -680,7 +690,10 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
         RecordSrc src{d_recs, nullptr, 0, 0, compact_now ? 1u : 0u, compact_now};
         int r = launch_front(e, D, B, src);
         if (r) return r;
-        return mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src) : launch_main<RecordSrc, 0>(e, D, B, src);
+        r = mode == 2 ? launch_main<RecordSrc, 2>(e, D, B, src) : launch_main<RecordSrc, 0>(e, D, B, src);
+        if (r == RL_OK && e->ns_hook && mode == 0 && o.limited)
+            r = e->ns_hook(e, e->stream, n, d_recs, compact_now ? 16 : 32, o.limited, o.first);
+        return r;
     }
     if (compact_now) return fail(e, RL_FATAL, "16-byte records need single-row namespaces (use the 32-byte form)");
     // some namespace spans several rows: materialise accesses (stride = max limits per ns)
@@ -697,7 +710,9 @@ int run_record_pipeline(rl_engine* e, uint32_t n, const rl_record* d_recs, int m
         int r = check_resolve_error(e);
         if (r) return r;
     }
-    return run_acc_pipeline(e, (uint32_t)n_acc, n, e->d_delta.p, e->d_now.p, mode, lc, o);
+    int r = run_acc_pipeline(e, (uint32_t)n_acc, n, e->d_delta.p, e->d_now.p, mode, lc, o);
+    if (r == RL_OK && e->ns_hook && mode == 0 && o.limited) r = e->ns_hook(e, e->stream, n, d_recs, 32, o.limited, o.first);
+    return r;
 }
 
 int ensure_ready(rl_engine* e, uint64_t n, bool fence = true) {
@@ -894,6 +909,11 @@ void rl_engine_destroy(rl_engine* e) {
     cudaSetDevice(e->device);
     if (e->sp) cudaStreamSynchronize(e->sp);
     if (e->sm) cudaStreamSynchronize(e->sm);
+    if (e->ext && e->ext_free) {
+        if (e->stream) cudaStreamSynchronize(e->stream);
+        e->ext_free(e->ext);
+        e->ext = nullptr;
+    }
     for (int k = 0; k < rl_engine::kRing; k++) {
         e->ring_recs[k].release();
         e->ring_lim[k].release();
@@ -1772,3 +1792,38 @@ int rl_unpermute_u8(rl_engine* e, uint64_t n, const uint8_t* d_in, const uint32_
 #include "rl_shard_host.inc"
 
 }  // extern "C"
+
+// ---- what rl_maint.cu may do with an engine (rl_internal.h) -------------------------------------------------------------
+int rl_internal_view(rl_engine* e, RlTableView* out) {
+    if (!e || !out) return RL_FATAL;
+    RL_CUDA(e, cudaSetDevice(e->device));
+    int r = pipe_fence(e);
+    if (r) return r;
+    r = upload_tables(e);
+    if (r) return r;
+    out->rows = e->d_rows;
+    out->cells = e->cells;
+    out->log2P = e->log2P;
+    out->log2R = e->log2R;
+    out->row_bytes = e->row_bytes;
+    out->capacity = e->capacity;
+    out->ns_cap = e->ns_cap;
+    out->limits_cap = e->limits_cap;
+    out->stream = e->stream;
+    out->device = e->device;
+    return RL_OK;
+}
+int rl_internal_fail(rl_engine* e, int status, const char* msg) { return fail(e, status, "%s", msg); }
+void rl_internal_launched(rl_engine* e, uint32_t kernels) {
+    if (e) e->stats.kernel_launches += kernels;
+}
+void** rl_internal_ext(rl_engine* e, void (*ext_free)(void*)) {
+    e->ext_free = ext_free;
+    return &e->ext;
+}
+void rl_internal_set_ns_hook(rl_engine* e, rl_ns_hook_fn fn) { e->ns_hook = fn; }
+int rl_internal_reset_hot_rows(rl_engine* e) {
+    RL_CUDA(e, cudaMemsetAsync(e->d_hot.p, 0xFF, (RL_HOT_SLOTS + RL_HOT_CAND) * sizeof(uint32_t), e->stream));
+    RL_CUDA(e, cudaMemsetAsync(e->d_hot.p + RL_HOT_SLOTS + RL_HOT_CAND, 0, 4 * sizeof(uint32_t), e->stream));
+    return RL_OK;
+}

@@ -53,6 +53,7 @@ ABI_SYMBOLS = [
     "rl_shard_create", "rl_shard_destroy", "rl_shard_ipc_handle", "rl_shard_connect_ipc", "rl_shard_connect_ptrs",
     "rl_shard_slab", "rl_shard_slab_bytes", "rl_shard_send", "rl_shard_decide", "rl_shard_collect", "rl_shard_step",
     "rl_shard_flush", "rl_shard_debug", "rl_trace_dump", "rl_check_and_update_compact", "rl_shard_fence",
+    "rl_compact", "rl_ns_metrics_enable", "rl_ns_metrics_accumulate", "rl_ns_metrics_read",
 ]
 
 
@@ -121,6 +122,10 @@ def load_library(path: str | None = None):
     L.rl_delete_counters.argtypes = [vp, vp, u32]
     L.rl_clear.argtypes = [vp]
     L.rl_sweep.argtypes = [vp, u64, vp]
+    L.rl_compact.argtypes = [vp, u32, vp]
+    L.rl_ns_metrics_enable.argtypes = [vp, i32]
+    L.rl_ns_metrics_accumulate.argtypes = [vp, u64, vp, u32, vp, vp, i32]
+    L.rl_ns_metrics_read.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, i32]
     L.rl_dump_table.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
     L.rl_bucket_by_owner.argtypes = [vp, u64, vp, u32, vp, vp, vp]
     L.rl_unpermute_u8.argtypes = [vp, u64, vp, vp, vp]
@@ -392,6 +397,34 @@ class Engine:
         cnt = C.c_uint64(0)
         self._check(self._lib.rl_sweep(self._h, now_us, C.byref(cnt)))
         return cnt.value
+
+    def compact(self, min_tombstone_pct: int = 25) -> dict:
+        """rl_compact: rebuild the regions whose tombstones reach the given share of their rows -> rl_compact_stats."""
+        st = (C.c_uint64 * 6)()
+        self._check(self._lib.rl_compact(self._h, min_tombstone_pct, st))
+        return dict(zip(("regions", "regions_rebuilt", "rows_live", "rows_tombstoned", "rows_moved", "rows_reclaimed"),
+                        [int(x) for x in st]))
+
+    def ns_metrics_enable(self, on: bool = True):
+        """Per-namespace authorized_calls / authorized_hits / limited_calls reduced on the device behind every
+        check_and_update_records / _compact call from now on."""
+        self._check(self._lib.rl_ns_metrics_enable(self._h, int(on)))
+
+    def ns_metrics_accumulate(self, recs, limited, first_limited=None):
+        """Add an already decided batch (RECORD_DTYPE or RECORD16_DTYPE records + verdict bytes [+ limit ids named])."""
+        recs = np.ascontiguousarray(recs)
+        limited = np.ascontiguousarray(limited, dtype=np.uint8)
+        fl = None if first_limited is None else np.ascontiguousarray(first_limited, dtype=np.uint32)
+        self._check(self._lib.rl_ns_metrics_accumulate(self._h, len(recs), _p(recs), recs.dtype.itemsize, _p(limited),
+                                                       None if fl is None else _p(fl), MEM_HOST))
+
+    def ns_metrics_read(self, ns_cap: int, limits_cap: int = 0, reset: bool = False) -> dict:
+        ac, ah, lc = (np.zeros(max(ns_cap, 1), dtype=np.uint64) for _ in range(3))
+        bl = np.zeros(max(limits_cap, 1), dtype=np.uint64)
+        dropped = C.c_uint64(0)
+        self._check(self._lib.rl_ns_metrics_read(self._h, ns_cap, _p(ac), _p(ah), _p(lc), limits_cap, _p(bl), C.byref(dropped), int(reset)))
+        return {"authorized_calls": ac[:ns_cap], "authorized_hits": ah[:ns_cap], "limited_calls": lc[:ns_cap],
+                "limited_by_limit": bl[:limits_cap], "dropped": int(dropped.value)}
 
     def dump_arrays(self, cap=1 << 22):
         lid = np.zeros(cap, dtype=np.uint32)

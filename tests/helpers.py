@@ -263,3 +263,107 @@ def random_records(descs, n, seed, n_keys=5, monotone=True):
         t = t - rng.choice([0, 0, 2_000_000], size=n)
     r["now_us"] = t
     return r
+
+
+_emu_maint = None
+
+
+def emu_maint_lib():
+    """tests/emu/emu_maint.cpp: the maintenance / CRDT kernels (rl_maint.cuh, rl_crdt.cuh) compiled for the host under
+    tests/emu/cuda_shim.h."""
+    global _emu_maint
+    if _emu_maint is None:
+        src = os.path.join(HERE, "emu", "emu_maint.cpp")
+        so = os.path.join(HERE, "emu", "librl_emu_maint.so")
+        csrc = os.path.join(os.path.dirname(HERE), "limitador_b200", "csrc")
+        deps = [src, os.path.join(HERE, "emu", "cuda_shim.h")] + [os.path.join(csrc, f) for f in
+                                                                ("rl_core.h", "rl_devmem.cuh", "rl_maint.cuh", "rl_crdt.cuh")]
+        deps.append(os.path.join(os.path.dirname(HERE), "include", "rl_crdt.h"))
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+        L = C.CDLL(so)
+        vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+        L.emu_seed.argtypes = [u64]
+        L.emu_ns_metrics.argtypes = [vp, u32, u32, vp, vp, u32, u32, vp]
+        L.emu_ns_metrics.restype = None
+        L.emu_table_create.restype = vp
+        L.emu_table_create.argtypes = [u32, u32, u32]
+        L.emu_table_destroy.argtypes = [vp]
+        L.emu_table_raw.restype = vp
+        L.emu_table_raw.argtypes = [vp]
+        L.emu_table_bytes.restype = u64
+        L.emu_table_bytes.argtypes = [vp]
+        for f in (L.emu_table_put, L.emu_table_get):
+            f.restype = C.c_int64
+            f.argtypes = [vp, u64, u64, vp]
+        L.emu_table_tombstone.restype = C.c_int64
+        L.emu_table_tombstone.argtypes = [vp, u64, u64]
+        L.emu_table_compact.argtypes = [vp, u32, vp, vp]
+        L.emu_table_compact.restype = None
+        L.emu_crdt_create.restype = vp
+        L.emu_crdt_create.argtypes = [u64, u32, u32]
+        L.emu_crdt_destroy.argtypes = [vp]
+        L.emu_crdt_inc.argtypes = [vp, u32, vp, vp, vp, vp, u64]
+        L.emu_crdt_inc.restype = u32
+        L.emu_crdt_merge.argtypes = [vp, u32, vp, vp, vp, u64, u64]
+        L.emu_crdt_merge.restype = u32
+        L.emu_crdt_read.argtypes = [vp, u32, vp, u64, vp, vp]
+        L.emu_crdt_read.restype = u32
+        L.emu_crdt_scan.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp, vp]
+        L.emu_crdt_scan.restype = u64
+        _emu_maint = L
+    return _emu_maint
+
+
+class EmuCrdt:
+    """The CRDT kernels on the host (same interface as limitador_b200.crdt.CrdtTable)."""
+
+    def __init__(self, capacity_rows, actors, self_actor):
+        from limitador_b200 import crdt as CR
+        self.CR = CR
+        self.L = emu_maint_lib()
+        self.actors, self.self_actor = actors, self_actor
+        self.h = self.L.emu_crdt_create(capacity_rows, actors, self_actor)
+        self.capacity = capacity_rows
+
+    def __del__(self):
+        try:
+            self.L.emu_crdt_destroy(self.h)
+        except Exception:
+            pass
+
+    def inc(self, keys, actor, increment, window_us, now_us):
+        keys = np.ascontiguousarray(keys, dtype=self.CR.KEY_DTYPE)
+        n = len(keys)
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(actor, dtype=np.uint32), (n,)))
+        inc = np.ascontiguousarray(np.broadcast_to(np.asarray(increment, dtype=np.uint64), (n,)))
+        win = np.ascontiguousarray(np.broadcast_to(np.asarray(window_us, dtype=np.uint64), (n,)))
+        return self.L.emu_crdt_inc(self.h, n, _p(keys), _p(a), _p(inc), _p(win), now_us)
+
+    def merge(self, ups, actors, values, now_us):
+        ups = np.ascontiguousarray(ups, dtype=self.CR.UPDATE_DTYPE)
+        actors = np.ascontiguousarray(actors, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        return self.L.emu_crdt_merge(self.h, len(ups), _p(ups), _p(actors), _p(values), len(values), now_us)
+
+    def read(self, keys, now_us):
+        keys = np.ascontiguousarray(keys, dtype=self.CR.KEY_DTYPE)
+        val = np.zeros(len(keys), dtype=np.uint64)
+        exp = np.zeros(len(keys), dtype=np.uint64)
+        assert self.L.emu_crdt_read(self.h, len(keys), _p(keys), now_us, _p(val), _p(exp)) == 0
+        return val, exp
+
+    def export(self, now_us, cap=1 << 16):
+        k = np.zeros(cap, dtype=self.CR.KEY_DTYPE)
+        val = np.zeros(cap, dtype=np.uint64)
+        exp = np.zeros(cap, dtype=np.uint64)
+        n = self.L.emu_crdt_scan(self.h, 0, now_us, cap, _p(k), _p(val), _p(exp), None)
+        return sorted(zip(k["lo"][:n].tolist(), k["hi"][:n].tolist(), val[:n].tolist(), exp[:n].tolist()))
+
+    def dump(self, cap=1 << 16):
+        k = np.zeros(cap, dtype=self.CR.KEY_DTYPE)
+        exp = np.zeros(cap, dtype=np.uint64)
+        vals = np.zeros(cap * self.actors, dtype=np.uint64)
+        n = self.L.emu_crdt_scan(self.h, 1, 0, cap, _p(k), None, _p(exp), _p(vals))
+        v = vals[:n * self.actors].reshape(n, self.actors)
+        return sorted((int(k["lo"][i]), int(k["hi"][i]), int(exp[i]), tuple(v[i].tolist())) for i in range(n))

@@ -38,6 +38,12 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert sorted(rls.RLS_SYMBOLS) == rnames
     for n in rnames:
         assert hasattr(lib, n), f"{n} declared in include/rl_rls.h but not exported"
+    # the replicated counter value
+    from limitador_b200 import crdt
+    cnames = declared_functions("rl_crdt.h")
+    assert sorted(crdt.CRDT_SYMBOLS) == cnames
+    for n in cnames:
+        assert hasattr(lib, n), f"{n} declared in include/rl_crdt.h but not exported"
 
 
 def test_binary_targets_sm_100a_only():
@@ -68,3 +74,6 @@ def test_engine_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(engine.EngineError):
         engine.Engine(1024)
+    from limitador_b200 import crdt
+    with pytest.raises(crdt.CrdtError, match="no CPU implementation"):
+        crdt.CrdtTable(1024, 2, 0)
