@@ -102,6 +102,18 @@ int rl_matcher_counters_batch(rl_matcher *m, uint64_t n, const uint32_t *ns_id, 
 int rl_matcher_response_headers(rl_matcher *m, const rl_counter *ctrs, const uint64_t *remaining,
                                 const uint64_t *ttl_us, uint32_t n, char *out_limit, uint32_t cap_limit,
                                 char *out_remaining, uint32_t cap_remaining, char *out_reset, uint32_t cap_reset);
+/* The matcher inside the batching front (SURVEY §8 f1 + §8b "Threading"): one request as the reference's callers have it
+ * — a namespace and a context — through counters_that_apply on the CALLING thread (matching threads run in parallel:
+ * the matcher is read-shared) and then through the front's queue (include/rl_engine.h: rl_front_check_and_update), i.e.
+ * RateLimiter::check_rate_limited_and_update (lib.rs:425-464) end to end.  out_ctrs (nullable, capacity
+ * RL_MAX_COUNTERS_PER_REQUEST) / *out_n_ctrs (nullable) receive the counters that applied; out_remaining / out_ttl_us
+ * are indexed like them.  A namespace without limits, or a context no limit applies to, is "not limited" without
+ * touching the store (lib.rs:434-440). */
+int rl_front_check_and_update_bindings(rl_front *f, rl_matcher *m, const char *ns, const rl_binding *binds, uint32_t n_binds,
+                                       uint64_t delta, uint64_t now_us, int load_counters, uint8_t *out_limited,
+                                       uint32_t *out_first_limited, rl_counter *out_ctrs, uint32_t *out_n_ctrs,
+                                       uint64_t *out_remaining, uint64_t *out_ttl_us, uint64_t *out_seq);
+
 /* The 96-bit counter key of n (variable source, value) pairs (any order): key_lo = digest bits 0..63,
  * key_hi = bits 64..95.  BLAKE2b-96 over the pairs sorted by source, each string length-prefixed (u32 LE).
  * (0, 0) for n == 0 (unqualified counter). */

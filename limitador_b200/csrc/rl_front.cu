@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/rl_engine.h"
+#include "../../include/rl_match.h"
 
 namespace {
 struct Pending {
@@ -172,6 +173,24 @@ int rl_front_check_and_update(rl_front* f, const rl_counter* ctrs, uint32_t m, u
     f->cv_done.wait(lk, [&] { return p.done; });
     if (out_seq) *out_seq = p.seq;
     return p.status;
+}
+
+int rl_front_check_and_update_bindings(rl_front* f, rl_matcher* m, const char* ns, const rl_binding* binds, uint32_t n_binds,
+                                       uint64_t delta, uint64_t now_us, int load_counters, uint8_t* out_limited,
+                                       uint32_t* out_first_limited, rl_counter* out_ctrs, uint32_t* out_n_ctrs,
+                                       uint64_t* out_remaining, uint64_t* out_ttl_us, uint64_t* out_seq) {
+    if (!f || !m || !ns) return RL_FATAL;
+    rl_counter local[RL_MAX_COUNTERS_PER_REQUEST];
+    rl_counter* ctrs = out_ctrs ? out_ctrs : local;
+    uint32_t n = 0, ns_id = 0;
+    // counters_that_apply on the caller's thread (lib.rs:507-522); a namespace no limit was ever added for has none
+    if (rl_matcher_namespace_id(m, ns, &ns_id) == RL_OK) {
+        const int r = rl_matcher_counters(m, ns_id, binds, n_binds, ctrs, RL_MAX_COUNTERS_PER_REQUEST, &n);
+        if (r != RL_OK) return r;
+    }
+    if (out_n_ctrs) *out_n_ctrs = n;
+    return rl_front_check_and_update(f, ctrs, n, delta, now_us, load_counters, out_limited, out_first_limited, out_remaining,
+                                     out_ttl_us, out_seq);
 }
 
 int rl_front_stats(rl_front* f, uint64_t* out_batches, uint64_t* out_requests) {

@@ -21,6 +21,7 @@ MATCH_SYMBOLS = (
     "rl_matcher_delete_limit", "rl_matcher_namespace_id", "rl_matcher_limit_name", "rl_matcher_counters",
     "rl_matcher_counters_batch", "rl_counter_key", "rl_matcher_response_headers",
     "rl_matcher_add_limit_ex", "rl_matcher_limit_name_copy", "rl_matcher_last_error_copy",
+    "rl_front_check_and_update_bindings",
 )
 
 
@@ -57,6 +58,8 @@ def _lib():
     L.rl_matcher_response_headers.argtypes = [vp, vp, vp, vp, u32, C.c_char_p, u32, C.c_char_p, u32, C.c_char_p, u32]
     L.rl_counter_key.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u32, C.POINTER(u64), C.POINTER(u64)]
     L.rl_counter_key.restype = None
+    L.rl_front_check_and_update_bindings.argtypes = [vp, vp, C.c_char_p, C.POINTER(RlBinding), u32, u64, u64, C.c_int, vp, vp, vp,
+                                                     vp, vp, vp, vp]
     L._rl_match_ready = True
     return L
 
@@ -186,3 +189,27 @@ class Matcher:
         self._check(self._lib.rl_matcher_counters_batch(self._h, n, ids.ctypes.data, off.ctypes.data, binds,
                                                         ctr_off.ctypes.data, ctrs.ctypes.data, cap))
         return ctr_off, ctrs[:int(ctr_off[-1])]
+
+
+def front_check_and_update(front, matcher: "Matcher", namespace: str, root: Optional[Dict[str, str]] = None,
+                           descriptors: Optional[List[Dict[str, str]]] = None, delta: int = 1, now_us: int = 0,
+                           load_counters: bool = False):
+    """rl_front_check_and_update_bindings: RateLimiter::check_rate_limited_and_update for one request — the native
+    matcher on the calling thread, then the batching front.  -> (limited, first_limited limit id | None, seq, counters
+    (COUNTER_DTYPE), remaining, ttl_us)."""
+    L = _lib()
+    flat = _bindings(root, descriptors)
+    binds = (RlBinding * max(len(flat), 1))()
+    for i, (d, k, v) in enumerate(flat):
+        binds[i] = RlBinding(d, 0, k.encode(), v.encode())
+    lim, first, seq, n = C.c_uint8(0), C.c_uint32(_eng.NONE), C.c_uint64(0), C.c_uint32(0)
+    ctrs = np.zeros(16, dtype=_eng.COUNTER_DTYPE)
+    rem = np.zeros(16, dtype=np.uint64)
+    ttl = np.zeros(16, dtype=np.uint64)
+    st = L.rl_front_check_and_update_bindings(front._h, matcher._h, namespace.encode(), binds, len(flat), delta, now_us,
+                                              int(load_counters), C.addressof(lim), C.addressof(first), ctrs.ctypes.data,
+                                              C.addressof(n), rem.ctypes.data, ttl.ctypes.data, C.addressof(seq))
+    if st != 0:
+        raise MatcherError(L.rl_matcher_last_error(matcher._h).decode() or "rl_front_check_and_update_bindings failed")
+    k = n.value
+    return bool(lim.value), (None if first.value == _eng.NONE else first.value), seq.value, ctrs[:k], rem[:k], ttl[:k]
