@@ -449,6 +449,95 @@ _REAL_STDOUT = None
 _T0 = time.perf_counter()
 
 
+def run_rls_leg(threads: int = 0, batch: int = 32768, steps: int = 6):
+    """`extra.rls`: the Envoy RLS v3 wire surface end to end on this box — `batch` RateLimitRequest
+    messages per step (domain + one descriptor with method and user, the shape of limitador-server/sandbox/load-test.json)
+    through rl_rls_serve: decode + counters_that_apply on `threads` CPU workers, ONE rl_check_and_update_batch on the GPU,
+    RateLimitResponse bytes with the draft-03 headers.  The first step is also run through the CPU stages wrapped around
+    the oracle (plan -> oracle -> finish) and the response bytes compared."""
+    from limitador_b200 import Engine
+    from limitador_b200 import matcher as MT
+    from limitador_b200 import rls as R
+    from oracle import binding as ob
+    rng = np.random.default_rng(42)
+    n_ns, n_users = 32, 200_000
+    limits = []
+    for ns in range(n_ns):
+        limits.append((f"ns{ns}", 100, 60, ["descriptors[0].method == 'GET'"], ["descriptors[0].user"], "get-per-user"))
+        limits.append((f"ns{ns}", 1000, 3600, [], ["descriptors[0].user"], "hourly-per-user"))
+        limits.append((f"ns{ns}", 1 << 40, 60, ["descriptors[0].method != 'OPTIONS'"], [], None))
+    m, m2 = MT.Matcher(), MT.Matcher()
+    descs = [m.add_limit(*l) for l in limits]
+    for l in limits:
+        m2.add_limit(*l)
+    eng = Engine(capacity_rows=1 << 20, cells_per_row=3, max_batch=batch, max_counters=4 * batch)
+    eng.limits_set(np.array(descs))
+    threads = threads or min(os.cpu_count() or 1, 64)
+    svc = R.RlsService(m, eng, R.HEADERS_DRAFT_VERSION_03, threads)
+    methods = ["GET", "GET", "GET", "POST", "OPTIONS"]
+    zipf = rng.zipf(1.1, size=(steps + 1) * batch) % n_users
+
+    def make(step):
+        u = zipf[step * batch:(step + 1) * batch]
+        ns = rng.integers(0, n_ns, size=batch)
+        me = rng.integers(0, len(methods), size=batch)
+        return R.pack_requests([R.encode_request(f"ns{ns[i]}", [[("method", methods[me[i]]), ("user", f"u{u[i]}")]], 1) for i in range(batch)])
+
+    t0 = 1_700_000_000_000_000
+    msgs = [make(s) for s in range(steps + 1)]
+    # parity of the first step: the engine's responses against plan -> oracle -> finish
+    ref = R.RlsService(m2, None, R.HEADERS_DRAFT_VERSION_03, threads)
+    orc = ob.Oracle(1 << 20)
+    for d in descs:
+        orc.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    p = ref.plan(R.SHOULD_RATE_LIMIT, *msgs[0], t0)
+    want = ref.finish(*orc.batch_csr(0, p["ctr_off"], p["ctrs"], p["delta"], p["now_us"], p["load_counters"]))
+    svc.serve(R.SHOULD_RATE_LIMIT, *msgs[0], t0)
+    got = svc.responses()
+    mism = sum(1 for a, b in zip(got, want) if a != b)
+    svc.serve(R.SHOULD_RATE_LIMIT, *msgs[1], t0 + 1_000_000)  # second warm-up
+    tim = {"plan_us": 0.0, "store_us": 0.0, "finish_us": 0.0}
+    t_start = time.perf_counter()
+    for s in range(2, steps + 1):
+        svc.serve(R.SHOULD_RATE_LIMIT, *msgs[s], t0 + s * 1_000_000)
+        for k, v in svc.timings().items():
+            tim[k] += v
+    wall = time.perf_counter() - t_start
+    k = steps - 1
+    codes = svc.codes()
+    wire_in = int(sum(len(b) for b, _ in msgs[2:])) // k
+    out = {"value": k * batch / wall, "unit": "ShouldRateLimit requests/s (wire bytes in, wire bytes out)", "batch": batch,
+           "steps": k, "threads": threads, "nproc": os.cpu_count(), "ms_per_step": wall / k * 1e3,
+           "stage_ms_per_step": {a[:-3]: round(v / k / 1e3, 3) for a, v in tim.items()},
+           "wire_bytes_in_per_request": wire_in / batch, "over_limit_frac_last_step": float((codes == R.CODE_OVER_LIMIT).mean()),
+           "counters_per_request": float(len(p["ctrs"]) / max(1, p["n_store"])),
+           "wire_parity": {"responses_compared": len(want), "response_mismatches": mism,
+                      "against": "plan -> CPU oracle -> finish on the same wire bytes (byte-equal responses incl. X-RateLimit-* headers)"},
+           "note": "the store call moves pageable host arrays (RL_MEM_HOST, CSR form); decode+match and encode run on the CPU workers"}
+    svc.close()
+    ref.close()
+    eng.close()
+    return out
+
+
+def run_matcher_leg(threads: int = 0, requests: int = 4000):
+    """`extra.matcher`: counters_that_apply of the native matcher on the reference's four bench scenarios
+    (limitador/benches/bench.rs:65-90) on this box's cores."""
+    from limitador_b200 import bench_matcher as BM
+    threads = threads or min(os.cpu_count() or 1, 32)
+    rows = []
+    for scn in BM.SCENARIOS:
+        one = BM.run(scn, requests, 1)
+        many = BM.run(scn, requests, threads)
+        rows.append({"scenario": one["scenario"], "ns_per_request_1_thread": round(one["ns_per_request"], 1),
+                     "requests_per_s_1_thread": one["requests_per_s"], "threads": threads,
+                     "requests_per_s_all_threads": many["requests_per_s"], "counters_per_request": one["counters_per_request"],
+                     "fits_one_engine_request": one["fits_one_engine_request"]})
+    return {"scenarios": rows, "nproc": os.cpu_count(),
+            "note": "one rl_matcher_counters_batch call per thread over prebuilt bindings; the reference's Criterion bench of "
+                    "these scenarios times CEL matching + moka together and cannot be built here (no Rust toolchain)"}
+
+
 def log(msg: str):
     """progress line on stderr, stamped with the seconds since start (where does a run spend its wall time?)"""
     print(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
@@ -900,6 +989,18 @@ def main():
                          f"pre-faulted table, {cores} persistent threads ({pinned} pinned), namespaces assigned to threads by load",
                "threads_pinned": pinned, "nproc": os.cpu_count(), "gpu_verdict_mismatches": mism}
 
+    # ---- the CPU front and the RLS wire surface on this box; an extra must not take the headline down ----
+    if world == 1 and not args.no_extra and args.workload == "C2":
+        for xn, fn in (("rls", run_rls_leg), ("matcher", run_matcher_leg)):
+            try:
+                log(f"extra {xn}: start")
+                extra[xn] = fn()
+                log(f"extra {xn}: {extra[xn]}")
+            except Exception as ex:
+                import traceback
+                traceback.print_exc()
+                extra[xn] = {"error": f"{type(ex).__name__}: {ex}"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_a / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -936,6 +1037,7 @@ def main():
     line["hot_rows"] = eng_stats.get("hot_rows")
     failed = any(isinstance(x, dict) and x.get("parity") and (x["parity"]["gpu_verdict_mismatches"] != 0 or x["parity"]["table_mismatch_ranks"])
                  for x in extra.values())
+    failed = failed or any(isinstance(x, dict) and x.get("wire_parity", {}).get("response_mismatches") for x in extra.values())
     if parity is not None:
         # N>1: the live check against ONE global oracle (no CPU throughput is quoted from it: a single thread)
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",

@@ -75,6 +75,11 @@ int rl_matcher_add_limit_ex(rl_matcher *m, const char *ns, uint64_t max_value, u
                             uint32_t n_var, const char *name /* nullable */, int keep_existing,
                             rl_limit_desc *out_desc, int *out_existed /* nullable */);
 int rl_matcher_delete_limit(rl_matcher *m, uint32_t limit_id);
+/* Counters one request may produce before matching fails (default RL_MAX_COUNTERS_PER_REQUEST = what the engine takes
+ * per request, so that an oversized request is refused here, before anything is enqueued).  A caller that only matches
+ * — the matcher benchmark on the reference's "50 limits per namespace" scenarios, limitador/benches/bench.rs:65-90 — may
+ * raise it; such requests cannot be shipped to the engine. */
+int rl_matcher_set_counter_cap(rl_matcher *m, uint32_t cap);
 /* RL_OK and *out_ns_id, or RL_FATAL if no limit was ever added for the namespace (no limits => allow,
  * lib.rs:434-440: the caller skips the engine). */
 int rl_matcher_namespace_id(rl_matcher *m, const char *ns, uint32_t *out_ns_id);

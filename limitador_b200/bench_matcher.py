@@ -27,6 +27,7 @@ SCENARIOS = [(10, 50, 10, 0), (1, 1, 1, 1), (10, 10, 10, 10), (10, 50, 10, 10)] 
 
 def build(n_ns, n_lim, n_cond, n_var):
     m = MT.Matcher()
+    m.set_counter_cap(max(16, n_lim))  # matching only: the engine itself takes at most 16 counters per request
     conds = [f"cond_{i} == '1'" for i in range(n_cond)]
     vars_ = [f"var_{j}" for j in range(n_var)]
     for ns in range(n_ns):
@@ -73,7 +74,8 @@ def run(scn, n_req, threads):
     assert n_ctr == n_req * n_lim
     return {"scenario": f"{n_ns} namespaces with {n_lim} limits each with {n_cond} conditions and {n_var} variables",
             "threads": threads, "requests_per_s": threads * n_req / per_call, "counters_per_s": threads * n_ctr / per_call,
-            "ns_per_request": per_call / n_req * 1e9, "counters_per_request": n_lim, "wall_s": wall}
+            "ns_per_request": per_call / n_req * 1e9, "counters_per_request": n_lim, "wall_s": wall,
+            "fits_one_engine_request": n_lim <= 16}
 
 
 def main():

@@ -294,6 +294,7 @@ thread_local Scratch tls_scratch;
 
 struct rl_matcher {
     std::shared_mutex mu;
+    uint32_t counter_cap = RL_MAX_COUNTERS_PER_REQUEST;  // rl_matcher_set_counter_cap
     std::mutex err_mu;  // last_error is also written by matching calls, which hold `mu` shared
     std::string last_error;
     SlotTable slots;
@@ -371,7 +372,7 @@ int match_one(const rl_matcher* m, uint32_t ns_id, const rl_binding* binds, uint
         if (!ok) continue;
         // the engine takes at most RL_MAX_COUNTERS_PER_REQUEST counters per request: refuse here, before
         // anything is enqueued, instead of letting the device resolve fail the batch half-applied
-        if (n_out >= cap || n_out >= RL_MAX_COUNTERS_PER_REQUEST) return RL_FATAL;
+        if (n_out >= cap || n_out >= m->counter_cap) return RL_FATAL;
         rl_counter& c = out[n_out++];
         c.limit_id = lid;
         c._pad = 0;
@@ -511,6 +512,13 @@ int rl_matcher_add_limit_ex(rl_matcher* m, const char* ns, uint64_t max_value, u
     out_desc->qualified = R.vars.empty() ? 0 : 1;  // counter.rs:108-110
     out_desc->max_value = R.max_value;
     out_desc->window_us = R.seconds * 1000000ull;  // counter.rs:76-78
+    return RL_OK;
+}
+
+int rl_matcher_set_counter_cap(rl_matcher* m, uint32_t cap) {
+    if (!m || cap == 0) return RL_FATAL;
+    std::unique_lock<std::shared_mutex> lock(m->mu);
+    m->counter_cap = cap;
     return RL_OK;
 }
 

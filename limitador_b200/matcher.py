@@ -21,7 +21,7 @@ MATCH_SYMBOLS = (
     "rl_matcher_delete_limit", "rl_matcher_namespace_id", "rl_matcher_limit_name", "rl_matcher_counters",
     "rl_matcher_counters_batch", "rl_counter_key", "rl_matcher_response_headers",
     "rl_matcher_add_limit_ex", "rl_matcher_limit_name_copy", "rl_matcher_last_error_copy",
-    "rl_front_check_and_update_bindings",
+    "rl_front_check_and_update_bindings", "rl_matcher_set_counter_cap",
 )
 
 
@@ -50,6 +50,7 @@ def _lib():
     L.rl_matcher_limit_name_copy.argtypes = [vp, u32, C.c_char_p, u32, C.POINTER(C.c_int)]
     L.rl_matcher_last_error_copy.argtypes = [vp, C.c_char_p, u32]
     L.rl_matcher_delete_limit.argtypes = [vp, u32]
+    L.rl_matcher_set_counter_cap.argtypes = [vp, u32]
     L.rl_matcher_namespace_id.argtypes = [vp, C.c_char_p, C.POINTER(u32)]
     L.rl_matcher_limit_name.argtypes = [vp, u32]
     L.rl_matcher_limit_name.restype = C.c_char_p
@@ -130,6 +131,10 @@ class Matcher:
                                                       _strs(vars_), len(vars_), None if name is None else name.encode(), 1,
                                                       desc.ctypes.data, C.byref(existed)))
         return desc[0], bool(existed.value)
+
+    def set_counter_cap(self, cap: int):
+        """Counters one request may produce (default 16 = what the engine takes); raise it only to match without the engine."""
+        self._check(self._lib.rl_matcher_set_counter_cap(self._h, cap))
 
     def delete_limit(self, limit_id: int):
         self._check(self._lib.rl_matcher_delete_limit(self._h, limit_id))

@@ -463,3 +463,18 @@ def test_response_headers_render_the_reference_strings():
         want = LM.CheckResult(False, cs).response_header()
         got = m.response_headers(np.array([(lid, 0, 1, 0) for _, lid in pick], dtype=COUNTER_DTYPE), rem, ttl)
         assert got == want
+
+
+def test_counter_cap_defaults_to_what_the_engine_takes_and_can_be_raised_for_matching_only():
+    """The reference's bench scenarios hold 50 limits per namespace (benches/bench.rs:65-90): 50 counters per request.
+    The engine takes 16 per request, so the matcher refuses such a request before anything is enqueued — unless the
+    caller only matches and raises the cap."""
+    m = MT.Matcher()
+    for l in range(50):
+        m.add_limit("ns", 10, 10 + l, ["cond == '1'"], ["var"])
+    with pytest.raises(MT.MatcherError, match="counters"):
+        m.counters(m.namespace_id("ns"), {"cond": "1", "var": "v"}, cap=64)
+    m.set_counter_cap(64)
+    got = m.counters(m.namespace_id("ns"), {"cond": "1", "var": "v"}, cap=64)
+    assert len(got) == 50 and len(set(got["limit_id"].tolist())) == 50
+    assert len({(int(c["key_lo"]), int(c["key_hi"])) for c in got}) == 1  # one variable set: one key digest
