@@ -189,6 +189,33 @@ def sharded_parity(dist, world, rank, dev, eng, limits, recs_steps, out_steps, o
     return res
 
 
+def place_namespaces(dist, world, dev, recs, limits, sample_steps, log):
+    """Static namespace -> GPU placement for a sharded run (SURVEY §8e "Skew"): observe the namespaces' traffic in the first
+    steps of every rank's stream, place them heaviest-first on the least loaded rank and give each the ns_id that hashes to
+    its rank (exchange.balanced_namespace_ids) — the data path still computes owner = rl_owner_of(ns_id, world).  Rewrites
+    the records' ns_id in place and returns (limits with the new ids, a summary for the JSON line)."""
+    import torch
+    from limitador_b200 import exchange
+    n_ns = int(limits["ns_id"].max()) + 1
+    cnt = torch.bincount((recs[:sample_steps, :, 0] & 0xFFFFFFFF).reshape(-1), minlength=n_ns).to(torch.float64)
+    dist.all_reduce(cnt)  # the same counts, hence the same ids, on every rank
+    load = cnt.cpu().numpy()[:n_ns]
+    hashed = np.zeros(world)
+    for j in range(n_ns):
+        hashed[exchange.owner_of(j, world)] += load[j]
+    ids, owner_load = exchange.balanced_namespace_ids(load, world)
+    exchange.remap_namespace_ids(recs, torch.from_numpy(ids).to(dev))
+    out = limits.copy()
+    out["ns_id"] = ids[limits["ns_id"].astype(np.int64)].astype(out["ns_id"].dtype)
+    summary = {"policy": "balanced: namespaces placed heaviest-first on the least loaded rank, through the ns_id they are given "
+                         "(owner = rl_owner_of(ns_id, world) on the data path, unchanged)",
+               "owner_load_max_over_mean": float(owner_load.max() / owner_load.mean()),
+               "owner_load_max_over_mean_if_ids_were_hashed_as_generated": float(hashed.max() / hashed.mean()),
+               "top_namespace_share": float(load.max() / load.sum()), "sampled_steps_per_rank": int(sample_steps)}
+    log(f"namespace placement: {summary}")
+    return out, summary
+
+
 def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
     """A short pass of another BASELINE.json config, reported under `extra` in the one JSON line:
     C3 (configs[2], single GPU), C4 / C5 (configs[3], configs[4]: namespace-sharded over all ranks).
@@ -221,6 +248,9 @@ def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
     S_par = 1 if world > 1 else 3
     total = S_par + Wx + 2 * K
     recs = gen(total)
+    placement = None
+    if world > 1 and args.placement == "balanced":
+        limits, placement = place_namespaces(dist, world, dev, recs, limits, min(total, 2), log)
     out = torch.zeros((total, batch), dtype=torch.uint8, device=dev)
     max_batch = batch if world == 1 else min(world, 4) * batch  # an owner may receive up to 4 source batches in a step
     # C5 is the hot-key regime: rows that dominate their chunks get partitions of their own (RL_FLAG_HOT_ROWS = 16)
@@ -310,6 +340,8 @@ def run_extra(name, world, rank, local_rank, dev, dist, args, stream):
            "ms_per_step": ms_a / K, "parity": par, "table_rows": cap, "row_bytes": 16 * (1 + cells)}
     if imbalance:
         res["imbalance"] = imbalance
+    if placement:
+        res["placement"] = placement
     if world == 1 and L is not None:
         eng.profile_begin()
         ms_b = timed(S_par + Wx + K, K)
@@ -582,6 +614,9 @@ def main():
     ap.add_argument("--trace", default="", help="RL_FLAG_TRACE: write every rank's device-side event trace of pass A to <path>.rank<r>.json")
     ap.add_argument("--extra-batch", type=int, default=0, help="requests per GPU and step of the `extra` workloads (default 1048576)")
     ap.add_argument("--device-pass-only", action="store_true", help="(internal: the traffic leg) stop after the device-resident pass")
+    ap.add_argument("--placement", default="balanced", choices=["balanced", "hash"],
+                    help="N>1, peer exchange: namespace -> GPU placement. balanced = ids assigned so that rl_owner_of spreads the "
+                         "observed namespace load evenly (SURVEY 8e static override); hash = the generator's ids as they are")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads / legs reported under `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -647,6 +682,9 @@ def main():
         dist.all_reduce(seen, op=dist.ReduceOp.MAX)
         slot_cap = exchange.slot_cap_for(int(seen.item()), batch)
         log(f"largest exchange block in the sample: {int(seen.item())} records -> slot_cap {slot_cap}")
+    placement = None
+    if use_peer and args.placement == "balanced":
+        limits, placement = place_namespaces(dist, world, dev, recs_pool, limits, min(pool, 16), log)
     max_batch = batch if world == 1 else (world * batch if use_peer else world * slot_cap)
     # RL_FLAG_PIPELINE (2): the front of step s+1 overlaps the replay of step s on the device
     eng = Engine(capacity_rows=cap, cells_per_row=cells, max_batch=max_batch, max_counters=max_batch, device=local_rank,
@@ -1034,6 +1072,9 @@ def main():
         line["cpu_baseline"] = cpu
     if extra:
         line["extra"] = extra
+    if placement:
+        line["placement"] = placement
+        line["config"]["parallelism"] += "; namespace -> GPU placement balanced through the ids (see `placement`)"
     line["hot_rows"] = eng_stats.get("hot_rows")
     failed = any(isinstance(x, dict) and x.get("parity") and (x["parity"]["gpu_verdict_mismatches"] != 0 or x["parity"]["table_mismatch_ranks"])
                  for x in extra.values())

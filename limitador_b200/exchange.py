@@ -154,3 +154,51 @@ def slot_cap_for(largest_block: int, batch: int, headroom: float = 1.2) -> int:
     """Exchange block size (record slots per peer) for an observed largest block: headroom on top, a multiple
     of 256, never more than a whole batch."""
     return int(min(batch, (int(largest_block * headroom) + 255) // 256 * 256))
+
+
+def balanced_namespace_ids(load, world: int):
+    """A static namespace -> GPU placement (SURVEY §8e "Skew": "allow a static namespace→GPU override table") without
+    touching the data path: the owner of a request is rl_owner_of(ns_id, world) and ns_id is an interned id the front
+    chooses, so the front gives every namespace an id whose owner is the rank it wants the namespace on.
+
+    load[j] = observed traffic of namespace j (any unit).  Namespaces are placed heaviest first on the least loaded
+    rank (LPT), then given the smallest unused id that hashes to that rank.  Returns (ids int64[len(load)],
+    owner_load float64[world]); ids[j] replaces j everywhere the front names the namespace (rl_limit_desc.ns_id,
+    rl_record.ns_id).  Deterministic: equal inputs give equal ids on every rank."""
+    import numpy as np
+    load = np.asarray(load, dtype=np.float64)
+    n = len(load)
+    owner_load = np.zeros(world, dtype=np.float64)
+    want = np.zeros(n, dtype=np.int64)
+    for j in np.argsort(-load, kind="stable"):
+        r = int(np.argmin(owner_load))  # ties: the lowest rank
+        want[j] = r
+        owner_load[r] += load[j]
+    need = np.bincount(want, minlength=world)
+    pools = [[] for _ in range(world)]
+    cand = 0
+    while any(len(pools[r]) < need[r] for r in range(world)):
+        r = owner_of(cand, world)
+        if len(pools[r]) < need[r]:
+            pools[r].append(cand)
+        cand += 1
+        if cand > (1 << 24):
+            raise RuntimeError("no namespace ids left below 2^24 (the 16-byte record form's id range)")
+    ids = np.zeros(n, dtype=np.int64)
+    taken = [0] * world
+    for j in range(n):  # ids in namespace order inside a rank: stable and easy to read in a dump
+        r = int(want[j])
+        ids[j] = pools[r][taken[r]]
+        taken[r] += 1
+    return ids, owner_load
+
+
+def remap_namespace_ids(recs, id_lut):
+    """In place: rl_record word 0 (ns_id | hits_addend << 32) of `recs` ([..., 4] int64) gets ns_id = id_lut[ns_id].
+    `id_lut` is an int64 tensor on the records' device."""
+    flat = recs.view(-1, 4)
+    step = 1 << 22
+    for a in range(0, flat.shape[0], step):
+        w0 = flat[a:a + step, 0]
+        flat[a:a + step, 0] = id_lut[w0 & 0xFFFFFFFF] | ((w0 >> 32) << 32)
+    return recs
