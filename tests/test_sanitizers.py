@@ -40,3 +40,21 @@ def test_matcher_is_clean_under_asan_and_ubsan(tmp_path):
                                           os.path.join(ROOT, "limitador_b200", "csrc", "rl_match.cpp")],
                         [os.path.join(ROOT, "include")], extra=("-std=c++17",))
     assert out.startswith("ok added=")
+
+
+def test_rls_wire_surface_is_clean_under_asan_and_ubsan(tmp_path):
+    """The decoder reads bytes from the network: 200 000 mutated / truncated / random messages, then the plan and finish
+    stages over batches mixing good, malformed and unsupported requests, 1 and 3 workers."""
+    csrc = os.path.join(ROOT, "limitador_b200", "csrc")
+    out = build_and_run(tmp_path, "g++", [os.path.join(ROOT, "tests", "san", "san_rls.cpp"), os.path.join(csrc, "rl_rls.cpp"),
+                                          os.path.join(csrc, "rl_match.cpp")],
+                        [os.path.join(ROOT, "include")], extra=("-std=c++17",))
+    assert out.startswith("ok decoded=")
+
+
+def test_crdt_oracle_and_shim_kernels_are_clean_under_asan_and_ubsan(tmp_path):
+    """The maintenance / CRDT kernels under the host shim with ASan + UBSan: out-of-bounds row arithmetic in a kernel shows
+    up here, in the container without a GPU (tests/san/san_kernels.cpp)."""
+    out = build_and_run(tmp_path, "g++", [os.path.join(ROOT, "tests", "san", "san_kernels.cpp")],
+                        [os.path.join(ROOT, "include")], extra=("-std=c++17",))
+    assert out.startswith("ok kernels")
