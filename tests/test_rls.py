@@ -371,3 +371,68 @@ def test_a_batch_equals_the_python_mirror_called_request_by_request(threads, hea
         want_h = sorted(w.response_header().items()) if headers != R.HEADERS_NONE else []
         assert resp[1] == want_h
     assert 50 < n_over < 650
+
+
+# ---- the Kuadrant service's own tests (limitador-server/src/envoy_rls/kuadrant_service.rs:189-650), one by one ---------
+_KUADRANT_LIMIT = ("test_namespace", 1, 60, ["descriptors[0]['req.method'] == 'GET'"], ["descriptors[0]['app.id']"], None)
+_KUADRANT_REQ = [[("req.method", "GET"), ("app.id", "1")]]
+
+
+def test_kuadrant_check_returns_ok_correctly():
+    """:209-268 — checks never count: a limit of 1 answers OK twice."""
+    h = CpuHarness([_KUADRANT_LIMIT])
+    for _ in range(2):
+        assert h.call(R.CHECK_RATE_LIMIT, [_req("test_namespace", _KUADRANT_REQ, 1)])[0] == (0, (R.CODE_OK, []))
+
+
+def test_kuadrant_check_returns_overlimit_correctly():
+    """:270-323 — max 0: the first check is already over the limit."""
+    h = CpuHarness([("test_namespace", 0, 60) + _KUADRANT_LIMIT[3:]])
+    assert h.call(R.CHECK_RATE_LIMIT, [_req("test_namespace", _KUADRANT_REQ, 1)])[0] == (0, (R.CODE_OVER_LIMIT, []))
+
+
+def test_kuadrant_check_returns_ok_when_no_limits_apply():
+    """:325-357"""
+    h = CpuHarness([])
+    assert h.call(R.CHECK_RATE_LIMIT, [_req("test_namespace", [[("req.method", "GET")]], 1)])[0] == (0, (R.CODE_OK, []))
+
+
+def test_kuadrant_check_returns_unknown_when_domain_is_empty():
+    """:359-389"""
+    h = CpuHarness([])
+    assert h.call(R.CHECK_RATE_LIMIT, [_req("", [[("req.method", "GET")]], 1)])[0] == (0, (R.CODE_UNKNOWN, []))
+
+
+def test_kuadrant_check_takes_into_account_all_the_descriptors():
+    """:391-471 — the max-0 limit needs descriptors[1].y == '2'."""
+    h = CpuHarness([("test_namespace", 10, 60, ["descriptors[0].x == '1'"], ["descriptors[0].z"], None),
+                    ("test_namespace", 0, 60, ["descriptors[0].x == '1'", "descriptors[1].y == '2'"], ["descriptors[0].z"], None)])
+    r, = h.call(R.CHECK_RATE_LIMIT, [_req("test_namespace", [[("x", "1"), ("z", "1")], [("y", "2")]], 1)])
+    assert r == (0, (R.CODE_OVER_LIMIT, []))
+
+
+def test_kuadrant_report_returns_ok_correctly():
+    """:487-537"""
+    h = CpuHarness([_KUADRANT_LIMIT])
+    assert h.call(R.REPORT, [_req("test_namespace", _KUADRANT_REQ, 1)])[0] == (0, (R.CODE_OK, []))
+
+
+def test_kuadrant_report_going_overlimit_is_ok():
+    """:539-589 — Report 20 hits against a limit of 5: still OK (update_counters never refuses), and the counter holds 20."""
+    h = CpuHarness([("test_namespace", 5, 60) + _KUADRANT_LIMIT[3:]])
+    assert h.call(R.REPORT, [_req("test_namespace", _KUADRANT_REQ, 20)])[0] == (0, (R.CODE_OK, []))
+    assert h.last_plan["delta"].tolist() == [20]
+    assert [row[3] for row in h.o.dump()] == [20]
+    assert h.call(R.CHECK_RATE_LIMIT, [_req("test_namespace", _KUADRANT_REQ, 1)])[0] == (0, (R.CODE_OVER_LIMIT, []))
+
+
+def test_kuadrant_report_returns_ok_when_no_limits_apply():
+    """:591-619"""
+    h = CpuHarness([])
+    assert h.call(R.REPORT, [_req("test_namespace", [[("req.method", "GET")]], 1)])[0] == (0, (R.CODE_OK, []))
+
+
+def test_kuadrant_report_returns_unknown_when_domain_is_empty():
+    """:621-647"""
+    h = CpuHarness([])
+    assert h.call(R.REPORT, [_req("", [[("req.method", "GET")]], 1)])[0] == (0, (R.CODE_UNKNOWN, []))
