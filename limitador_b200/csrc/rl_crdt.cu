@@ -72,6 +72,16 @@ struct In {
     }
 };
 
+// A device scratch array freed at scope exit (every exit path of a call, the error ones included).
+template <class E>
+struct Scratch {
+    E* p = nullptr;
+    ~Scratch() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(uint64_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(E)); }
+};
+
 // Wait for the call's kernels and translate the sticky device error.
 int finish(rl_crdt* c) {
     uint32_t code = 0;
@@ -165,17 +175,14 @@ int rl_crdt_merge(rl_crdt* c, uint64_t n, const rl_crdt_update* updates, const u
     RLC_CUDA(c, u.set(updates, n, mem, c->stream));
     RLC_CUDA(c, a.set(actors, n_values, mem, c->stream));
     RLC_CUDA(c, v.set(values, n_values, mem, c->stream));
-    unsigned long long* d_row_of = nullptr;
-    RLC_CUDA(c, cudaMalloc((void**)&d_row_of, n * sizeof(unsigned long long)));
+    Scratch<unsigned long long> row_of;
+    RLC_CUDA(c, row_of.alloc(n));
     // two launches: every reset (expiry + zeroed values) is complete before any value is merged
-    k_crdt_merge_expiry<<<blocks_for(n), 256, 0, c->stream>>>(tab_of(c), (uint32_t)n, u.p, now_us, d_row_of);
-    k_crdt_merge_values<<<blocks_for(n), 256, 0, c->stream>>>(tab_of(c), (uint32_t)n, u.p, a.p, v.p, n_values, d_row_of);
-    const cudaError_t le = cudaGetLastError();
+    k_crdt_merge_expiry<<<blocks_for(n), 256, 0, c->stream>>>(tab_of(c), (uint32_t)n, u.p, now_us, row_of.p);
+    k_crdt_merge_values<<<blocks_for(n), 256, 0, c->stream>>>(tab_of(c), (uint32_t)n, u.p, a.p, v.p, n_values, row_of.p);
+    RLC_CUDA(c, cudaGetLastError());
     c->launches += 2;
-    const int r = le == cudaSuccess ? finish(c) : cfail(c, RL_FATAL, "launch failed: %s", cudaGetErrorString(le));
-    cudaStreamSynchronize(c->stream);
-    cudaFree(d_row_of);
-    return r;
+    return finish(c);  // synchronises the stream before the scratch and the staged inputs are freed
 }
 
 int rl_crdt_read(rl_crdt* c, uint64_t n, const rl_crdt_key* keys, uint64_t now_us, int mem, uint64_t* out_value,
@@ -185,28 +192,24 @@ int rl_crdt_read(rl_crdt* c, uint64_t n, const rl_crdt_key* keys, uint64_t now_u
     RLC_CUDA(c, cudaSetDevice(c->device));
     In<rl_crdt_key> k;
     RLC_CUDA(c, k.set(keys, n, mem, c->stream));
-    uint64_t *d_val = out_value, *d_exp = out_expiry_us, *own_val = nullptr, *own_exp = nullptr;
+    Scratch<uint64_t> own_val, own_exp;
+    uint64_t *d_val = out_value, *d_exp = out_expiry_us;
     if (mem != RL_MEM_DEVICE) {
-        RLC_CUDA(c, cudaMalloc((void**)&own_val, n * sizeof(uint64_t)));
-        d_val = own_val;
+        RLC_CUDA(c, own_val.alloc(n));
+        d_val = own_val.p;
         if (out_expiry_us) {
-            RLC_CUDA(c, cudaMalloc((void**)&own_exp, n * sizeof(uint64_t)));
-            d_exp = own_exp;
+            RLC_CUDA(c, own_exp.alloc(n));
+            d_exp = own_exp.p;
         }
     }
     k_crdt_read<<<blocks_for(n), 256, 0, c->stream>>>(tab_of(c), (uint32_t)n, k.p, now_us, d_val, d_exp);
-    const cudaError_t le = cudaGetLastError();
+    RLC_CUDA(c, cudaGetLastError());
     c->launches++;
-    int r = le == cudaSuccess ? RL_OK : cfail(c, RL_FATAL, "launch failed: %s", cudaGetErrorString(le));
-    if (r == RL_OK && mem != RL_MEM_DEVICE) {
-        cudaMemcpyAsync(out_value, own_val, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
-        if (out_expiry_us) cudaMemcpyAsync(out_expiry_us, own_exp, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+    if (mem != RL_MEM_DEVICE) {
+        RLC_CUDA(c, cudaMemcpyAsync(out_value, own_val.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        if (out_expiry_us) RLC_CUDA(c, cudaMemcpyAsync(out_expiry_us, own_exp.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     }
-    if (r == RL_OK) r = finish(c);
-    cudaStreamSynchronize(c->stream);
-    if (own_val) cudaFree(own_val);
-    if (own_exp) cudaFree(own_exp);
-    return r;
+    return finish(c);
 }
 
 static int scan(rl_crdt* c, int mode, uint64_t now_us, uint64_t cap, rl_crdt_key* out_keys, uint64_t* out_a,
@@ -214,38 +217,31 @@ static int scan(rl_crdt* c, int mode, uint64_t now_us, uint64_t cap, rl_crdt_key
     if (!c || (cap && (!out_keys || !out_expiry_us))) return cfail(c, RL_FATAL, "scan: bad arguments");
     RLC_CUDA(c, cudaSetDevice(c->device));
     const uint64_t dcap = cap ? cap : 1;
-    rl_crdt_key* d_keys = nullptr;
-    uint64_t *d_a = nullptr, *d_exp = nullptr, *d_vals = nullptr;
-    unsigned long long* d_cnt = nullptr;
-    RLC_CUDA(c, cudaMalloc((void**)&d_keys, dcap * sizeof(rl_crdt_key)));
-    RLC_CUDA(c, cudaMalloc((void**)&d_a, dcap * sizeof(uint64_t)));
-    RLC_CUDA(c, cudaMalloc((void**)&d_exp, dcap * sizeof(uint64_t)));
-    RLC_CUDA(c, cudaMalloc((void**)&d_vals, dcap * c->actors * sizeof(uint64_t)));
-    RLC_CUDA(c, cudaMalloc((void**)&d_cnt, sizeof(unsigned long long)));
-    RLC_CUDA(c, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream));
-    k_crdt_scan<<<blocks_for(c->capacity), 256, 0, c->stream>>>(tab_of(c), mode, now_us, cap, d_keys, d_a, d_exp, d_vals, d_cnt);
-    const cudaError_t le = cudaGetLastError();
+    Scratch<rl_crdt_key> keys;
+    Scratch<uint64_t> a, exp, vals;
+    Scratch<unsigned long long> cnt_d;
+    RLC_CUDA(c, keys.alloc(dcap));
+    RLC_CUDA(c, a.alloc(dcap));
+    RLC_CUDA(c, exp.alloc(dcap));
+    RLC_CUDA(c, vals.alloc(dcap * c->actors));
+    RLC_CUDA(c, cnt_d.alloc(1));
+    RLC_CUDA(c, cudaMemsetAsync(cnt_d.p, 0, sizeof(unsigned long long), c->stream));
+    k_crdt_scan<<<blocks_for(c->capacity), 256, 0, c->stream>>>(tab_of(c), mode, now_us, cap, keys.p, a.p, exp.p, vals.p, cnt_d.p);
+    RLC_CUDA(c, cudaGetLastError());
     c->launches++;
     unsigned long long cnt = 0;
-    int r = le == cudaSuccess ? RL_OK : cfail(c, RL_FATAL, "launch failed: %s", cudaGetErrorString(le));
-    if (r == RL_OK) {
-        cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, c->stream);
-        r = finish(c);
-    }
+    RLC_CUDA(c, cudaMemcpyAsync(&cnt, cnt_d.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    const int r = finish(c);
+    if (r) return r;
     const uint64_t got = cnt < cap ? cnt : cap;
-    if (r == RL_OK && got) {
-        cudaMemcpy(out_keys, d_keys, got * sizeof(rl_crdt_key), cudaMemcpyDeviceToHost);
-        cudaMemcpy(out_expiry_us, d_exp, got * sizeof(uint64_t), cudaMemcpyDeviceToHost);
-        if (mode == 0 && out_a) cudaMemcpy(out_a, d_a, got * sizeof(uint64_t), cudaMemcpyDeviceToHost);
-        if (mode == 1 && out_values) cudaMemcpy(out_values, d_vals, got * c->actors * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if (got) {
+        RLC_CUDA(c, cudaMemcpy(out_keys, keys.p, got * sizeof(rl_crdt_key), cudaMemcpyDeviceToHost));
+        RLC_CUDA(c, cudaMemcpy(out_expiry_us, exp.p, got * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (mode == 0 && out_a) RLC_CUDA(c, cudaMemcpy(out_a, a.p, got * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (mode == 1 && out_values) RLC_CUDA(c, cudaMemcpy(out_values, vals.p, got * c->actors * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     }
-    cudaFree(d_keys);
-    cudaFree(d_a);
-    cudaFree(d_exp);
-    cudaFree(d_vals);
-    cudaFree(d_cnt);
     if (out_count) *out_count = cnt;
-    return r;
+    return RL_OK;
 }
 
 int rl_crdt_export(rl_crdt* c, uint64_t now_us, uint64_t cap, rl_crdt_key* out_keys, uint64_t* out_value,

@@ -311,7 +311,6 @@ enum : uint8_t { REQ_BAD_WIRE = 1, REQ_UNKNOWN_DOMAIN = 2, REQ_NO_LIMITS = 3, RE
 
 struct ReqPlan {
     uint8_t kind = 0;
-    uint32_t domain_off = 0, domain_len = 0;
     uint32_t hits = 1;
     uint32_t n_ctr = 0;
     uint32_t store = RL_RLS_NO_STORE;
@@ -408,8 +407,6 @@ void plan_range(rl_rls* s, const uint64_t* off, uint32_t w) {
             sink = EntrySink{W.entries.data(), (uint32_t)W.entries.size()};
             decode_request(msg, len, q, sink);
         }
-        P.domain_off = (uint32_t)(off[i] - off[0]) + q.domain_off;
-        P.domain_len = q.domain_len;
         P.hits = q.hits_addend ? q.hits_addend : 1;  // server.rs:131-135
         s->domains[i].assign((const char*)msg + q.domain_off, q.domain_len);
         if (q.domain_len == 0) {  // server.rs:106-116
@@ -462,8 +459,7 @@ void plan_range(rl_rls* s, const uint64_t* off, uint32_t w) {
     }
 }
 
-void finish_range(rl_rls* s, int store_status, const uint8_t* limited, const uint32_t* first, const uint64_t* rem,
-                  const uint64_t* ttl, uint32_t w) {
+void finish_range(rl_rls* s, int store_status, const uint8_t* limited, const uint64_t* rem, const uint64_t* ttl, uint32_t w) {
     uint64_t lo, hi;
     range_of(s->n, s->pool->n, w, lo, hi);
     WorkerOut& W = s->wout[w];
@@ -515,7 +511,6 @@ void finish_range(rl_rls* s, int store_status, const uint8_t* limited, const uin
             encode_response(W.resp, code, kKeys, vals, nh);
             W.resp_len[i - lo] = W.resp.size() - before;
         }
-        (void)first;
     }
 }
 
@@ -635,7 +630,7 @@ int rl_rls_finish(rl_rls* s, int store_status, const uint8_t* limited, const uin
         return sfail(s, "finish needs remaining / ttl of the store call (draft-03 headers)");
     s->grpc.assign(s->n, 0);
     s->code.assign(s->n, 0);
-    s->pool->run([&](uint32_t w) { finish_range(s, store_status, limited, first_limited, remaining, ttl_us, w); });
+    s->pool->run([&](uint32_t w) { finish_range(s, store_status, limited, remaining, ttl_us, w); });
     // concatenate the workers' responses
     s->resp.clear();
     s->resp_off.assign(1, 0);
