@@ -51,6 +51,16 @@ MaintState* state_of(rl_engine* e, int device) {
         }                                                                                                   \
     } while (0)
 
+// A device scratch array freed at scope exit (every exit path of a call, the error ones included).
+template <class E>
+struct Scratch {
+    E* p = nullptr;
+    ~Scratch() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(E)); }
+};
+
 size_t metrics_words(uint32_t ns_cap, uint32_t limits_cap) { return (size_t)3 * ns_cap + limits_cap + 1; }
 
 RlNsMetricsDev metrics_dev(const MaintState* s) {
@@ -142,20 +152,16 @@ int rl_ns_metrics_accumulate(rl_engine* e, uint64_t n, const void* recs, uint32_
     if (r || n == 0) return r;
     if (mem == RL_MEM_DEVICE) return launch_metrics(e, s, v.stream, (uint32_t)n, recs, (int)record_bytes, limited, first_limited);
     // host arrays: staged for the call
-    void* d_recs = nullptr;
-    uint8_t* d_lim = nullptr;
-    uint32_t* d_first = nullptr;
-    RLM_CUDA(e, cudaMalloc(&d_recs, n * record_bytes));
-    RLM_CUDA(e, cudaMalloc((void**)&d_lim, n));
-    if (first_limited) RLM_CUDA(e, cudaMalloc((void**)&d_first, n * sizeof(uint32_t)));
-    RLM_CUDA(e, cudaMemcpyAsync(d_recs, recs, n * record_bytes, cudaMemcpyHostToDevice, v.stream));
-    RLM_CUDA(e, cudaMemcpyAsync(d_lim, limited, n, cudaMemcpyHostToDevice, v.stream));
-    if (first_limited) RLM_CUDA(e, cudaMemcpyAsync(d_first, first_limited, n * sizeof(uint32_t), cudaMemcpyHostToDevice, v.stream));
-    r = launch_metrics(e, s, v.stream, (uint32_t)n, d_recs, (int)record_bytes, d_lim, d_first);
-    cudaStreamSynchronize(v.stream);
-    cudaFree(d_recs);
-    cudaFree(d_lim);
-    if (d_first) cudaFree(d_first);
+    Scratch<uint8_t> d_recs, d_lim;
+    Scratch<uint32_t> d_first;
+    RLM_CUDA(e, d_recs.alloc(n * record_bytes));
+    RLM_CUDA(e, d_lim.alloc(n));
+    if (first_limited) RLM_CUDA(e, d_first.alloc(n));
+    RLM_CUDA(e, cudaMemcpyAsync(d_recs.p, recs, n * record_bytes, cudaMemcpyHostToDevice, v.stream));
+    RLM_CUDA(e, cudaMemcpyAsync(d_lim.p, limited, n, cudaMemcpyHostToDevice, v.stream));
+    if (first_limited) RLM_CUDA(e, cudaMemcpyAsync(d_first.p, first_limited, n * sizeof(uint32_t), cudaMemcpyHostToDevice, v.stream));
+    r = launch_metrics(e, s, v.stream, (uint32_t)n, d_recs.p, (int)record_bytes, d_lim.p, d_first.p);
+    RLM_CUDA(e, cudaStreamSynchronize(v.stream));  // before the staged copies are freed
     return r;
 }
 
@@ -198,18 +204,17 @@ int rl_compact(rl_engine* e, uint32_t min_tombstone_pct, rl_compact_stats* out) 
     if (out) memset(out, 0, sizeof *out);
     const uint32_t P = 1u << v.log2P;
     const uint64_t R = 1ull << v.log2R;
-    uint32_t* d_census = nullptr;  // live[P] | tomb[P]
-    RLM_CUDA(e, cudaMalloc((void**)&d_census, 2 * (size_t)P * sizeof(uint32_t)));
-    RLM_CUDA(e, cudaMemsetAsync(d_census, 0, 2 * (size_t)P * sizeof(uint32_t), v.stream));
+    Scratch<uint32_t> d_census;  // live[P] | tomb[P]
+    RLM_CUDA(e, d_census.alloc(2 * (size_t)P));
+    RLM_CUDA(e, cudaMemsetAsync(d_census.p, 0, 2 * (size_t)P * sizeof(uint32_t), v.stream));
     const uint32_t threads = 256;
     const uint32_t blocks = (uint32_t)((v.capacity + threads - 1) / threads);
-    k_region_census<<<blocks, threads, 0, v.stream>>>(v.rows, v.row_bytes, v.log2R, v.capacity, d_census, d_census + P);
+    k_region_census<<<blocks, threads, 0, v.stream>>>(v.rows, v.row_bytes, v.log2R, v.capacity, d_census.p, d_census.p + P);
     RLM_CUDA(e, cudaGetLastError());
     rl_internal_launched(e, 1);
     std::vector<uint32_t> census(2 * (size_t)P);
-    RLM_CUDA(e, cudaMemcpyAsync(census.data(), d_census, census.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream));
+    RLM_CUDA(e, cudaMemcpyAsync(census.data(), d_census.p, census.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream));
     RLM_CUDA(e, cudaStreamSynchronize(v.stream));
-    cudaFree(d_census);
     std::vector<uint8_t> sel(P, 0);
     uint64_t live = 0, tomb = 0, chosen = 0, tomb_chosen = 0;
     for (uint32_t g = 0; g < P; g++) {
@@ -229,29 +234,25 @@ int rl_compact(rl_engine* e, uint32_t min_tombstone_pct, rl_compact_stats* out) 
         out->regions_rebuilt = chosen;
     }
     if (!chosen) return RL_OK;
-    uint8_t *d_sel = nullptr, *d_scratch = nullptr;
-    unsigned long long* d_counts = nullptr;
-    RLM_CUDA(e, cudaMalloc((void**)&d_sel, P));
-    if (cudaMalloc((void**)&d_scratch, (size_t)v.capacity * v.row_bytes) != cudaSuccess) {
+    Scratch<uint8_t> d_sel, d_scratch;
+    Scratch<unsigned long long> d_counts;
+    RLM_CUDA(e, d_sel.alloc(P));
+    if (d_scratch.alloc((size_t)v.capacity * v.row_bytes) != cudaSuccess) {
         cudaGetLastError();
-        cudaFree(d_sel);
         return rl_internal_fail(e, RL_TRANSIENT, "rl_compact: no device memory for the scratch slab (one copy of the table)");
     }
-    RLM_CUDA(e, cudaMalloc((void**)&d_counts, 3 * sizeof(unsigned long long)));
-    RLM_CUDA(e, cudaMemcpyAsync(d_sel, sel.data(), P, cudaMemcpyHostToDevice, v.stream));
-    RLM_CUDA(e, cudaMemsetAsync(d_counts, 0, 3 * sizeof(unsigned long long), v.stream));
-    k_compact_move<<<blocks, threads, 0, v.stream>>>(v.rows, d_scratch, v.row_bytes, v.log2R, v.capacity, d_sel);
+    RLM_CUDA(e, d_counts.alloc(3));
+    RLM_CUDA(e, cudaMemcpyAsync(d_sel.p, sel.data(), P, cudaMemcpyHostToDevice, v.stream));
+    RLM_CUDA(e, cudaMemsetAsync(d_counts.p, 0, 3 * sizeof(unsigned long long), v.stream));
+    k_compact_move<<<blocks, threads, 0, v.stream>>>(v.rows, d_scratch.p, v.row_bytes, v.log2R, v.capacity, d_sel.p);
     RLM_CUDA(e, cudaGetLastError());
-    k_compact_reinsert<<<blocks, threads, 0, v.stream>>>(v.rows, d_scratch, v.row_bytes, v.log2P, v.log2R, v.capacity, d_sel, d_counts);
+    k_compact_reinsert<<<blocks, threads, 0, v.stream>>>(v.rows, d_scratch.p, v.row_bytes, v.log2P, v.log2R, v.capacity, d_sel.p, d_counts.p);
     RLM_CUDA(e, cudaGetLastError());
     rl_internal_launched(e, 2);
     r = rl_internal_reset_hot_rows(e);  // table row indices changed
     unsigned long long counts[3] = {0, 0, 0};
-    RLM_CUDA(e, cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, v.stream));
-    RLM_CUDA(e, cudaStreamSynchronize(v.stream));
-    cudaFree(d_sel);
-    cudaFree(d_scratch);
-    cudaFree(d_counts);
+    RLM_CUDA(e, cudaMemcpyAsync(counts, d_counts.p, sizeof counts, cudaMemcpyDeviceToHost, v.stream));
+    RLM_CUDA(e, cudaStreamSynchronize(v.stream));  // before the scratch slab is freed
     if (r) return r;
     if (out) {
         out->rows_moved = counts[0];
