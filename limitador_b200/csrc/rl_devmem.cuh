@@ -1,9 +1,10 @@
 // rl_devmem.cuh — the few global-memory primitives the maintenance and CRDT kernels use, in two forms: the real ones
-// (ld.global.cg / st.global.cg / atom.cas.b128, as in rl_kernels.cuh) and plain host ones for tests/emu/cuda_shim.h.
+// (ld.global.cg / st.global.cg / atom.cas.b128, as in rl_kernels.cuh) and plain host ones for tests/emu/cuda_shim.h
+// (RL_SHIM: one thread after the other) and tests/emu/cuda_simt.h (RL_SIMT: fibers; the kernels' warp-level branches run).
 #pragma once
 #include <stdint.h>
 
-#ifndef RL_SHIM
+#if !defined(RL_SHIM) && !defined(RL_SIMT)
 __device__ __forceinline__ ulonglong2 rlm_ld(const void* p) { return __ldcg(reinterpret_cast<const ulonglong2*>(p)); }
 __device__ __forceinline__ void rlm_st(void* p, unsigned long long a, unsigned long long b) {
     __stcg(reinterpret_cast<ulonglong2*>(p), make_ulonglong2(a, b));
@@ -36,7 +37,7 @@ inline ulonglong2 rlm_cas128(void* addr, ulonglong2 cmp, ulonglong2 val) {
 #endif
 
 // 64-bit load that bypasses L1 (other threads' atomics on the word are visible)
-#ifndef RL_SHIM
+#if !defined(RL_SHIM) && !defined(RL_SIMT)
 __device__ __forceinline__ unsigned long long rlm_ld64(const void* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
 #else
 inline unsigned long long rlm_ld64(const void* p) { return *reinterpret_cast<const unsigned long long*>(p); }

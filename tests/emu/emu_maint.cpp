@@ -3,8 +3,17 @@
 // shuffled order.  Not shipped, not a fallback.  The launch geometry and the call sequences follow rl_maint.cu /
 // rl_crdt.cu; the table helpers restate rl_kernels.cuh's rl_probe so that a rebuilt region is checked by the rule the
 // hot path looks rows up with.
+// Built twice: plain (cuda_shim.h: one thread after the other, the kernels' `#ifndef RL_SHIM` fast paths compiled out) and
+// with -DEMU_SIMT (cuda_simt.h: the threads of a block as fibers, warp intrinsics as rendezvous — the DEVICE branches run).
+#ifdef EMU_SIMT
+#include "cuda_simt.h"
+#define shim_launch simt_launch
+static uint64_t shim_seed = 0;
+#else
 #include "cuda_shim.h"
+#endif
 // (the shim must come first: it defines __global__ & co. away)
+#include <algorithm>
 #include <cstring>
 #include <vector>
 

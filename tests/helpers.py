@@ -265,22 +265,22 @@ def random_records(descs, n, seed, n_keys=5, monotone=True):
     return r
 
 
-_emu_maint = None
+_emu_maint = {}
 
 
-def emu_maint_lib():
-    """tests/emu/emu_maint.cpp: the maintenance / CRDT kernels (rl_maint.cuh, rl_crdt.cuh) compiled for the host under
-    tests/emu/cuda_shim.h."""
-    global _emu_maint
-    if _emu_maint is None:
+def emu_maint_lib(simt: bool = False):
+    """tests/emu/emu_maint.cpp: the maintenance / CRDT kernels (rl_maint.cuh, rl_crdt.cuh) compiled for the host — under
+    tests/emu/cuda_shim.h (one CUDA thread after the other; the kernels' warp-aggregated branches compiled out), or with
+    simt=True under tests/emu/cuda_simt.h (fibers + warp rendezvous: the device branches themselves run)."""
+    if simt not in _emu_maint:
         src = os.path.join(HERE, "emu", "emu_maint.cpp")
-        so = os.path.join(HERE, "emu", "librl_emu_maint.so")
+        so = os.path.join(HERE, "emu", "librl_emu_simt.so" if simt else "librl_emu_maint.so")
         csrc = os.path.join(os.path.dirname(HERE), "limitador_b200", "csrc")
-        deps = [src, os.path.join(HERE, "emu", "cuda_shim.h")] + [os.path.join(csrc, f) for f in
-                                                                ("rl_core.h", "rl_devmem.cuh", "rl_maint.cuh", "rl_crdt.cuh")]
+        deps = [src, os.path.join(HERE, "emu", "cuda_simt.h" if simt else "cuda_shim.h")] + [
+            os.path.join(csrc, f) for f in ("rl_core.h", "rl_devmem.cuh", "rl_maint.cuh", "rl_crdt.cuh")]
         deps.append(os.path.join(os.path.dirname(HERE), "include", "rl_crdt.h"))
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", *(["-DEMU_SIMT"] if simt else []), "-o", so, src])
         L = C.CDLL(so)
         vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
         L.emu_seed.argtypes = [u64]
@@ -311,17 +311,17 @@ def emu_maint_lib():
         L.emu_crdt_read.restype = u32
         L.emu_crdt_scan.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp, vp]
         L.emu_crdt_scan.restype = u64
-        _emu_maint = L
-    return _emu_maint
+        _emu_maint[simt] = L
+    return _emu_maint[simt]
 
 
 class EmuCrdt:
     """The CRDT kernels on the host (same interface as limitador_b200.crdt.CrdtTable)."""
 
-    def __init__(self, capacity_rows, actors, self_actor):
+    def __init__(self, capacity_rows, actors, self_actor, simt=False):
         from limitador_b200 import crdt as CR
         self.CR = CR
-        self.L = emu_maint_lib()
+        self.L = emu_maint_lib(simt)
         self.actors, self.self_actor = actors, self_actor
         self.h = self.L.emu_crdt_create(capacity_rows, actors, self_actor)
         self.capacity = capacity_rows

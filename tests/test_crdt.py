@@ -187,6 +187,12 @@ def test_kernels_under_the_host_shim_match_the_oracle(seed, actors, self_actor):
     _random_session(H.EmuCrdt(1024, actors, self_actor), CrdtOracle(actors, self_actor), seed, actors)
 
 
+def test_kernels_under_the_fiber_emulator_match_the_oracle():
+    """The same kernels with the threads of a block interleaved as fibers (tests/emu/cuda_simt.h) instead of run one after
+    the other: another thread order, the device flavour of the memory helpers' callers."""
+    _random_session(H.EmuCrdt(1024, 3, 1, simt=True), CrdtOracle(3, 1), 6, 3, steps=25)
+
+
 def test_two_replicas_converge_through_export_and_merge():
     """The gossip loop: each replica increments its own values, exports the re-sync stream (distributed/mod.rs:294-332)
     and the peer merges it as CounterUpdate{key, {actor: value}, expires_at} (:236-246): both read the same totals."""
