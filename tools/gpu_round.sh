@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, bench lines, ncu launch lists.  Everything lands in gpurun_out/<tag>_*.
-# usage: tools/gpu_round.sh <tag> [what...]   what: tests bench c3 ncu ncufull san
+# usage: tools/gpu_round.sh <tag> [what...]   what: tests newtests bench c3 ncu ncufull san sannew
 tag=${1:-r02}; shift
 what=${*:-tests bench c3 ncu}
 out=gpurun_out
@@ -10,6 +10,12 @@ for w in $what; do
 case $w in
 tests)
   timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log; tail -3 $out/${tag}_pytest.log;;
+newtests)  # the entry points added without GPU time: their tests alone, each file reported
+  for f in tests/test_zz_crdt_gpu.py tests/test_zz_maint_gpu.py tests/test_zz_rls_gpu.py; do
+    timeout 600 python -m pytest $f -m gpu -q > $out/${tag}_$(basename $f .py).log 2>&1; echo "$f rc=$?"; tail -3 $out/${tag}_$(basename $f .py).log; done;;
+sannew)
+  timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_zz_crdt_gpu.py tests/test_zz_maint_gpu.py -m gpu -x -q -k "not large" > $out/${tag}_san_new_memcheck.log 2>&1; tail -5 $out/${tag}_san_new_memcheck.log
+  timeout 1200 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_maint_gpu.py -m gpu -x -q -k "metrics" > $out/${tag}_san_new_racecheck.log 2>&1; tail -5 $out/${tag}_san_new_racecheck.log;;
 bench)
   timeout 600 python bench.py --steps 1000 --warmup 20 > $out/${tag}_bench_c2.json 2> $out/${tag}_bench_c2.err; echo "bench rc=$?"; grep -h "passes\|host enq" $out/${tag}_bench_c2.err; python tools/bench_summary.py $out/${tag}_bench_c2.json;;
 c3)
