@@ -203,7 +203,11 @@ def place_namespaces(dist, world, dev, recs, limits, sample_steps, log):
     hashed = np.zeros(world)
     for j in range(n_ns):
         hashed[exchange.owner_of(j, world)] += load[j]
-    ids, owner_load = exchange.balanced_namespace_ids(load, world)
+    try:
+        ids, owner_load = exchange.balanced_namespace_ids(load, world)
+    except Exception as ex:  # deterministic in its inputs, which are equal on every rank: all ranks fall back together
+        log(f"namespace placement failed ({type(ex).__name__}: {ex}); the ids stay as generated")
+        return limits, None
     exchange.remap_namespace_ids(recs, torch.from_numpy(ids).to(dev))
     out = limits.copy()
     out["ns_id"] = ids[limits["ns_id"].astype(np.int64)].astype(out["ns_id"].dtype)
