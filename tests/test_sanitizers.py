@@ -58,3 +58,28 @@ def test_crdt_oracle_and_shim_kernels_are_clean_under_asan_and_ubsan(tmp_path):
     out = build_and_run(tmp_path, "g++", [os.path.join(ROOT, "tests", "san", "san_kernels.cpp")],
                         [os.path.join(ROOT, "include")], extra=("-std=c++17",))
     assert out.startswith("ok kernels")
+
+
+@pytest.mark.parametrize("flags", [SAN, ["-g", "-O1", "-fsanitize=thread"]], ids=["asan+ubsan", "tsan"])
+def test_front_with_the_matcher_inside_is_clean_under_the_sanitizers(tmp_path, flags):
+    """rl_front_check_and_update_bindings from 8 threads while limits are added and deleted: address / UB and data races
+    (the store call is a stub that answers from the CSR the dispatcher built)."""
+    import shutil as _sh
+    cc = _sh.which("g++")
+    if cc is None:
+        pytest.skip("g++ not found")
+    csrc = os.path.join(ROOT, "limitador_b200", "csrc")
+    exe = str(tmp_path / "san_front")
+    cmd = [cc, *flags, "-std=c++17", f"-I{os.path.join(ROOT, 'include')}", os.path.join(ROOT, "tests", "san", "san_front.cpp"),
+           "-x", "c++", os.path.join(csrc, "rl_front.cu"), "-x", "none", os.path.join(csrc, "rl_match.cpp"), "-lpthread", "-o", exe]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0 and ("sanitize" in b.stderr or "tsan" in b.stderr.lower() or "asan" in b.stderr.lower()):
+        pytest.skip("no sanitizer runtime for this compiler")
+    assert b.returncode == 0, b.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1", TSAN_OPTIONS="halt_on_error=1")
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=600)
+    if "FATAL: ThreadSanitizer" in r.stderr and "unexpected memory mapping" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory in this container")
+    assert r.returncode == 0 and "ERROR" not in r.stderr and "WARNING: ThreadSanitizer" not in r.stderr and "runtime error" not in r.stderr, \
+        (r.stdout + r.stderr)[-3000:]
+    assert r.stdout.startswith("ok front")
