@@ -630,6 +630,47 @@ def run_metrics_leg(dev, stream, batch: int = 65536, steps: int = 40):
     return res
 
 
+def run_leg_child(name: str):
+    """`bench.py --leg NAME`: one extra leg on cuda:0 in a process of its own; its result (or its error) is the one JSON
+    line on stdout."""
+    try:
+        import torch
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
+        if name == "rls":
+            res = run_rls_leg()
+        else:
+            stream = torch.cuda.Stream(device=dev)
+            torch.cuda.set_stream(stream)
+            res = run_metrics_leg(dev, stream)
+    except Exception as ex:
+        import traceback
+        traceback.print_exc()
+        res = {"error": f"{type(ex).__name__}: {ex}"}
+    emit(res)
+
+
+def run_leg_isolated(name: str, timeout_s: int = 240):
+    """Run an extra leg as `bench.py --leg NAME` in a child process: whatever it does to its CUDA context — these legs
+    launch the entry points added beside the headline path — the parent's context, its numbers and its JSON line are safe."""
+    import subprocess
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--leg", name], capture_output=True, text=True,
+                           timeout=timeout_s, env=env)
+    except subprocess.TimeoutExpired:
+        return {"error": f"the leg did not finish within {timeout_s} s"}
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": f"child exited with {r.returncode}", "stderr_tail": r.stderr[-600:]}
+    try:
+        return json.loads(lines[-1])
+    except ValueError:
+        return {"error": "the child's output is not JSON", "stdout_tail": r.stdout[-300:]}
+
+
 def log(msg: str):
     """progress line on stderr, stamped with the seconds since start (where does a run spend its wall time?)"""
     print(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
@@ -678,7 +719,13 @@ def main():
                     help="N>1, peer exchange: namespace -> GPU placement. balanced = ids assigned so that rl_owner_of spreads the "
                          "observed namespace load evenly (SURVEY 8e static override); hash = the generator's ids as they are")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads / legs reported under `extra`")
+    ap.add_argument("--leg", default="", choices=["", "rls", "ns_metrics"],
+                    help="(internal) run ONE extra leg in this process and print its JSON: the parent run isolates the legs that "
+                         "launch entry points beside the headline path in a child process")
     args = ap.parse_args()
+    if args.leg:
+        run_leg_child(args.leg)
+        return
     args.warmup = max(args.warmup, 3)
     if not args.batch:
         args.batch = 65536 if args.workload == "C2" else 1 << 20
@@ -1089,7 +1136,8 @@ def main():
 
     # ---- the CPU front and the RLS wire surface on this box; an extra must not take the headline down ----
     if world == 1 and not args.no_extra and args.workload == "C2":
-        for xn, fn in (("rls", run_rls_leg), ("matcher", run_matcher_leg), ("ns_metrics", lambda: run_metrics_leg(dev, stream))):
+        for xn, fn in (("rls", lambda: run_leg_isolated("rls")), ("matcher", run_matcher_leg),
+                       ("ns_metrics", lambda: run_leg_isolated("ns_metrics"))):
             try:
                 log(f"extra {xn}: start")
                 extra[xn] = fn()
