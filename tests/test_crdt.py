@@ -4,7 +4,7 @@
    (limitador/src/storage/distributed/cr_counter_value.rs:177-300), ported with explicit clocks.
 2. The kernels of rl_crdt.cuh run on the host under tests/emu/cuda_shim.h (the same source the GPU compiles) against that
    oracle on random inc / merge / read / export streams — so the kernel logic is checked in the GPU-less container.
-The GPU run of the same streams through the C-ABI is tests/test_zz_crdt_gpu.py."""
+The GPU run of the same streams through the C-ABI is tests/test_zz2_crdt_gpu.py."""
 import numpy as np
 import pytest
 

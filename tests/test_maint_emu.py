@@ -3,7 +3,7 @@ source the GPU compiles, one CUDA thread after the other in a shuffled order:
   * k_ns_metrics against a plain numpy reduction (prometheus_metrics.rs:93-125 semantics);
   * k_region_census / k_compact_move / k_compact_reinsert: a region rebuilt in place keeps every counter findable by the
     hot path's probing rule, frees its tombstones and leaves the other regions byte-identical.
-The GPU runs of rl_compact / rl_ns_metrics_* through the C-ABI are in tests/test_zz_maint_gpu.py."""
+The GPU runs of rl_compact / rl_ns_metrics_* through the C-ABI are in tests/test_zz3_maint_gpu.py."""
 import ctypes as C
 
 import numpy as np

@@ -1,7 +1,7 @@
 """Envoy RLS v3 wire surface (include/rl_rls.h): the hand-written codec against the protobuf runtime,
 and the service's plan -> store -> finish stages against the reference's own server tests
 (limitador-server/src/envoy_rls/server.rs:337-771, kuadrant_service.rs tests), with the CPU oracle as the store
-between the two CPU stages (tests/test_zz_rls_gpu.py runs the same scenarios through rl_rls_serve on the GPU)."""
+between the two CPU stages (tests/test_zz1_rls_gpu.py runs the same scenarios through rl_rls_serve on the GPU)."""
 import numpy as np
 import pytest
 

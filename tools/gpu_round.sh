@@ -11,11 +11,11 @@ case $w in
 tests)
   timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log; tail -3 $out/${tag}_pytest.log;;
 newtests)  # the entry points added without GPU time: their tests alone, each file reported
-  for f in tests/test_zz_crdt_gpu.py tests/test_zz_maint_gpu.py tests/test_zz_rls_gpu.py; do
+  for f in tests/test_zz2_crdt_gpu.py tests/test_zz3_maint_gpu.py tests/test_zz1_rls_gpu.py; do
     timeout 600 python -m pytest $f -m gpu -q > $out/${tag}_$(basename $f .py).log 2>&1; echo "$f rc=$?"; tail -3 $out/${tag}_$(basename $f .py).log; done;;
 sannew)
-  timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_zz_crdt_gpu.py tests/test_zz_maint_gpu.py -m gpu -x -q -k "not large" > $out/${tag}_san_new_memcheck.log 2>&1; tail -5 $out/${tag}_san_new_memcheck.log
-  timeout 1200 compute-sanitizer --tool racecheck python -m pytest tests/test_zz_maint_gpu.py -m gpu -x -q -k "metrics" > $out/${tag}_san_new_racecheck.log 2>&1; tail -5 $out/${tag}_san_new_racecheck.log;;
+  timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_zz2_crdt_gpu.py tests/test_zz3_maint_gpu.py -m gpu -x -q -k "not large" > $out/${tag}_san_new_memcheck.log 2>&1; tail -5 $out/${tag}_san_new_memcheck.log
+  timeout 1200 compute-sanitizer --tool racecheck python -m pytest tests/test_zz3_maint_gpu.py -m gpu -x -q -k "metrics" > $out/${tag}_san_new_racecheck.log 2>&1; tail -5 $out/${tag}_san_new_racecheck.log;;
 bench)
   timeout 600 python bench.py --steps 1000 --warmup 20 > $out/${tag}_bench_c2.json 2> $out/${tag}_bench_c2.err; echo "bench rc=$?"; grep -h "passes\|host enq" $out/${tag}_bench_c2.err; python tools/bench_summary.py $out/${tag}_bench_c2.json;;
 c3)
