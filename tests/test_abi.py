@@ -59,6 +59,12 @@ def test_struct_layouts_match_header():
     assert engine.LIMIT_DESC_DTYPE.itemsize == 32
     assert ctypes.sizeof(engine.RlConfig) == 40
     assert ctypes.sizeof(engine.RlStats) == 136
+    # include/rl_rls.h, include/rl_crdt.h
+    from limitador_b200 import crdt, rls
+    assert rls.ENTRY_DTYPE.itemsize == 20 and ctypes.sizeof(rls.RlsRequest) == 20
+    assert ctypes.sizeof(crdt.CrdtConfig) == 24 and crdt.KEY_DTYPE.itemsize == 16 and crdt.UPDATE_DTYPE.itemsize == 32
+    hdr = open(os.path.join(ROOT, "include", "rl_engine.h")).read()
+    assert len(re.findall(r"uint64_t \w+;", hdr[hdr.index("typedef struct rl_compact_stats"):hdr.index("} rl_compact_stats;")])) == 6
 
 
 def test_owner_of_is_pure_host_function():
