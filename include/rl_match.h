@@ -96,6 +96,14 @@ int rl_matcher_counters(rl_matcher *m, uint32_t ns_id, const rl_binding *binds, 
  * other matching calls; rl_matcher_add_limit / _delete_limit take the matcher exclusively. */
 int rl_matcher_counters_batch(rl_matcher *m, uint64_t n, const uint32_t *ns_id, const uint32_t *bind_off,
                               const rl_binding *binds, uint32_t *out_ctr_off, rl_counter *out_ctrs, uint64_t cap);
+/* counters_that_apply for n requests named by their namespace STRING, under ONE reader section (a batching stage matches
+ * thousands of requests per call: no lock traffic per request — per-request calls from many threads bounce the matcher's
+ * reader/writer lock between cores and stop scaling).  out_status[i]: 0 = matched (possibly no counter); 1 = no limit was
+ * ever added for the namespace (nothing applies, lib.rs:434-440); 2 = more counters apply than one request may carry (the
+ * request gets none).  out_ctr_off has n + 1 entries; out_ctrs needs room for the counter cap beyond the counters written. */
+int rl_matcher_counters_batch_ns(rl_matcher *m, uint64_t n, const char *const *ns, const uint32_t *bind_off,
+                                 const rl_binding *binds, uint32_t *out_ctr_off, rl_counter *out_ctrs, uint64_t cap,
+                                 uint8_t *out_status);
 /* CheckResult::response_header (lib.rs:235-275) for one request, from the load_counters outputs of
  * rl_check_and_update_batch: the request's counters are ordered by remaining (stable), then
  *   X-RateLimit-Limit     = "<max>, <max>;w=<seconds>[;name=\"<name>\"], ..."  (most restrictive first; a '"' in a
@@ -107,6 +115,13 @@ int rl_matcher_counters_batch(rl_matcher *m, uint64_t n, const uint32_t *ns_id, 
 int rl_matcher_response_headers(rl_matcher *m, const rl_counter *ctrs, const uint64_t *remaining,
                                 const uint64_t *ttl_us, uint32_t n, char *out_limit, uint32_t cap_limit,
                                 char *out_remaining, uint32_t cap_remaining, char *out_reset, uint32_t cap_reset);
+/* The same for the n requests of a CSR (request i owns ctrs[ctr_off[i] .. ctr_off[i+1]), remaining / ttl_us indexed like
+ * ctrs) under one reader section: request i's three values are written NUL-terminated, one after the other (Limit,
+ * Remaining, Reset), at out + out_off[i]; out_off has n + 1 entries; a request without counters gets three empty strings.
+ * *out_len = bytes needed; RL_FATAL if cap is too small (out_len still set). */
+int rl_matcher_response_headers_batch(rl_matcher *m, uint64_t n, const uint32_t *ctr_off, const rl_counter *ctrs,
+                                      const uint64_t *remaining, const uint64_t *ttl_us, char *out, uint64_t cap,
+                                      uint64_t *out_off, uint64_t *out_len);
 /* The matcher inside the batching front (SURVEY §8 f1 + §8b "Threading"): one request as the reference's callers have it
  * — a namespace and a context — through counters_that_apply on the CALLING thread (matching threads run in parallel:
  * the matcher is read-shared) and then through the front's queue (include/rl_engine.h: rl_front_check_and_update), i.e.

@@ -592,6 +592,101 @@ int rl_matcher_counters_batch(rl_matcher* m, uint64_t n, const uint32_t* ns_id, 
     return RL_OK;
 }
 
+// CheckResult::response_header (lib.rs:235-275) of one request into `out`: three NUL-terminated values one after the other
+// (X-RateLimit-Limit, -Remaining, -Reset).  Returns the bytes written, 0 when they do not fit in cap, or -1 for an unknown
+// limit id.  The caller holds the matcher's lock (shared).  No heap traffic: a batching stage calls it per request.
+static int64_t format_headers(const rl_matcher* m, const rl_counter* ctrs, const uint64_t* remaining, const uint64_t* ttl_us, uint32_t n,
+                              char* out, uint64_t cap) {
+    if (n == 0) {
+        if (cap < 3) return 0;
+        out[0] = out[1] = out[2] = 0;
+        return 3;
+    }
+    uint32_t small[64];
+    std::vector<uint32_t> big;
+    uint32_t* order = small;
+    if (n > 64) {
+        big.resize(n);
+        order = big.data();
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        if (ctrs[i].limit_id >= m->limits.size()) return -1;
+        // insertion sort by remaining, stable: the most restrictive first (lib.rs:238-242; sort_by is stable)
+        uint32_t k = i;
+        while (k > 0 && remaining[order[k - 1]] > remaining[i]) {
+            order[k] = order[k - 1];
+            k--;
+        }
+        order[k] = i;
+    }
+    uint64_t w = 0;
+    auto put = [&](const char* fmt, unsigned long long a, unsigned long long b) {
+        if (w >= cap) return false;
+        const int k = snprintf(out + w, cap - w, fmt, a, b);
+        if (k < 0 || (uint64_t)k >= cap - w) return false;
+        w += (uint64_t)k;
+        return true;
+    };
+    const uint32_t f = order[0];
+    if (!put("%llu", m->limits[ctrs[f].limit_id].max_value, 0)) return 0;
+    for (uint32_t q = 0; q < n; q++) {  // ", <max>;w=<secs>[;name=\"...\"]" for every counter (lib.rs:244-252)
+        const MLimit& L = m->limits[ctrs[order[q]].limit_id];
+        if (!put(", %llu;w=%llu", L.max_value, L.seconds)) return 0;
+        if (L.has_name) {
+            if (w + L.name.size() + 9 >= cap) return 0;
+            memcpy(out + w, ";name=\"", 7);
+            w += 7;
+            for (const char c : L.name) out[w++] = c == '"' ? '\'' : c;
+            out[w++] = '"';
+        }
+    }
+    if (w >= cap) return 0;
+    out[w++] = 0;
+    if (!put("%llu", remaining[f], 0)) return 0;
+    if (w >= cap) return 0;
+    out[w++] = 0;
+    if (!put("%llu", ttl_us[f] / 1000000ull, 0)) return 0;  // Duration::as_secs (lib.rs:268-270)
+    if (w >= cap) return 0;
+    out[w++] = 0;
+    return (int64_t)w;
+}
+
+int rl_matcher_counters_batch_ns(rl_matcher* m, uint64_t n, const char* const* ns, const uint32_t* bind_off, const rl_binding* binds,
+                                 uint32_t* out_ctr_off, rl_counter* out_ctrs, uint64_t cap, uint8_t* out_status) {
+    if (!m || !out_ctr_off || (n && (!ns || !bind_off || !out_status)) || (cap && !out_ctrs)) return RL_FATAL;
+    std::shared_lock<std::shared_mutex> lock(m->mu);  // one reader section for the whole range
+    Scratch& s = tls_scratch;
+    uint64_t total = 0;
+    out_ctr_off[0] = 0;
+    const char* last_ns = nullptr;  // consecutive requests of one namespace look it up once
+    bool last_known = false;
+    uint32_t last_id = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        out_status[i] = 0;
+        if (!ns[i]) return mfail(m, "request %llu has no namespace", (unsigned long long)i);
+        if (!last_ns || strcmp(ns[i], last_ns) != 0) {
+            const auto it = m->ns_ids.find(ns[i]);
+            last_ns = ns[i];
+            last_known = it != m->ns_ids.end();
+            last_id = last_known ? it->second : 0;
+        }
+        if (!last_known) {
+            out_status[i] = 1;  // no limit was ever added for the namespace: nothing applies (lib.rs:434-440)
+        } else {
+            uint64_t k = 0;
+            if (cap - total < m->counter_cap) return mfail(m, "counter capacity %llu exhausted at request %llu", (unsigned long long)cap, (unsigned long long)i);
+            if (match_one(m, last_id, binds + bind_off[i], bind_off[i + 1] - bind_off[i], out_ctrs + total, cap - total, k, s) != RL_OK) {
+                out_status[i] = 2;  // more counters apply than one request may carry: the request gets none
+                k = 0;
+            }
+            total += k;
+        }
+        if (total > 0xFFFFFFFFull) return mfail(m, "more than 2^32 counters in one batch");
+        out_ctr_off[i + 1] = (uint32_t)total;
+    }
+    return RL_OK;
+}
+
 int rl_matcher_response_headers(rl_matcher* m, const rl_counter* ctrs, const uint64_t* remaining, const uint64_t* ttl_us,
                                 uint32_t n, char* out_limit, uint32_t cap_limit, char* out_remaining, uint32_t cap_remaining,
                                 char* out_reset, uint32_t cap_reset) {
@@ -601,33 +696,49 @@ int rl_matcher_response_headers(rl_matcher* m, const rl_counter* ctrs, const uin
     out_limit[0] = out_remaining[0] = out_reset[0] = 0;
     if (n == 0) return RL_OK;
     std::shared_lock<std::shared_mutex> lock(m->mu);
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; i++) {
-        if (ctrs[i].limit_id >= m->limits.size()) return mfail(m, "unknown limit_id %u", ctrs[i].limit_id);
-        order[i] = i;
-    }
-    // sort by the remaining of the counters, most restrictive first (lib.rs:238-242; sort_by is stable)
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return remaining[a] < remaining[b]; });
-    std::string text;
-    for (const uint32_t i : order) {  // ", <max>;w=<secs>[;name=\"...\"]" for every counter (lib.rs:244-252)
-        const MLimit& L = m->limits[ctrs[i].limit_id];
-        text += ", " + std::to_string(L.max_value) + ";w=" + std::to_string(L.seconds);
-        if (L.has_name) {
-            std::string nm = L.name;
-            std::replace(nm.begin(), nm.end(), '"', '\'');
-            text += ";name=\"" + nm + "\"";
-        }
-    }
-    const uint32_t f = order[0];
-    const std::string lim = std::to_string(m->limits[ctrs[f].limit_id].max_value) + text;
-    const std::string rem = std::to_string(remaining[f]);
-    const std::string rst = std::to_string(ttl_us[f] / 1000000ull);  // Duration::as_secs (lib.rs:268-270)
-    if (lim.size() + 1 > cap_limit || rem.size() + 1 > cap_remaining || rst.size() + 1 > cap_reset)
-        return mfail(m, "header buffer too small (%zu bytes needed for X-RateLimit-Limit)", lim.size() + 1);
-    memcpy(out_limit, lim.c_str(), lim.size() + 1);
-    memcpy(out_remaining, rem.c_str(), rem.size() + 1);
-    memcpy(out_reset, rst.c_str(), rst.size() + 1);
+    std::vector<char> text((size_t)cap_limit + 64);
+    const int64_t w = format_headers(m, ctrs, remaining, ttl_us, n, text.data(), text.size());
+    if (w < 0) return mfail(m, "unknown limit_id in the counters of a response");
+    const char* lim = text.data();
+    const char* rem = w ? lim + strlen(lim) + 1 : lim;
+    const char* rst = w ? rem + strlen(rem) + 1 : lim;
+    if (w == 0 || strlen(lim) + 1 > cap_limit || strlen(rem) + 1 > cap_remaining || strlen(rst) + 1 > cap_reset)
+        return mfail(m, "header buffer too small for X-RateLimit-Limit (%u bytes given)", cap_limit);
+    memcpy(out_limit, lim, strlen(lim) + 1);
+    memcpy(out_remaining, rem, strlen(rem) + 1);
+    memcpy(out_reset, rst, strlen(rst) + 1);
     return RL_OK;
+}
+
+int rl_matcher_response_headers_batch(rl_matcher* m, uint64_t n, const uint32_t* ctr_off, const rl_counter* ctrs, const uint64_t* remaining,
+                                      const uint64_t* ttl_us, char* out, uint64_t cap, uint64_t* out_off, uint64_t* out_len) {
+    if (!m || !out_off || !out_len || (n && (!ctr_off || !ctrs || !remaining || !ttl_us)) || (cap && !out)) return RL_FATAL;
+    std::shared_lock<std::shared_mutex> lock(m->mu);  // one reader section for the whole range
+    uint64_t w = 0;
+    bool fits = true;
+    out_off[0] = 0;
+    char scratch[4096];
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t o = ctr_off[i], k = ctr_off[i + 1] - o;
+        int64_t got = fits ? format_headers(m, ctrs + o, remaining + o, ttl_us + o, k, out + w, cap - w) : 0;
+        if (got < 0) return mfail(m, "unknown limit_id in the counters of request %llu", (unsigned long long)i);
+        if (got == 0) {  // does not fit (any more): keep measuring so that *out_len tells the caller what to bring
+            fits = false;
+            std::vector<char> big;
+            char* tmp = scratch;
+            uint64_t tcap = sizeof scratch;
+            while ((got = format_headers(m, ctrs + o, remaining + o, ttl_us + o, k, tmp, tcap)) == 0) {
+                big.resize(tcap * 4);
+                tmp = big.data();
+                tcap = big.size();
+            }
+            if (got < 0) return mfail(m, "unknown limit_id in the counters of request %llu", (unsigned long long)i);
+        }
+        w += (uint64_t)got;
+        out_off[i + 1] = w;
+    }
+    *out_len = w;
+    return fits ? RL_OK : mfail(m, "header text needs %llu bytes", (unsigned long long)w);
 }
 
 void rl_counter_key(const char* const* sources, const char* const* values, uint32_t n, uint64_t* key_lo, uint64_t* key_hi) {

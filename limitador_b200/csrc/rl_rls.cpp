@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -303,6 +304,24 @@ struct Pool {
     }
 };
 
+// A per-batch buffer that is NOT value-initialised when it is sized (std::vector::resize would zero megabytes per batch);
+// its contents do not survive ensure().
+template <class T>
+struct RawBuf {
+    std::unique_ptr<T[]> p;
+    size_t cap = 0, n = 0;
+    void ensure(size_t want) {
+        if (want > cap) {
+            cap = want + want / 2 + 16;
+            p.reset(new T[cap]);
+        }
+        n = want;
+    }
+    T* data() { return p.get(); }
+    const T* data() const { return p.get(); }
+    size_t size() const { return n; }
+};
+
 struct NsCounts {
     uint64_t authorized_calls = 0, authorized_hits = 0, limited_calls = 0;
 };
@@ -317,13 +336,23 @@ struct ReqPlan {
 };
 
 struct WorkerOut {
-    std::vector<rl_counter> ctrs;
+    // plan: the requests of the range that go to the matcher, as rl_matcher_counters_batch_ns takes them
+    RawBuf<rl_counter> ctrs;            // the range's counters, request after request (ctr_off)
     std::vector<rl_rls_entry> entries;
-    std::vector<char> arena;
+    RawBuf<char> arena;                 // NUL-terminated copies of the keys and values (the bindings point into it)
+    uint64_t n_store = 0;               // requests of the range that reach the store
     std::vector<rl_binding> binds;
-    std::vector<uint8_t> resp;          // finish: this worker's responses, concatenated
+    std::vector<uint32_t> bind_off, ctr_off;
+    std::vector<const char*> ns;
+    std::vector<uint64_t> req_of;       // matcher request k = batch request req_of[k]
+    std::vector<uint8_t> status;
+    // finish
+    std::vector<uint8_t> resp;          // this worker's responses, concatenated
     std::vector<uint64_t> resp_len;     // one per request of the worker's range
-    std::string error;
+    std::vector<char> hdr;              // header values of the range's store requests (rl_matcher_response_headers_batch)
+    std::vector<uint64_t> hdr_off;
+    std::unordered_map<std::string, NsCounts> by_ns;  // the range's metrics, merged into the service's after the workers
+    std::map<std::pair<std::string, std::string>, uint64_t> limited_by_name;
 };
 
 }  // namespace
@@ -348,7 +377,7 @@ struct rl_rls {
     // store call
     uint64_t n_store = 0;
     std::vector<uint32_t> ctr_off;
-    std::vector<rl_counter> ctrs;
+    RawBuf<rl_counter> ctrs;
     std::vector<uint64_t> delta, now;
     int load_counters = 0;
     // engine outputs (serve)
@@ -356,7 +385,7 @@ struct rl_rls {
     std::vector<uint32_t> o_first;
     std::vector<uint64_t> o_rem, o_ttl;
     // responses
-    std::vector<uint8_t> resp;
+    RawBuf<uint8_t> resp;
     std::vector<uint64_t> resp_off;
     std::vector<uint8_t> grpc, code;
     // metrics
@@ -384,12 +413,22 @@ void range_of(uint64_t n, uint32_t workers, uint32_t w, uint64_t& lo, uint64_t& 
     hi = std::min<uint64_t>(n, lo + per);
 }
 
+// Requests [lo, hi) of worker w: decode every message and lay its CEL context out (pass 1), then ONE matcher call for
+// the whole range (pass 2) — a reader section per range, not per request: eight workers taking the matcher's
+// reader/writer lock twice per request spent their time passing its cache line around and did not scale at all.
 void plan_range(rl_rls* s, const uint64_t* off, uint32_t w) {
     uint64_t lo, hi;
     range_of(s->n, s->pool->n, w, lo, hi);
     WorkerOut& W = s->wout[w];
-    W.ctrs.clear();
-    W.error.clear();
+    W.n_store = 0;
+    W.binds.clear();
+    W.bind_off.assign(1, 0);
+    W.ns.clear();
+    W.req_of.clear();
+    // every string gets a NUL behind it: an entry is at least two bytes on the wire, so twice the range's bytes is enough
+    // — sized up front, because the bindings point into it
+    W.arena.ensure(2 * (size_t)(off[hi] - off[lo]) + 16);
+    char* a = W.arena.data();
     for (uint64_t i = lo; i < hi; i++) {
         ReqPlan& P = s->plan[i];
         P = ReqPlan();
@@ -413,23 +452,17 @@ void plan_range(rl_rls* s, const uint64_t* off, uint32_t w) {
             P.kind = REQ_UNKNOWN_DOMAIN;
             continue;
         }
-        uint32_t ns_id;
-        if (memchr(msg + q.domain_off, 0, q.domain_len) != nullptr ||
-            rl_matcher_namespace_id(s->m, s->domains[i].c_str(), &ns_id) != RL_OK) {
-            P.kind = REQ_NO_LIMITS;  // no limit was ever added for the namespace: nothing applies (lib.rs:434-440)
+        if (memchr(msg + q.domain_off, 0, q.domain_len) != nullptr) {
+            P.kind = REQ_NO_LIMITS;  // no namespace the matcher knows holds a NUL: nothing applies (lib.rs:434-440)
             continue;
         }
         // the CEL context: descriptors[d] = map of the d-th descriptor's entries (server.rs:121-127, 137-139)
-        size_t bytes = 0;
-        for (uint32_t k = 0; k < sink.n; k++) bytes += (size_t)W.entries[k].key_len + W.entries[k].val_len + 2;
-        W.arena.resize(bytes + 1);
-        W.binds.resize(sink.n);
-        char* a = W.arena.data();
         bool nul = false;
+        const size_t first_bind = W.binds.size();
         for (uint32_t k = 0; k < sink.n; k++) {
             const rl_rls_entry& e = W.entries[k];
             nul = nul || memchr(msg + e.key_off, 0, e.key_len) || memchr(msg + e.val_off, 0, e.val_len);
-            rl_binding& b = W.binds[k];
+            rl_binding b;
             b.descriptor = e.descriptor;
             b._pad = 0;
             b.key = a;
@@ -440,38 +473,108 @@ void plan_range(rl_rls* s, const uint64_t* off, uint32_t w) {
             memcpy(a, msg + e.val_off, e.val_len);
             a[e.val_len] = 0;
             a += e.val_len + 1;
+            W.binds.push_back(b);
         }
         if (nul) {  // the matcher compares NUL-terminated strings: an embedded NUL would be cut, not compared
+            W.binds.resize(first_bind);
             P.kind = REQ_UNSUPPORTED;
             continue;
         }
-        const size_t base = W.ctrs.size();
-        W.ctrs.resize(base + RL_MAX_COUNTERS_PER_REQUEST);
-        uint32_t got = 0;
-        if (rl_matcher_counters(s->m, ns_id, W.binds.data(), sink.n, W.ctrs.data() + base, RL_MAX_COUNTERS_PER_REQUEST, &got) != RL_OK) {
-            W.ctrs.resize(base);
-            P.kind = REQ_UNSUPPORTED;  // more counters than the engine takes per request
-            continue;
-        }
-        W.ctrs.resize(base + got);
-        P.n_ctr = got;
-        P.kind = got ? REQ_STORE : REQ_NO_LIMITS;
+        W.bind_off.push_back((uint32_t)W.binds.size());
+        W.ns.push_back(s->domains[i].c_str());  // (s->domains was sized before the workers started: the pointer stays)
+        W.req_of.push_back(i);
+    }
+    const uint64_t k_req = W.req_of.size();
+    W.ctr_off.assign(k_req + 1, 0);
+    W.status.assign(k_req, 0);
+    W.ctrs.ensure((k_req + 1) * (size_t)RL_MAX_COUNTERS_PER_REQUEST);
+    if (rl_matcher_counters_batch_ns(s->m, k_req, W.ns.data(), W.bind_off.data(), W.binds.data(), W.ctr_off.data(), W.ctrs.data(),
+                                     W.ctrs.size(), W.status.data()) != RL_OK) {
+        for (const uint64_t i : W.req_of) s->plan[i].kind = REQ_UNSUPPORTED;  // (the matcher's cap was raised past the engine's)
+        W.ctr_off.assign(k_req + 1, 0);
+        return;
+    }
+    for (uint64_t k = 0; k < k_req; k++) {
+        ReqPlan& P = s->plan[W.req_of[k]];
+        P.n_ctr = W.ctr_off[k + 1] - W.ctr_off[k];
+        // 2 = more counters than the engine takes per request; 1 = a namespace without limits (lib.rs:434-440)
+        P.kind = W.status[k] == 2 ? REQ_UNSUPPORTED : (P.n_ctr ? REQ_STORE : REQ_NO_LIMITS);
+        W.n_store += P.kind == REQ_STORE;
     }
 }
 
-void finish_range(rl_rls* s, int store_status, const uint8_t* limited, const uint64_t* rem, const uint64_t* ttl, uint32_t w) {
+// Second pass of the plan: worker w copies its counters into the batch's CSR at the offsets the prefix over the workers
+// gave it (store requests in batch order: worker ranges are consecutive).
+void plan_scatter(rl_rls* s, uint32_t w, uint64_t store_base, uint64_t ctr_base) {
+    WorkerOut& W = s->wout[w];
+    uint64_t j = store_base, c = ctr_base;
+    for (uint64_t k = 0; k < W.req_of.size(); k++) {
+        const uint64_t i = W.req_of[k];
+        ReqPlan& P = s->plan[i];
+        if (P.kind != REQ_STORE) continue;
+        P.store = (uint32_t)j;
+        s->store_index[i] = (uint32_t)j;
+        s->ctr_off[j] = (uint32_t)c;
+        memcpy(s->ctrs.data() + c, W.ctrs.data() + W.ctr_off[k], (size_t)P.n_ctr * sizeof(rl_counter));
+        // CheckRateLimit asks with delta 1 whatever hits_addend says (kuadrant_service.rs:62-65)
+        s->delta[j] = s->method == RL_RLS_CHECK_RATE_LIMIT ? 1 : P.hits;
+        c += P.n_ctr;
+        j++;
+    }
+}
+
+// Second pass of the finish: worker w copies its responses behind those of the workers before it.
+void finish_scatter(rl_rls* s, uint32_t w, uint64_t byte_base) {
+    uint64_t lo, hi;
+    range_of(s->n, s->pool->n, w, lo, hi);
+    const WorkerOut& W = s->wout[w];
+    if (!W.resp.empty()) memcpy(s->resp.data() + byte_base, W.resp.data(), W.resp.size());
+    uint64_t at = byte_base;
+    for (uint64_t i = lo; i < hi; i++) {
+        at += W.resp_len[i - lo];
+        s->resp_off[i + 1] = at;
+    }
+}
+
+void finish_range(rl_rls* s, int store_status, const uint8_t* limited, const uint32_t* first, const uint64_t* rem, const uint64_t* ttl,
+                  uint32_t w) {
     uint64_t lo, hi;
     range_of(s->n, s->pool->n, w, lo, hi);
     WorkerOut& W = s->wout[w];
     W.resp.clear();
     W.resp_len.assign(hi - lo, 0);
-    char h_lim[1024], h_rem[32], h_rst[32];
+    W.by_ns.clear();
+    W.limited_by_name.clear();
     static const char* const kKeys[3] = {"X-RateLimit-Limit", "X-RateLimit-Remaining", "X-RateLimit-Reset"};  // sorted by key (server.rs:55)
+    // the store requests of the range are one run of store indices: their header values in ONE matcher call
+    const bool with_headers = store_status == RL_OK && s->method == RL_RLS_SHOULD_RATE_LIMIT && s->load_counters;
+    uint64_t j0 = RL_RLS_NO_STORE, j1 = 0;
+    for (uint64_t i = lo; i < hi; i++)
+        if (s->plan[i].kind == REQ_STORE) {
+            if (j0 == RL_RLS_NO_STORE) j0 = s->plan[i].store;
+            j1 = (uint64_t)s->plan[i].store + 1;
+        }
+    bool headers_ok = false;
+    if (with_headers && j0 != RL_RLS_NO_STORE) {
+        W.hdr_off.assign(j1 - j0 + 1, 0);
+        uint64_t need = 0;
+        W.hdr.resize(std::max<size_t>(W.hdr.size(), (size_t)(j1 - j0) * 96));
+        int r = rl_matcher_response_headers_batch(s->m, j1 - j0, s->ctr_off.data() + j0, s->ctrs.data(), rem, ttl, W.hdr.data(), W.hdr.size(),
+                                                  W.hdr_off.data(), &need);
+        if (r != RL_OK && need > W.hdr.size()) {
+            W.hdr.resize(need);
+            r = rl_matcher_response_headers_batch(s->m, j1 - j0, s->ctr_off.data() + j0, s->ctrs.data(), rem, ttl, W.hdr.data(), W.hdr.size(),
+                                                  W.hdr_off.data(), &need);
+        }
+        headers_ok = r == RL_OK;
+    }
+    const std::string* last_ns = nullptr;  // consecutive requests of one namespace share the metrics entry
+    NsCounts* last_counts = nullptr;
     for (uint64_t i = lo; i < hi; i++) {
         const ReqPlan& P = s->plan[i];
         uint8_t grpc = RL_GRPC_OK, code = RL_RLS_CODE_UNKNOWN;
         uint32_t nh = 0;
-        const char* vals[3] = {h_lim, h_rem, h_rst};
+        const char* vals[3] = {"", "", ""};
         switch (P.kind) {
             case REQ_BAD_WIRE: grpc = RL_GRPC_INTERNAL; break;
             case REQ_UNSUPPORTED: grpc = RL_GRPC_UNAVAILABLE; break;
@@ -492,13 +595,15 @@ void finish_range(rl_rls* s, int store_status, const uint8_t* limited, const uin
                     break;
                 }
                 code = limited[j] ? RL_RLS_CODE_OVER_LIMIT : RL_RLS_CODE_OK;
-                if (s->method == RL_RLS_SHOULD_RATE_LIMIT && s->load_counters) {
-                    const uint32_t o = s->ctr_off[j];
-                    if (rl_matcher_response_headers(s->m, s->ctrs.data() + o, rem + o, ttl + o, P.n_ctr, h_lim, sizeof h_lim,
-                                                    h_rem, sizeof h_rem, h_rst, sizeof h_rst) == RL_OK)
-                        nh = 3;
-                    else
+                if (with_headers) {
+                    if (!headers_ok) {
                         grpc = RL_GRPC_UNAVAILABLE;
+                        break;
+                    }
+                    vals[0] = W.hdr.data() + W.hdr_off[j - j0];
+                    vals[1] = vals[0] + strlen(vals[0]) + 1;
+                    vals[2] = vals[1] + strlen(vals[1]) + 1;
+                    nh = 3;
                 }
                 break;
             }
@@ -506,10 +611,35 @@ void finish_range(rl_rls* s, int store_status, const uint8_t* limited, const uin
         }
         s->grpc[i] = grpc;
         s->code[i] = grpc == RL_GRPC_OK ? code : 0;
-        if (grpc == RL_GRPC_OK) {
-            const size_t before = W.resp.size();
-            encode_response(W.resp, code, kKeys, vals, nh);
-            W.resp_len[i - lo] = W.resp.size() - before;
+        if (grpc != RL_GRPC_OK) continue;
+        const size_t before = W.resp.size();
+        encode_response(W.resp, code, kKeys, vals, nh);
+        W.resp_len[i - lo] = W.resp.size() - before;
+        // metrics, once per request after the decision (server.rs:183-195, kuadrant_service.rs:81-92,173-174), into the
+        // worker's own table (merged after the workers are done)
+        if (P.kind == REQ_UNKNOWN_DOMAIN) continue;
+        if (!last_ns || *last_ns != s->domains[i]) {
+            last_ns = &s->domains[i];
+            last_counts = &W.by_ns[s->domains[i]];
+        }
+        NsCounts& c = *last_counts;
+        if (s->method == RL_RLS_REPORT) {
+            c.authorized_hits += P.hits;
+        } else if (code == RL_RLS_CODE_OVER_LIMIT) {
+            c.limited_calls++;
+            if (s->use_limit_name) {
+                std::string name;
+                const uint32_t lid = first ? first[P.store] : RL_NONE;
+                if (lid != RL_NONE) {
+                    char nb[512];
+                    int has = 0;
+                    if (rl_matcher_limit_name_copy(s->m, lid, nb, sizeof nb, &has) == RL_OK && has) name = nb;
+                }
+                W.limited_by_name[{s->domains[i], name}]++;
+            }
+        } else {
+            c.authorized_calls++;
+            if (s->method == RL_RLS_SHOULD_RATE_LIMIT) c.authorized_hits += P.hits;
         }
     }
 }
@@ -573,32 +703,23 @@ int rl_rls_plan(rl_rls* s, int method, uint64_t n, const uint8_t* buf, const uin
     s->domains.resize(n);
     s->pool->run([&](uint32_t w) { plan_range(s, off, w); });
     s->buf = nullptr;
-    // lay the workers' counters out as one CSR, requests in batch order
-    s->store_index.assign(n, RL_RLS_NO_STORE);
-    s->ctr_off.assign(1, 0);
-    s->ctrs.clear();
-    s->delta.clear();
-    uint64_t total = 0;
-    for (const auto& W : s->wout) total += W.ctrs.size();
-    s->ctrs.reserve(total);
+    // lay the workers' counters out as one CSR, requests in batch order: a prefix over the workers, then every worker
+    // copies its own slice
+    std::vector<uint64_t> store_base(s->pool->n + 1, 0), ctr_base(s->pool->n + 1, 0);
     for (uint32_t w = 0; w < s->pool->n; w++) {
-        uint64_t lo, hi;
-        range_of(n, s->pool->n, w, lo, hi);
         const WorkerOut& W = s->wout[w];
-        size_t at = 0;
-        for (uint64_t i = lo; i < hi; i++) {
-            ReqPlan& P = s->plan[i];
-            if (P.kind != REQ_STORE) continue;
-            P.store = (uint32_t)s->delta.size();
-            s->store_index[i] = P.store;
-            s->ctrs.insert(s->ctrs.end(), W.ctrs.begin() + at, W.ctrs.begin() + at + P.n_ctr);
-            at += P.n_ctr;
-            s->ctr_off.push_back((uint32_t)s->ctrs.size());
-            // CheckRateLimit asks with delta 1 whatever hits_addend says (kuadrant_service.rs:62-65)
-            s->delta.push_back(method == RL_RLS_CHECK_RATE_LIMIT ? 1 : P.hits);
-        }
+        store_base[w + 1] = store_base[w] + W.n_store;
+        ctr_base[w + 1] = ctr_base[w] + (W.ctr_off.empty() ? 0 : W.ctr_off.back());
     }
-    s->n_store = s->delta.size();
+    const uint64_t n_store = store_base[s->pool->n], n_ctr = ctr_base[s->pool->n];
+    if (n_ctr > 0xFFFFFFFFull) return sfail(s, "more than 2^32 counters in one batch");
+    s->store_index.assign(n, RL_RLS_NO_STORE);
+    s->ctr_off.assign(n_store + 1, 0);
+    s->ctr_off[n_store] = (uint32_t)n_ctr;
+    s->ctrs.ensure(n_ctr);
+    s->delta.assign(n_store, 0);
+    s->pool->run([&](uint32_t w) { plan_scatter(s, w, store_base[w], ctr_base[w]); });
+    s->n_store = n_store;
     s->now.assign(s->n_store, now_us ? now_us : wall_us());
     s->load_counters = (method == RL_RLS_SHOULD_RATE_LIMIT && s->header_mode != RL_RLS_HEADERS_NONE) ? 1 : 0;  // server.rs:146
     s->planned = true;
@@ -630,40 +751,23 @@ int rl_rls_finish(rl_rls* s, int store_status, const uint8_t* limited, const uin
         return sfail(s, "finish needs remaining / ttl of the store call (draft-03 headers)");
     s->grpc.assign(s->n, 0);
     s->code.assign(s->n, 0);
-    s->pool->run([&](uint32_t w) { finish_range(s, store_status, limited, remaining, ttl_us, w); });
-    // concatenate the workers' responses
-    s->resp.clear();
-    s->resp_off.assign(1, 0);
-    s->resp_off.reserve(s->n + 1);
+    s->pool->run([&](uint32_t w) { finish_range(s, store_status, limited, first_limited, remaining, ttl_us, w); });
+    // the workers' responses behind one another (a prefix over the workers, then every worker copies its own), their
+    // metrics merged
+    std::vector<uint64_t> byte_base(s->pool->n + 1, 0);
+    for (uint32_t w = 0; w < s->pool->n; w++) byte_base[w + 1] = byte_base[w] + s->wout[w].resp.size();
+    s->resp.ensure(byte_base[s->pool->n]);
+    s->resp_off.assign(s->n + 1, 0);
+    s->pool->run([&](uint32_t w) { finish_scatter(s, w, byte_base[w]); });
     for (uint32_t w = 0; w < s->pool->n; w++) {
         const WorkerOut& W = s->wout[w];
-        s->resp.insert(s->resp.end(), W.resp.begin(), W.resp.end());
-        for (const uint64_t l : W.resp_len) s->resp_off.push_back(s->resp_off.back() + l);
-    }
-    // metrics, once per request after the decision (server.rs:183-195, kuadrant_service.rs:81-92,173-174)
-    for (uint64_t i = 0; i < s->n; i++) {
-        if (s->grpc[i] != RL_GRPC_OK) continue;
-        const ReqPlan& P = s->plan[i];
-        if (P.kind == REQ_UNKNOWN_DOMAIN) continue;
-        NsCounts& c = s->by_ns[s->domains[i]];
-        if (s->method == RL_RLS_REPORT) {
-            c.authorized_hits += P.hits;
-        } else if (s->code[i] == RL_RLS_CODE_OVER_LIMIT) {
-            c.limited_calls++;
-            if (s->use_limit_name) {
-                std::string name;
-                const uint32_t lid = first_limited ? first_limited[P.store] : RL_NONE;
-                if (lid != RL_NONE) {
-                    char nb[512];
-                    int has = 0;
-                    if (rl_matcher_limit_name_copy(s->m, lid, nb, sizeof nb, &has) == RL_OK && has) name = nb;
-                }
-                s->limited_by_name[{s->domains[i], name}]++;
-            }
-        } else {
-            c.authorized_calls++;
-            if (s->method == RL_RLS_SHOULD_RATE_LIMIT) c.authorized_hits += P.hits;
+        for (const auto& kv : W.by_ns) {
+            NsCounts& c = s->by_ns[kv.first];
+            c.authorized_calls += kv.second.authorized_calls;
+            c.authorized_hits += kv.second.authorized_hits;
+            c.limited_calls += kv.second.limited_calls;
         }
+        for (const auto& kv : W.limited_by_name) s->limited_by_name[kv.first] += kv.second;
     }
     s->finished = true;
     return RL_OK;
@@ -673,7 +777,7 @@ int rl_rls_responses(rl_rls* s, const uint8_t** out_buf, const uint64_t** out_of
     if (!s) return RL_FATAL;
     if (!s->finished) return sfail(s, "no finished batch");
     static const uint8_t kEmpty = 0;
-    if (out_buf) *out_buf = s->resp.empty() ? &kEmpty : s->resp.data();
+    if (out_buf) *out_buf = s->resp.size() ? s->resp.data() : &kEmpty;
     if (out_off) *out_off = s->resp_off.data();
     if (out_grpc) *out_grpc = s->grpc.empty() ? &kEmpty : s->grpc.data();
     if (out_code) *out_code = s->code.empty() ? &kEmpty : s->code.data();
@@ -693,7 +797,7 @@ int rl_rls_serve(rl_rls* s, int method, uint64_t n, const uint8_t* buf, const ui
         s->o_limited.assign(m, 0);
         s->o_first.assign(m, RL_NONE);
         if (s->load_counters) {
-            s->o_rem.assign(s->ctrs.size(), 0);
+            s->o_rem.assign(s->ctrs.size(), 0);  // (slots of a refused call stay 0)
             s->o_ttl.assign(s->ctrs.size(), 0);
         }
         if (method == RL_RLS_SHOULD_RATE_LIMIT)

@@ -21,7 +21,8 @@ MATCH_SYMBOLS = (
     "rl_matcher_delete_limit", "rl_matcher_namespace_id", "rl_matcher_limit_name", "rl_matcher_counters",
     "rl_matcher_counters_batch", "rl_counter_key", "rl_matcher_response_headers",
     "rl_matcher_add_limit_ex", "rl_matcher_limit_name_copy", "rl_matcher_last_error_copy",
-    "rl_front_check_and_update_bindings", "rl_matcher_set_counter_cap",
+    "rl_front_check_and_update_bindings", "rl_matcher_set_counter_cap", "rl_matcher_counters_batch_ns",
+    "rl_matcher_response_headers_batch",
 )
 
 
@@ -51,6 +52,8 @@ def _lib():
     L.rl_matcher_last_error_copy.argtypes = [vp, C.c_char_p, u32]
     L.rl_matcher_delete_limit.argtypes = [vp, u32]
     L.rl_matcher_set_counter_cap.argtypes = [vp, u32]
+    L.rl_matcher_counters_batch_ns.argtypes = [vp, u64, C.POINTER(C.c_char_p), vp, C.POINTER(RlBinding), vp, vp, u64, vp]
+    L.rl_matcher_response_headers_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, u64, vp, C.POINTER(u64)]
     L.rl_matcher_namespace_id.argtypes = [vp, C.c_char_p, C.POINTER(u32)]
     L.rl_matcher_limit_name.argtypes = [vp, u32]
     L.rl_matcher_limit_name.restype = C.c_char_p
@@ -173,6 +176,49 @@ class Matcher:
             return {}
         return {"X-RateLimit-Limit": bl.value.decode(), "X-RateLimit-Remaining": br.value.decode(),
                 "X-RateLimit-Reset": bs.value.decode()}
+
+    def counters_batch_ns(self, namespaces: Sequence[str], contexts: Sequence[Tuple[Optional[dict], Optional[list]]]):
+        """rl_matcher_counters_batch_ns: requests named by namespace string, one reader section for the whole batch.
+        -> (ctr_off uint32[n+1], ctrs COUNTER_DTYPE, status uint8[n]: 0 matched, 1 namespace without limits, 2 too many counters)."""
+        n = len(namespaces)
+        flats = [_bindings(r, d) for r, d in contexts]
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(f) for f in flats])
+        binds = (RlBinding * max(int(off[-1]), 1))()
+        j = 0
+        for f in flats:
+            for d, k, v in f:
+                binds[j] = RlBinding(d, 0, k.encode(), v.encode())
+                j += 1
+        ctr_off = np.zeros(n + 1, dtype=np.uint32)
+        ctrs = np.zeros(64 * (n + 1), dtype=_eng.COUNTER_DTYPE)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self._lib.rl_matcher_counters_batch_ns(self._h, n, _strs(list(namespaces)), off.ctypes.data, binds, ctr_off.ctypes.data,
+                                                           ctrs.ctypes.data, len(ctrs), status.ctypes.data))
+        return ctr_off, ctrs[:int(ctr_off[-1])], status[:n]
+
+    def response_headers_batch(self, ctr_off, ctrs, remaining, ttl_us, cap: int = 0) -> List[Dict[str, str]]:
+        """rl_matcher_response_headers_batch: the draft-03 header values of every request of a CSR in one call."""
+        ctr_off = np.ascontiguousarray(ctr_off, dtype=np.uint32)
+        ctrs = np.ascontiguousarray(ctrs, dtype=_eng.COUNTER_DTYPE)
+        rem = np.ascontiguousarray(remaining, dtype=np.uint64)
+        ttl = np.ascontiguousarray(ttl_us, dtype=np.uint64)
+        n = len(ctr_off) - 1
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        need = C.c_uint64()
+        buf = C.create_string_buffer(max(cap, 1))
+        st = self._lib.rl_matcher_response_headers_batch(self._h, n, ctr_off.ctypes.data, ctrs.ctypes.data, rem.ctypes.data, ttl.ctypes.data,
+                                                         buf, cap, out_off.ctypes.data, C.byref(need))
+        if st != 0 and need.value > cap:  # too small: the call said how much it needs
+            return self.response_headers_batch(ctr_off, ctrs, rem, ttl, int(need.value))
+        self._check(st)
+        raw = buf.raw
+        out = []
+        for i in range(n):
+            lim, r, rst = raw[int(out_off[i]):int(out_off[i + 1])].split(b"\0")[:3]
+            out.append({} if ctr_off[i + 1] == ctr_off[i] else
+                       {"X-RateLimit-Limit": lim.decode(), "X-RateLimit-Remaining": r.decode(), "X-RateLimit-Reset": rst.decode()})
+        return out
 
     def counters_batch(self, ns_ids: Sequence[int], contexts: Sequence[Tuple[Optional[dict], Optional[list]]],
                        cap: Optional[int] = None):

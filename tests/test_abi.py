@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     # the CPU front's header (limits -> counters)
     from limitador_b200 import matcher
     mnames = declared_functions("rl_match.h")
-    assert len(mnames) == 16 and sorted(matcher.MATCH_SYMBOLS) == mnames
+    assert len(mnames) == 18 and sorted(matcher.MATCH_SYMBOLS) == mnames
     for n in mnames:
         assert hasattr(lib, n), f"{n} declared in include/rl_match.h but not exported"
     # the RLS wire surface

@@ -478,3 +478,45 @@ def test_counter_cap_defaults_to_what_the_engine_takes_and_can_be_raised_for_mat
     got = m.counters(m.namespace_id("ns"), {"cond": "1", "var": "v"}, cap=64)
     assert len(got) == 50 and len(set(got["limit_id"].tolist())) == 50
     assert len({(int(c["key_lo"]), int(c["key_hi"])) for c in got}) == 1  # one variable set: one key digest
+
+
+def test_batch_matching_by_namespace_string_equals_the_per_request_calls():
+    """rl_matcher_counters_batch_ns (one reader section per batch — what the RLS stage uses) against rl_matcher_counters
+    request by request, including namespaces without limits and a request with more counters than the engine takes."""
+    limits, reqs = _serving_scenario(7, n_req=300)
+    m = MT.Matcher()
+    for lim in limits:
+        m.add_limit(lim.namespace, lim.max_value, lim.seconds, lim.conditions, lim.variables, lim.name)
+    for l in range(20):  # a namespace in which 20 limits apply at once
+        m.add_limit("wide", 10, 10 + l, [], ["descriptors[0].user"])
+    names = [ns for ns, _, _, _ in reqs] + ["wide", "nobody", "api"]
+    ctxs = [({}, [d]) for _, d, _, _ in reqs] + [({}, [{"user": "u"}]), ({}, [{"user": "u"}]), ({}, [{"method": "GET", "user": "z"}])]
+    off, ctrs, status = m.counters_batch_ns(names, ctxs)
+    for i, (ns, ctx) in enumerate(zip(names, ctxs)):
+        nid = m.namespace_id(ns)
+        got = ctrs[off[i]:off[i + 1]]
+        if nid is None:
+            assert status[i] == 1 and len(got) == 0
+        elif ns == "wide":
+            assert status[i] == 2 and len(got) == 0
+        else:
+            assert status[i] == 0 and got.tobytes() == m.counters(nid, *ctx).tobytes()
+    assert status[-1] == 0 and off[-1] - off[-2] >= 2  # the request behind the refused one is matched as usual
+
+
+def test_batch_header_rendering_equals_the_per_request_rendering():
+    rng = np.random.default_rng(4)
+    m = MT.Matcher()
+    ids = [int(m.add_limit("ns", 10 * (k + 1), 60 * (k + 1), [], ["descriptors[0].u"], name=('a "q" name' if k % 2 else None))["limit_id"])
+           for k in range(6)]
+    sizes = [0, 1, 3, 6, 2, 0, 5]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    ctrs = np.zeros(int(off[-1]), dtype=MT._eng.COUNTER_DTYPE)
+    ctrs["limit_id"] = rng.choice(ids, size=len(ctrs))
+    rem = rng.integers(0, 50, size=len(ctrs)).astype(np.uint64)
+    ttl = rng.integers(0, 120_000_000, size=len(ctrs)).astype(np.uint64)
+    got = m.response_headers_batch(off, ctrs, rem, ttl)  # starts with no room at all: the call says what it needs
+    for i, n in enumerate(sizes):
+        sl = slice(int(off[i]), int(off[i + 1]))
+        assert got[i] == m.response_headers(ctrs[sl], rem[sl], ttl[sl])
+    assert got[3]["X-RateLimit-Limit"].count(";w=") == 6 and "name=\"a 'q' name\"" in got[3]["X-RateLimit-Limit"]
