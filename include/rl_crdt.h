@@ -86,6 +86,8 @@ int rl_crdt_export(rl_crdt *c, uint64_t now_us, uint64_t cap, rl_crdt_key *out_k
 /* Parity aid: every row as (key, expiry, values[actors]); out_values holds cap * actors words.  Host outputs. */
 int rl_crdt_dump(rl_crdt *c, uint64_t cap, rl_crdt_key *out_keys, uint64_t *out_expiry_us, uint64_t *out_values,
                  uint64_t *out_count);
+/* CounterStorage::clear of the replicated store (distributed/mod.rs:210-213): every counter is forgotten. */
+int rl_crdt_clear(rl_crdt *c);
 /* kernels launched by this handle since creation */
 uint64_t rl_crdt_kernel_launches(rl_crdt *c);
 

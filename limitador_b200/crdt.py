@@ -12,7 +12,7 @@ from . import engine as _eng
 
 CRDT_SYMBOLS = (
     "rl_crdt_create", "rl_crdt_destroy", "rl_crdt_last_error", "rl_crdt_inc", "rl_crdt_merge", "rl_crdt_read",
-    "rl_crdt_export", "rl_crdt_dump", "rl_crdt_kernel_launches",
+    "rl_crdt_export", "rl_crdt_dump", "rl_crdt_kernel_launches", "rl_crdt_clear",
 )
 KEY_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8")])
 UPDATE_DTYPE = np.dtype([("key_lo", "<u8"), ("key_hi", "<u8"), ("expires_at_us", "<u8"), ("val_off", "<u4"), ("n_vals", "<u4")])
@@ -44,6 +44,7 @@ def _lib():
     L.rl_crdt_read.argtypes = [vp, u64, vp, u64, i32, vp, vp]
     L.rl_crdt_export.argtypes = [vp, u64, u64, vp, vp, vp, C.POINTER(u64)]
     L.rl_crdt_dump.argtypes = [vp, u64, vp, vp, vp, C.POINTER(u64)]
+    L.rl_crdt_clear.argtypes = [vp]
     L.rl_crdt_kernel_launches.argtypes = [vp]
     L.rl_crdt_kernel_launches.restype = u64
     L._rl_crdt_ready = True
@@ -140,6 +141,10 @@ class CrdtTable:
         m = min(n.value, cap)
         v = vals[:m * self.actors].reshape(m, self.actors)
         return sorted((int(k["lo"][i]), int(k["hi"][i]), int(exp[i]), tuple(v[i].tolist())) for i in range(m))
+
+    def clear(self):
+        """CounterStorage::clear: every counter is forgotten."""
+        self._check(self._lib.rl_crdt_clear(self._h))
 
     def kernel_launches(self) -> int:
         return int(self._lib.rl_crdt_kernel_launches(self._h))

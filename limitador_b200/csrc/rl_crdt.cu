@@ -244,6 +244,14 @@ static int scan(rl_crdt* c, int mode, uint64_t now_us, uint64_t cap, rl_crdt_key
     return RL_OK;
 }
 
+int rl_crdt_clear(rl_crdt* c) {
+    if (!c) return RL_FATAL;
+    RLC_CUDA(c, cudaSetDevice(c->device));
+    RLC_CUDA(c, cudaMemsetAsync(c->d_rows, 0, c->capacity * c->row_bytes, c->stream));
+    RLC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RL_OK;
+}
+
 int rl_crdt_export(rl_crdt* c, uint64_t now_us, uint64_t cap, rl_crdt_key* out_keys, uint64_t* out_value,
                    uint64_t* out_expiry_us, uint64_t* out_count) {
     if (cap && !out_value) return cfail(c, RL_FATAL, "rl_crdt_export: bad arguments");

@@ -75,3 +75,7 @@ def test_errors_are_loud():
     with pytest.raises(CR.CrdtError) as ei:
         t.inc(CR.keys_array([(i + 1, 5) for i in range(9)]), 0, 1, SEC, T0)
     assert ei.value.status == 1  # a full table is TRANSIENT, never a dropped update
+    t.clear()  # CounterStorage::clear: the table is empty again and takes new counters
+    assert t.dump() == []
+    t.inc(CR.keys_array([(i + 1, 5) for i in range(8)]), 1, 3, SEC, T0)
+    assert t.read(CR.keys_array([(8, 5)]), T0)[0].tolist() == [3] and len(t.dump()) == 8
