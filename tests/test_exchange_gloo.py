@@ -200,3 +200,73 @@ def test_exchange_blocks_are_sized_from_the_observed_traffic():
     cap = exchange.slot_cap_for(got, batch)
     assert cap % 256 == 0 and got * 1.2 <= cap + 255 and cap >= got and cap <= batch
     assert exchange.slot_cap_for(batch, batch) == batch
+
+
+def _placement_worker(rank, port, ret):
+    """Two gloo ranks: bench.place_namespaces over each rank's own stream (the all-reduce makes the observed load, hence
+    the ids, equal on both), then the sharded step over the re-identified records with the oracle as the decider."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    import bench
+    lib = load_library()
+    n_ns = 64 * WORLD
+    limits = bench.c2_limits(n_ns)
+    recs = streams.c2_device_stream(N_BATCHES, BATCH, "cpu", n_rows=200_000, n_ns=n_ns, seed=streams.SEED + 1000 * rank)
+    limits, summary = bench.place_namespaces(dist, WORLD, torch.device("cpu"), recs, limits, N_BATCHES, lambda m: None)
+    orc = ob.Oracle(1 << 16)
+    for d in limits:
+        orc.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    verdicts, inbox = [], 0
+    for b in range(N_BATCHES):
+        def bucket(t):
+            a = t.numpy().view(RECORD_DTYPE).reshape(-1)
+            owners = np.array([lib.rl_owner_of(int(ns), WORLD) for ns in a["ns_id"]], dtype=np.int64)
+            perm, src, counts = exchange.stable_bucket_numpy(t.numpy(), owners, WORLD)
+            return torch.from_numpy(perm.copy()), torch.from_numpy(src.copy()), counts
+
+        def decide(buf, m, verdict):
+            nonlocal inbox
+            a = buf[:m].numpy().view(RECORD_DTYPE).reshape(-1)
+            inbox += m
+            lim, _, _, _ = orc.batch_records(0, a)
+            verdict[:m] = torch.from_numpy(lim)
+
+        def unpermute(vb, src, out):
+            out[src.long()] = vb[:len(src)]
+
+        out = torch.zeros(BATCH, dtype=torch.uint8)
+        exchange.sharded_step(recs[b].clone(), WORLD, dist, bucket, decide, unpermute, out)
+        verdicts.append(out.numpy().copy())
+    ret[rank] = (np.concatenate(verdicts), limits["ns_id"].copy(), recs.numpy().copy(), summary, inbox)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_placement_gives_both_ranks_the_same_ids_and_keeps_the_sharded_step_exact():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_placement_worker, args=(port, ret), nprocs=WORLD, join=True)
+    (v0, ids0, recs0, sum0, in0), (v1, ids1, recs1, sum1, in1) = ret[0], ret[1]
+    assert ids0.tolist() == ids1.tolist() and sum0 == sum1  # the same placement on every rank
+    assert sum0["owner_load_max_over_mean"] < 1.02 <= sum0["owner_load_max_over_mean_if_ids_were_hashed_as_generated"]
+    assert abs(in0 - in1) < 0.04 * (in0 + in1)  # the two owners decide (almost) the same number of requests
+    # the global reference: ONE oracle over the re-identified records in (step, rank, index) order
+    import bench
+    limits = bench.c2_limits(64 * WORLD)
+    limits["ns_id"] = ids0
+    orc = ob.Oracle(1 << 16)
+    for d in limits:
+        orc.limit_set(int(d["limit_id"]), int(d["ns_id"]), int(d["max_value"]), int(d["window_us"]), bool(d["qualified"]))
+    want0, want1 = [], []
+    for b in range(N_BATCHES):
+        glob = np.concatenate([recs0[b].view(RECORD_DTYPE).reshape(-1), recs1[b].view(RECORD_DTYPE).reshape(-1)])
+        lim = orc.batch_records(0, glob)[0]
+        want0.append(lim[:BATCH])
+        want1.append(lim[BATCH:])
+    assert np.array_equal(v0, np.concatenate(want0)) and np.array_equal(v1, np.concatenate(want1))
+    assert 0 < int(v0.sum()) < len(v0)
