@@ -81,7 +81,7 @@ def test_compact_on_a_table_without_tombstones_does_nothing():
     descs = _limits(1)
     e = Engine(capacity_rows=1 << 10, cells_per_row=1, max_batch=4096, regions=4)
     e.limits_set(descs)
-    e.check_and_update_records(_records(descs, 2000, 1, H.T0, 300), False, stride=1)
+    e.check_and_update_records(_records(descs, 2000, 1, H.T0, 100), False, stride=1)  # <= 500 rows in a table of 1024
     before = e.dump()
     st = e.compact(0)
     assert st["regions_rebuilt"] == 0 and st["rows_tombstoned"] == 0 and st["rows_live"] > 100 and st["rows_moved"] == 0
