@@ -770,6 +770,7 @@ int rl_rls_finish(rl_rls* s, int store_status, const uint8_t* limited, const uin
         for (const auto& kv : W.limited_by_name) s->limited_by_name[kv.first] += kv.second;
     }
     s->finished = true;
+    s->planned = false;  // a batch is finished once: its metrics are counted once
     return RL_OK;
 }
 

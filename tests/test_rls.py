@@ -436,3 +436,11 @@ def test_kuadrant_report_returns_unknown_when_domain_is_empty():
     """:621-647"""
     h = CpuHarness([])
     assert h.call(R.REPORT, [_req("", [[("req.method", "GET")]], 1)])[0] == (0, (R.CODE_UNKNOWN, []))
+
+
+def test_a_batch_is_finished_once():
+    h = CpuHarness([("ns", 5, 60, [], [], None)])
+    h.call(R.SHOULD_RATE_LIMIT, [_req("ns", [])] * 3)
+    with pytest.raises(R.RlsError, match="no planned batch"):
+        h.svc.finish(np.zeros(3, np.uint8), np.zeros(3, np.uint32), np.zeros(3, np.uint64), np.zeros(3, np.uint64))
+    assert 'authorized_calls{limitador_namespace="ns"} 3' in h.svc.metrics()
