@@ -90,8 +90,8 @@ int rl_rls_plan(rl_rls *s, int method, uint64_t n, const uint8_t *buf, const uin
 int rl_rls_plan_view(rl_rls *s, uint64_t *out_n_store, const uint32_t **out_ctr_off, const rl_counter **out_ctrs,
                      const uint64_t **out_delta, const uint64_t **out_now_us, int *out_load_counters,
                      const uint32_t **out_store_index);
-/* Stage 3 (once per planned batch).  store_status = status of the store call (non-OK: every store request is answered UNAVAILABLE);
- * limited / first_limited: n_store entries; remaining / ttl_us: one per counter (only read with headers). */
+/* Stage 3 (once per planned batch).  store_status = status of the store call (non-OK: every store request is answered
+ * UNAVAILABLE); limited / first_limited: n_store entries; remaining / ttl_us: one per counter (only read with headers). */
 int rl_rls_finish(rl_rls *s, int store_status, const uint8_t *limited, const uint32_t *first_limited,
                   const uint64_t *remaining, const uint64_t *ttl_us);
 /* Responses of the last finished batch: response i = (*out_buf)[(*out_off)[i] .. (*out_off)[i+1]) (empty for a
